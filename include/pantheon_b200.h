@@ -1,0 +1,344 @@
+/*
+ * pantheon_b200.h — C ABI of libpantheon_b200.so
+ *
+ * The drop-in boundary for the PPO rollout -> GAE -> update hot path of
+ * Stanford-ILIAD/PantheonRL, rebuilt as hand-written sm_100a CUDA.
+ *
+ * The reference has no FFI: its "operator API" for this path is a duck-typed
+ * Python interface (pantheonrl/common/agents.py:24-51 Agent.get_action/update,
+ * agents.py:111-203 OnPolicyAgent) that reaches into Stable-Baselines3 objects
+ * (policy.forward, rollout_buffer.add / compute_returns_and_advantage,
+ * model.train).  Each entry point below cites the reference call site it
+ * replaces.  The Python facade in pantheonrl_b200/ binds these with ctypes
+ * (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PTH_E* code;
+ *     pth_last_error() gives a thread-local message for the last failure.
+ *   - all pointers named d_* (or inside *_args structs unless stated) are
+ *     DEVICE pointers owned by the caller (PyTorch tensors: tensor.data_ptr()).
+ *     The library never allocates, frees or retains device memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Calls are asynchronous with respect to the host unless stated.
+ *   - layouts are time-major like SB3's RolloutBuffer: [T][N] with the env
+ *     index contiguous.
+ *   - all floating point is IEEE fp32, round-to-nearest, no fast-math; the
+ *     evaluation order of every reduction is fixed (see DESIGN.md "numeric
+ *     contract") so results are run-to-run and CPU-oracle bit-reproducible.
+ */
+#ifndef PANTHEON_B200_H
+#define PANTHEON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTH_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define PTH_OK 0
+#define PTH_EINVAL (-1)   /* bad argument (null pointer, bad size, bad space) */
+#define PTH_ECUDA (-2)    /* CUDA runtime error (message in pth_last_error) */
+#define PTH_ENOSUP (-3)   /* configuration not supported by this build */
+#define PTH_ENODEV (-4)   /* no usable sm_100 device */
+
+typedef struct pth_ctx pth_ctx;
+
+int pth_version(void);
+const char* pth_last_error(void);
+
+/* One ctx per (process, device).  Queries SM count / limits once.
+ * Fails with PTH_ENODEV when no CUDA device is present: there is NO CPU
+ * fallback anywhere in this library. */
+int pth_ctx_create(int device, pth_ctx** out);
+int pth_ctx_destroy(pth_ctx* ctx);
+int pth_ctx_sm_count(const pth_ctx* ctx);
+/* debug only: cudaStreamSynchronize(stream) and surface async errors */
+int pth_sync_debug(pth_ctx* ctx, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Spaces and policy parameter layout                                  */
+/* ------------------------------------------------------------------ */
+
+#define PTH_MAX_OBS_SLOTS 64
+#define PTH_MAX_HEADS 4
+#define PTH_HIDDEN 64 /* SB3 MlpPolicy default: pi=[64,64], vf=[64,64], tanh */
+
+enum { PTH_OBS_ONEHOT = 0, PTH_OBS_BOX = 1 };
+
+/* Observation / action description of one agent's policy.
+ *   PTH_OBS_ONEHOT: obs is obs_len small integers (Discrete(n): obs_len=1,
+ *     MultiDiscrete(nvec): obs_len=len(nvec)); features = concat of one-hots,
+ *     width = sum(obs_nvec)   (SB3 preprocess_obs)
+ *   PTH_OBS_BOX: obs is obs_len fp32 values, features = obs.
+ * Action: n_heads independent categoricals (Discrete: 1 head;
+ * MultiDiscrete([7,12]): 2 heads), logits concatenated (SB3
+ * MultiCategoricalDistribution; Appendix A3). */
+typedef struct pth_space {
+  int32_t obs_kind;
+  int32_t obs_len;
+  int32_t obs_nvec[PTH_MAX_OBS_SLOTS];
+  int32_t n_heads;
+  int32_t head_n[PTH_MAX_HEADS];
+} pth_space;
+
+/* Flat fp32 parameter vector, SB3 registration order (Appendix A2), torch
+ * nn.Linear layout weight[out][in]:
+ *   pi0.w[64][F] pi0.b[64] pi1.w[64][64] pi1.b[64]
+ *   vf0.w[64][F] vf0.b[64] vf1.w[64][64] vf1.b[64]
+ *   act.w[L][64] act.b[L]  val.w[1][64]  val.b[1]
+ * F = feature width, L = sum(head_n). */
+int pth_space_feature_dim(const pth_space* sp);
+int pth_space_logit_dim(const pth_space* sp);
+int64_t pth_policy_param_count(const pth_space* sp);
+
+/* ------------------------------------------------------------------ */
+/* a4: GAE / returns                                                   */
+/* replaces RolloutBuffer.compute_returns_and_advantage called at      */
+/* pantheonrl/common/agents.py:127-130 (partner) and by SB3            */
+/* collect_rollouts for the ego (restated adap_learn.py:468-469)       */
+/* ------------------------------------------------------------------ */
+
+/* Dense buffer: rewards, values, episode_starts, advantages, returns are
+ * [T][N] fp32; last_values, dones are [N] fp32.
+ *   nnt_t   = 1 - episode_starts[t+1]        (t < T-1),  1 - dones  (t = T-1)
+ *   delta_t = rewards[t] + gamma*V_{t+1}*nnt_t - values[t]
+ *   A_t     = delta_t + gamma*lambda*nnt_t*A_{t+1};   R_t = A_t + values[t]
+ * One thread per env walks t = T-1..0 with a software-pipelined window of
+ * loads; bit-exact with the sequential CPU recurrence.  20 B per (t, env).
+ * variant: 0 = auto, 1 = register-window LDG kernel, 2 = TMA/mbarrier
+ * smem-staged kernel, 3 = time-parallel warp affine scan (small N; agrees with
+ * the sequential recurrence to rounding, not bit-exact). */
+int pth_gae_f32(pth_ctx* ctx, const float* d_rewards, const float* d_values,
+                const float* d_episode_starts, const float* d_last_values,
+                const float* d_dones, float* d_advantages, float* d_returns,
+                int64_t T, int64_t N, double gamma, double gae_lambda,
+                int variant, void* stream);
+
+/* Ragged buffer (vectorised partner, DESIGN.md "partner buffer"): same arrays
+ * with leading dimension Tcap, per-env valid prefix length d_count[n] <= Tcap.
+ * Bootstrap follows agents.py:127-129 exactly: last_values = the value stored
+ * with the env's LAST recorded decision, dones = d_last_done[n] (the flag
+ * latched by the last update(), agents.py:197).  Rows >= count are untouched. */
+int pth_gae_ragged_f32(pth_ctx* ctx, const float* d_rewards,
+                       const float* d_values, const float* d_episode_starts,
+                       const int32_t* d_count, const float* d_last_done,
+                       float* d_advantages, float* d_returns, int64_t Tcap,
+                       int64_t N, double gamma, double gae_lambda,
+                       void* stream);
+
+/* ------------------------------------------------------------------ */
+/* a8/a9: game rules as standalone step kernels (one thread per env)   */
+/* ------------------------------------------------------------------ */
+
+/* RPSEnv.multi_step, pantheonrl/envs/rpsgym/rps.py:41-45.
+ * actions int32 [N] in {0,1,2}; rewards fp32 [N] (ego, alt); done always. */
+int pth_env_rps_step(pth_ctx* ctx, const int32_t* d_ego_action,
+                     const int32_t* d_alt_action, float* d_ego_reward,
+                     float* d_alt_reward, int64_t N, void* stream);
+
+/* Liar's Dice state, one 32-byte record per env (liar.py:45-102):
+ *   hands[0..5] = ego histogram, hands[6..11] = partner histogram
+ *   hist[i] = face | (count << 3), newest bid first (liar.py:82), hist_len bids
+ */
+#define PTH_LIAR_SIDES 6
+#define PTH_LIAR_DICE 6
+#define PTH_LIAR_MAX_MOVES 12
+#define PTH_LIAR_OBS_LEN 30
+typedef struct pth_liar_state {
+  uint8_t hands[12];
+  uint8_t hist[12];
+  uint8_t hist_len;
+  uint8_t pad[7];
+} pth_liar_state;
+
+/* LiarEnv.multi_reset (liar.py:97-102) with the dice supplied by the caller's
+ * counter-based RNG: hands drawn from Philox4x32-10(seed, stream ENV) at
+ * (env0 + n, tick); also draws ego_first = u < probegostart
+ * (multiagentenv.py:325).  obs out: u8 [N][32] observation of the mover. */
+int pth_env_liar_reset(pth_ctx* ctx, pth_liar_state* d_state,
+                       uint8_t* d_ego_first, uint8_t* d_obs, int64_t N,
+                       uint64_t seed, uint32_t tick, int64_t env0,
+                       float probegostart, void* stream);
+
+/* LiarEnv.player_step (liar.py:77-83) for the player given per env by
+ * d_is_ego[n] (1 = ego_step, 0 = alt_step): sanitize_action (liar.py:58-67),
+ * eval_bluff (liar.py:69-75).  action u8 [N][2] (face 0..6, count 0..11).
+ * Outputs: obs of the OTHER player u8 [N][32], rewards (ego, alt) fp32, done. */
+int pth_env_liar_step(pth_ctx* ctx, pth_liar_state* d_state,
+                      const uint8_t* d_is_ego, const uint8_t* d_action,
+                      uint8_t* d_obs, float* d_ego_reward, float* d_alt_reward,
+                      uint8_t* d_done, int64_t N, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* a1 + a2: policy forward + sample + log-prob + value (+ buffer row)  */
+/* replaces util.action_from_policy (util.py:63-81) ->                 */
+/* ActorCriticPolicy.forward and RolloutBuffer.add (agents.py:162-179) */
+/* ------------------------------------------------------------------ */
+
+/* B independent observations.  obs: u8 [B][obs_stride] (ONEHOT) or fp32
+ * [B][obs_stride] (BOX).  Sampling: inverse-CDF on one Philox uniform per
+ * head, counter (idx0 + b, tick, slot), stream = rng_stream.  If
+ * d_action_in != NULL no sampling happens and log-prob/entropy are evaluated
+ * for the given actions (ActorCriticPolicy.evaluate_actions).
+ * Outputs (any may be NULL): action u8 [B][4], value fp32 [B], logp fp32 [B],
+ * entropy fp32 [B], logits fp32 [B][L]. */
+typedef struct pth_forward_args {
+  const pth_space* space;      /* HOST pointer */
+  const float* d_params;
+  const void* d_obs;
+  int64_t obs_stride;          /* elements per row */
+  int64_t B;
+  uint64_t seed;
+  uint32_t rng_stream;
+  uint32_t tick;
+  uint32_t slot;
+  int64_t idx0;
+  const uint8_t* d_action_in;
+  uint8_t* d_action;
+  float* d_value;
+  float* d_logp;
+  float* d_entropy;
+  float* d_logits;
+} pth_forward_args;
+int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* a1+a2+a3+a7+a8/a9 fused: T-tick rollout with on-device envs         */
+/* replaces the Python loop OnPolicyAlgorithm.collect_rollouts ->      */
+/* MultiAgentEnv.step (multiagentenv.py:172-215) -> partner.get_action */
+/* / update (agents.py:111-203) -> n_step / n_reset                    */
+/* ------------------------------------------------------------------ */
+
+enum { PTH_ENV_RPS = 0, PTH_ENV_LIAR = 1 };
+
+/* rollout buffer of one learner; all arrays [Tcap][N] (row = 32 B obs).
+ * Ego: Tcap = T, dense (count unused, may be NULL).
+ * Partner: Tcap >= 2*T, ragged, count[n] decisions recorded this rollout. */
+typedef struct pth_buffer {
+  uint8_t* d_obs;            /* [Tcap][N][32] */
+  uint8_t* d_actions;        /* [Tcap][N][4]  */
+  float* d_rewards;          /* [Tcap][N] */
+  float* d_values;           /* [Tcap][N] */
+  float* d_logp;             /* [Tcap][N] */
+  float* d_episode_starts;   /* [Tcap][N] */
+  int32_t* d_count;          /* [N] or NULL */
+  int64_t Tcap;
+} pth_buffer;
+
+/* persistent per-env driver state carried across rollouts (the fields of
+ * MultiAgentEnv, multiagentenv.py:58-66, plus agents.py:97 latches) */
+typedef struct pth_env_carry {
+  float* d_ego_last_start;     /* [N] ego _last_episode_starts            */
+  float* d_alt_last_done;      /* [N] partner _last_episode_starts latch  */
+  float* d_total_rew;          /* [2][N] total_rews                       */
+  uint8_t* d_flags;            /* [N] bit0 ego_moved, bit1 should_update  */
+  void* d_game_state;          /* PTH_ENV_LIAR: pth_liar_state[N]; RPS: NULL */
+  float* d_ego_last_value;     /* [N] out: V(obs_T) bootstrap for the ego  */
+  float* d_ego_last_done;      /* [N] out: done flag after the last tick   */
+  float* d_ep_stats;           /* [4] += {episodes, sum ego ep reward, sum ep len, partner decisions} or NULL */
+} pth_env_carry;
+
+typedef struct pth_rollout_args {
+  int32_t env_kind;
+  int32_t partner_records;     /* 1: partner is a learner (OnPolicyAgent); 0: StaticPolicyAgent */
+  const pth_space* space;      /* HOST pointer; ego and partner share spaces (getDummyEnv, multiagentenv.py:72-79) */
+  const float* d_ego_params;
+  const float* d_alt_params;   /* == d_ego_params for self-play */
+  pth_buffer ego;
+  pth_buffer alt;
+  pth_env_carry carry;
+  int64_t N;
+  int64_t T;
+  int64_t env0;                /* global index of env 0 of this shard (multi-GPU) */
+  uint64_t seed;
+  uint32_t tick0;              /* global tick of the first tick of this rollout */
+  float probegostart;          /* TurnBasedEnv.probegostart */
+  int32_t first_rollout;       /* 1: envs are reset before tick 0 (SB3 _setup_learn) */
+} pth_rollout_args;
+int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* args, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* a5: PPO update                                                      */
+/* replaces model.train() at agents.py:155 -> SB3 PPO.train            */
+/* (restated pantheonrl/algos/adap/adap_learn.py:229-347)              */
+/* ------------------------------------------------------------------ */
+
+/* Keyed bijection on [0, M): perm[e][i] for epochs e in [0, n_epochs).
+ * Stands in for np.random.permutation (SB3 RolloutBuffer.get): 4-round
+ * Feistel on ceil-pow2 domain with cycle walking, keyed by Philox(seed,
+ * stream SHUFFLE, epoch_counter0 + e).  d_perm int32 [n_epochs][M]. */
+int pth_perm_feistel(pth_ctx* ctx, int32_t* d_perm, int64_t M, int32_t n_epochs,
+                     uint64_t seed, uint32_t stream_id, uint32_t epoch0,
+                     void* stream);
+
+/* Compact the valid (row, env) cells of a ragged buffer into flat sample
+ * offsets row*N + env, env-major order (SB3 swap_and_flatten): d_index int32
+ * [>= sum(count)], *d_total = sum(count).  For a dense buffer pass
+ * d_count = NULL and every env gets T rows. */
+int pth_index_build(pth_ctx* ctx, const int32_t* d_count, int64_t T, int64_t N,
+                    int32_t* d_index, int32_t* d_total, void* stream);
+int64_t pth_index_workspace_bytes(int64_t N);
+
+typedef struct pth_update_args {
+  const pth_space* space;   /* HOST pointer */
+  float* d_params;          /* [P] in/out */
+  float* d_adam_m;          /* [P] in/out */
+  float* d_adam_v;          /* [P] in/out */
+  int64_t adam_step;        /* optimiser steps already taken */
+  /* flat sample arrays indexed by offset = d_index[perm[...]] */
+  const uint8_t* d_obs;     /* [*][32] u8 (ONEHOT) ; BOX: fp32 rows via d_obs_f32 */
+  const float* d_obs_f32;   /* [*][obs_stride] or NULL */
+  int64_t obs_stride;
+  const uint8_t* d_actions; /* [*][4] */
+  const float* d_old_logp;
+  const float* d_advantages;
+  const float* d_returns;
+  int64_t rec_stride;       /* 0: separate arrays (32 B obs rows, 4 B others); else common byte stride (packed records) */
+  const int32_t* d_index;   /* [M] sample -> flat offset, or NULL = identity */
+  const int32_t* d_perm;    /* [n_epochs][M] */
+  int64_t M;                /* samples in the buffer */
+  int64_t batch_size;       /* SB3 batch_size; last minibatch may be short */
+  int32_t n_epochs;
+  float learning_rate, clip_range, ent_coef, vf_coef, max_grad_norm;
+  float adam_beta1, adam_beta2, adam_eps;
+  int32_t normalize_advantage;
+  void* d_workspace;        /* pth_update_workspace_bytes() */
+  int64_t workspace_bytes;
+  float* d_stats;           /* [n_epochs*n_minibatch][8]: pg_loss, value_loss, entropy_loss, approx_kl, clip_frac, loss, grad_norm, n */
+} pth_update_args;
+int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
+                                   int64_t M, int64_t batch_size);
+int pth_ppo_update(pth_ctx* ctx, const pth_update_args* args, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* e: multi-GPU exchange staging                                       */
+/* ------------------------------------------------------------------ */
+
+/* Pack one rank's ego transitions [T][N] into a contiguous record stream
+ * (48 B / sample: obs 32, action 4, old_logp 4, advantage 4, return 4) for a
+ * single all-gather per rollout. */
+#define PTH_PACKED_BYTES 48
+int pth_pack_transitions(pth_ctx* ctx, const uint8_t* d_obs,
+                         const uint8_t* d_actions, const float* d_logp,
+                         const float* d_advantages, const float* d_returns,
+                         int64_t count, uint8_t* d_packed, void* stream);
+/* Same, but stores each record straight into every peer's gather buffer
+ * (peer pointers mapped by the caller via CUDA IPC): pack + all-gather in one
+ * kernel over NVLink, no intermediate staging. d_peer_bufs: DEVICE array of
+ * world pointers; records land at rank*count. */
+int pth_pack_allgather_p2p(pth_ctx* ctx, const uint8_t* d_obs,
+                           const uint8_t* d_actions, const float* d_logp,
+                           const float* d_advantages, const float* d_returns,
+                           int64_t count, uint8_t* const* d_peer_bufs,
+                           int32_t world, int32_t rank, void* stream);
+/* The update reads a packed stream directly: point d_obs / d_actions /
+ * d_old_logp / d_advantages / d_returns at offsets 0 / 32 / 36 / 40 / 44 of the
+ * first record and set rec_stride = PTH_PACKED_BYTES. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANTHEON_B200_H */

@@ -1,0 +1,256 @@
+"""ctypes binding of libpantheon_b200.so (include/pantheon_b200.h).
+
+There is no fallback: if the shared library is missing, or a call returns an
+error, this module raises.  PyTorch tensors are passed as raw device pointers
+(``tensor.data_ptr()``) plus the current CUDA stream handle.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpantheon_b200.so")
+
+PTH_MAX_OBS_SLOTS = 64
+PTH_MAX_HEADS = 4
+PTH_HIDDEN = 64
+PTH_OBS_ONEHOT, PTH_OBS_BOX = 0, 1
+PTH_ENV_RPS, PTH_ENV_LIAR = 0, 1
+PTH_PACKED_BYTES = 48
+
+STREAM_ENV, STREAM_EGO, STREAM_ALT, STREAM_SHUFFLE_EGO, STREAM_SHUFFLE_ALT = 1, 2, 3, 4, 5
+
+
+class PthError(RuntimeError):
+    pass
+
+
+class Space(C.Structure):
+    _fields_ = [
+        ("obs_kind", C.c_int32),
+        ("obs_len", C.c_int32),
+        ("obs_nvec", C.c_int32 * PTH_MAX_OBS_SLOTS),
+        ("n_heads", C.c_int32),
+        ("head_n", C.c_int32 * PTH_MAX_HEADS),
+    ]
+
+    @classmethod
+    def onehot(cls, nvec, heads):
+        s = cls()
+        s.obs_kind = PTH_OBS_ONEHOT
+        s.obs_len = len(nvec)
+        for i, v in enumerate(nvec):
+            s.obs_nvec[i] = int(v)
+        s.n_heads = len(heads)
+        for i, v in enumerate(heads):
+            s.head_n[i] = int(v)
+        return s
+
+    @classmethod
+    def box(cls, dim, heads):
+        s = cls()
+        s.obs_kind = PTH_OBS_BOX
+        s.obs_len = int(dim)
+        s.n_heads = len(heads)
+        for i, v in enumerate(heads):
+            s.head_n[i] = int(v)
+        return s
+
+    @property
+    def nvec(self):
+        return [self.obs_nvec[i] for i in range(self.obs_len)]
+
+    @property
+    def heads(self):
+        return [self.head_n[i] for i in range(self.n_heads)]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("space", C.POINTER(Space)),
+        ("d_params", C.c_void_p),
+        ("d_obs", C.c_void_p),
+        ("obs_stride", C.c_int64),
+        ("B", C.c_int64),
+        ("seed", C.c_uint64),
+        ("rng_stream", C.c_uint32),
+        ("tick", C.c_uint32),
+        ("slot", C.c_uint32),
+        ("idx0", C.c_int64),
+        ("d_action_in", C.c_void_p),
+        ("d_action", C.c_void_p),
+        ("d_value", C.c_void_p),
+        ("d_logp", C.c_void_p),
+        ("d_entropy", C.c_void_p),
+        ("d_logits", C.c_void_p),
+    ]
+
+
+class Buffer(C.Structure):
+    _fields_ = [
+        ("d_obs", C.c_void_p),
+        ("d_actions", C.c_void_p),
+        ("d_rewards", C.c_void_p),
+        ("d_values", C.c_void_p),
+        ("d_logp", C.c_void_p),
+        ("d_episode_starts", C.c_void_p),
+        ("d_count", C.c_void_p),
+        ("Tcap", C.c_int64),
+    ]
+
+
+class EnvCarry(C.Structure):
+    _fields_ = [
+        ("d_ego_last_start", C.c_void_p),
+        ("d_alt_last_done", C.c_void_p),
+        ("d_total_rew", C.c_void_p),
+        ("d_flags", C.c_void_p),
+        ("d_game_state", C.c_void_p),
+        ("d_ego_last_value", C.c_void_p),
+        ("d_ego_last_done", C.c_void_p),
+        ("d_ep_stats", C.c_void_p),
+    ]
+
+
+class RolloutArgs(C.Structure):
+    _fields_ = [
+        ("env_kind", C.c_int32),
+        ("partner_records", C.c_int32),
+        ("space", C.POINTER(Space)),
+        ("d_ego_params", C.c_void_p),
+        ("d_alt_params", C.c_void_p),
+        ("ego", Buffer),
+        ("alt", Buffer),
+        ("carry", EnvCarry),
+        ("N", C.c_int64),
+        ("T", C.c_int64),
+        ("env0", C.c_int64),
+        ("seed", C.c_uint64),
+        ("tick0", C.c_uint32),
+        ("probegostart", C.c_float),
+        ("first_rollout", C.c_int32),
+    ]
+
+
+class UpdateArgs(C.Structure):
+    _fields_ = [
+        ("space", C.POINTER(Space)),
+        ("d_params", C.c_void_p),
+        ("d_adam_m", C.c_void_p),
+        ("d_adam_v", C.c_void_p),
+        ("adam_step", C.c_int64),
+        ("d_obs", C.c_void_p),
+        ("d_obs_f32", C.c_void_p),
+        ("obs_stride", C.c_int64),
+        ("d_actions", C.c_void_p),
+        ("d_old_logp", C.c_void_p),
+        ("d_advantages", C.c_void_p),
+        ("d_returns", C.c_void_p),
+        ("rec_stride", C.c_int64),
+        ("d_index", C.c_void_p),
+        ("d_perm", C.c_void_p),
+        ("M", C.c_int64),
+        ("batch_size", C.c_int64),
+        ("n_epochs", C.c_int32),
+        ("learning_rate", C.c_float),
+        ("clip_range", C.c_float),
+        ("ent_coef", C.c_float),
+        ("vf_coef", C.c_float),
+        ("max_grad_norm", C.c_float),
+        ("adam_beta1", C.c_float),
+        ("adam_beta2", C.c_float),
+        ("adam_eps", C.c_float),
+        ("normalize_advantage", C.c_int32),
+        ("d_workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+        ("d_stats", C.c_void_p),
+    ]
+
+
+_vp, _i64, _i32, _u64, _u32, _f, _d = (C.c_void_p, C.c_int64, C.c_int32, C.c_uint64,
+                                       C.c_uint32, C.c_float, C.c_double)
+
+# name -> (restype, argtypes).  Every symbol declared in include/pantheon_b200.h.
+SIGNATURES = {
+    "pth_version": (C.c_int, []),
+    "pth_last_error": (C.c_char_p, []),
+    "pth_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "pth_ctx_destroy": (C.c_int, [_vp]),
+    "pth_ctx_sm_count": (C.c_int, [_vp]),
+    "pth_sync_debug": (C.c_int, [_vp, _vp]),
+    "pth_space_feature_dim": (C.c_int, [C.POINTER(Space)]),
+    "pth_space_logit_dim": (C.c_int, [C.POINTER(Space)]),
+    "pth_policy_param_count": (_i64, [C.POINTER(Space)]),
+    "pth_gae_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _d, _d, C.c_int, _vp]),
+    "pth_gae_ragged_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _d, _d, _vp]),
+    "pth_env_rps_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pth_env_liar_reset": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _u64, _u32, _i64, _f, _vp]),
+    "pth_env_liar_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pth_policy_forward": (C.c_int, [_vp, C.POINTER(ForwardArgs), _vp]),
+    "pth_rollout_run": (C.c_int, [_vp, C.POINTER(RolloutArgs), _vp]),
+    "pth_perm_feistel": (C.c_int, [_vp, _vp, _i64, _i32, _u64, _u32, _u32, _vp]),
+    "pth_index_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "pth_index_workspace_bytes": (_i64, [_i64]),
+    "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
+    "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),
+    "pth_pack_transitions": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "pth_pack_allgather_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and bind every declared symbol.  No device calls."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PthError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().pth_last_error().decode("utf-8", "replace")
+        raise PthError(f"{what} failed ({rc}): {msg}")
+
+
+class Context:
+    """pth_ctx wrapper; one per (process, device)."""
+
+    _cache = {}
+
+    def __init__(self, device=0):
+        lib = load()
+        h = _vp()
+        check(lib.pth_ctx_create(int(device), C.byref(h)), "pth_ctx_create")
+        self.handle = h
+        self.device = int(device)
+        self.sm_count = lib.pth_ctx_sm_count(h)
+
+    @classmethod
+    def get(cls, device=0):
+        device = int(device)
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor, None -> NULL."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,100 @@
+// pth_api.cu — context, error reporting and space helpers of the C ABI.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "pth_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void pth_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+int pth_version(void) { return PTH_VERSION; }
+
+const char* pth_last_error(void) { return g_err; }
+
+int pth_ctx_create(int device, pth_ctx** out) {
+  PTH_CHECK_ARG(out != nullptr, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    pth_set_error("pth_ctx_create: no CUDA device (%s); this library has no CPU path",
+                  e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    return PTH_ENODEV;
+  }
+  PTH_CHECK_ARG(device >= 0 && device < count, "device index out of range");
+  cudaDeviceProp prop;
+  PTH_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    pth_set_error("pth_ctx_create: device %d is sm_%d%d; kernels are built for sm_100a only",
+                  device, prop.major, prop.minor);
+    return PTH_ENODEV;
+  }
+  pth_ctx* c = (pth_ctx*)calloc(1, sizeof(pth_ctx));
+  PTH_CHECK_ARG(c != nullptr, "out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->coop_launch = prop.cooperativeLaunch;
+  *out = c;
+  return PTH_OK;
+}
+
+int pth_ctx_destroy(pth_ctx* ctx) {
+  if (ctx) free(ctx);
+  return PTH_OK;
+}
+
+int pth_ctx_sm_count(const pth_ctx* ctx) { return ctx ? ctx->sm_count : PTH_EINVAL; }
+
+int pth_sync_debug(pth_ctx* ctx, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr, "ctx is NULL");
+  PTH_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  PTH_CUDA(cudaGetLastError());
+  return PTH_OK;
+}
+
+static int space_ok(const pth_space* sp) {
+  if (!sp) return 0;
+  if (sp->obs_kind != PTH_OBS_ONEHOT && sp->obs_kind != PTH_OBS_BOX) return 0;
+  if (sp->obs_len < 1 || sp->obs_len > PTH_MAX_OBS_SLOTS) return 0;
+  if (sp->n_heads < 1 || sp->n_heads > PTH_MAX_HEADS) return 0;
+  for (int h = 0; h < sp->n_heads; ++h)
+    if (sp->head_n[h] < 1 || sp->head_n[h] > 32) return 0;
+  if (sp->obs_kind == PTH_OBS_ONEHOT)
+    for (int s = 0; s < sp->obs_len; ++s)
+      if (sp->obs_nvec[s] < 1 || sp->obs_nvec[s] > 255) return 0;
+  return 1;
+}
+
+int pth_space_feature_dim(const pth_space* sp) {
+  if (!space_ok(sp)) return PTH_EINVAL;
+  if (sp->obs_kind == PTH_OBS_BOX) return sp->obs_len;
+  int f = 0;
+  for (int s = 0; s < sp->obs_len; ++s) f += sp->obs_nvec[s];
+  return f;
+}
+
+int pth_space_logit_dim(const pth_space* sp) {
+  if (!space_ok(sp)) return PTH_EINVAL;
+  int l = 0;
+  for (int h = 0; h < sp->n_heads; ++h) l += sp->head_n[h];
+  return l;
+}
+
+int64_t pth_policy_param_count(const pth_space* sp) {
+  if (!space_ok(sp)) return PTH_EINVAL;
+  int64_t F = pth_space_feature_dim(sp), L = pth_space_logit_dim(sp), H = PTH_HIDDEN;
+  return 2 * (H * F + H + H * H + H) + L * H + L + H + 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+"""CPU tests of the C-ABI boundary: the shared library loads and exports every
+symbol include/pantheon_b200.h declares; no compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pantheon_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pth_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_entry_points():
+    names = declared_symbols()
+    for must in ("pth_gae_f32", "pth_env_rps_step", "pth_env_liar_step", "pth_policy_forward",
+                 "pth_rollout_run", "pth_ppo_update", "pth_pack_transitions", "pth_version"):
+        assert must in names
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build_cuda()
+    from pantheonrl_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert sorted(_lib.SIGNATURES) == names, set(names) ^ set(_lib.SIGNATURES)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.pth_version() == 100
+
+
+def test_struct_sizes_match_the_header():
+    from pantheonrl_b200 import _lib
+    assert ctypes.sizeof(_lib.Space) == 4 * (2 + 64 + 1 + 4)
+    assert ctypes.sizeof(_lib.Buffer) == 8 * 8
+    assert ctypes.sizeof(_lib.EnvCarry) == 8 * 8
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pantheonrl_b200 import _lib
+    with pytest.raises(_lib.PthError):
+        _lib.Context(0)
+    # host-only helpers still work without a device
+    lib = _lib.load()
+    sp = _lib.Space.onehot([7] * 6 + [7, 12] * 12, [7, 12])
+    assert lib.pth_space_feature_dim(ctypes.byref(sp)) == 270
+    assert lib.pth_space_logit_dim(ctypes.byref(sp)) == 19
+    assert lib.pth_policy_param_count(ctypes.byref(sp)) == 44308
+    assert lib.pth_policy_param_count(ctypes.byref(_lib.Space.onehot([1], [3]))) == 8836
+    assert lib.pth_policy_param_count(ctypes.byref(_lib.Space.box(62, [6]))) == 16839
