@@ -84,12 +84,15 @@ typedef struct pth_space {
   int32_t head_n[PTH_MAX_HEADS];
 } pth_space;
 
-/* Flat fp32 parameter vector, SB3 registration order (Appendix A2), torch
- * nn.Linear layout weight[out][in]:
- *   pi0.w[64][F] pi0.b[64] pi1.w[64][64] pi1.b[64]
- *   vf0.w[64][F] vf0.b[64] vf1.w[64][64] vf1.b[64]
+/* Flat fp32 parameter vector, SB3 registration order (Appendix A2):
+ *   pi0.w[F][64] pi0.b[64] pi1.w[64][64] pi1.b[64]
+ *   vf0.w[F][64] vf0.b[64] vf1.w[64][64] vf1.b[64]
  *   act.w[L][64] act.b[L]  val.w[1][64]  val.b[1]
- * F = feature width, L = sum(head_n). */
+ * F = feature width, L = sum(head_n).  The two first-layer matrices are stored
+ * INPUT-MAJOR [F][64] — the transpose of torch's nn.Linear.weight — so that a
+ * one-hot row gather reads 256 contiguous bytes; every other tensor keeps
+ * torch's weight[out][in] layout.  (The Python facade transposes at the
+ * state_dict boundary.) */
 int pth_space_feature_dim(const pth_space* sp);
 int pth_space_logit_dim(const pth_space* sp);
 int64_t pth_policy_param_count(const pth_space* sp);

@@ -341,7 +341,9 @@ static void split_params(const orc_space* sp, const float* p, orc_params* q) {
 
 /* features: SB3 preprocess_obs (one-hot concat) — Appendix A2.  A linear layer
  * is evaluated as acc = bias; for k ascending: acc = fma(x_k, w[j][k], acc).
- * With x in {0,1} this equals adding the selected columns in ascending order. */
+ * With x in {0,1} this equals adding the selected columns in ascending order.
+ * Storage: the two first-layer matrices are kept input-major [F][64] (the
+ * transpose of torch's nn.Linear.weight); every other tensor is [out][in]. */
 static void first_layer(const orc_space* sp, const void* obs_row, const float* w, const float* b,
                         int F, float* out /*H, pre-activation*/) {
   if (sp->obs_kind == 0) {
@@ -350,7 +352,7 @@ static void first_layer(const orc_space* sp, const void* obs_row, const float* w
       float acc = b[j];
       int off = 0;
       for (int s = 0; s < sp->obs_len; ++s) {
-        acc = acc + w[j * F + off + o[s]];
+        acc = acc + w[(off + o[s]) * H + j];
         off += sp->obs_nvec[s];
       }
       out[j] = acc;
@@ -359,7 +361,7 @@ static void first_layer(const orc_space* sp, const void* obs_row, const float* w
     const float* x = (const float*)obs_row;
     for (int j = 0; j < H; ++j) {
       float acc = b[j];
-      for (int k = 0; k < F; ++k) acc = fmaf(x[k], w[j * F + k], acc);
+      for (int k = 0; k < F; ++k) acc = fmaf(x[k], w[k * H + j], acc);
       out[j] = acc;
     }
   }

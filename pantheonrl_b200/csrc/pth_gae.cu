@@ -264,8 +264,14 @@ extern "C" int pth_gae_f32(pth_ctx* ctx, const float* d_rewards, const float* d_
     tune = variant & 0xfff;
   }
   if (v == 0) {
+    // measured on B200 (profiles/gae_tuning_r01.md): the TMA-staged kernel wins
+    // once every SM has a few hundred envs; below that the register-window
+    // kernel has lower fixed cost; tiny N is latency bound -> time-parallel scan.
     if (N < 512 && T >= 64)
       v = 3;
+    else if (N % 4 == 0 && N >= (int64_t)ctx->sm_count * 128 &&
+             (((uintptr_t)d_rewards | (uintptr_t)d_values | (uintptr_t)d_episode_starts) % 16) == 0)
+      v = 2;
     else
       v = 1;
   }
@@ -278,8 +284,13 @@ extern "C" int pth_gae_f32(pth_ctx* ctx, const float* d_rewards, const float* d_
                                       (uintptr_t)d_dones | (uintptr_t)d_advantages |
                                       (uintptr_t)d_returns) % 8 == 0);
   if (v == 1) {
-    // tune: bits 8..11 vec (1,2,4), bits 4..7 window U (4,8,16), bits 0..3 block/32
-    int vec = (tune >> 8) & 0xf, U = (tune >> 4) & 0xf, blk = (tune & 0xf) * 32;
+    // tune: bits 8..11 vec (1,2,4), bits 4..7 window code (1:4 2:8 3:16), bits 0..3 block/32
+    int vec = (tune >> 8) & 0xf, ucode = (tune >> 4) & 0xf, blk = (tune & 0xf) * 32;
+    int U = ucode == 0 ? 0 : (ucode == 1 ? 4 : (ucode == 2 ? 8 : (ucode == 3 ? 16 : -1)));
+    if (blk > 128 || U < 0) {
+      pth_set_error("pth_gae_f32: bad tuning code 0x%x", variant);
+      return PTH_EINVAL;
+    }
     if (vec == 0) {
       // auto: keep >= ~2 warps per SM worth of threads before widening loads
       const int64_t sm = ctx->sm_count;

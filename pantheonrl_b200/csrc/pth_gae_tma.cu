@@ -167,8 +167,9 @@ int launch(pth_ctx* ctx, const float* rew, const float* val, const float* start,
 
 }  // namespace
 
-// tune: bits 8..11 = CTAs per SM target (0 -> 2), bits 4..7 = TT code (0 -> 8;
-// 1:4 2:8 3:16), bits 0..3 = stages (0 -> 4).
+// tune: bits 8..11 = CTAs per SM target (0 -> 3), bits 4..7 = TT code (0 -> 4;
+// 1:4 2:8 3:16 4:2), bits 0..3 = stages (0 -> 8).  Defaults = best measured on
+// B200 at (T, N) = (2048, 65536): 6155 GB/s.
 int pth_gae_tma_launch(pth_ctx* ctx, const float* rew, const float* val, const float* start,
                        const float* lv, const float* dn, float* adv, float* ret, int64_t T,
                        int64_t N, float g, float c, int tune, cudaStream_t st) {
@@ -177,9 +178,9 @@ int pth_gae_tma_launch(pth_ctx* ctx, const float* rew, const float* val, const f
     return PTH_ENOSUP;
   }
   int per_sm = (tune >> 8) & 0xf, ttc = (tune >> 4) & 0xf, stages = tune & 0xf;
-  if (per_sm == 0) per_sm = 2;
-  if (ttc == 0) ttc = 2;
-  if (stages == 0) stages = 4;
+  if (per_sm == 0) per_sm = 3;
+  if (ttc == 0) ttc = 1;
+  if (stages == 0) stages = 8;
   // slab width: spread N over (per_sm * SMs) CTAs in as few equal waves as
   // possible, W a multiple of 4 and <= 256 consumers.
   const int64_t G = (int64_t)per_sm * ctx->sm_count;
@@ -191,11 +192,15 @@ int pth_gae_tma_launch(pth_ctx* ctx, const float* rew, const float* val, const f
   }
   if (W < 4) W = 4;
 #define PTH_TMA_CASE(TTV, SV)                                                         \
-  if (ttc == (TTV == 4 ? 1 : (TTV == 8 ? 2 : 3)) && stages == SV)                     \
+  if (ttc == (TTV == 4 ? 1 : (TTV == 8 ? 2 : (TTV == 16 ? 3 : 4))) && stages == SV)  \
     return launch<TTV, SV>(ctx, rew, val, start, lv, dn, adv, ret, T, N, (int)W, g, c, st);
+  PTH_TMA_CASE(2, 8)
+  PTH_TMA_CASE(2, 12)
   PTH_TMA_CASE(4, 2)
   PTH_TMA_CASE(4, 4)
+  PTH_TMA_CASE(4, 6)
   PTH_TMA_CASE(4, 8)
+  PTH_TMA_CASE(4, 12)
   PTH_TMA_CASE(8, 2)
   PTH_TMA_CASE(8, 3)
   PTH_TMA_CASE(8, 4)

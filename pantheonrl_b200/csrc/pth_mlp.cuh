@@ -1,0 +1,354 @@
+// pth_mlp.cuh — CTA-cooperative building blocks of the SB3 MlpPolicy
+// (two separate 64-64 tanh towers + categorical heads) for tiles of BT = 128
+// samples held in shared memory.  Used by the forward kernel, the rollout
+// megakernel and the PPO update kernel, so all three produce identical bits.
+//
+// Reference semantics: stable-baselines3 1.7.0 ActorCriticPolicy.forward /
+// evaluate_actions as called from pantheonrl/common/util.py:63-81 (restated
+// in-tree at pantheonrl/algos/modular/policies.py:273-290, 364-383).
+//
+// Numeric contract: every linear output is acc = bias; for k ascending:
+// acc = fma(x_k, w_jk, acc).  Thread tiles only change WHO computes an output,
+// never the order of its additions.
+#pragma once
+#include "pth_common.cuh"
+
+namespace pthmlp {
+
+constexpr int BT = 128;    // samples per tile
+constexpr int NT = 128;    // threads per tile
+constexpr int HID = 64;
+constexpr int LDA = 132;   // activation row stride (floats): [feature][sample]
+constexpr int LDW = 68;    // hidden weight row stride (floats): [out][in]
+constexpr int MAXL = 32;   // max total logits
+
+// Device copy of pth_space with slot offsets precomputed.
+struct SpaceDev {
+  int obs_kind, obs_len, n_heads, F, L;
+  int head_n[PTH_MAX_HEADS];
+  int16_t slot_off[PTH_MAX_OBS_SLOTS];
+};
+
+// Offsets (floats) into the flat parameter vector.  NOTE: pi0.w / vf0.w are
+// stored INPUT-MAJOR [F][64] (transpose of torch's nn.Linear.weight) so that a
+// one-hot row gather reads 256 contiguous bytes; all other tensors keep torch's
+// [out][in] layout.  Order = SB3 registration order.
+struct Layout {
+  int w_pi0, b_pi0, w_pi1, b_pi1, w_vf0, b_vf0, w_vf1, b_vf1, w_act, b_act, w_val, b_val, total;
+};
+
+__host__ __device__ inline Layout make_layout(int F, int L) {
+  Layout o;
+  int p = 0;
+  o.w_pi0 = p; p += HID * F;
+  o.b_pi0 = p; p += HID;
+  o.w_pi1 = p; p += HID * HID;
+  o.b_pi1 = p; p += HID;
+  o.w_vf0 = p; p += HID * F;
+  o.b_vf0 = p; p += HID;
+  o.w_vf1 = p; p += HID * HID;
+  o.b_vf1 = p; p += HID;
+  o.w_act = p; p += L * HID;
+  o.b_act = p; p += L;
+  o.w_val = p; p += HID;
+  o.b_val = p; p += 1;
+  o.total = p;
+  return o;
+}
+
+inline int fill_space(const pth_space* sp, SpaceDev* d) {
+  int F = pth_space_feature_dim(sp), L = pth_space_logit_dim(sp);
+  if (F < 0 || L < 0 || L > MAXL) return -1;
+  memset(d, 0, sizeof(*d));
+  d->obs_kind = sp->obs_kind;
+  d->obs_len = sp->obs_len;
+  d->n_heads = sp->n_heads;
+  d->F = F;
+  d->L = L;
+  for (int h = 0; h < sp->n_heads; ++h) d->head_n[h] = sp->head_n[h];
+  if (sp->obs_kind == PTH_OBS_ONEHOT) {
+    if (sp->obs_len > 32) return -1;  // obs rows are 32 bytes
+    int off = 0;
+    for (int s = 0; s < sp->obs_len; ++s) {
+      d->slot_off[s] = (int16_t)off;
+      off += sp->obs_nvec[s];
+    }
+  }
+  return 0;
+}
+
+// Shared-memory image of everything except the two first-layer matrices.
+struct SmemPolicy {
+  float w_pi1[HID * LDW];
+  float w_vf1[HID * LDW];
+  float w_act[MAXL * LDW];
+  float w_val[HID];
+  float b_pi0[HID], b_pi1[HID], b_vf0[HID], b_vf1[HID];
+  float b_act[MAXL];
+  float b_val;
+  float pad_[3];
+};
+
+__device__ __forceinline__ void load_policy(SmemPolicy& s, const float* __restrict__ p,
+                                            const Layout& lo, int L, int tid, int nthreads) {
+  for (int i = tid; i < HID * HID; i += nthreads) {
+    int j = i >> 6, k = i & 63;
+    s.w_pi1[j * LDW + k] = p[lo.w_pi1 + i];
+    s.w_vf1[j * LDW + k] = p[lo.w_vf1 + i];
+  }
+  for (int i = tid; i < L * HID; i += nthreads) {
+    int j = i >> 6, k = i & 63;
+    s.w_act[j * LDW + k] = p[lo.w_act + i];
+  }
+  for (int i = tid; i < HID; i += nthreads) {
+    s.w_val[i] = p[lo.w_val + i];
+    s.b_pi0[i] = p[lo.b_pi0 + i];
+    s.b_pi1[i] = p[lo.b_pi1 + i];
+    s.b_vf0[i] = p[lo.b_vf0 + i];
+    s.b_vf1[i] = p[lo.b_vf1 + i];
+  }
+  for (int i = tid; i < L; i += nthreads) s.b_act[i] = p[lo.b_act + i];
+  if (tid == 0) s.b_val = p[lo.b_val];
+}
+
+// ---------------------------------------------------------------------------
+// First layer, one-hot observations: Out[j][b] = tanh(bias[j] + sum_s W[f_s][j]),
+// f_s = slot_off[s] + obs[b][s], slots ascending.  W is input-major [F][64] in
+// global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
+// so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
+// ILP.  obs: [BT][32] bytes in shared memory.
+__device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uint8_t* obs_s,
+                                                   const float* __restrict__ W,
+                                                   const float* bias_s, float* Out, int tid,
+                                                   bool apply_tanh = true) {
+  const int jq = tid & 15;   // outputs jq*4 .. +3
+  const int bs = tid >> 4;   // sample within the group of 8
+  const float4 bv = *reinterpret_cast<const float4*>(bias_s + jq * 4);
+  const float4* W4 = reinterpret_cast<const float4*>(W);
+#pragma unroll 1
+  for (int g0 = 0; g0 < BT / 8; g0 += 4) {
+    float4 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = bv;
+    for (int s = 0; s < sp.obs_len; ++s) {
+      const int off = sp.slot_off[s];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = (g0 + u) * 8 + bs;
+        const int f = off + obs_s[b * 32 + s];
+        const float4 w = __ldg(W4 + f * (HID / 4) + jq);
+        acc[u].x = acc[u].x + w.x;
+        acc[u].y = acc[u].y + w.y;
+        acc[u].z = acc[u].z + w.z;
+        acc[u].w = acc[u].w + w.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = (g0 + u) * 8 + bs;
+      float* o = Out + (jq * 4) * LDA + b;
+      if (apply_tanh) {
+        o[0 * LDA] = pth_tanhf(acc[u].x);
+        o[1 * LDA] = pth_tanhf(acc[u].y);
+        o[2 * LDA] = pth_tanhf(acc[u].z);
+        o[3 * LDA] = pth_tanhf(acc[u].w);
+      } else {
+        o[0 * LDA] = acc[u].x;
+        o[1 * LDA] = acc[u].y;
+        o[2 * LDA] = acc[u].z;
+        o[3 * LDA] = acc[u].w;
+      }
+    }
+  }
+}
+
+// First layer, Box observations: X[k][b] (k < F) in shared memory, W
+// input-major [F][64] in global memory.  Thread tile 8 samples x 8 outputs.
+__device__ __forceinline__ void first_layer_box(int F, const float* X, const float* __restrict__ W,
+                                                const float* bias_s, float* Out, int tid) {
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float bj = bias_s[ty * 8 + jj];
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = bj;
+  }
+  for (int k = 0; k < F; ++k) {
+    const float4 a0 = *reinterpret_cast<const float4*>(X + k * LDA + tx * 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(X + k * LDA + 64 + tx * 4);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + k * HID + ty * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + k * HID + ty * 8 + 4));
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = fmaf(a[ss], w[jj], acc[jj][ss]);
+  }
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    float* o = Out + (ty * 8 + jj) * LDA;
+    float4 v0 = make_float4(pth_tanhf(acc[jj][0]), pth_tanhf(acc[jj][1]), pth_tanhf(acc[jj][2]),
+                            pth_tanhf(acc[jj][3]));
+    float4 v1 = make_float4(pth_tanhf(acc[jj][4]), pth_tanhf(acc[jj][5]), pth_tanhf(acc[jj][6]),
+                            pth_tanhf(acc[jj][7]));
+    *reinterpret_cast<float4*>(o + tx * 4) = v0;
+    *reinterpret_cast<float4*>(o + 64 + tx * 4) = v1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Hidden layer: Out[j][b] = act(bias[j] + sum_{k<64} A[k][b] * W[j][k]).
+// Thread (tx, ty) owns samples {tx*4..+3, 64+tx*4..+3} and outputs j = jj*8+ty.
+// Per 4 k: 8 LDS.128 of weights + 8 LDS.128 of activations feed 256 FFMA.
+template <bool TANH>
+__device__ __forceinline__ void dense64(const float* A, const float* W, const float* bias,
+                                        float* Out, int tid) {
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float bj = bias[jj * 8 + ty];
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = bj;
+  }
+#pragma unroll 2
+  for (int k0 = 0; k0 < HID; k0 += 4) {
+    float4 w[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      w[jj] = *reinterpret_cast<const float4*>(W + (jj * 8 + ty) * LDW + k0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + tx * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + 64 + tx * 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float wk = kk == 0 ? w[jj].x : (kk == 1 ? w[jj].y : (kk == 2 ? w[jj].z : w[jj].w));
+#pragma unroll
+        for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = fmaf(a[ss], wk, acc[jj][ss]);
+      }
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    float* o = Out + (jj * 8 + ty) * LDA;
+    float v[8];
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) v[ss] = TANH ? pth_tanhf(acc[jj][ss]) : acc[jj][ss];
+    *reinterpret_cast<float4*>(o + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Heads, one thread per sample.  The thread pulls its 64 latent activations
+// into registers once; weights are broadcast reads.
+__device__ __forceinline__ void load_column(const float* A, int b, float (&h)[HID]) {
+#pragma unroll
+  for (int k = 0; k < HID; ++k) h[k] = A[k * LDA + b];
+}
+
+__device__ __forceinline__ float dot64(const float (&h)[HID], const float* w, float bias) {
+  float acc = bias;
+#pragma unroll
+  for (int k0 = 0; k0 < HID; k0 += 4) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + k0);
+    acc = fmaf(h[k0 + 0], wv.x, acc);
+    acc = fmaf(h[k0 + 1], wv.y, acc);
+    acc = fmaf(h[k0 + 2], wv.z, acc);
+    acc = fmaf(h[k0 + 3], wv.w, acc);
+  }
+  return acc;
+}
+
+// logits[l][b] for l < L into Lg (row stride LDA)
+__device__ __forceinline__ void action_head(const float* A, const SmemPolicy& s, int L, float* Lg,
+                                            int b) {
+  float h[HID];
+  load_column(A, b, h);
+  for (int l = 0; l < L; ++l) Lg[l * LDA + b] = dot64(h, s.w_act + l * LDW, s.b_act[l]);
+}
+
+__device__ __forceinline__ float value_head(const float* A, const SmemPolicy& s, int b) {
+  float h[HID];
+  load_column(A, b, h);
+  return dot64(h, s.w_val, s.b_val);
+}
+
+// One categorical head over logits z[i] = Lg[(off+i)*LDA + b].
+// Inverse-CDF sampling on one uniform: p_i = exp(z_i - max), S = sum ascending,
+// first i with cumsum_i > u*S (fallback n-1).  log_prob = (z_a - max) - log S,
+// entropy = sum fma(-(p_i/S), (z_i - max) - log S, .).
+struct HeadOut {
+  int action;
+  float logp, entropy;
+};
+
+__device__ __forceinline__ HeadOut head_eval(const float* Lg, int off, int n, int b, bool sample,
+                                             float u, int action_in, float* probs_out = nullptr) {
+  float m = Lg[off * LDA + b];
+  for (int i = 1; i < n; ++i) {
+    float z = Lg[(off + i) * LDA + b];
+    m = z > m ? z : m;
+  }
+  float S = 0.f;
+  for (int i = 0; i < n; ++i) S = S + pth_expf(Lg[(off + i) * LDA + b] - m);
+  const float logS = pth_logf(S);
+  HeadOut o;
+  o.action = action_in;
+  if (sample) {
+    const float thr = u * S;
+    float cum = 0.f;
+    int a = n - 1;
+    bool found = false;
+    for (int i = 0; i < n; ++i) {
+      cum = cum + pth_expf(Lg[(off + i) * LDA + b] - m);
+      if (!found && cum > thr) {
+        a = i;
+        found = true;
+      }
+    }
+    o.action = a;
+  }
+  o.logp = (Lg[(off + o.action) * LDA + b] - m) - logS;
+  float ent = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float zi = Lg[(off + i) * LDA + b];
+    const float lp = (zi - m) - logS;
+    const float pi = pth_expf(zi - m) / S;
+    ent = fmaf(-pi, lp, ent);
+    if (probs_out) probs_out[(off + i) * LDA + b] = pi;
+  }
+  o.entropy = ent;
+  return o;
+}
+
+struct DistOut {
+  uint32_t action;  // 4 packed bytes
+  float logp, entropy;
+};
+
+__device__ __forceinline__ DistOut dist_eval(const SpaceDev& sp, const float* Lg, int b,
+                                             bool sample, pth_u4 rnd, uint32_t action_in,
+                                             float* probs_out = nullptr) {
+  DistOut d;
+  d.action = 0;
+  d.logp = 0.f;
+  d.entropy = 0.f;
+  int off = 0;
+  const uint32_t r[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+  for (int h = 0; h < sp.n_heads; ++h) {
+    HeadOut o = head_eval(Lg, off, sp.head_n[h], b, sample, pth_u01(r[h]),
+                          (int)((action_in >> (8 * h)) & 0xffu), probs_out);
+    d.action |= ((uint32_t)o.action & 0xffu) << (8 * h);
+    d.logp = d.logp + o.logp;
+    d.entropy = d.entropy + o.entropy;
+    off += sp.head_n[h];
+  }
+  return d;
+}
+
+}  // namespace pthmlp

@@ -1,0 +1,140 @@
+// pth_policy.cu — a1 (+ the value/log-prob part of a2): batched policy forward,
+// categorical sampling, log-prob, entropy, value.
+//
+// Replaces util.action_from_policy (pantheonrl/common/util.py:63-81) ->
+// ActorCriticPolicy.forward and, with d_action_in, evaluate_actions.
+#include "pth_mlp.cuh"
+
+using namespace pthmlp;
+
+namespace {
+
+struct FwdSmem {
+  SmemPolicy pol;
+  float A[HID * LDA];
+  float Bf[HID * LDA];
+  float Lg[MAXL * LDA];
+  uint8_t obs[BT * 32];
+  // Box observations only: X[F][LDA] follows (F <= 64)
+};
+
+struct FwdParams {
+  SpaceDev sp;
+  Layout lo;
+  const float* params;
+  const void* obs;
+  int64_t obs_stride;
+  int64_t B;
+  uint64_t seed;
+  uint32_t rng_stream, tick, slot;
+  int64_t idx0;
+  const uint8_t* action_in;
+  uint8_t* action;
+  float* value;
+  float* logp;
+  float* entropy;
+  float* logits;
+};
+
+__global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem));
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * BT;
+  const int64_t b = b0 + tid;
+  const bool live = b < p.B;
+
+  load_policy(sm.pol, p.params, p.lo, p.sp.L, tid, NT);
+  if (p.sp.obs_kind == PTH_OBS_ONEHOT) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.obs);
+    for (int s = 0; s < 32; ++s) {
+      uint8_t v = 0;
+      if (live && s < p.sp.obs_len) v = src[b * p.obs_stride + s];
+      sm.obs[tid * 32 + s] = v;
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(p.obs);
+    for (int k = 0; k < p.sp.F; ++k) Xs[k * LDA + tid] = live ? src[b * p.obs_stride + k] : 0.f;
+  }
+  __syncthreads();
+
+  // ---- policy tower
+  if (p.sp.obs_kind == PTH_OBS_ONEHOT)
+    first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
+  else
+    first_layer_box(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
+  __syncthreads();
+  dense64<true>(sm.A, sm.pol.w_pi1, sm.pol.b_pi1, sm.Bf, tid);
+  __syncthreads();
+  action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
+  // ---- value tower (A is free again)
+  if (p.sp.obs_kind == PTH_OBS_ONEHOT)
+    first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
+  else
+    first_layer_box(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
+  __syncthreads();
+  dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, sm.Bf, tid);
+  __syncthreads();
+  const float v = value_head(sm.Bf, sm.pol, tid);
+
+  // ---- distribution
+  const bool sample = p.action_in == nullptr;
+  pth_u4 rnd = {0, 0, 0, 0};
+  uint32_t ain = 0;
+  if (sample)
+    rnd = pth_philox(p.seed, p.rng_stream, (uint64_t)(p.idx0 + b), p.tick, p.slot);
+  else if (live)
+    ain = *reinterpret_cast<const uint32_t*>(p.action_in + 4 * b);
+  DistOut d = dist_eval(p.sp, sm.Lg, tid, sample, rnd, ain);
+  if (!live) return;
+  if (p.action) *reinterpret_cast<uint32_t*>(p.action + 4 * b) = d.action;
+  if (p.value) p.value[b] = v;
+  if (p.logp) p.logp[b] = d.logp;
+  if (p.entropy) p.entropy[b] = d.entropy;
+  if (p.logits)
+    for (int l = 0; l < p.sp.L; ++l) p.logits[b * p.sp.L + l] = sm.Lg[l * LDA + tid];
+}
+
+}  // namespace
+
+extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");
+  PTH_CHECK_ARG(a->space != nullptr && a->d_params != nullptr && a->d_obs != nullptr,
+                "NULL space/params/obs");
+  PTH_CHECK_ARG(a->B >= 0, "negative batch");
+  if (a->B == 0) return PTH_OK;
+  FwdParams p;
+  if (fill_space(a->space, &p.sp) != 0) {
+    pth_set_error("pth_policy_forward: unsupported space");
+    return PTH_ENOSUP;
+  }
+  if (p.sp.obs_kind == PTH_OBS_BOX && p.sp.F > HID) {
+    pth_set_error("pth_policy_forward: Box observations wider than 64 are not supported");
+    return PTH_ENOSUP;
+  }
+  PTH_CHECK_ARG(a->obs_stride >= p.sp.obs_len, "obs_stride smaller than obs_len");
+  PTH_CHECK_ARG(((uintptr_t)a->d_params % 16) == 0, "params must be 16-byte aligned");
+  p.lo = make_layout(p.sp.F, p.sp.L);
+  p.params = a->d_params;
+  p.obs = a->d_obs;
+  p.obs_stride = a->obs_stride;
+  p.B = a->B;
+  p.seed = a->seed;
+  p.rng_stream = a->rng_stream;
+  p.tick = a->tick;
+  p.slot = a->slot;
+  p.idx0 = a->idx0;
+  p.action_in = a->d_action_in;
+  p.action = a->d_action;
+  p.value = a->d_value;
+  p.logp = a->d_logp;
+  p.entropy = a->d_entropy;
+  p.logits = a->d_logits;
+  size_t smem = sizeof(FwdSmem) + (p.sp.obs_kind == PTH_OBS_BOX ? sizeof(float) * HID * LDA : 0);
+  PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  policy_forward_kernel<<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);
+  PTH_LAUNCH_CHECK();
+  return PTH_OK;
+}

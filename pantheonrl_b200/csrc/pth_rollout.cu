@@ -1,0 +1,389 @@
+// pth_rollout.cu — the T-tick rollout megakernel: ego forward + sample, env
+// step, partner forward + sample, reward routing, auto-reset and all rollout
+// buffer writes for 128 env instances per CTA, without returning to the host.
+//
+// Replaces the Python loop  SB3 OnPolicyAlgorithm.collect_rollouts (restated
+// pantheonrl/algos/adap/adap_learn.py:415-471) -> MultiAgentEnv.step / reset
+// (pantheonrl/common/multiagentenv.py:172-243) -> OnPolicyAgent.get_action /
+// update (pantheonrl/common/agents.py:111-203) -> RPSEnv / LiarEnv rules.
+//
+// Envs are independent and both policies are frozen during a rollout, so a CTA
+// owns its 128 envs for the whole horizon: weights of both agents live in
+// shared memory, game state and routing latches live in registers, and every
+// tick runs up to three CTA-wide batched forwards (ego; partner reply; partner
+// opening move after an auto-reset) with lane masks.  Event order and RNG slots
+// follow oracle/pth_oracle_rollout.inc exactly.
+#include "pth_games.cuh"
+#include "pth_mlp.cuh"
+
+using namespace pthmlp;
+
+namespace {
+
+struct RollSmem {
+  SmemPolicy pol_ego;
+  SmemPolicy pol_alt;
+  float A[HID * LDA];
+  float Bf[HID * LDA];
+  float Lg[MAXL * LDA];
+  uint32_t obs[BT * 8];
+  float red[4 * (NT / 32)];
+};
+
+struct RollParams {
+  SpaceDev sp;
+  Layout lo;
+  pth_rollout_args a;
+};
+
+struct FwdOut {
+  uint32_t action;
+  float value, logp;
+};
+
+// One CTA-wide forward over the observations currently in sm.obs.
+__device__ __forceinline__ FwdOut cta_forward(const RollParams& p, const float* __restrict__ params,
+                                              const SmemPolicy& pol, RollSmem& sm, int tid,
+                                              bool with_policy, pth_u4 rnd) {
+  FwdOut o;
+  o.action = 0;
+  o.logp = 0.f;
+  const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
+  __syncthreads();  // obs written by all lanes; previous users of A/Bf/Lg are done
+  if (with_policy) {
+    first_layer_onehot(p.sp, obs_s, params + p.lo.w_pi0, pol.b_pi0, sm.A, tid);
+    __syncthreads();
+    dense64<true>(sm.A, pol.w_pi1, pol.b_pi1, sm.Bf, tid);
+    __syncthreads();
+    action_head(sm.Bf, pol, p.sp.L, sm.Lg, tid);
+  }
+  first_layer_onehot(p.sp, obs_s, params + p.lo.w_vf0, pol.b_vf0, sm.A, tid);
+  __syncthreads();
+  dense64<true>(sm.A, pol.w_vf1, pol.b_vf1, sm.Bf, tid);
+  __syncthreads();
+  o.value = value_head(sm.Bf, pol, tid);
+  if (with_policy) {
+    DistOut d = dist_eval(p.sp, sm.Lg, tid, true, rnd, 0u);
+    o.action = d.action;
+    o.logp = d.logp;
+  }
+  return o;
+}
+
+struct EnvRegs {
+  LiarRegs liar;
+  float total_ego, total_alt;
+  float ego_last_start, alt_last_done;
+  float alt_pending;   // reward accumulated on the partner's latest row
+  int alt_count;
+  uint32_t flags;      // bit0 ego_moved, bit1 should_update
+  float st_eps, st_rew, st_steps, st_alt;
+};
+
+__device__ __forceinline__ void store_obs_row(uint8_t* base, int64_t row, const uint32_t (&w)[8]) {
+  uint4* q = reinterpret_cast<uint4*>(base + row * 32);
+  q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// OnPolicyAgent.update (agents.py:196-198)
+__device__ __forceinline__ void alt_update(EnvRegs& e, float reward, bool done) {
+  e.alt_last_done = done ? 1.f : 0.f;
+  if (e.alt_count > 0) e.alt_pending = e.alt_pending + reward;
+}
+
+__device__ __forceinline__ void alt_flush(const RollParams& p, const EnvRegs& e, int64_t n) {
+  if (p.a.partner_records && e.alt_count > 0)
+    p.a.alt.d_rewards[(int64_t)(e.alt_count - 1) * p.a.N + n] = e.alt_pending;
+}
+
+// partner.get_action bookkeeping after the batched forward: record the row
+// (agents.py:172-179), then the first-move hand-off (multiagentenv.py:158-160).
+__device__ __forceinline__ void alt_record(const RollParams& p, EnvRegs& e, int64_t n,
+                                           const uint32_t (&obs)[8], const FwdOut& f) {
+  if (p.a.partner_records && e.alt_count < p.a.alt.Tcap) {
+    alt_flush(p, e, n);
+    const int64_t o = (int64_t)e.alt_count * p.a.N + n;
+    store_obs_row(p.a.alt.d_obs, o, obs);
+    *reinterpret_cast<uint32_t*>(p.a.alt.d_actions + 4 * o) = f.action;
+    p.a.alt.d_values[o] = f.value;
+    p.a.alt.d_logp[o] = f.logp;
+    p.a.alt.d_episode_starts[o] = e.alt_last_done;
+    e.alt_count += 1;
+    e.alt_pending = 0.f;
+  }
+  e.st_alt += 1.f;
+  if (!(e.flags & 2u)) alt_update(e, e.total_alt, false);
+  e.flags |= 2u;
+}
+
+// MultiAgentEnv._update_players (multiagentenv.py:163-170)
+__device__ __forceinline__ void update_players(EnvRegs& e, float r_ego, float r_alt, bool done) {
+  if (e.flags & 2u) alt_update(e, r_alt, done);
+  e.total_ego = e.total_ego + r_ego;
+  e.total_alt = e.total_alt + r_alt;
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ RollParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RollSmem& sm = *reinterpret_cast<RollSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * BT + tid;
+  const int64_t N = p.a.N;
+  const bool valid = n < N;
+  const uint64_t genv = (uint64_t)(p.a.env0 + n);
+  const bool selfplay = p.a.d_alt_params == p.a.d_ego_params;
+  const float* ego_w = p.a.d_ego_params;
+  const float* alt_w = p.a.d_alt_params;
+
+  load_policy(sm.pol_ego, ego_w, p.lo, p.sp.L, tid, NT);
+  if (!selfplay) load_policy(sm.pol_alt, alt_w, p.lo, p.sp.L, tid, NT);
+  const SmemPolicy& pol_alt = selfplay ? sm.pol_ego : sm.pol_alt;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = 0u;
+
+  EnvRegs e;
+  memset(&e, 0, sizeof(e));
+  const pth_env_carry& cr = p.a.carry;
+  if (valid) {
+    if (p.a.first_rollout) {
+      e.ego_last_start = 1.f;  // SB3 _setup_learn: _last_episode_starts = ones
+      e.alt_last_done = 1.f;   // agents.py:97
+    } else {
+      e.ego_last_start = cr.d_ego_last_start[n];
+      e.alt_last_done = cr.d_alt_last_done[n];
+      e.total_ego = cr.d_total_rew[n];
+      e.total_alt = cr.d_total_rew[N + n];
+      e.flags = cr.d_flags[n];
+      if (ENV == PTH_ENV_LIAR)
+        liar_load(reinterpret_cast<const pth_liar_state*>(cr.d_game_state) + n, e.liar);
+    }
+  }
+
+  uint32_t w[8];
+  // ---- initial reset (MultiAgentEnv.reset from SB3 _setup_learn)
+  if (ENV == PTH_ENV_LIAR && p.a.first_rollout) {
+    bool ego_first = true;
+    if (valid) ego_first = liar_reset(e.liar, p.a.seed, genv, p.a.tick0, 8u, p.a.probegostart);
+    const bool act_c = valid && !ego_first;
+    if (__syncthreads_or(act_c)) {
+      if (act_c) {
+        liar_obs(e.liar, 1, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+      }
+      pth_u4 rnd = pth_philox(p.a.seed, PTH_STREAM_ALT, genv, p.a.tick0, 2u);
+      FwdOut f = cta_forward(p, alt_w, pol_alt, sm, tid, true, rnd);
+      if (act_c) {
+        alt_record(p, e, n, w, f);
+        float re, ra;
+        liar_step(e.liar, 1, (int)(f.action & 0xffu), (int)((f.action >> 8) & 0xffu), re, ra);
+        update_players(e, re, ra, false);
+      }
+    }
+  }
+
+  for (int64_t t = 0; t < p.a.T; ++t) {
+    const uint32_t g = p.a.tick0 + (uint32_t)t;
+    const int64_t o = t * N + n;
+    // ================= ego decision
+    if (ENV == PTH_ENV_LIAR) {
+      liar_obs(e.liar, 0, w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = 0u;
+    }
+    __syncthreads();  // previous forward finished reading sm.obs
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+    FwdOut fe = cta_forward(p, ego_w, sm.pol_ego, sm, tid, true,
+                            pth_philox(p.a.seed, PTH_STREAM_EGO, genv, g, 0u));
+    if (valid) {
+      store_obs_row(p.a.ego.d_obs, o, w);
+      *reinterpret_cast<uint32_t*>(p.a.ego.d_actions + 4 * o) = fe.action;
+      p.a.ego.d_values[o] = fe.value;
+      p.a.ego.d_logp[o] = fe.logp;
+      p.a.ego.d_episode_starts[o] = e.ego_last_start;
+    }
+    float ego_rew = 0.f;
+    bool done = false;
+    if (ENV == PTH_ENV_RPS) {
+      // ================= SimultaneousEnv: partner acts on the same tick
+      __syncthreads();
+      FwdOut fa = cta_forward(p, alt_w, pol_alt, sm, tid, true,
+                              pth_philox(p.a.seed, PTH_STREAM_ALT, genv, g, 0u));
+      if (valid) {
+        alt_record(p, e, n, w, fa);
+        float re, ra;
+        pth_rps_outcome((int)(fe.action & 0xffu), (int)(fa.action & 0xffu), re, ra);
+        done = true;
+        update_players(e, re, ra, done);
+        ego_rew = ego_rew + ((e.flags & 1u) ? re : e.total_ego);
+        e.flags |= 1u;
+      }
+    } else {
+      // ================= TurnBasedEnv: ego_step, then the partner's reply
+      float re = 0.f, ra = 0.f;
+      if (valid) {
+        done = liar_step(e.liar, 0, (int)(fe.action & 0xffu), (int)((fe.action >> 8) & 0xffu), re, ra);
+        update_players(e, re, ra, done);
+        ego_rew = ego_rew + ((e.flags & 1u) ? re : e.total_ego);
+        e.flags |= 1u;
+      }
+      const bool act_b = valid && !done;
+      if (__syncthreads_or(act_b)) {
+        if (act_b) {
+          liar_obs(e.liar, 1, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+        }
+        FwdOut fa = cta_forward(p, alt_w, pol_alt, sm, tid, true,
+                                pth_philox(p.a.seed, PTH_STREAM_ALT, genv, g, 0u));
+        if (act_b) {
+          alt_record(p, e, n, w, fa);
+          done = liar_step(e.liar, 1, (int)(fa.action & 0xffu), (int)((fa.action >> 8) & 0xffu), re, ra);
+          update_players(e, re, ra, done);
+          ego_rew = ego_rew + re;
+        }
+      }
+    }
+    if (valid) {
+      p.a.ego.d_rewards[o] = ego_rew;
+      e.ego_last_start = done ? 1.f : 0.f;
+      e.st_steps += 1.f;
+      if (done) {
+        e.st_eps += 1.f;
+        e.st_rew += e.total_ego;
+      }
+    }
+    // ================= DummyVecEnv auto-reset -> MultiAgentEnv.reset
+    if (ENV == PTH_ENV_RPS) {
+      if (valid && done) {
+        e.flags = 0u;
+        e.total_ego = 0.f;
+        e.total_alt = 0.f;
+      }
+    } else {
+      bool ego_first = true;
+      if (valid && done) {
+        ego_first = liar_reset(e.liar, p.a.seed, genv, g, 0u, p.a.probegostart);
+        e.flags = 0u;
+        e.total_ego = 0.f;
+        e.total_alt = 0.f;
+      }
+      const bool act_c = valid && done && !ego_first;
+      if (__syncthreads_or(act_c)) {
+        if (act_c) {
+          liar_obs(e.liar, 1, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+        }
+        FwdOut fa = cta_forward(p, alt_w, pol_alt, sm, tid, true,
+                                pth_philox(p.a.seed, PTH_STREAM_ALT, genv, g, 1u));
+        if (act_c) {
+          alt_record(p, e, n, w, fa);
+          float re, ra;
+          liar_step(e.liar, 1, (int)(fa.action & 0xffu), (int)((fa.action >> 8) & 0xffu), re, ra);
+          update_players(e, re, ra, false);
+        }
+      }
+    }
+  }
+
+  // ---- bootstrap value of the ego's next observation (SB3 predict_values)
+  if (ENV == PTH_ENV_LIAR) {
+    liar_obs(e.liar, 0, w);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+  pth_u4 zero = {0, 0, 0, 0};
+  FwdOut fl = cta_forward(p, ego_w, sm.pol_ego, sm, tid, false, zero);
+
+  if (valid) {
+    alt_flush(p, e, n);
+    cr.d_ego_last_value[n] = fl.value;
+    cr.d_ego_last_done[n] = e.ego_last_start;
+    cr.d_ego_last_start[n] = e.ego_last_start;
+    cr.d_alt_last_done[n] = e.alt_last_done;
+    cr.d_total_rew[n] = e.total_ego;
+    cr.d_total_rew[N + n] = e.total_alt;
+    cr.d_flags[n] = (uint8_t)e.flags;
+    if (ENV == PTH_ENV_LIAR)
+      liar_store(reinterpret_cast<pth_liar_state*>(cr.d_game_state) + n, e.liar);
+    if (p.a.alt.d_count) p.a.alt.d_count[n] = e.alt_count;
+  }
+  // ---- episode statistics (integer-valued floats: exact in any order)
+  if (cr.d_ep_stats) {
+    float v[4] = {e.st_eps, e.st_rew, e.st_steps, e.st_alt};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x = v[i];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+      if ((tid & 31) == 0) atomicAdd(cr.d_ep_stats + i, x);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");
+  PTH_CHECK_ARG(a->space && a->d_ego_params && a->d_alt_params, "NULL space/params");
+  PTH_CHECK_ARG(a->env_kind == PTH_ENV_RPS || a->env_kind == PTH_ENV_LIAR, "unknown env_kind");
+  PTH_CHECK_ARG(a->N >= 0 && a->T >= 0, "negative size");
+  PTH_CHECK_ARG(a->ego.d_obs && a->ego.d_actions && a->ego.d_rewards && a->ego.d_values &&
+                    a->ego.d_logp && a->ego.d_episode_starts,
+                "NULL ego buffer");
+  PTH_CHECK_ARG(a->ego.Tcap >= a->T, "ego buffer shorter than T");
+  if (a->partner_records) {
+    PTH_CHECK_ARG(a->alt.d_obs && a->alt.d_actions && a->alt.d_rewards && a->alt.d_values &&
+                      a->alt.d_logp && a->alt.d_episode_starts && a->alt.d_count,
+                  "NULL partner buffer");
+    PTH_CHECK_ARG(a->alt.Tcap >= (a->env_kind == PTH_ENV_LIAR ? 2 * a->T : a->T),
+                  "partner buffer must hold 2*T rows (T for simultaneous envs)");
+  }
+  const pth_env_carry& c = a->carry;
+  PTH_CHECK_ARG(c.d_ego_last_start && c.d_alt_last_done && c.d_total_rew && c.d_flags &&
+                    c.d_ego_last_value && c.d_ego_last_done,
+                "NULL carry array");
+  PTH_CHECK_ARG(a->env_kind != PTH_ENV_LIAR || c.d_game_state, "NULL game state");
+  PTH_CHECK_ARG(((uintptr_t)a->ego.d_obs % 16) == 0 &&
+                    (!a->partner_records || ((uintptr_t)a->alt.d_obs % 16) == 0) &&
+                    ((uintptr_t)c.d_game_state % 16) == 0 && ((uintptr_t)a->d_ego_params % 16) == 0 &&
+                    ((uintptr_t)a->d_alt_params % 16) == 0,
+                "obs/state/params must be 16-byte aligned");
+  if (a->N == 0) return PTH_OK;
+  RollParams p;
+  if (fill_space(a->space, &p.sp) != 0 || p.sp.obs_kind != PTH_OBS_ONEHOT) {
+    pth_set_error("pth_rollout_run: on-device envs need a one-hot observation space");
+    return PTH_ENOSUP;
+  }
+  const int want_len = a->env_kind == PTH_ENV_LIAR ? PTH_LIAR_OBS_LEN : 1;
+  const int want_heads = a->env_kind == PTH_ENV_LIAR ? 2 : 1;
+  if (p.sp.obs_len != want_len || p.sp.n_heads != want_heads) {
+    pth_set_error("pth_rollout_run: space does not match env_kind %d", a->env_kind);
+    return PTH_EINVAL;
+  }
+  p.lo = make_layout(p.sp.F, p.sp.L);
+  p.a = *a;
+  const size_t smem = sizeof(RollSmem);
+  const int grid = pth_ceil_div(a->N, BT);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->env_kind == PTH_ENV_RPS) {
+    PTH_CUDA(cudaFuncSetAttribute(rollout_kernel<PTH_ENV_RPS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_kernel<PTH_ENV_RPS><<<grid, NT, smem, st>>>(p);
+  } else {
+    PTH_CUDA(cudaFuncSetAttribute(rollout_kernel<PTH_ENV_LIAR>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rollout_kernel<PTH_ENV_LIAR><<<grid, NT, smem, st>>>(p);
+  }
+  PTH_LAUNCH_CHECK();
+  return PTH_OK;
+}

@@ -7,8 +7,6 @@
   return PTH_ENOSUP;
 
 extern "C" {
-int pth_policy_forward(pth_ctx*, const pth_forward_args*, void*) { PTH_TODO(pth_policy_forward) }
-int pth_rollout_run(pth_ctx*, const pth_rollout_args*, void*) { PTH_TODO(pth_rollout_run) }
 int pth_perm_feistel(pth_ctx*, int32_t*, int64_t, int32_t, uint64_t, uint32_t, uint32_t, void*) { PTH_TODO(pth_perm_feistel) }
 int pth_index_build(pth_ctx*, const int32_t*, int64_t, int64_t, int32_t*, int32_t*, void*) { PTH_TODO(pth_index_build) }
 int64_t pth_index_workspace_bytes(int64_t) { return 0; }

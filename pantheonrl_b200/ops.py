@@ -109,3 +109,50 @@ def liar_step(state, is_ego, action):
                                         ptr(obs), ptr(re), ptr(ra), ptr(done), N, current_stream()),
           "pth_env_liar_step")
     return obs, re, ra, done
+
+
+# ----------------------------------------------------------------------- policy
+def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=0, slot=0, idx0=0,
+                   action_in=None, want=("action", "value", "logp", "entropy", "logits")):
+    """ActorCriticPolicy.forward (sampling) or evaluate_actions (action_in given).
+
+    obs: [B, stride] uint8 (one-hot spaces) or float32 (Box). Returns a dict of
+    tensors for the names in ``want``."""
+    _need(params, torch.float32, "params")
+    if space.obs_kind == _lib.PTH_OBS_ONEHOT:
+        _need(obs, torch.uint8, "obs")
+    else:
+        _need(obs, torch.float32, "obs")
+    B, stride = obs.shape
+    dev = obs.device
+    L = sum(space.heads)
+    out = {}
+    if "action" in want:
+        out["action"] = torch.zeros(B, 4, dtype=torch.uint8, device=dev)
+    for k in ("value", "logp", "entropy"):
+        if k in want:
+            out[k] = torch.empty(B, dtype=torch.float32, device=dev)
+    if "logits" in want:
+        out["logits"] = torch.empty(B, L, dtype=torch.float32, device=dev)
+    if action_in is not None:
+        _need(action_in, torch.uint8, "action_in")
+    a = _lib.ForwardArgs()
+    a.space = C.pointer(space)
+    a.d_params = params.data_ptr()
+    a.d_obs = obs.data_ptr()
+    a.obs_stride = stride
+    a.B = B
+    a.seed = int(seed)
+    a.rng_stream = int(rng_stream)
+    a.tick = int(tick)
+    a.slot = int(slot)
+    a.idx0 = int(idx0)
+    a.d_action_in = action_in.data_ptr() if action_in is not None else None
+    a.d_action = out["action"].data_ptr() if "action" in out else None
+    a.d_value = out["value"].data_ptr() if "value" in out else None
+    a.d_logp = out["logp"].data_ptr() if "logp" in out else None
+    a.d_entropy = out["entropy"].data_ptr() if "entropy" in out else None
+    a.d_logits = out["logits"].data_ptr() if "logits" in out else None
+    check(_lib.load().pth_policy_forward(_ctx(obs).handle, C.byref(a), current_stream()),
+          "pth_policy_forward")
+    return out

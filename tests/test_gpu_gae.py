@@ -29,7 +29,7 @@ def _run(ctx, args, variant):
     return adv.cpu().numpy(), ret.cpu().numpy()
 
 
-SEQ_VARIANTS = [0, 1, 2, 0x1000 | 0x148, 0x1000 | 0x282, 0x1000 | 0x4F4, 0x2000 | 0x112, 0x2000 | 0x236]
+SEQ_VARIANTS = [0, 1, 2, 0x1000 | 0x114, 0x1000 | 0x222, 0x1000 | 0x431, 0x2000 | 0x112, 0x2000 | 0x234, 0x2000 | 0x44C]
 
 
 @pytest.mark.parametrize("T,N,p", [(2048, 1, 1.0), (128, 4096, 0.25), (33, 1000, 0.5), (1, 7, 0.5),

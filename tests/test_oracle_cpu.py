@@ -206,9 +206,9 @@ def _ref_forward64(space_kw, params, obs):
         w = p[o:o + n].reshape(shape)
         o += n
         return w
-    w_pi0, b_pi0 = take(H * F, (H, F)), take(H, (H,))
+    w_pi0, b_pi0 = take(H * F, (F, H)).T, take(H, (H,))  # stored input-major
     w_pi1, b_pi1 = take(H * H, (H, H)), take(H, (H,))
-    w_vf0, b_vf0 = take(H * F, (H, F)), take(H, (H,))
+    w_vf0, b_vf0 = take(H * F, (F, H)).T, take(H, (H,))
     w_vf1, b_vf1 = take(H * H, (H, H)), take(H, (H,))
     w_act, b_act = take(L * H, (L, H)), take(L, (L,))
     w_val, b_val = take(H, (1, H)), take(1, (1,))

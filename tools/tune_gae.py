@@ -43,13 +43,14 @@ def main():
         nbytes = 20 * T * N + 8 * N
         variants = [("auto", 0), ("ldg", 1), ("tma", 2)]
         for vec in (1, 2, 4):
-            for U in (4, 8, 16):
+            for uc, U in ((1, 4), (2, 8), (3, 16)):
                 for blk in (1, 2, 4):
-                    variants.append((f"ldg v{vec} u{U} b{blk*32}", 0x1000 | (vec << 8) | (U << 4) | blk))
+                    variants.append((f"ldg v{vec} u{U} b{blk*32}", 0x1000 | (vec << 8) | (uc << 4) | blk))
         for per_sm in (1, 2, 3, 4):
-            for ttc, tt in ((1, 4), (2, 8), (3, 16)):
-                for st in (2, 3, 4, 6, 8):
-                    if (tt, st) not in ((4, 2), (4, 4), (4, 8), (8, 2), (8, 3), (8, 4), (8, 6), (16, 2), (16, 3), (16, 4)):
+            for ttc, tt in ((4, 2), (1, 4), (2, 8), (3, 16)):
+                for st in (2, 3, 4, 6, 8, 12):
+                    if (tt, st) not in ((2, 8), (2, 12), (4, 2), (4, 4), (4, 6), (4, 8), (4, 12), (8, 2), (8, 3),
+                                        (8, 4), (8, 6), (16, 2), (16, 3), (16, 4)):
                         continue
                     variants.append((f"tma sm{per_sm} tt{tt} s{st}", 0x2000 | (per_sm << 8) | (ttc << 4) | st))
         for name, v in variants:
