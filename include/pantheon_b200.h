@@ -282,7 +282,8 @@ int pth_perm_feistel(pth_ctx* ctx, int32_t* d_perm, int64_t M, int32_t n_epochs,
  * [>= sum(count)], *d_total = sum(count).  For a dense buffer pass
  * d_count = NULL and every env gets T rows. */
 int pth_index_build(pth_ctx* ctx, const int32_t* d_count, int64_t T, int64_t N,
-                    int32_t* d_index, int32_t* d_total, void* stream);
+                    int32_t* d_index, int32_t* d_total, void* d_workspace,
+                    void* stream);
 int64_t pth_index_workspace_bytes(int64_t N);
 
 typedef struct pth_update_args {
@@ -308,12 +309,18 @@ typedef struct pth_update_args {
   float learning_rate, clip_range, ent_coef, vf_coef, max_grad_norm;
   float adam_beta1, adam_beta2, adam_eps;
   int32_t normalize_advantage;
+  int32_t grid_ctas;        /* 0 = auto (pth_update_grid); tests pin it to compare with the oracle */
   void* d_workspace;        /* pth_update_workspace_bytes() */
   int64_t workspace_bytes;
   float* d_stats;           /* [n_epochs*n_minibatch][8]: pg_loss, value_loss, entropy_loss, approx_kl, clip_frac, loss, grad_norm, n */
 } pth_update_args;
 int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
                                    int64_t M, int64_t batch_size);
+/* Number of CTAs the persistent cooperative update kernel will run with for
+ * this problem (it is part of the reduction contract: tile t of a minibatch is
+ * summed by CTA t mod grid, CTAs are added in ascending order). */
+int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
+                    int64_t batch_size);
 int pth_ppo_update(pth_ctx* ctx, const pth_update_args* args, void* stream);
 
 /* ------------------------------------------------------------------ */

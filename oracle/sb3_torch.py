@@ -1,0 +1,164 @@
+"""CPU ORACLE (test infrastructure, not product code): torch-eager restatement
+of the stable-baselines3==1.7.0 arithmetic the reference drives.
+
+SB3 is pinned by the reference (setup.py:17) but NOT vendored and not
+installable here, so this file restates its published algorithm (SURVEY.md
+Appendix A) with the same torch op sequence, cross-checked against the
+reference's in-tree near copies:
+  * ActorCriticPolicy construction / forward / evaluate_actions:
+      pantheonrl/algos/modular/policies.py:84-118, 214-241, 273-290, 364-383
+  * PPO.train:  pantheonrl/algos/adap/adap_learn.py:229-347 (minus context loss)
+  * collect_rollouts: pantheonrl/algos/adap/adap_learn.py:415-471
+PARITY UNPINNED for this half: the reference holds no golden vectors for it.
+This module is (a) the independent tolerance check of pth_oracle.c's hand-written
+backward pass / Adam and of the CUDA update kernel, and (b) the CPU arm that
+bench.py --impl reference times (torch CPU eager is what SB3 executes).
+"""
+import math
+
+import numpy as np
+import torch as th
+from torch import nn
+
+
+class MlpPolicy(nn.Module):
+    """SB3 ActorCriticPolicy with MlpExtractor [dict(pi=[64,64], vf=[64,64])], Tanh."""
+
+    def __init__(self, nvec=None, heads=(3,), box_dim=None, seed=None, lr=3e-4, adam_eps=1e-5):
+        super().__init__()
+        if seed is not None:
+            th.manual_seed(seed)  # SB3 set_random_seed (Appendix A1)
+        self.nvec = None if nvec is None else [int(v) for v in nvec]
+        self.heads = [int(h) for h in heads]
+        F = int(box_dim) if box_dim is not None else sum(self.nvec)
+        self.F, self.L = F, sum(self.heads)
+        # creation order pi0, vf0, pi1, vf1 (MlpExtractor interleaves), then heads
+        pi0, vf0 = nn.Linear(F, 64), nn.Linear(F, 64)
+        pi1, vf1 = nn.Linear(64, 64), nn.Linear(64, 64)
+        self.policy_net = nn.Sequential(pi0, nn.Tanh(), pi1, nn.Tanh())
+        self.value_net_body = nn.Sequential(vf0, nn.Tanh(), vf1, nn.Tanh())
+        self.action_net = nn.Linear(64, self.L)
+        self.value_net = nn.Linear(64, 1)
+        # orthogonal init, module by module (modular/policies.py:229-241)
+        for mod, gain in ((self.policy_net, math.sqrt(2)), (self.value_net_body, math.sqrt(2)),
+                          (self.action_net, 0.01), (self.value_net, 1.0)):
+            for m in mod.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain=gain)
+                    m.bias.data.fill_(0.0)
+        # registration order of SB3: mlp_extractor.policy_net, .value_net, action_net, value_net
+        self.optimizer = th.optim.Adam(self.ordered_parameters(), lr=lr, eps=adam_eps)
+
+    def ordered_parameters(self):
+        pi0, pi1 = self.policy_net[0], self.policy_net[2]
+        vf0, vf1 = self.value_net_body[0], self.value_net_body[2]
+        return [pi0.weight, pi0.bias, pi1.weight, pi1.bias, vf0.weight, vf0.bias, vf1.weight,
+                vf1.bias, self.action_net.weight, self.action_net.bias, self.value_net.weight,
+                self.value_net.bias]
+
+    # ---- flat parameter vector in the engine's layout (first layers input-major)
+    def to_flat(self):
+        out = []
+        for i, p in enumerate(self.ordered_parameters()):
+            t = p.detach()
+            if i in (0, 4):
+                t = t.t()
+            out.append(t.contiguous().reshape(-1))
+        return th.cat(out).numpy().astype(np.float32)
+
+    def from_flat(self, flat):
+        flat = th.as_tensor(np.asarray(flat, np.float32))
+        o = 0
+        with th.no_grad():
+            for i, p in enumerate(self.ordered_parameters()):
+                n = p.numel()
+                chunk = flat[o:o + n]
+                if i in (0, 4):
+                    p.copy_(chunk.reshape(p.shape[1], p.shape[0]).t())
+                else:
+                    p.copy_(chunk.reshape(p.shape))
+                o += n
+        return self
+
+    def flat_grad(self):
+        out = []
+        for i, p in enumerate(self.ordered_parameters()):
+            t = p.grad.detach()
+            if i in (0, 4):
+                t = t.t()
+            out.append(t.contiguous().reshape(-1))
+        return th.cat(out).numpy().astype(np.float32)
+
+    # ---- SB3 preprocess_obs
+    def features(self, obs):
+        if self.nvec is None:
+            return th.as_tensor(obs).float()
+        obs = th.as_tensor(np.asarray(obs)).long()
+        return th.cat([nn.functional.one_hot(obs[:, s], n).float() for s, n in enumerate(self.nvec)], dim=1)
+
+    def _dists(self, latent_pi):
+        logits = self.action_net(latent_pi)
+        return logits, [th.distributions.Categorical(logits=lg) for lg in th.split(logits, self.heads, dim=1)]
+
+    def evaluate_actions(self, obs, actions):
+        x = self.features(obs)
+        latent_pi, latent_vf = self.policy_net(x), self.value_net_body(x)
+        _, dists = self._dists(latent_pi)
+        actions = th.as_tensor(np.asarray(actions)).long()
+        log_prob = th.stack([d.log_prob(actions[:, h]) for h, d in enumerate(dists)], dim=1).sum(dim=1)
+        entropy = th.stack([d.entropy() for d in dists], dim=1).sum(dim=1)
+        return self.value_net(latent_vf), log_prob, entropy
+
+    def forward_logits(self, obs):
+        with th.no_grad():
+            x = self.features(obs)
+            logits = self.action_net(self.policy_net(x))
+            values = self.value_net(self.value_net_body(x))
+        return logits, values[:, 0]
+
+
+def ppo_minibatch_step(policy, obs, actions, old_log_prob, advantages, returns, clip_range=0.2,
+                       ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, normalize_advantage=True):
+    """One iteration of the inner loop of SB3 PPO.train (adap_learn.py:252-346)."""
+    advantages = th.as_tensor(advantages).float()
+    returns = th.as_tensor(returns).float()
+    old_log_prob = th.as_tensor(old_log_prob).float()
+    values, log_prob, entropy = policy.evaluate_actions(obs, actions)
+    values = values.flatten()
+    if normalize_advantage and len(advantages) > 1:
+        advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+    ratio = th.exp(log_prob - old_log_prob)
+    policy_loss_1 = advantages * ratio
+    policy_loss_2 = advantages * th.clamp(ratio, 1 - clip_range, 1 + clip_range)
+    policy_loss = -th.min(policy_loss_1, policy_loss_2).mean()
+    clip_fraction = th.mean((th.abs(ratio - 1) > clip_range).float()).item()
+    value_loss = nn.functional.mse_loss(returns, values)
+    entropy_loss = -th.mean(entropy)
+    loss = policy_loss + ent_coef * entropy_loss + vf_coef * value_loss
+    with th.no_grad():
+        log_ratio = log_prob - old_log_prob
+        approx_kl = th.mean((th.exp(log_ratio) - 1) - log_ratio).item()
+    policy.optimizer.zero_grad()
+    loss.backward()
+    grad = policy.flat_grad()
+    total_norm = th.nn.utils.clip_grad_norm_(policy.ordered_parameters(), max_grad_norm)
+    policy.optimizer.step()
+    return dict(pg_loss=policy_loss.item(), value_loss=value_loss.item(),
+                entropy_loss=entropy_loss.item(), approx_kl=approx_kl, clip_fraction=clip_fraction,
+                loss=loss.item(), grad_norm=float(total_norm), grad=grad)
+
+
+def ppo_train(policy, obs, actions, old_log_prob, advantages, returns, perms, batch_size,
+              **kw):
+    """SB3 PPO.train over a flattened buffer: for each epoch's permutation
+    (RolloutBuffer.get: indices = permutation(M); consecutive slices of
+    batch_size; the last one may be short) run ppo_minibatch_step."""
+    stats = []
+    M = len(advantages)
+    for perm in perms:
+        perm = np.asarray(perm)
+        for s in range(0, M, batch_size):
+            idx = perm[s:s + batch_size]
+            stats.append(ppo_minibatch_step(policy, obs[idx], actions[idx], old_log_prob[idx],
+                                            advantages[idx], returns[idx], **kw))
+    return stats

@@ -1,0 +1,79 @@
+"""CPU ORACLE (test infrastructure): Python driver for orc_ppo_update,
+orc_perm_feistel and orc_index_build (pth_oracle_update.inc)."""
+import ctypes as C
+
+import numpy as np
+
+from . import OrcSpace, lib
+
+
+class OrcUpdateArgs(C.Structure):
+    _fields_ = [
+        ("space", C.POINTER(OrcSpace)),
+        ("params", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+        ("adam_step", C.c_int64),
+        ("obs", C.c_void_p), ("actions", C.c_void_p), ("old_logp", C.c_void_p),
+        ("advantages", C.c_void_p), ("returns", C.c_void_p), ("index", C.c_void_p),
+        ("perm", C.c_void_p),
+        ("M", C.c_int64), ("batch_size", C.c_int64), ("n_epochs", C.c_int32),
+        ("learning_rate", C.c_float), ("clip_range", C.c_float), ("ent_coef", C.c_float),
+        ("vf_coef", C.c_float), ("max_grad_norm", C.c_float),
+        ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
+        ("normalize_advantage", C.c_int32), ("grid", C.c_int32),
+        ("stats", C.c_void_p), ("grad_out", C.c_void_p),
+    ]
+
+
+def perm_feistel(M, n_epochs, seed, stream, epoch0=0):
+    perm = np.zeros((n_epochs, M), np.int32)
+    lib().orc_perm_feistel(perm.ctypes.data_as(C.c_void_p), C.c_int64(M), C.c_int32(n_epochs),
+                           C.c_uint64(seed), C.c_uint32(stream), C.c_uint32(epoch0))
+    return perm
+
+
+def index_build(count, T, N):
+    index = np.zeros(T * N, np.int32)
+    total = np.zeros(1, np.int32)
+    cp = None if count is None else np.ascontiguousarray(count, np.int32)
+    lib().orc_index_build(None if cp is None else cp.ctypes.data_as(C.c_void_p), C.c_int64(T),
+                          C.c_int64(N), index.ctypes.data_as(C.c_void_p),
+                          total.ctypes.data_as(C.c_void_p))
+    return index[:int(total[0])].copy()
+
+
+def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp, advantages,
+               returns, perm, batch_size, grid, index=None, learning_rate=3e-4, clip_range=0.2,
+               ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, betas=(0.9, 0.999), eps=1e-5,
+               normalize_advantage=True):
+    """Runs PPO.train on flat sample arrays; params / adam state are updated IN PLACE
+    (float32 numpy arrays). Returns (stats [n_epochs*n_mb, 8], last pre-clip gradient)."""
+    f32 = lambda x: np.ascontiguousarray(x, np.float32)  # noqa: E731
+    for a in (params, adam_m, adam_v):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+    obs = np.ascontiguousarray(obs, np.uint8).reshape(-1, 32)
+    actions = np.ascontiguousarray(actions, np.uint8).reshape(-1, 4)
+    old_logp, advantages, returns = f32(old_logp).reshape(-1), f32(advantages).reshape(-1), f32(returns).reshape(-1)
+    perm = np.ascontiguousarray(perm, np.int32)
+    n_epochs, M = perm.shape
+    n_mb = (M + batch_size - 1) // batch_size
+    stats = np.zeros((n_epochs * n_mb, 8), np.float32)
+    grad = np.zeros(params.size, np.float32)
+    a = OrcUpdateArgs()
+    a.space = C.pointer(space)
+    a.params, a.adam_m, a.adam_v = params.ctypes.data, adam_m.ctypes.data, adam_v.ctypes.data
+    a.adam_step = int(adam_step)
+    a.obs, a.actions = obs.ctypes.data, actions.ctypes.data
+    a.old_logp, a.advantages, a.returns = old_logp.ctypes.data, advantages.ctypes.data, returns.ctypes.data
+    if index is not None:
+        index = np.ascontiguousarray(index, np.int32)
+        a.index = index.ctypes.data
+    a.perm = perm.ctypes.data
+    a.M, a.batch_size, a.n_epochs = M, int(batch_size), n_epochs
+    a.learning_rate, a.clip_range, a.ent_coef = learning_rate, clip_range, ent_coef
+    a.vf_coef, a.max_grad_norm = vf_coef, max_grad_norm
+    a.adam_beta1, a.adam_beta2, a.adam_eps = betas[0], betas[1], eps
+    a.normalize_advantage = int(normalize_advantage)
+    a.grid = int(grid)
+    a.stats, a.grad_out = stats.ctypes.data, grad.ctypes.data
+    lib().orc_ppo_update(C.byref(a))
+    return stats, grad

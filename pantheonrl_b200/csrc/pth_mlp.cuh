@@ -89,26 +89,38 @@ struct SmemPolicy {
   float pad_[3];
 };
 
-__device__ __forceinline__ void load_policy(SmemPolicy& s, const float* __restrict__ p,
+// COHERENT = true: loads go to L2 (ld.global.cg) — required when the parameters are
+// rewritten by other CTAs between grid-wide barriers inside one kernel (the update).
+template <bool COHERENT>
+__device__ __forceinline__ float ld_param(const float* p) {
+  return COHERENT ? __ldcg(p) : __ldg(p);
+}
+template <bool COHERENT>
+__device__ __forceinline__ float4 ld_param4(const float4* p) {
+  return COHERENT ? __ldcg(p) : __ldg(p);
+}
+
+template <bool COHERENT = false>
+__device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
                                             const Layout& lo, int L, int tid, int nthreads) {
   for (int i = tid; i < HID * HID; i += nthreads) {
     int j = i >> 6, k = i & 63;
-    s.w_pi1[j * LDW + k] = p[lo.w_pi1 + i];
-    s.w_vf1[j * LDW + k] = p[lo.w_vf1 + i];
+    s.w_pi1[j * LDW + k] = ld_param<COHERENT>(p + lo.w_pi1 + i);
+    s.w_vf1[j * LDW + k] = ld_param<COHERENT>(p + lo.w_vf1 + i);
   }
   for (int i = tid; i < L * HID; i += nthreads) {
     int j = i >> 6, k = i & 63;
-    s.w_act[j * LDW + k] = p[lo.w_act + i];
+    s.w_act[j * LDW + k] = ld_param<COHERENT>(p + lo.w_act + i);
   }
   for (int i = tid; i < HID; i += nthreads) {
-    s.w_val[i] = p[lo.w_val + i];
-    s.b_pi0[i] = p[lo.b_pi0 + i];
-    s.b_pi1[i] = p[lo.b_pi1 + i];
-    s.b_vf0[i] = p[lo.b_vf0 + i];
-    s.b_vf1[i] = p[lo.b_vf1 + i];
+    s.w_val[i] = ld_param<COHERENT>(p + lo.w_val + i);
+    s.b_pi0[i] = ld_param<COHERENT>(p + lo.b_pi0 + i);
+    s.b_pi1[i] = ld_param<COHERENT>(p + lo.b_pi1 + i);
+    s.b_vf0[i] = ld_param<COHERENT>(p + lo.b_vf0 + i);
+    s.b_vf1[i] = ld_param<COHERENT>(p + lo.b_vf1 + i);
   }
-  for (int i = tid; i < L; i += nthreads) s.b_act[i] = p[lo.b_act + i];
-  if (tid == 0) s.b_val = p[lo.b_val];
+  for (int i = tid; i < L; i += nthreads) s.b_act[i] = ld_param<COHERENT>(p + lo.b_act + i);
+  if (tid == 0) s.b_val = ld_param<COHERENT>(p + lo.b_val);
 }
 
 // ---------------------------------------------------------------------------
@@ -117,8 +129,9 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* __restri
 // global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
 // so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
 // ILP.  obs: [BT][32] bytes in shared memory.
+template <bool COHERENT = false>
 __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uint8_t* obs_s,
-                                                   const float* __restrict__ W,
+                                                   const float* W,
                                                    const float* bias_s, float* Out, int tid,
                                                    bool apply_tanh = true) {
   const int jq = tid & 15;   // outputs jq*4 .. +3
@@ -136,7 +149,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
       for (int u = 0; u < 4; ++u) {
         const int b = (g0 + u) * 8 + bs;
         const int f = off + obs_s[b * 32 + s];
-        const float4 w = __ldg(W4 + f * (HID / 4) + jq);
+        const float4 w = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
         acc[u].x = acc[u].x + w.x;
         acc[u].y = acc[u].y + w.y;
         acc[u].z = acc[u].z + w.z;

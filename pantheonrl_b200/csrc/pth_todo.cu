@@ -7,11 +7,6 @@
   return PTH_ENOSUP;
 
 extern "C" {
-int pth_perm_feistel(pth_ctx*, int32_t*, int64_t, int32_t, uint64_t, uint32_t, uint32_t, void*) { PTH_TODO(pth_perm_feistel) }
-int pth_index_build(pth_ctx*, const int32_t*, int64_t, int64_t, int32_t*, int32_t*, void*) { PTH_TODO(pth_index_build) }
-int64_t pth_index_workspace_bytes(int64_t) { return 0; }
-int64_t pth_update_workspace_bytes(const pth_ctx*, const pth_space*, int64_t, int64_t) { return 0; }
-int pth_ppo_update(pth_ctx*, const pth_update_args*, void*) { PTH_TODO(pth_ppo_update) }
 int pth_pack_transitions(pth_ctx*, const uint8_t*, const uint8_t*, const float*, const float*, const float*, int64_t, uint8_t*, void*) { PTH_TODO(pth_pack_transitions) }
 int pth_pack_allgather_p2p(pth_ctx*, const uint8_t*, const uint8_t*, const float*, const float*, const float*, int64_t, uint8_t* const*, int32_t, int32_t, void*) { PTH_TODO(pth_pack_allgather_p2p) }
 }

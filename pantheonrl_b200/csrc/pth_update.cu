@@ -1,0 +1,809 @@
+// pth_update.cu — a5: the whole of PPO.train for one learner in ONE persistent
+// cooperative kernel: per epoch / minibatch {gather by permutation, forward,
+// advantage normalisation, clipped surrogate + value + entropy losses, hand
+// written backward, ordered cross-CTA gradient reduction, global-norm clip,
+// Adam}, plus the shuffle and buffer-compaction helpers.
+//
+// Replaces model.train() at pantheonrl/common/agents.py:155 -> SB3 PPO.train
+// (restated in-tree at pantheonrl/algos/adap/adap_learn.py:229-347; Adam eps at
+// pantheonrl/algos/modular/policies.py:84-88).
+//
+// Reduction contract (mirrored by oracle/pth_oracle_update.inc): samples of a
+// minibatch are cut into tiles of 128; tile t belongs to CTA t mod G; inside a
+// tile every gradient entry is a sequential fma chain over the tile's samples in
+// ascending order; a CTA adds its tiles in order; CTAs are added in ascending
+// order; cross-lane sums use the fixed 128-lane tree.  Three grid-wide barriers
+// per minibatch: partials -> (reduce, norm partials) -> (clip, Adam).
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "pth_mlp.cuh"
+
+namespace cg = cooperative_groups;
+using namespace pthmlp;
+
+namespace {
+
+constexpr int LDT = 65;                        // stride of the transposed dz1 tile [sample][unit]
+constexpr int CHUNK_ROWS = (MAXL * LDA) / HID;  // first-layer grad rows staged in smem at once (66)
+constexpr int MAX_GROUPS = 32;
+
+struct SlotGroup {
+  int16_t s_begin, s_end, row_base, n_rows;
+};
+
+struct UpdSmem {
+  SmemPolicy pol;
+  float H1[HID * LDA];
+  float H2[HID * LDA];  // later: dz1 transposed [sample][LDT]
+  float D1[HID * LDA];  // dz2
+  float Lg[MAXL * LDA]; // logits -> dlogits -> first-layer gradient chunk
+  uint32_t obs[BT * 8];
+  float red[8];
+};
+
+struct UpdParams {
+  SpaceDev sp;
+  Layout lo;
+  float* params;
+  float* adam_m;
+  float* adam_v;
+  const uint8_t* obs;
+  const uint8_t* actions;
+  const uint8_t* old_logp;
+  const uint8_t* adv;
+  const uint8_t* ret;
+  int64_t obs_stride, act_stride, f_stride;  // bytes
+  const int32_t* index;
+  const int32_t* perm;
+  int64_t M, BS;
+  int n_epochs;
+  float lr, clip, ent_coef, vf_coef, max_norm, b1, b2, eps;
+  int normalize;
+  double b1pow0, b2pow0;
+  float* part;       // [G][P]
+  float* grad;       // [P]
+  float* norm_part;  // [G]
+  float* stat_part;  // [G][8]
+  float* advstat;    // [n_epochs * n_mb][2]
+  float* stats;      // [n_epochs * n_mb][8] or NULL
+  int n_groups;
+  SlotGroup groups[MAX_GROUPS];
+};
+
+__device__ __forceinline__ float block_tree(float x, float* red, int tid) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, d);
+  __syncthreads();  // red may still be read by the previous call
+  if ((tid & 31) == 0) red[tid >> 5] = x;
+  __syncthreads();
+  return ((red[0] + red[1]) + red[2]) + red[3];
+}
+
+__device__ __forceinline__ void acc_store(float* g, float v, bool first) {
+  *g = first ? v : (__ldcg(g) + v);
+}
+
+__device__ __forceinline__ int64_t sample_offset(const UpdParams& p, int e, int64_t i) {
+  const int64_t j = __ldg(p.perm + (int64_t)e * p.M + i);
+  return p.index ? (int64_t)__ldg(p.index + j) : j;
+}
+
+// gW[j][k] = sum_b fma(Dz[j][b], Hh[k][b], .)  (64 x 64 outputs, b ascending)
+__device__ __forceinline__ void wgrad64(const float* Dz, const float* Hh, float* gout, bool first,
+                                        int tid) {
+  const int kt = tid & 15, jt = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) acc[jj][kk] = 0.f;
+#pragma unroll 2
+  for (int b0 = 0; b0 < BT; b0 += 4) {
+    float4 d[8], h[4];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      d[jj] = *reinterpret_cast<const float4*>(Dz + (jt + 8 * jj) * LDA + b0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      h[kk] = *reinterpret_cast<const float4*>(Hh + (kt + 16 * kk) * LDA + b0);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float a = acc[jj][kk];
+        a = fmaf(d[jj].x, h[kk].x, a);
+        a = fmaf(d[jj].y, h[kk].y, a);
+        a = fmaf(d[jj].z, h[kk].z, a);
+        a = fmaf(d[jj].w, h[kk].w, a);
+        acc[jj][kk] = a;
+      }
+  }
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      acc_store(gout + (jt + 8 * jj) * HID + (kt + 16 * kk), acc[jj][kk], first);
+}
+
+// head weight gradient: gWa[l][k] = sum_b fma(Lg[l][b], H2[k][b], .), l < L
+__device__ __forceinline__ void head_wgrad(const float* Lg, const float* Hh, int L, float* gout,
+                                           bool first, int tid) {
+  const int nlt = (L + 3) >> 2;
+  if (tid >= nlt * 16) return;
+  const int kt = tid & 15, lt = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int ll = 0; ll < 4; ++ll)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) acc[ll][kk] = 0.f;
+  for (int b0 = 0; b0 < BT; b0 += 4) {
+    float4 d[4], h[4];
+#pragma unroll
+    for (int ll = 0; ll < 4; ++ll) {
+      const int l = lt * 4 + ll;
+      d[ll] = l < L ? *reinterpret_cast<const float4*>(Lg + l * LDA + b0) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      h[kk] = *reinterpret_cast<const float4*>(Hh + (kt + 16 * kk) * LDA + b0);
+#pragma unroll
+    for (int ll = 0; ll < 4; ++ll)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float a = acc[ll][kk];
+        a = fmaf(d[ll].x, h[kk].x, a);
+        a = fmaf(d[ll].y, h[kk].y, a);
+        a = fmaf(d[ll].z, h[kk].z, a);
+        a = fmaf(d[ll].w, h[kk].w, a);
+        acc[ll][kk] = a;
+      }
+  }
+#pragma unroll
+  for (int ll = 0; ll < 4; ++ll) {
+    const int l = lt * 4 + ll;
+    if (l < L)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) acc_store(gout + l * HID + (kt + 16 * kk), acc[ll][kk], first);
+  }
+}
+
+// row sums over the tile: gout[r] = sum_b X[r][b], threads [t0, t0 + rows)
+__device__ __forceinline__ void row_sums(const float* X, int rows, float* gout, bool first, int tid,
+                                         int t0) {
+  const int r = tid - t0;
+  if (r < 0 || r >= rows) return;
+  float s = 0.f;
+  for (int b0 = 0; b0 < BT; b0 += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(X + r * LDA + b0);
+    s = s + v.x;
+    s = s + v.y;
+    s = s + v.z;
+    s = s + v.w;
+  }
+  acc_store(gout + r, s, first);
+}
+
+// dzT[b][k] = (sum_j fma(W[j][k], Dz[j][b], .)) * (1 - Hact[k][b]^2)
+__device__ __forceinline__ void backprop64(const float* Dz, const float* W, const float* Hact,
+                                           float* outT, int tid) {
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+    for (int ss = 0; ss < 8; ++ss) acc[kk][ss] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < HID; ++j) {
+    const float4 a0 = *reinterpret_cast<const float4*>(Dz + j * LDA + tx * 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(Dz + j * LDA + 64 + tx * 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(W + j * LDW + ty * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(W + j * LDW + ty * 8 + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+      for (int ss = 0; ss < 8; ++ss) acc[kk][ss] = fmaf(w[kk], a[ss], acc[kk][ss]);
+  }
+#pragma unroll
+  for (int ss = 0; ss < 8; ++ss) {
+    const int b = ss < 4 ? tx * 4 + ss : 64 + tx * 4 + (ss - 4);
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = ty * 8 + kk;
+      const float h = Hact[k * LDA + b];
+      outT[b * LDT + k] = acc[kk][ss] * (1.0f - h * h);
+    }
+  }
+}
+
+// first-layer (one-hot) weight gradient: gW0[f][j] += dz1T[b][j] for the active
+// row of every slot, b ascending; rows staged through smem chunk by chunk.
+__device__ __forceinline__ void scatter_w1(const UpdParams& p, const uint8_t* obs_s, const float* dzT,
+                                           float* chunk, float* gW0, int nb, bool first, int tid) {
+  const int j = tid & 63, half = tid >> 6;
+  for (int g = 0; g < p.n_groups; ++g) {
+    const SlotGroup sg = p.groups[g];
+    const int n = sg.n_rows * HID;
+    for (int i = tid; i < n; i += NT) chunk[i] = 0.f;
+    __syncthreads();
+    for (int b = 0; b < nb; ++b) {
+      const float d = dzT[b * LDT + j];
+      for (int s = sg.s_begin + half; s < sg.s_end; s += 2) {
+        const int f = p.sp.slot_off[s] - sg.row_base + obs_s[b * 32 + s];
+        chunk[f * HID + j] = chunk[f * HID + j] + d;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) acc_store(gW0 + sg.row_base * HID + i, chunk[i], first);
+    __syncthreads();
+  }
+}
+
+// body of one tower after dz2 (in sm.D1) is known
+__device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, const float* w1_s,
+                                               float* g_w0, float* g_b0, float* g_w1, float* g_b1,
+                                               int nb, bool first, int tid) {
+  __syncthreads();  // D1 complete
+  wgrad64(sm.D1, sm.H1, g_w1, first, tid);
+  row_sums(sm.D1, HID, g_b1, first, tid, 64);
+  backprop64(sm.D1, w1_s, sm.H1, sm.H2, tid);
+  __syncthreads();  // dz1T complete (in H2)
+  if (tid < HID) {
+    float s = 0.f;
+    for (int b = 0; b < BT; ++b) s = s + sm.H2[b * LDT + tid];
+    acc_store(g_b0 + tid, s, first);
+  }
+  scatter_w1(p, reinterpret_cast<const uint8_t*>(sm.obs), sm.H2, sm.Lg, g_w0, nb, first, tid);
+}
+
+__global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  UpdSmem& sm = *reinterpret_cast<UpdSmem*>(smem_raw);
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+  const int c = blockIdx.x;
+  const int P = p.lo.total;
+  const int64_t n_mb = (p.M + p.BS - 1) / p.BS;
+  float* part = p.part + (size_t)c * P;
+  const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
+
+  // ------------------------------------------------ prologue: advantage statistics
+  for (int64_t id = c; id < (int64_t)p.n_epochs * n_mb; id += G) {
+    const int e = (int)(id / n_mb);
+    const int64_t m = id % n_mb;
+    const int64_t i0 = m * p.BS;
+    const int64_t B = (i0 + p.BS <= p.M) ? p.BS : (p.M - i0);
+    float mean = 0.f, stdv = 0.f;
+    if (p.normalize && B > 1) {
+      float s = 0.f;
+      for (int64_t i = tid; i < B; i += NT)
+        s = s + *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride);
+      mean = block_tree(s, sm.red, tid) / (float)B;
+      float q = 0.f;
+      for (int64_t i = tid; i < B; i += NT) {
+        const float d =
+            *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride) - mean;
+        q = fmaf(d, d, q);
+      }
+      stdv = sqrtf(block_tree(q, sm.red, tid) / (float)(B - 1));
+    }
+    if (tid == 0) {
+      p.advstat[2 * id] = mean;
+      p.advstat[2 * id + 1] = stdv;
+    }
+  }
+  grid.sync();
+
+  double b1pow = p.b1pow0, b2pow = p.b2pow0;
+  const float omb1 = (float)(1.0 - (double)p.b1), omb2 = (float)(1.0 - (double)p.b2);
+  const float clip_lo = 1.0f - p.clip, clip_hi = 1.0f + p.clip;
+  const int S = ((P + G - 1) / G + 3) / 4 * 4;
+
+  for (int e = 0; e < p.n_epochs; ++e) {
+    for (int64_t m = 0; m < n_mb; ++m) {
+      const int64_t id = (int64_t)e * n_mb + m;
+      const int64_t i0 = m * p.BS;
+      const int64_t B = (i0 + p.BS <= p.M) ? p.BS : (p.M - i0);
+      const float Bf = (float)B, invB = 1.0f / Bf;
+      const bool norm = p.normalize && B > 1;
+      const float mean = __ldcg(p.advstat + 2 * id), stdv = __ldcg(p.advstat + 2 * id + 1);
+      const int64_t n_tiles = (B + BT - 1) / BT;
+      const int A = (int)(n_tiles < G ? n_tiles : G);
+
+      __syncthreads();
+      load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, NT);
+      float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      bool first = true;
+
+      for (int64_t tau = c; tau < n_tiles; tau += G) {
+        const int64_t t0 = tau * BT;
+        const int nb = (int)((B - t0 < BT) ? (B - t0) : BT);
+        const bool valid = tid < nb;
+        // ---- gather this thread's sample
+        uint32_t act = 0;
+        float adv = 0.f, oldlp = 0.f, ret = 0.f;
+        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+        if (valid) {
+          const int64_t off = sample_offset(p, e, i0 + t0 + tid);
+          const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
+          o0 = __ldg(q);
+          o1 = __ldg(q + 1);
+          act = *reinterpret_cast<const uint32_t*>(p.actions + off * p.act_stride);
+          adv = *reinterpret_cast<const float*>(p.adv + off * p.f_stride);
+          oldlp = *reinterpret_cast<const float*>(p.old_logp + off * p.f_stride);
+          ret = *reinterpret_cast<const float*>(p.ret + off * p.f_stride);
+        }
+        __syncthreads();  // previous tile done with sm.obs / Lg / H2
+        *reinterpret_cast<uint4*>(&sm.obs[tid * 8]) = o0;
+        *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
+        __syncthreads();
+
+        // ================= policy tower: forward
+        first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
+        __syncthreads();
+        dense64<true>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
+        __syncthreads();
+        action_head(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
+        // ---- per-sample losses and d loss / d logits (own column of Lg)
+        pth_u4 zero = {0, 0, 0, 0};
+        const DistOut dist = dist_eval(p.sp, sm.Lg, tid, false, zero, act);
+        if (norm) adv = (adv - mean) / (stdv + 1e-8f);
+        const float lr_ = dist.logp - oldlp;
+        const float ratio = pth_expf(lr_);
+        const float pl1 = adv * ratio;
+        const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
+        const float pl2 = adv * rc;
+        const bool inside = ratio >= clip_lo && ratio <= clip_hi;
+        const bool gmask = inside || (pl1 < pl2);
+        const float glp = (valid && gmask) ? -((adv * ratio) * invB) : 0.f;
+        const float gH = valid ? -(p.ent_coef * invB) : 0.f;
+        float s_pl = valid ? fminf(pl1, pl2) : 0.f;
+        float s_e = valid ? dist.entropy : 0.f;
+        float s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
+        float s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
+        {
+          int off = 0;
+          for (int h = 0; h < p.sp.n_heads; ++h) {
+            const int n = p.sp.head_n[h];
+            const int a_h = (int)((act >> (8 * h)) & 0xffu);
+            float mx = sm.Lg[off * LDA + tid];
+            for (int i = 1; i < n; ++i) {
+              const float z = sm.Lg[(off + i) * LDA + tid];
+              mx = z > mx ? z : mx;
+            }
+            float Ssum = 0.f;
+            for (int i = 0; i < n; ++i) Ssum = Ssum + pth_expf(sm.Lg[(off + i) * LDA + tid] - mx);
+            const float logS = pth_logf(Ssum);
+            float Hh = 0.f;
+            for (int i = 0; i < n; ++i) {
+              const float zi = sm.Lg[(off + i) * LDA + tid];
+              const float lp = (zi - mx) - logS;
+              const float pi = pth_expf(zi - mx) / Ssum;
+              Hh = fmaf(-pi, lp, Hh);
+            }
+            for (int i = 0; i < n; ++i) {
+              const float zi = sm.Lg[(off + i) * LDA + tid];
+              const float lp = (zi - mx) - logS;
+              const float pi = pth_expf(zi - mx) / Ssum;
+              const float t1 = (i == a_h ? 1.0f : 0.0f) - pi;
+              const float dzv = glp * t1;
+              const float t2 = (gH * pi) * (lp + Hh);
+              sm.Lg[(off + i) * LDA + tid] = dzv - t2;
+            }
+            off += n;
+          }
+        }
+        __syncthreads();  // dlogits complete
+        // ================= policy tower: backward
+        head_wgrad(sm.Lg, sm.H2, p.sp.L, part + p.lo.w_act, first, tid);
+        row_sums(sm.Lg, p.sp.L, part + p.lo.b_act, first, tid, 96);
+        {
+          float acc[HID];
+#pragma unroll
+          for (int k = 0; k < HID; ++k) acc[k] = 0.f;
+          for (int l = 0; l < p.sp.L; ++l) {
+            const float d = sm.Lg[l * LDA + tid];
+#pragma unroll
+            for (int k0 = 0; k0 < HID; k0 += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(sm.pol.w_act + l * LDW + k0);
+              acc[k0 + 0] = fmaf(w.x, d, acc[k0 + 0]);
+              acc[k0 + 1] = fmaf(w.y, d, acc[k0 + 1]);
+              acc[k0 + 2] = fmaf(w.z, d, acc[k0 + 2]);
+              acc[k0 + 3] = fmaf(w.w, d, acc[k0 + 3]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < HID; ++k) {
+            const float h = sm.H2[k * LDA + tid];
+            sm.D1[k * LDA + tid] = acc[k] * (1.0f - h * h);
+          }
+        }
+        tower_backward(p, sm, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0, part + p.lo.w_pi1,
+                       part + p.lo.b_pi1, nb, first, tid);
+
+        // ================= value tower
+        __syncthreads();
+        first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
+        __syncthreads();
+        dense64<true>(sm.H1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
+        __syncthreads();
+        const float v = value_head(sm.H2, sm.pol, tid);
+        const float dret = ret - v;
+        float s_v = valid ? dret * dret : 0.f;
+        const float dv = valid ? ((p.vf_coef * 2.0f) * (v - ret)) * invB : 0.f;
+        sm.Lg[tid] = dv;
+        {
+#pragma unroll
+          for (int k = 0; k < HID; ++k) {
+            const float h = sm.H2[k * LDA + tid];
+            sm.D1[k * LDA + tid] = (sm.pol.w_val[k] * dv) * (1.0f - h * h);
+          }
+        }
+        __syncthreads();  // dv vector + D1 complete
+        if (tid < HID) {
+          float acc = 0.f;
+          for (int b0 = 0; b0 < BT; b0 += 4) {
+            const float4 d = *reinterpret_cast<const float4*>(sm.Lg + b0);
+            const float4 h = *reinterpret_cast<const float4*>(sm.H2 + tid * LDA + b0);
+            acc = fmaf(d.x, h.x, acc);
+            acc = fmaf(d.y, h.y, acc);
+            acc = fmaf(d.z, h.z, acc);
+            acc = fmaf(d.w, h.w, acc);
+          }
+          acc_store(part + p.lo.w_val + tid, acc, first);
+        } else if (tid == HID) {
+          float s = 0.f;
+          for (int b = 0; b < BT; ++b) s = s + sm.Lg[b];
+          acc_store(part + p.lo.b_val, s, first);
+        }
+        tower_backward(p, sm, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0, part + p.lo.w_vf1,
+                       part + p.lo.b_vf1, nb, first, tid);
+
+        // ---- tile statistics
+        const float ts[5] = {block_tree(s_pl, sm.red, tid), block_tree(s_v, sm.red, tid),
+                             block_tree(s_e, sm.red, tid), block_tree(s_kl, sm.red, tid),
+                             block_tree(s_cf, sm.red, tid)};
+#pragma unroll
+        for (int i = 0; i < 5; ++i) cta_stat[i] = first ? ts[i] : cta_stat[i] + ts[i];
+        first = false;
+      }
+      if (tid < 5) p.stat_part[c * 8 + tid] = cta_stat[tid];
+      grid.sync();  // ---------------------------------------------- (1) partials written
+
+      // ---- ordered reduction of this CTA's parameter slice + squared-norm partial
+      float q = 0.f;
+      for (int i = tid; i < S; i += NT) {
+        const int pi = c * S + i;
+        if (pi < P) {
+          float g = __ldcg(p.part + pi);
+          for (int cc = 1; cc < A; ++cc) g = g + __ldcg(p.part + (size_t)cc * P + pi);
+          p.grad[pi] = g;
+          q = fmaf(g, g, q);
+        }
+      }
+      const float sq = block_tree(q, sm.red, tid);
+      if (tid == 0) p.norm_part[c] = sq;
+      grid.sync();  // ---------------------------------------------- (2) gradient + norm partials
+
+      float total_sq = __ldcg(p.norm_part);
+      for (int cc = 1; cc < G; ++cc) total_sq = total_sq + __ldcg(p.norm_part + cc);
+      const float gnorm = sqrtf(total_sq);
+      float coef = p.max_norm / (gnorm + 1e-6f);
+      if (coef > 1.0f) coef = 1.0f;
+      b1pow *= (double)p.b1;
+      b2pow *= (double)p.b2;
+      const float step_size = (float)((double)p.lr / (1.0 - b1pow));
+      const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
+      for (int i = tid; i < S; i += NT) {
+        const int pi = c * S + i;
+        if (pi < P) {
+          const float g = p.grad[pi] * coef;
+          const float mm = fmaf(omb1, g, p.b1 * p.adam_m[pi]);
+          const float vv = fmaf(omb2 * g, g, p.b2 * p.adam_v[pi]);
+          const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
+          p.adam_m[pi] = mm;
+          p.adam_v[pi] = vv;
+          p.params[pi] = fmaf(-step_size, mm / denom, p.params[pi]);
+        }
+      }
+      if (c == 0 && tid == 0 && p.stats) {
+        float st[5];
+        for (int i = 0; i < 5; ++i) {
+          float s = __ldcg(p.stat_part + i);
+          for (int cc = 1; cc < A; ++cc) s = s + __ldcg(p.stat_part + cc * 8 + i);
+          st[i] = s;
+        }
+        float* o = p.stats + 8 * id;
+        o[0] = -(st[0] / Bf);
+        o[1] = st[1] / Bf;
+        o[2] = -(st[2] / Bf);
+        o[3] = st[3] / Bf;
+        o[4] = st[4] / Bf;
+        o[5] = (o[0] + p.ent_coef * o[2]) + p.vf_coef * o[1];
+        o[6] = gnorm;
+        o[7] = Bf;
+      }
+      grid.sync();  // ---------------------------------------------- (3) parameters updated
+    }
+  }
+}
+
+// ----------------------------------------------------------------- helpers
+__device__ __forceinline__ uint32_t feistel(uint32_t x, int half_bits, const pth_u4& key) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t l = x >> half_bits, r = x & mask;
+  const uint32_t k[4] = {key.x, key.y, key.z, key.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t f = (r ^ k[i]) * 0x9E3779B1u;
+    f ^= f >> 15;
+    f *= 0x85EBCA77u;
+    f ^= f >> 13;
+    const uint32_t nl = r, nr = (l ^ f) & mask;
+    l = nl;
+    r = nr;
+  }
+  return (l << half_bits) | r;
+}
+
+__global__ void perm_feistel_kernel(int32_t* perm, int64_t M, int n_epochs, uint64_t seed,
+                                    uint32_t stream, uint32_t epoch0, int half_bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (i >= M) return;
+  const pth_u4 key = pth_philox(seed, stream, 0, epoch0 + (uint32_t)e, 0);
+  uint32_t x = (uint32_t)i;
+  do {
+    x = feistel(x, half_bits, key);
+  } while ((int64_t)x >= M);
+  perm[(int64_t)e * M + i] = (int32_t)x;
+}
+
+// exclusive prefix of min(count, T) over envs, single CTA (N is at most a few 1e5)
+__global__ void __launch_bounds__(1024) index_scan_kernel(const int32_t* count, int64_t T, int64_t N,
+                                                          int32_t* offsets, int32_t* total) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < N; base += 1024) {
+    const int64_t n = base + tid;
+    int32_t v = 0;
+    if (n < N) {
+      v = count ? count[n] : (int32_t)T;
+      if (v > T) v = (int32_t)T;
+      if (v < 0) v = 0;
+    }
+    int32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int32_t w = warp_tot[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int32_t before = carry_s + (wid > 0 ? warp_tot[wid - 1] : 0) + (x - v);
+    if (n < N) offsets[n] = before;
+    __syncthreads();
+    if (tid == 1023) carry_s = before + v;
+    __syncthreads();
+  }
+  if (tid == 0) *total = carry_s;
+}
+
+__global__ void index_fill_kernel(const int32_t* count, const int32_t* offsets, int64_t T, int64_t N,
+                                  int32_t* index) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int32_t c = count ? count[n] : (int32_t)T;
+  if (c > T) c = (int32_t)T;
+  const int32_t o = offsets[n];
+  for (int32_t t = 0; t < c; ++t) index[o + t] = (int32_t)(t * N + n);
+}
+
+struct WsLayout {
+  size_t part, grad, norm_part, stat_part, advstat, total;
+};
+
+WsLayout ws_layout(int G, int P, int64_t n_stat) {
+  WsLayout w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += (bytes + 255) / 256 * 256;
+    return r;
+  };
+  w.part = take(sizeof(float) * (size_t)G * P);
+  w.grad = take(sizeof(float) * P);
+  w.norm_part = take(sizeof(float) * G);
+  w.stat_part = take(sizeof(float) * G * 8);
+  w.advstat = take(sizeof(float) * 2 * n_stat);
+  w.total = o;
+  return w;
+}
+
+int max_coop_ctas(const pth_ctx* ctx) {
+  static int cached = -1;
+  if (cached < 0) {
+    cudaFuncSetAttribute(ppo_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(UpdSmem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_update_kernel, NT,
+                                                      sizeof(UpdSmem)) != cudaSuccess)
+      per_sm = 0;
+    cached = per_sm * ctx->sm_count;
+  }
+  return cached;
+}
+
+int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS) {
+  const int64_t eff = BS < M ? BS : M;
+  int64_t tiles = (eff + BT - 1) / BT;
+  int cap = max_coop_ctas(ctx);
+  if (cap < 1) return 0;
+  int64_t g = tiles < cap ? tiles : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
+                               int64_t batch_size) {
+  (void)sp;
+  if (!ctx || M <= 0 || batch_size <= 0) return PTH_EINVAL;
+  return auto_grid(ctx, M, batch_size);
+}
+
+extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int64_t M,
+                                              int64_t batch_size) {
+  if (!ctx || !sp || M <= 0 || batch_size <= 0) return PTH_EINVAL;
+  const int64_t P = pth_policy_param_count(sp);
+  if (P < 0) return PTH_EINVAL;
+  const int cap = max_coop_ctas(ctx);  // worst case grid (tests may pin any G <= cap)
+  const int64_t n_mb = (M + batch_size - 1) / batch_size;
+  return (int64_t)ws_layout(cap > 0 ? cap : 1, (int)P, 64 * n_mb).total;
+}
+
+extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");
+  PTH_CHECK_ARG(a->space && a->d_params && a->d_adam_m && a->d_adam_v, "NULL space/params/adam");
+  PTH_CHECK_ARG(a->d_obs && a->d_actions && a->d_old_logp && a->d_advantages && a->d_returns &&
+                    a->d_perm && a->d_workspace,
+                "NULL sample array / perm / workspace");
+  PTH_CHECK_ARG(a->M > 0 && a->batch_size > 0 && a->n_epochs > 0 && a->n_epochs <= 64,
+                "bad M / batch_size / n_epochs");
+  PTH_CHECK_ARG(a->M < ((int64_t)1 << 31), "buffer too large for int32 indices");
+  UpdParams p;
+  if (fill_space(a->space, &p.sp) != 0) {
+    pth_set_error("pth_ppo_update: unsupported space");
+    return PTH_ENOSUP;
+  }
+  if (p.sp.obs_kind != PTH_OBS_ONEHOT) {
+    pth_set_error("pth_ppo_update: Box observations are not supported by this build");
+    return PTH_ENOSUP;
+  }
+  p.lo = make_layout(p.sp.F, p.sp.L);
+  // slot groups for the staged first-layer gradient
+  p.n_groups = 0;
+  {
+    int s = 0;
+    while (s < p.sp.obs_len) {
+      SlotGroup g;
+      g.s_begin = (int16_t)s;
+      g.row_base = p.sp.slot_off[s];
+      int rows = 0;
+      while (s < p.sp.obs_len && rows + a->space->obs_nvec[s] <= CHUNK_ROWS) {
+        rows += a->space->obs_nvec[s];
+        ++s;
+      }
+      if (rows == 0) {
+        pth_set_error("pth_ppo_update: an observation slot has more than %d values", CHUNK_ROWS);
+        return PTH_ENOSUP;
+      }
+      g.s_end = (int16_t)s;
+      g.n_rows = (int16_t)rows;
+      PTH_CHECK_ARG(p.n_groups < MAX_GROUPS, "too many slot groups");
+      p.groups[p.n_groups++] = g;
+    }
+  }
+  const int cap = max_coop_ctas(ctx);
+  if (cap < 1 || !ctx->coop_launch) {
+    pth_set_error("pth_ppo_update: cooperative launch unavailable on this device");
+    return PTH_ENOSUP;
+  }
+  int G = a->grid_ctas > 0 ? a->grid_ctas : auto_grid(ctx, a->M, a->batch_size);
+  PTH_CHECK_ARG(G >= 1 && G <= cap, "grid_ctas exceeds the co-resident CTA capacity");
+  const int64_t n_mb = (a->M + a->batch_size - 1) / a->batch_size;
+  const WsLayout w = ws_layout(G, p.lo.total, (int64_t)a->n_epochs * n_mb);
+  PTH_CHECK_ARG((int64_t)w.total <= a->workspace_bytes, "workspace too small");
+  PTH_CHECK_ARG(((uintptr_t)a->d_workspace % 256) == 0 && ((uintptr_t)a->d_params % 16) == 0,
+                "workspace must be 256-byte aligned, params 16-byte aligned");
+
+  p.params = a->d_params;
+  p.adam_m = a->d_adam_m;
+  p.adam_v = a->d_adam_v;
+  p.obs = a->d_obs;
+  p.actions = a->d_actions;
+  p.old_logp = reinterpret_cast<const uint8_t*>(a->d_old_logp);
+  p.adv = reinterpret_cast<const uint8_t*>(a->d_advantages);
+  p.ret = reinterpret_cast<const uint8_t*>(a->d_returns);
+  if (a->rec_stride > 0) {
+    PTH_CHECK_ARG(a->rec_stride % 16 == 0, "rec_stride must be a multiple of 16");
+    p.obs_stride = p.act_stride = p.f_stride = a->rec_stride;
+  } else {
+    p.obs_stride = 32;
+    p.act_stride = 4;
+    p.f_stride = 4;
+  }
+  PTH_CHECK_ARG(((uintptr_t)a->d_obs % 16) == 0, "obs rows must be 16-byte aligned");
+  p.index = a->d_index;
+  p.perm = a->d_perm;
+  p.M = a->M;
+  p.BS = a->batch_size;
+  p.n_epochs = a->n_epochs;
+  p.lr = a->learning_rate;
+  p.clip = a->clip_range;
+  p.ent_coef = a->ent_coef;
+  p.vf_coef = a->vf_coef;
+  p.max_norm = a->max_grad_norm;
+  p.b1 = a->adam_beta1;
+  p.b2 = a->adam_beta2;
+  p.eps = a->adam_eps;
+  p.normalize = a->normalize_advantage;
+  p.b1pow0 = pow((double)a->adam_beta1, (double)a->adam_step);
+  p.b2pow0 = pow((double)a->adam_beta2, (double)a->adam_step);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(a->d_workspace);
+  p.part = reinterpret_cast<float*>(ws + w.part);
+  p.grad = reinterpret_cast<float*>(ws + w.grad);
+  p.norm_part = reinterpret_cast<float*>(ws + w.norm_part);
+  p.stat_part = reinterpret_cast<float*>(ws + w.stat_part);
+  p.advstat = reinterpret_cast<float*>(ws + w.advstat);
+  p.stats = a->d_stats;
+
+  void* kargs[] = {(void*)&p};
+  PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel, dim3(G), dim3(NT), kargs,
+                                       sizeof(UpdSmem), (cudaStream_t)stream));
+  return PTH_OK;
+}
+
+extern "C" int pth_perm_feistel(pth_ctx* ctx, int32_t* d_perm, int64_t M, int32_t n_epochs,
+                                uint64_t seed, uint32_t stream_id, uint32_t epoch0, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && d_perm != nullptr, "NULL ctx/perm");
+  PTH_CHECK_ARG(M > 0 && M < ((int64_t)1 << 31) && n_epochs > 0 && n_epochs <= 65535, "bad M / n_epochs");
+  int bits = 2;
+  while (((int64_t)1 << bits) < M) ++bits;
+  if (bits & 1) ++bits;
+  dim3 grid((unsigned)pth_ceil_div(M, 256), (unsigned)n_epochs);
+  perm_feistel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_perm, M, n_epochs, seed, stream_id,
+                                                              epoch0, bits / 2);
+  PTH_LAUNCH_CHECK();
+  return PTH_OK;
+}
+
+extern "C" int64_t pth_index_workspace_bytes(int64_t N) { return N > 0 ? N * 4 + 256 : 256; }
+
+extern "C" int pth_index_build(pth_ctx* ctx, const int32_t* d_count, int64_t T, int64_t N,
+                               int32_t* d_index, int32_t* d_total, void* d_workspace, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && d_index && d_total && d_workspace, "NULL pointer");
+  PTH_CHECK_ARG(T > 0 && N > 0 && T * N < ((int64_t)1 << 31), "bad T / N");
+  int32_t* offsets = reinterpret_cast<int32_t*>(d_workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  index_scan_kernel<<<1, 1024, 0, st>>>(d_count, T, N, offsets, d_total);
+  index_fill_kernel<<<pth_ceil_div(N, 128), 128, 0, st>>>(d_count, offsets, T, N, d_index);
+  PTH_LAUNCH_CHECK();
+  return PTH_OK;
+}

@@ -1,0 +1,83 @@
+"""Bindings of the update-side C-ABI entry points: pth_perm_feistel,
+pth_index_build, pth_ppo_update (one cooperative launch = one PPO.train())."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Context, check, current_stream
+
+
+def _ctx(t):
+    return Context.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def perm_feistel(M, n_epochs, seed, stream_id, epoch0=0, device="cuda", out=None):
+    """[n_epochs, M] int32 keyed permutations (stands in for np.random.permutation)."""
+    perm = out if out is not None else torch.empty(n_epochs, M, dtype=torch.int32, device=device)
+    check(_lib.load().pth_perm_feistel(_ctx(perm).handle, perm.data_ptr(), int(M), int(n_epochs),
+                                       int(seed), int(stream_id), int(epoch0) & 0xffffffff,
+                                       current_stream()), "pth_perm_feistel")
+    return perm
+
+
+def index_build(count, T, N, device="cuda"):
+    """Env-major list of the valid (row, env) cells: returns (index[T*N] int32, total[1] int32)."""
+    lib = _lib.load()
+    index = torch.empty(T * N, dtype=torch.int32, device=device)
+    total = torch.zeros(1, dtype=torch.int32, device=device)
+    ws = torch.empty(int(lib.pth_index_workspace_bytes(N)), dtype=torch.uint8, device=device)
+    check(lib.pth_index_build(_ctx(index).handle, count.data_ptr() if count is not None else None,
+                              int(T), int(N), index.data_ptr(), total.data_ptr(), ws.data_ptr(),
+                              current_stream()), "pth_index_build")
+    return index, total
+
+
+def update_grid(space, M, batch_size, device=0):
+    return int(_lib.load().pth_update_grid(Context.get(device).handle, C.byref(space), int(M),
+                                           int(batch_size)))
+
+
+class UpdateWorkspace:
+    """Caller-owned scratch for pth_ppo_update (the library never allocates)."""
+
+    def __init__(self, space, M, batch_size, device="cuda"):
+        ctx = Context.get(torch.device(device).index or 0)
+        n = int(_lib.load().pth_update_workspace_bytes(ctx.handle, C.byref(space), int(M), int(batch_size)))
+        if n <= 0:
+            raise _lib.PthError("pth_update_workspace_bytes failed")
+        self.buf = torch.empty(n, dtype=torch.uint8, device=device)
+        self.M, self.batch_size = M, batch_size
+
+
+def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp, advantages,
+               returns, perm, batch_size, workspace, index=None, M=None, rec_stride=0,
+               learning_rate=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
+               betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None):
+    """SB3 PPO.train() over flat sample arrays on the device, in place on
+    params / adam_m / adam_v. Returns the stats tensor [n_epochs * n_mb, 8]."""
+    n_epochs = perm.shape[0]
+    M = int(M if M is not None else perm.shape[1])
+    n_mb = (M + batch_size - 1) // batch_size
+    if stats is None:
+        stats = torch.zeros(n_epochs * n_mb, 8, dtype=torch.float32, device=params.device)
+    a = _lib.UpdateArgs()
+    a.space = C.pointer(space)
+    a.d_params, a.d_adam_m, a.d_adam_v = params.data_ptr(), adam_m.data_ptr(), adam_v.data_ptr()
+    a.adam_step = int(adam_step)
+    a.d_obs, a.d_obs_f32, a.obs_stride = obs.data_ptr(), None, 32
+    a.d_actions = actions.data_ptr()
+    a.d_old_logp, a.d_advantages, a.d_returns = old_logp.data_ptr(), advantages.data_ptr(), returns.data_ptr()
+    a.rec_stride = int(rec_stride)
+    a.d_index = index.data_ptr() if index is not None else None
+    a.d_perm = perm.data_ptr()
+    a.M, a.batch_size, a.n_epochs = M, int(batch_size), int(n_epochs)
+    a.learning_rate, a.clip_range, a.ent_coef = learning_rate, clip_range, ent_coef
+    a.vf_coef, a.max_grad_norm = vf_coef, max_grad_norm
+    a.adam_beta1, a.adam_beta2, a.adam_eps = betas[0], betas[1], eps
+    a.normalize_advantage = int(normalize_advantage)
+    a.grid_ctas = int(grid_ctas)
+    a.d_workspace, a.workspace_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
+    a.d_stats = stats.data_ptr()
+    check(_lib.load().pth_ppo_update(_ctx(params).handle, C.byref(a), current_stream()), "pth_ppo_update")
+    return stats
