@@ -16,7 +16,7 @@
 namespace pthmlp {
 
 constexpr int BT = 128;    // samples per tile
-constexpr int NT = 128;    // threads per tile
+constexpr int NT = 256;    // threads cooperating on a tile (2 warps per SM sub-partition)
 constexpr int HID = 64;
 constexpr int LDA = 132;   // activation row stride (floats): [feature][sample]
 constexpr int LDW = 68;    // hidden weight row stride (floats): [out][in]
@@ -129,25 +129,52 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
 // global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
 // so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
 // ILP.  obs: [BT][32] bytes in shared memory.
-template <bool COHERENT = false>
+template <bool COHERENT = false, int NTH = NT>
 __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uint8_t* obs_s,
                                                    const float* W,
                                                    const float* bias_s, float* Out, int tid,
                                                    bool apply_tanh = true) {
+  constexpr int GS = NTH / 16;  // samples the CTA covers at a time (16 threads per row)
   const int jq = tid & 15;   // outputs jq*4 .. +3
-  const int bs = tid >> 4;   // sample within the group of 8
+  const int bs = tid >> 4;   // sample within the group of GS
   const float4 bv = *reinterpret_cast<const float4*>(bias_s + jq * 4);
   const float4* W4 = reinterpret_cast<const float4*>(W);
 #pragma unroll 1
-  for (int g0 = 0; g0 < BT / 8; g0 += 4) {
+  for (int g0 = 0; g0 < BT / GS; g0 += 4) {
     float4 acc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc[u] = bv;
-    for (int s = 0; s < sp.obs_len; ++s) {
+    // slots in blocks of SB: all SB*4 row loads are issued before the adds
+    // (the adds themselves stay in ascending slot order per sample).
+    constexpr int SB = 6;
+    int s0 = 0;
+    for (; s0 + SB <= sp.obs_len; s0 += SB) {
+      float4 w[SB][4];
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        const int off = sp.slot_off[s0 + i];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = (g0 + u) * GS + bs;
+          const int f = off + obs_s[b * 32 + s0 + i];
+          w[i][u] = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < SB; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u].x = acc[u].x + w[i][u].x;
+          acc[u].y = acc[u].y + w[i][u].y;
+          acc[u].z = acc[u].z + w[i][u].z;
+          acc[u].w = acc[u].w + w[i][u].w;
+        }
+    }
+    for (int s = s0; s < sp.obs_len; ++s) {
       const int off = sp.slot_off[s];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int b = (g0 + u) * 8 + bs;
+        const int b = (g0 + u) * GS + bs;
         const int f = off + obs_s[b * 32 + s];
         const float4 w = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
         acc[u].x = acc[u].x + w.x;
@@ -158,7 +185,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int b = (g0 + u) * 8 + bs;
+      const int b = (g0 + u) * GS + bs;
       float* o = Out + (jq * 4) * LDA + b;
       if (apply_tanh) {
         o[0 * LDA] = pth_tanhf(acc[u].x);
@@ -177,31 +204,36 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
 
 // First layer, Box observations: X[k][b] (k < F) in shared memory, W
 // input-major [F][64] in global memory.  Thread tile 8 samples x 8 outputs.
+template <int NTH = NT>
 __device__ __forceinline__ void first_layer_box(int F, const float* X, const float* __restrict__ W,
                                                 const float* bias_s, float* Out, int tid) {
+  constexpr int JT = HID / (NTH / 16);  // outputs per thread (8 or 4), contiguous
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[JT][8];
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const float bj = bias_s[ty * 8 + jj];
+  for (int jj = 0; jj < JT; ++jj) {
+    const float bj = bias_s[ty * JT + jj];
 #pragma unroll
     for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = bj;
   }
   for (int k = 0; k < F; ++k) {
     const float4 a0 = *reinterpret_cast<const float4*>(X + k * LDA + tx * 4);
     const float4 a1 = *reinterpret_cast<const float4*>(X + k * LDA + 64 + tx * 4);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + k * HID + ty * 8));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + k * HID + ty * 8 + 4));
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float w[JT];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
+    for (int q = 0; q < JT / 4; ++q) {
+      const float4 wq = __ldg(reinterpret_cast<const float4*>(W + k * HID + ty * JT + 4 * q));
+      w[4 * q + 0] = wq.x; w[4 * q + 1] = wq.y; w[4 * q + 2] = wq.z; w[4 * q + 3] = wq.w;
+    }
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
       for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = fmaf(a[ss], w[jj], acc[jj][ss]);
   }
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    float* o = Out + (ty * 8 + jj) * LDA;
+  for (int jj = 0; jj < JT; ++jj) {
+    float* o = Out + (ty * JT + jj) * LDA;
     float4 v0 = make_float4(pth_tanhf(acc[jj][0]), pth_tanhf(acc[jj][1]), pth_tanhf(acc[jj][2]),
                             pth_tanhf(acc[jj][3]));
     float4 v1 = make_float4(pth_tanhf(acc[jj][4]), pth_tanhf(acc[jj][5]), pth_tanhf(acc[jj][6]),
@@ -213,32 +245,34 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
 
 // ---------------------------------------------------------------------------
 // Hidden layer: Out[j][b] = act(bias[j] + sum_{k<64} A[k][b] * W[j][k]).
-// Thread (tx, ty) owns samples {tx*4..+3, 64+tx*4..+3} and outputs j = jj*8+ty.
-// Per 4 k: 8 LDS.128 of weights + 8 LDS.128 of activations feed 256 FFMA.
-template <bool TANH>
+// Thread (tx, ty) owns samples {tx*4..+3, 64+tx*4..+3} and the JT outputs
+// j = jj*(NTH/16) + ty.  NTH = 256: per 4 k, 4 LDS.128 of weights + 8 LDS.128
+// of activations feed 128 FFMA per thread.
+template <bool TANH, int NTH = NT>
 __device__ __forceinline__ void dense64(const float* A, const float* W, const float* bias,
                                         float* Out, int tid) {
+  constexpr int NY = NTH / 16, JT = HID / NY;
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[JT][8];
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const float bj = bias[jj * 8 + ty];
+  for (int jj = 0; jj < JT; ++jj) {
+    const float bj = bias[jj * NY + ty];
 #pragma unroll
     for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = bj;
   }
 #pragma unroll 2
   for (int k0 = 0; k0 < HID; k0 += 4) {
-    float4 w[8];
+    float4 w[JT];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
-      w[jj] = *reinterpret_cast<const float4*>(W + (jj * 8 + ty) * LDW + k0);
+    for (int jj = 0; jj < JT; ++jj)
+      w[jj] = *reinterpret_cast<const float4*>(W + (jj * NY + ty) * LDW + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + tx * 4);
       const float4 a1 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + 64 + tx * 4);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
+      for (int jj = 0; jj < JT; ++jj) {
         const float wk = kk == 0 ? w[jj].x : (kk == 1 ? w[jj].y : (kk == 2 ? w[jj].z : w[jj].w));
 #pragma unroll
         for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = fmaf(a[ss], wk, acc[jj][ss]);
@@ -246,8 +280,8 @@ __device__ __forceinline__ void dense64(const float* A, const float* W, const fl
     }
   }
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    float* o = Out + (jj * 8 + ty) * LDA;
+  for (int jj = 0; jj < JT; ++jj) {
+    float* o = Out + (jj * NY + ty) * LDA;
     float v[8];
 #pragma unroll
     for (int ss = 0; ss < 8; ++ss) v[ss] = TANH ? pth_tanhf(acc[jj][ss]) : acc[jj][ss];

@@ -43,19 +43,22 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * BT;
   const int64_t b = b0 + tid;
-  const bool live = b < p.B;
+  const bool lane = tid < BT;          // threads [0, BT) own one sample each
+  const bool live = lane && b < p.B;   // threads [BT, NT) only help in the tiled layers
 
   load_policy(sm.pol, p.params, p.lo, p.sp.L, tid, NT);
-  if (p.sp.obs_kind == PTH_OBS_ONEHOT) {
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.obs);
-    for (int s = 0; s < 32; ++s) {
-      uint8_t v = 0;
-      if (live && s < p.sp.obs_len) v = src[b * p.obs_stride + s];
-      sm.obs[tid * 32 + s] = v;
+  if (lane) {
+    if (p.sp.obs_kind == PTH_OBS_ONEHOT) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.obs);
+      for (int s = 0; s < 32; ++s) {
+        uint8_t v = 0;
+        if (live && s < p.sp.obs_len) v = src[b * p.obs_stride + s];
+        sm.obs[tid * 32 + s] = v;
+      }
+    } else {
+      const float* src = reinterpret_cast<const float*>(p.obs);
+      for (int k = 0; k < p.sp.F; ++k) Xs[k * LDA + tid] = live ? src[b * p.obs_stride + k] : 0.f;
     }
-  } else {
-    const float* src = reinterpret_cast<const float*>(p.obs);
-    for (int k = 0; k < p.sp.F; ++k) Xs[k * LDA + tid] = live ? src[b * p.obs_stride + k] : 0.f;
   }
   __syncthreads();
 
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   __syncthreads();
   dense64<true>(sm.A, sm.pol.w_pi1, sm.pol.b_pi1, sm.Bf, tid);
   __syncthreads();
-  action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
+  if (lane) action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
   // ---- value tower (A is free again)
   if (p.sp.obs_kind == PTH_OBS_ONEHOT)
     first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   __syncthreads();
   dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, sm.Bf, tid);
   __syncthreads();
+  if (!lane) return;
   const float v = value_head(sm.Bf, sm.pol, tid);
 
   // ---- distribution

@@ -27,7 +27,7 @@ struct RollSmem {
   float Bf[HID * LDA];
   float Lg[MAXL * LDA];
   uint32_t obs[BT * 8];
-  float red[4 * (NT / 32)];
+  float red[32];
 };
 
 struct RollParams {
@@ -50,17 +50,20 @@ __device__ __forceinline__ FwdOut cta_forward(const RollParams& p, const float* 
   o.logp = 0.f;
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
   __syncthreads();  // obs written by all lanes; previous users of A/Bf/Lg are done
+  const bool lane = tid < BT;  // threads [BT, NT) only help in the tiled layers
   if (with_policy) {
     first_layer_onehot(p.sp, obs_s, params + p.lo.w_pi0, pol.b_pi0, sm.A, tid);
     __syncthreads();
     dense64<true>(sm.A, pol.w_pi1, pol.b_pi1, sm.Bf, tid);
     __syncthreads();
-    action_head(sm.Bf, pol, p.sp.L, sm.Lg, tid);
+    if (lane) action_head(sm.Bf, pol, p.sp.L, sm.Lg, tid);
   }
   first_layer_onehot(p.sp, obs_s, params + p.lo.w_vf0, pol.b_vf0, sm.A, tid);
   __syncthreads();
   dense64<true>(sm.A, pol.w_vf1, pol.b_vf1, sm.Bf, tid);
   __syncthreads();
+  o.value = 0.f;
+  if (!lane) return o;
   o.value = value_head(sm.Bf, pol, tid);
   if (with_policy) {
     DistOut d = dist_eval(p.sp, sm.Lg, tid, true, rnd, 0u);
@@ -129,9 +132,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RollSmem& sm = *reinterpret_cast<RollSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  const int64_t n = (int64_t)blockIdx.x * BT + tid;
+  const bool lane = tid < BT;  // one env per thread in [0, BT); the rest help with the MLP tiles
+  const int64_t n = (int64_t)blockIdx.x * BT + (lane ? tid : 0);
   const int64_t N = p.a.N;
-  const bool valid = n < N;
+  const bool valid = lane && n < N;
   const uint64_t genv = (uint64_t)(p.a.env0 + n);
   const bool selfplay = p.a.d_alt_params == p.a.d_ego_params;
   const float* ego_w = p.a.d_ego_params;
@@ -140,8 +144,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
   load_policy(sm.pol_ego, ego_w, p.lo, p.sp.L, tid, NT);
   if (!selfplay) load_policy(sm.pol_alt, alt_w, p.lo, p.sp.L, tid, NT);
   const SmemPolicy& pol_alt = selfplay ? sm.pol_ego : sm.pol_alt;
+  if (lane) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = 0u;
+    for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = 0u;
+  }
 
   EnvRegs e;
   memset(&e, 0, sizeof(e));
@@ -195,8 +201,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
       for (int i = 0; i < 8; ++i) w[i] = 0u;
     }
     __syncthreads();  // previous forward finished reading sm.obs
+    if (lane) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+      for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+    }
     FwdOut fe = cta_forward(p, ego_w, sm.pol_ego, sm, tid, true,
                             pth_philox(p.a.seed, PTH_STREAM_EGO, genv, g, 0u));
     if (valid) {
@@ -299,8 +307,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
     for (int i = 0; i < 8; ++i) w[i] = 0u;
   }
   __syncthreads();
+  if (lane) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+    for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
+  }
   pth_u4 zero = {0, 0, 0, 0};
   FwdOut fl = cta_forward(p, ego_w, sm.pol_ego, sm, tid, false, zero);
 

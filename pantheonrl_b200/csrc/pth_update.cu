@@ -24,13 +24,9 @@ using namespace pthmlp;
 
 namespace {
 
-constexpr int LDT = 65;                        // stride of the transposed dz1 tile [sample][unit]
-constexpr int CHUNK_ROWS = (MAXL * LDA) / HID;  // first-layer grad rows staged in smem at once (66)
-constexpr int MAX_GROUPS = 32;
-
-struct SlotGroup {
-  int16_t s_begin, s_end, row_base, n_rows;
-};
+constexpr int LDT = 66;  // stride of the transposed dz1 tile [sample][unit] (even: float2 loads)
+constexpr int MAX_SLOTS = 32;
+constexpr int MAX_ROWS = 2048;  // first-layer rows (one-hot feature width) supported by the update
 
 struct UpdSmem {
   SmemPolicy pol;
@@ -39,7 +35,13 @@ struct UpdSmem {
   float D1[HID * LDA];  // dz2
   float Lg[MAXL * LDA]; // logits -> dlogits -> first-layer gradient chunk
   uint32_t obs[BT * 8];
+  // per slot: the tile's samples stably sorted by observed value, and per
+  // first-layer row the number of samples selecting it (built once per tile,
+  // used by both towers)
+  uint8_t order[MAX_SLOTS * BT];
+  uint8_t rcount[MAX_ROWS];
   float red[8];
+  float bc[160];  // broadcast scratch (norm partials)
 };
 
 struct UpdParams {
@@ -67,21 +69,30 @@ struct UpdParams {
   float* stat_part;  // [G][8]
   float* advstat;    // [n_epochs * n_mb][2]
   float* stats;      // [n_epochs * n_mb][8] or NULL
-  int n_groups;
-  SlotGroup groups[MAX_GROUPS];
+  uint8_t nvec[MAX_SLOTS];
 };
 
+// The fixed 128-lane tree of the reduction contract: xor-shuffle tree inside
+// each of the first four warps, then the four warp sums left to right.  Threads
+// [128, NT) take part in the barriers only.
 __device__ __forceinline__ float block_tree(float x, float* red, int tid) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, d);
   __syncthreads();  // red may still be read by the previous call
-  if ((tid & 31) == 0) red[tid >> 5] = x;
+  if ((tid & 31) == 0 && tid < BT) red[tid >> 5] = x;
   __syncthreads();
   return ((red[0] + red[1]) + red[2]) + red[3];
 }
 
+// Partial-gradient accumulation across a CTA's tiles.  Every address is owned by
+// exactly one thread of one CTA, so tile t+1's add follows tile t's in program
+// order; a fire-and-forget L2 reduction (RED.ADD.F32, IEEE round-to-nearest)
+// gives the same bits as load-add-store without the load round trip.
 __device__ __forceinline__ void acc_store(float* g, float v, bool first) {
-  *g = first ? v : (__ldcg(g) + v);
+  if (first)
+    *g = v;
+  else
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ int64_t sample_offset(const UpdParams& p, int e, int64_t i) {
@@ -92,23 +103,24 @@ __device__ __forceinline__ int64_t sample_offset(const UpdParams& p, int e, int6
 // gW[j][k] = sum_b fma(Dz[j][b], Hh[k][b], .)  (64 x 64 outputs, b ascending)
 __device__ __forceinline__ void wgrad64(const float* Dz, const float* Hh, float* gout, bool first,
                                         int tid) {
+  constexpr int NY = NT / 16, JT = HID / NY;
   const int kt = tid & 15, jt = tid >> 4;
-  float acc[8][4];
+  float acc[JT][4];
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj)
+  for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) acc[jj][kk] = 0.f;
 #pragma unroll 2
   for (int b0 = 0; b0 < BT; b0 += 4) {
-    float4 d[8], h[4];
+    float4 d[JT], h[4];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
-      d[jj] = *reinterpret_cast<const float4*>(Dz + (jt + 8 * jj) * LDA + b0);
+    for (int jj = 0; jj < JT; ++jj)
+      d[jj] = *reinterpret_cast<const float4*>(Dz + (jt + NY * jj) * LDA + b0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)
       h[kk] = *reinterpret_cast<const float4*>(Hh + (kt + 16 * kk) * LDA + b0);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj)
+    for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         float a = acc[jj][kk];
@@ -120,10 +132,10 @@ __device__ __forceinline__ void wgrad64(const float* Dz, const float* Hh, float*
       }
   }
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj)
+  for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)
-      acc_store(gout + (jt + 8 * jj) * HID + (kt + 16 * kk), acc[jj][kk], first);
+      acc_store(gout + (jt + NY * jj) * HID + (kt + 16 * kk), acc[jj][kk], first);
 }
 
 // head weight gradient: gWa[l][k] = sum_b fma(Lg[l][b], H2[k][b], .), l < L
@@ -187,22 +199,26 @@ __device__ __forceinline__ void row_sums(const float* X, int rows, float* gout, 
 // dzT[b][k] = (sum_j fma(W[j][k], Dz[j][b], .)) * (1 - Hact[k][b]^2)
 __device__ __forceinline__ void backprop64(const float* Dz, const float* W, const float* Hact,
                                            float* outT, int tid) {
+  constexpr int KT = HID / (NT / 16);  // outputs per thread, contiguous (4)
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[KT][8];
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk)
+  for (int kk = 0; kk < KT; ++kk)
 #pragma unroll
     for (int ss = 0; ss < 8; ++ss) acc[kk][ss] = 0.f;
 #pragma unroll 4
   for (int j = 0; j < HID; ++j) {
     const float4 a0 = *reinterpret_cast<const float4*>(Dz + j * LDA + tx * 4);
     const float4 a1 = *reinterpret_cast<const float4*>(Dz + j * LDA + 64 + tx * 4);
-    const float4 w0 = *reinterpret_cast<const float4*>(W + j * LDW + ty * 8);
-    const float4 w1 = *reinterpret_cast<const float4*>(W + j * LDW + ty * 8 + 4);
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float w[KT];
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk)
+    for (int q = 0; q < KT / 4; ++q) {
+      const float4 wq = *reinterpret_cast<const float4*>(W + j * LDW + ty * KT + 4 * q);
+      w[4 * q + 0] = wq.x; w[4 * q + 1] = wq.y; w[4 * q + 2] = wq.z; w[4 * q + 3] = wq.w;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
 #pragma unroll
       for (int ss = 0; ss < 8; ++ss) acc[kk][ss] = fmaf(w[kk], a[ss], acc[kk][ss]);
   }
@@ -210,34 +226,86 @@ __device__ __forceinline__ void backprop64(const float* Dz, const float* W, cons
   for (int ss = 0; ss < 8; ++ss) {
     const int b = ss < 4 ? tx * 4 + ss : 64 + tx * 4 + (ss - 4);
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const int k = ty * 8 + kk;
+    for (int kk = 0; kk < KT; ++kk) {
+      const int k = ty * KT + kk;
       const float h = Hact[k * LDA + b];
       outT[b * LDT + k] = acc[kk][ss] * (1.0f - h * h);
     }
   }
 }
 
-// first-layer (one-hot) weight gradient: gW0[f][j] += dz1T[b][j] for the active
-// row of every slot, b ascending; rows staged through smem chunk by chunk.
-__device__ __forceinline__ void scatter_w1(const UpdParams& p, const uint8_t* obs_s, const float* dzT,
-                                           float* chunk, float* gW0, int nb, bool first, int tid) {
-  const int j = tid & 63, half = tid >> 6;
-  for (int g = 0; g < p.n_groups; ++g) {
-    const SlotGroup sg = p.groups[g];
-    const int n = sg.n_rows * HID;
-    for (int i = tid; i < n; i += NT) chunk[i] = 0.f;
-    __syncthreads();
-    for (int b = 0; b < nb; ++b) {
-      const float d = dzT[b * LDT + j];
-      for (int s = sg.s_begin + half; s < sg.s_end; s += 2) {
-        const int f = p.sp.slot_off[s] - sg.row_base + obs_s[b * 32 + s];
-        chunk[f * HID + j] = chunk[f * HID + j] + d;
+// Stable counting sort of the tile's nb samples by observed value, one slot per
+// warp at a time: order[s][pos] = sample id, rcount[row] = samples selecting the
+// first-layer row (row = slot_off[s] + value).
+__device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* obs_s, uint8_t* order,
+                                           uint8_t* rcount, int nb, int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+  for (int s = wid; s < p.sp.obs_len; s += NT / 32) {
+    int val[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int b = lane + 32 * r;
+      val[r] = b < nb ? (int)obs_s[b * 32 + s] : -1;
+    }
+    int base = 0;
+    const int nv = p.nvec[s];
+    const int row0 = p.sp.slot_off[s];
+    for (int v = 0; v < nv; ++v) {
+      const int before = base;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned m = __ballot_sync(0xffffffffu, val[r] == v);
+        if (val[r] == v)
+          order[s * BT + base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * r);
+        base += __popc(m);
+      }
+      if (lane == 0) rcount[row0 + v] = (uint8_t)(base - before);
+    }
+  }
+}
+
+// first-layer (one-hot) weight gradient: gW0[f][j] = sum over the samples whose
+// slot value selects row f of dz1T[b][j], b ascending (stable sort), as one
+// register chain per (row, column pair) — no read-modify-write through memory.
+// Thread = column pair (32 lanes) x slot subset (one warp each).
+__device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* order,
+                                          const uint8_t* rcount, const float* dzT, float* gW0,
+                                          bool first, int tid) {
+  const int jp = (tid & 31) * 2, wid = tid >> 5;
+  for (int s = wid; s < p.sp.obs_len; s += NT / 32) {
+    const int row0 = p.sp.slot_off[s];
+    const int nv = p.nvec[s];
+    const uint8_t* ord = order + s * BT;
+    int pos = 0;
+    for (int v = 0; v < nv; ++v) {
+      const int cnt = rcount[row0 + v];
+      float a0 = 0.f, a1 = 0.f;
+      int i = 0;
+      for (; i + 4 <= cnt; i += 4) {
+        float2 d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          d[u] = *reinterpret_cast<const float2*>(dzT + (int)ord[pos + i + u] * LDT + jp);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a0 = a0 + d[u].x;
+          a1 = a1 + d[u].y;
+        }
+      }
+      for (; i < cnt; ++i) {
+        const float2 d = *reinterpret_cast<const float2*>(dzT + (int)ord[pos + i] * LDT + jp);
+        a0 = a0 + d.x;
+        a1 = a1 + d.y;
+      }
+      pos += cnt;
+      float* g = gW0 + (row0 + v) * HID + jp;
+      if (first) {
+        *reinterpret_cast<float2*>(g) = make_float2(a0, a1);
+      } else if (cnt > 0) {
+        acc_store(g, a0, false);
+        acc_store(g + 1, a1, false);
       }
     }
-    __syncthreads();
-    for (int i = tid; i < n; i += NT) acc_store(gW0 + sg.row_base * HID + i, chunk[i], first);
-    __syncthreads();
   }
 }
 
@@ -250,12 +318,14 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, 
   row_sums(sm.D1, HID, g_b1, first, tid, 64);
   backprop64(sm.D1, w1_s, sm.H1, sm.H2, tid);
   __syncthreads();  // dz1T complete (in H2)
-  if (tid < HID) {
+  if (tid >= NT - HID) {
+    const int j = tid - (NT - HID);
     float s = 0.f;
-    for (int b = 0; b < BT; ++b) s = s + sm.H2[b * LDT + tid];
-    acc_store(g_b0 + tid, s, first);
+    for (int b = 0; b < BT; ++b) s = s + sm.H2[b * LDT + j];
+    acc_store(g_b0 + j, s, first);
   }
-  scatter_w1(p, reinterpret_cast<const uint8_t*>(sm.obs), sm.H2, sm.Lg, g_w0, nb, first, tid);
+  (void)nb;
+  segsum_w1(p, sm.order, sm.rcount, sm.H2, g_w0, first, tid);
 }
 
 __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
@@ -278,16 +348,19 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
     const int64_t B = (i0 + p.BS <= p.M) ? p.BS : (p.M - i0);
     float mean = 0.f, stdv = 0.f;
     if (p.normalize && B > 1) {
+      // 128 strided lanes (reduction contract), threads [BT, NT) idle here
       float s = 0.f;
-      for (int64_t i = tid; i < B; i += NT)
-        s = s + *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride);
+      if (tid < BT)
+        for (int64_t i = tid; i < B; i += BT)
+          s = s + *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride);
       mean = block_tree(s, sm.red, tid) / (float)B;
       float q = 0.f;
-      for (int64_t i = tid; i < B; i += NT) {
-        const float d =
-            *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride) - mean;
-        q = fmaf(d, d, q);
-      }
+      if (tid < BT)
+        for (int64_t i = tid; i < B; i += BT) {
+          const float d =
+              *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride) - mean;
+          q = fmaf(d, d, q);
+        }
       stdv = sqrtf(block_tree(q, sm.red, tid) / (float)(B - 1));
     }
     if (tid == 0) {
@@ -336,35 +409,40 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           oldlp = *reinterpret_cast<const float*>(p.old_logp + off * p.f_stride);
           ret = *reinterpret_cast<const float*>(p.ret + off * p.f_stride);
         }
+        const bool lane = tid < BT;  // threads [0, BT) own one sample each
         __syncthreads();  // previous tile done with sm.obs / Lg / H2
-        *reinterpret_cast<uint4*>(&sm.obs[tid * 8]) = o0;
-        *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
+        if (lane) {
+          *reinterpret_cast<uint4*>(&sm.obs[tid * 8]) = o0;
+          *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
+        }
         __syncthreads();
+        sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid);  // consumed after several barriers
 
         // ================= policy tower: forward
         first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         __syncthreads();
         dense64<true>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
         __syncthreads();
-        action_head(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
-        // ---- per-sample losses and d loss / d logits (own column of Lg)
-        pth_u4 zero = {0, 0, 0, 0};
-        const DistOut dist = dist_eval(p.sp, sm.Lg, tid, false, zero, act);
-        if (norm) adv = (adv - mean) / (stdv + 1e-8f);
-        const float lr_ = dist.logp - oldlp;
-        const float ratio = pth_expf(lr_);
-        const float pl1 = adv * ratio;
-        const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
-        const float pl2 = adv * rc;
-        const bool inside = ratio >= clip_lo && ratio <= clip_hi;
-        const bool gmask = inside || (pl1 < pl2);
-        const float glp = (valid && gmask) ? -((adv * ratio) * invB) : 0.f;
-        const float gH = valid ? -(p.ent_coef * invB) : 0.f;
-        float s_pl = valid ? fminf(pl1, pl2) : 0.f;
-        float s_e = valid ? dist.entropy : 0.f;
-        float s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
-        float s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
-        {
+        float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
+        if (lane) {
+          action_head(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
+          // ---- per-sample losses and d loss / d logits (own column of Lg)
+          pth_u4 zero = {0, 0, 0, 0};
+          const DistOut dist = dist_eval(p.sp, sm.Lg, tid, false, zero, act);
+          if (norm) adv = (adv - mean) / (stdv + 1e-8f);
+          const float lr_ = dist.logp - oldlp;
+          const float ratio = pth_expf(lr_);
+          const float pl1 = adv * ratio;
+          const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
+          const float pl2 = adv * rc;
+          const bool inside = ratio >= clip_lo && ratio <= clip_hi;
+          const bool gmask = inside || (pl1 < pl2);
+          const float glp = (valid && gmask) ? -((adv * ratio) * invB) : 0.f;
+          const float gH = valid ? -(p.ent_coef * invB) : 0.f;
+          s_pl = valid ? fminf(pl1, pl2) : 0.f;
+          s_e = valid ? dist.entropy : 0.f;
+          s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
+          s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
           int off = 0;
           for (int h = 0; h < p.sp.n_heads; ++h) {
             const int n = p.sp.head_n[h];
@@ -398,9 +476,11 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         }
         __syncthreads();  // dlogits complete
         // ================= policy tower: backward
-        head_wgrad(sm.Lg, sm.H2, p.sp.L, part + p.lo.w_act, first, tid);
-        row_sums(sm.Lg, p.sp.L, part + p.lo.b_act, first, tid, 96);
-        {
+        // upper half: head weight / bias gradients; lower half: dz2 of each sample
+        if (!lane) {
+          head_wgrad(sm.Lg, sm.H2, p.sp.L, part + p.lo.w_act, first, tid - BT);
+          row_sums(sm.Lg, p.sp.L, part + p.lo.b_act, first, tid, BT + 96);
+        } else {
           float acc[HID];
 #pragma unroll
           for (int k = 0; k < HID; ++k) acc[k] = 0.f;
@@ -430,12 +510,12 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         __syncthreads();
         dense64<true>(sm.H1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
         __syncthreads();
-        const float v = value_head(sm.H2, sm.pol, tid);
-        const float dret = ret - v;
-        float s_v = valid ? dret * dret : 0.f;
-        const float dv = valid ? ((p.vf_coef * 2.0f) * (v - ret)) * invB : 0.f;
-        sm.Lg[tid] = dv;
-        {
+        if (lane) {
+          const float v = value_head(sm.H2, sm.pol, tid);
+          const float dret = ret - v;
+          s_v = valid ? dret * dret : 0.f;
+          const float dv = valid ? ((p.vf_coef * 2.0f) * (v - ret)) * invB : 0.f;
+          sm.Lg[tid] = dv;
 #pragma unroll
           for (int k = 0; k < HID; ++k) {
             const float h = sm.H2[k * LDA + tid];
@@ -443,18 +523,19 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           }
         }
         __syncthreads();  // dv vector + D1 complete
-        if (tid < HID) {
+        if (tid >= BT && tid < BT + HID) {
+          const int k = tid - BT;
           float acc = 0.f;
           for (int b0 = 0; b0 < BT; b0 += 4) {
             const float4 d = *reinterpret_cast<const float4*>(sm.Lg + b0);
-            const float4 h = *reinterpret_cast<const float4*>(sm.H2 + tid * LDA + b0);
+            const float4 h = *reinterpret_cast<const float4*>(sm.H2 + k * LDA + b0);
             acc = fmaf(d.x, h.x, acc);
             acc = fmaf(d.y, h.y, acc);
             acc = fmaf(d.z, h.z, acc);
             acc = fmaf(d.w, h.w, acc);
           }
-          acc_store(part + p.lo.w_val + tid, acc, first);
-        } else if (tid == HID) {
+          acc_store(part + p.lo.w_val + k, acc, first);
+        } else if (tid == BT + HID) {
           float s = 0.f;
           for (int b = 0; b < BT; ++b) s = s + sm.Lg[b];
           acc_store(part + p.lo.b_val, s, first);
@@ -475,11 +556,19 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
 
       // ---- ordered reduction of this CTA's parameter slice + squared-norm partial
       float q = 0.f;
-      for (int i = tid; i < S; i += NT) {
+      for (int i = tid; i < S && tid < BT; i += BT) {  // 128 strided lanes (reduction contract)
         const int pi = c * S + i;
         if (pi < P) {
           float g = __ldcg(p.part + pi);
-          for (int cc = 1; cc < A; ++cc) g = g + __ldcg(p.part + (size_t)cc * P + pi);
+          int cc = 1;
+          for (; cc + 8 <= A; cc += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p.part + (size_t)(cc + u) * P + pi);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g = g + t[u];
+          }
+          for (; cc < A; ++cc) g = g + __ldcg(p.part + (size_t)cc * P + pi);
           p.grad[pi] = g;
           q = fmaf(g, g, q);
         }
@@ -488,8 +577,11 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       if (tid == 0) p.norm_part[c] = sq;
       grid.sync();  // ---------------------------------------------- (2) gradient + norm partials
 
-      float total_sq = __ldcg(p.norm_part);
-      for (int cc = 1; cc < G; ++cc) total_sq = total_sq + __ldcg(p.norm_part + cc);
+      __syncthreads();
+      for (int cc = tid; cc < G; cc += NT) sm.bc[cc] = __ldcg(p.norm_part + cc);
+      __syncthreads();
+      float total_sq = sm.bc[0];
+      for (int cc = 1; cc < G; ++cc) total_sq = total_sq + sm.bc[cc];
       const float gnorm = sqrtf(total_sq);
       float coef = p.max_norm / (gnorm + 1e-6f);
       if (coef > 1.0f) coef = 1.0f;
@@ -650,6 +742,8 @@ int max_coop_ctas(const pth_ctx* ctx) {
   return cached;
 }
 
+int cap_check_g(const pth_ctx* ctx) { return max_coop_ctas(ctx); }
+
 int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS) {
   const int64_t eff = BS < M ? BS : M;
   int64_t tiles = (eff + BT - 1) / BT;
@@ -697,29 +791,8 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     return PTH_ENOSUP;
   }
   p.lo = make_layout(p.sp.F, p.sp.L);
-  // slot groups for the staged first-layer gradient
-  p.n_groups = 0;
-  {
-    int s = 0;
-    while (s < p.sp.obs_len) {
-      SlotGroup g;
-      g.s_begin = (int16_t)s;
-      g.row_base = p.sp.slot_off[s];
-      int rows = 0;
-      while (s < p.sp.obs_len && rows + a->space->obs_nvec[s] <= CHUNK_ROWS) {
-        rows += a->space->obs_nvec[s];
-        ++s;
-      }
-      if (rows == 0) {
-        pth_set_error("pth_ppo_update: an observation slot has more than %d values", CHUNK_ROWS);
-        return PTH_ENOSUP;
-      }
-      g.s_end = (int16_t)s;
-      g.n_rows = (int16_t)rows;
-      PTH_CHECK_ARG(p.n_groups < MAX_GROUPS, "too many slot groups");
-      p.groups[p.n_groups++] = g;
-    }
-  }
+  for (int i = 0; i < MAX_SLOTS; ++i) p.nvec[i] = i < p.sp.obs_len ? (uint8_t)a->space->obs_nvec[i] : 0;
+  PTH_CHECK_ARG(cap_check_g(ctx) <= 160, "more than 160 co-resident CTAs are not supported");
   const int cap = max_coop_ctas(ctx);
   if (cap < 1 || !ctx->coop_launch) {
     pth_set_error("pth_ppo_update: cooperative launch unavailable on this device");

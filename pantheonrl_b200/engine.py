@@ -1,0 +1,176 @@
+"""Vectorised on-device trainer: one ego PPO learner + one partner (PPO learner
+or static / self-play policy) over N on-device env instances.
+
+One ``iteration()`` = SB3's learn-loop body for BOTH agents
+  collect_rollouts (pth_rollout_run)  ->  GAE (pth_gae_f32 / pth_gae_ragged_f32)
+  ->  PPO.train (pth_index_build + pth_perm_feistel + pth_ppo_update)
+which is what ``trainer.py ENV PPO PPO`` executes through
+``ego.learn()`` -> ``MultiAgentEnv.step`` -> ``OnPolicyAgent.get_action/update``
+(pantheonrl/common/agents.py:111-203), generalised to N envs.
+Python only sequences kernel launches; every number is computed on the device.
+"""
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib, ops, policy, rollout as ro, update as up
+
+
+@dataclasses.dataclass
+class PPOConfig:
+    """SB3 PPO keyword names (trainer.py forwards --ego-config / --alt-config JSON
+    verbatim); ``n_minibatches`` replaces ``batch_size`` when set, because SB3's
+    default 64 would mean millions of serial Adam steps at N >> 1."""
+    learning_rate: float = 3e-4
+    n_steps: int = 2048
+    batch_size: int = 64
+    n_epochs: int = 10
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    normalize_advantage: bool = True
+    ent_coef: float = 0.0
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    n_minibatches: int = 0
+
+
+class Learner:
+    """Device state of one PPO learner: parameters, Adam moments, step counters."""
+
+    def __init__(self, space, cfg, seed, device):
+        self.space, self.cfg, self.device = space, cfg, device
+        flat = policy.init_flat(space, seed)
+        self.params = torch.from_numpy(flat).to(device)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        self.adam_step = 0
+        self.n_updates = 0
+        self.last_stats = None
+
+    def batch_size_for(self, M):
+        if self.cfg.n_minibatches > 0:
+            return max(1, -(-M // self.cfg.n_minibatches))
+        return self.cfg.batch_size
+
+    def state_dict(self):
+        return policy.flat_to_state_dict(self.space, self.params.cpu().numpy())
+
+
+class VecTrainer:
+    def __init__(self, env_kind, n_envs, ego_cfg=None, alt_cfg=None, seed=10, partner="ppo",
+                 probegostart=0.5, device="cuda", env0=0):
+        if not torch.cuda.is_available():
+            raise _lib.PthError("VecTrainer needs a CUDA device: the hot path has no CPU implementation")
+        self.env_kind, self.N, self.seed = env_kind, int(n_envs), int(seed)
+        self.device, self.env0, self.probegostart = device, env0, probegostart
+        self.space = ro.space_for(env_kind)
+        self.ego_cfg = ego_cfg or PPOConfig()
+        self.alt_cfg = alt_cfg or self.ego_cfg
+        self.partner = partner
+        self.T = self.ego_cfg.n_steps
+        self.ego = Learner(self.space, self.ego_cfg, seed, device)
+        if partner == "ppo":
+            self.alt = Learner(self.space, self.alt_cfg, seed, device)  # same seed: identical init
+        elif partner == "selfplay":
+            self.alt = None  # StaticPolicyAgent(ego.policy): shares the ego's weights
+        else:
+            raise ValueError(partner)
+        N, T = self.N, self.T
+        self.ego_buf = ro.Buffer(T, N, False, device)
+        alt_cap = 2 * T if env_kind == "liar" else T
+        self.alt_buf = ro.Buffer(alt_cap, N, True, device)
+        self.carry = ro.Carry(N, device)
+        self.rollouts = 0
+        self.num_timesteps = 0
+        self.partner_decisions = 0
+        # dense env-major sample index of the ego buffer (SB3 swap_and_flatten), built once
+        self.ego_index, _ = up.index_build(None, T, N, device=device)
+        self.ego_M = T * N
+        self.ego_perm = torch.empty(self.ego_cfg.n_epochs, self.ego_M, dtype=torch.int32, device=device)
+        self.ego_ws = up.UpdateWorkspace(self.space, self.ego_M, self.ego.batch_size_for(self.ego_M), device)
+        if self.alt is not None:
+            cap = alt_cap * N
+            self.alt_perm_store = torch.empty(self.alt_cfg.n_epochs * cap, dtype=torch.int32, device=device)
+            self.alt_ws = up.UpdateWorkspace(self.space, cap, max(1, self.alt.batch_size_for(cap)), device)
+
+    # ------------------------------------------------------------------ phases
+    def collect(self):
+        alt_params = self.alt.params if self.alt is not None else self.ego.params
+        ro.run_rollout(self.env_kind, self.space, self.ego.params, alt_params, self.ego_buf,
+                       self.alt_buf, self.carry, self.T, self.seed, self.rollouts * self.T,
+                       env0=self.env0, probegostart=self.probegostart,
+                       first_rollout=self.rollouts == 0, partner_records=self.alt is not None)
+        self.rollouts += 1
+        self.num_timesteps += self.N * self.T
+
+    def compute_gae(self):
+        b, c = self.ego_buf, self.ego_cfg
+        ops.gae(b.rewards, b.values, b.episode_starts, self.carry.ego_last_value,
+                self.carry.ego_last_done, c.gamma, c.gae_lambda, out=(b.advantages, b.returns))
+        if self.alt is not None:
+            a, ac = self.alt_buf, self.alt_cfg
+            ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_last_done,
+                           ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
+
+    def _train_one(self, learner, buf, index, M, perm, ws, stream_id):
+        cfg = learner.cfg
+        up.perm_feistel(M, cfg.n_epochs, self.seed, stream_id, epoch0=learner.n_updates, out=perm)
+        bs = learner.batch_size_for(M)
+        stats = up.ppo_update(
+            learner.space, learner.params, learner.adam_m, learner.adam_v, learner.adam_step,
+            buf.obs, buf.actions, buf.logp, buf.advantages, buf.returns, perm, bs, ws, index=index,
+            M=M, learning_rate=cfg.learning_rate, clip_range=cfg.clip_range, ent_coef=cfg.ent_coef,
+            vf_coef=cfg.vf_coef, max_grad_norm=cfg.max_grad_norm,
+            normalize_advantage=cfg.normalize_advantage)
+        n_mb = -(-M // bs)
+        learner.adam_step += cfg.n_epochs * n_mb
+        learner.n_updates += cfg.n_epochs
+        learner.last_stats = stats
+        return stats
+
+    def train(self):
+        self._train_one(self.ego, self.ego_buf, self.ego_index, self.ego_M, self.ego_perm,
+                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO)
+        if self.alt is not None:
+            a = self.alt_buf
+            index, total = up.index_build(a.count, a.Tcap, self.N, device=self.device)
+            M = int(total.item())  # the one host read-back per train(): ragged sample count
+            self.partner_decisions += M
+            if M > 0:
+                perm = self.alt_perm_store[: self.alt_cfg.n_epochs * M].view(self.alt_cfg.n_epochs, M)
+                self._train_one(self.alt, a, index, M, perm, self.alt_ws, _lib.STREAM_SHUFFLE_ALT)
+            return M
+        return 0
+
+    def iteration(self):
+        """collect -> GAE -> train for both agents. Returns agent decisions made."""
+        self.collect()
+        self.compute_gae()
+        m_alt = self.train()
+        if self.alt is None:
+            m_alt = self.N * self.T  # the static partner still decides once per tick (RPS)
+        return self.N * self.T + m_alt
+
+    def learn(self, total_timesteps):
+        """SB3-style: run iterations until the ego has taken total_timesteps steps."""
+        while self.num_timesteps < total_timesteps:
+            self.iteration()
+        return self
+
+    # ------------------------------------------------------------------ logging
+    def train_stats(self, learner=None):
+        """Mean of the per-minibatch scalars SB3's PPO.train logs (adap_learn.py:354-371)."""
+        learner = learner or self.ego
+        s = learner.last_stats.cpu().numpy()
+        return {"train/policy_gradient_loss": float(s[:, 0].mean()), "train/value_loss": float(s[:, 1].mean()),
+                "train/entropy_loss": float(s[:, 2].mean()), "train/approx_kl": float(s[:, 3].mean()),
+                "train/clip_fraction": float(s[:, 4].mean()), "train/loss": float(s[-1, 5]),
+                "train/n_updates": learner.n_updates}
+
+    def episode_stats(self):
+        e = self.carry.ep_stats.cpu().numpy()
+        eps = max(1.0, float(e[0]))
+        return {"rollout/ep_rew_mean": float(e[1]) / eps, "rollout/ep_len_mean": float(e[2]) / eps,
+                "episodes": int(e[0]), "ego_steps": int(e[2]), "partner_decisions": int(e[3])}
