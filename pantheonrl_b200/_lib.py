@@ -199,6 +199,12 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = 0  # kernels of libpantheon_b200.so launched through the bindings (bench.py reports it)
+
+
+def count_launch(n=1):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def load():

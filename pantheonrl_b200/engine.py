@@ -60,7 +60,13 @@ class Learner:
 
 class VecTrainer:
     def __init__(self, env_kind, n_envs, ego_cfg=None, alt_cfg=None, seed=10, partner="ppo",
-                 probegostart=0.5, device="cuda", env0=0):
+                 probegostart=0.5, device="cuda", env0=0, group=None, exchange="nccl"):
+        """group: a torch.distributed process group for one-partner-per-GPU sharding
+        (SURVEY.md 8e): every rank owns n_envs envs and its own partner, the ego is
+        replicated; per rollout the ranks all-gather their packed ego transitions and
+        each runs the same deterministic ego update on the full batch.
+        exchange: "nccl" (pack kernel + ncclAllGather) or "p2p" (one kernel packs and
+        stores into every rank's gather buffer through NVLink peer mappings)."""
         if not torch.cuda.is_available():
             raise _lib.PthError("VecTrainer needs a CUDA device: the hot path has no CPU implementation")
         self.env_kind, self.N, self.seed = env_kind, int(n_envs), int(seed)
@@ -86,14 +92,64 @@ class VecTrainer:
         self.num_timesteps = 0
         self.partner_decisions = 0
         # dense env-major sample index of the ego buffer (SB3 swap_and_flatten), built once
-        self.ego_index, _ = up.index_build(None, T, N, device=device)
-        self.ego_M = T * N
+        self.group, self.exchange = group, exchange
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world == 1:
+            self.ego_index, _ = up.index_build(None, T, N, device=device)
+        else:
+            # gathered stream: rank r's record (t, n) sits at r*T*N + t*N + n; sample order is
+            # env-major over GLOBAL env ids (SB3 swap_and_flatten), built once (plumbing)
+            r = torch.arange(self.world, device=device, dtype=torch.int64).view(-1, 1, 1)
+            n = torch.arange(N, device=device, dtype=torch.int64).view(1, -1, 1)
+            t = torch.arange(T, device=device, dtype=torch.int64).view(1, 1, -1)
+            self.ego_index = (r * T * N + t * N + n).reshape(-1).to(torch.int32).contiguous()
+            self._setup_exchange()
+        self.ego_M = self.world * T * N
         self.ego_perm = torch.empty(self.ego_cfg.n_epochs, self.ego_M, dtype=torch.int32, device=device)
         self.ego_ws = up.UpdateWorkspace(self.space, self.ego_M, self.ego.batch_size_for(self.ego_M), device)
         if self.alt is not None:
             cap = alt_cap * N
             self.alt_perm_store = torch.empty(self.alt_cfg.n_epochs * cap, dtype=torch.int32, device=device)
             self.alt_ws = up.UpdateWorkspace(self.space, cap, max(1, self.alt.batch_size_for(cap)), device)
+
+    # ------------------------------------------------------------------ multi-GPU exchange
+    def _setup_exchange(self):
+        import torch.distributed as dist
+        count = self.T * self.N
+        nbytes = self.world * count * _lib.PTH_PACKED_BYTES
+        if self.exchange == "p2p":
+            import torch.distributed._symmetric_memory as symm
+            self.gather = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.symm = symm.rendezvous(self.gather, self.group)
+            self.peer_ptrs = torch.tensor(list(self.symm.buffer_ptrs), dtype=torch.int64, device=self.device)
+        else:
+            self.gather = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.packed = torch.empty(count * _lib.PTH_PACKED_BYTES, dtype=torch.uint8, device=self.device)
+        dist.barrier(self.group)
+
+    def exchange_ego(self):
+        """All-gather this rollout's ego transitions (one exchange per rollout)."""
+        import torch.distributed as dist
+        b, count = self.ego_buf, self.T * self.N
+        lib, ctx = _lib.load(), _lib.Context.get(torch.device(self.device).index or 0)
+        if self.exchange == "p2p":
+            self.symm.barrier()  # peers finished reading the previous rollout's records
+            _lib.check(lib.pth_pack_allgather_p2p(ctx.handle, b.obs.data_ptr(), b.actions.data_ptr(),
+                                                  b.logp.data_ptr(), b.advantages.data_ptr(),
+                                                  b.returns.data_ptr(), count, self.peer_ptrs.data_ptr(),
+                                                  self.world, self.rank, _lib.current_stream()),
+                       "pth_pack_allgather_p2p")
+            self.symm.barrier()  # every rank's stores have landed
+        else:
+            _lib.check(lib.pth_pack_transitions(ctx.handle, b.obs.data_ptr(), b.actions.data_ptr(),
+                                                b.logp.data_ptr(), b.advantages.data_ptr(),
+                                                b.returns.data_ptr(), count, self.packed.data_ptr(),
+                                                _lib.current_stream()), "pth_pack_transitions")
+            dist.all_gather_into_tensor(self.gather, self.packed, group=self.group)
+        _lib.count_launch()
 
     # ------------------------------------------------------------------ phases
     def collect(self):
@@ -114,13 +170,17 @@ class VecTrainer:
             ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_last_done,
                            ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
 
-    def _train_one(self, learner, buf, index, M, perm, ws, stream_id):
+    def _train_one(self, learner, buf, index, M, perm, ws, stream_id, packed=None):
         cfg = learner.cfg
         up.perm_feistel(M, cfg.n_epochs, self.seed, stream_id, epoch0=learner.n_updates, out=perm)
         bs = learner.batch_size_for(M)
+        if packed is None:
+            arrays, stride = (buf.obs, buf.actions, buf.logp, buf.advantages, buf.returns), 0
+        else:  # read the all-gathered 48-byte records in place
+            arrays, stride = tuple(packed[o:] for o in (0, 32, 36, 40, 44)), _lib.PTH_PACKED_BYTES
         stats = up.ppo_update(
             learner.space, learner.params, learner.adam_m, learner.adam_v, learner.adam_step,
-            buf.obs, buf.actions, buf.logp, buf.advantages, buf.returns, perm, bs, ws, index=index,
+            *arrays, perm, bs, ws, index=index, rec_stride=stride,
             M=M, learning_rate=cfg.learning_rate, clip_range=cfg.clip_range, ent_coef=cfg.ent_coef,
             vf_coef=cfg.vf_coef, max_grad_norm=cfg.max_grad_norm,
             normalize_advantage=cfg.normalize_advantage)
@@ -131,8 +191,12 @@ class VecTrainer:
         return stats
 
     def train(self):
+        packed = None
+        if self.world > 1:
+            self.exchange_ego()
+            packed = self.gather
         self._train_one(self.ego, self.ego_buf, self.ego_index, self.ego_M, self.ego_perm,
-                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO)
+                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO, packed=packed)
         if self.alt is not None:
             a = self.alt_buf
             index, total = up.index_build(a.count, a.Tcap, self.N, device=self.device)

@@ -49,6 +49,7 @@ def gae(rewards, values, episode_starts, last_values, dones, gamma=0.99, gae_lam
                                   ptr(last_values), ptr(dones), ptr(adv), ptr(ret), T, N,
                                   float(gamma), float(gae_lambda), int(variant), current_stream()),
           "pth_gae_f32")
+    _lib.count_launch()
     return adv, ret
 
 
@@ -70,6 +71,7 @@ def gae_ragged(rewards, values, episode_starts, count, last_done, gamma=0.99, ga
                                          ptr(count), ptr(last_done), ptr(adv), ptr(ret), T, N,
                                          float(gamma), float(gae_lambda), current_stream()),
           "pth_gae_ragged_f32")
+    _lib.count_launch()
     return adv, ret
 
 
@@ -155,4 +157,5 @@ def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=
     a.d_logits = out["logits"].data_ptr() if "logits" in out else None
     check(_lib.load().pth_policy_forward(_ctx(obs).handle, C.byref(a), current_stream()),
           "pth_policy_forward")
+    _lib.count_launch()
     return out

@@ -92,3 +92,4 @@ def run_rollout(env_kind, space, ego_params, alt_params, ego, alt, carry, T, see
     dev = ego_params.device
     ctx = Context.get(dev.index if dev.index is not None else torch.cuda.current_device())
     check(_lib.load().pth_rollout_run(ctx.handle, C.byref(a), current_stream()), "pth_rollout_run")
+    _lib.count_launch()

@@ -18,6 +18,7 @@ def perm_feistel(M, n_epochs, seed, stream_id, epoch0=0, device="cuda", out=None
     check(_lib.load().pth_perm_feistel(_ctx(perm).handle, perm.data_ptr(), int(M), int(n_epochs),
                                        int(seed), int(stream_id), int(epoch0) & 0xffffffff,
                                        current_stream()), "pth_perm_feistel")
+    _lib.count_launch()
     return perm
 
 
@@ -30,6 +31,7 @@ def index_build(count, T, N, device="cuda"):
     check(lib.pth_index_build(_ctx(index).handle, count.data_ptr() if count is not None else None,
                               int(T), int(N), index.data_ptr(), total.data_ptr(), ws.data_ptr(),
                               current_stream()), "pth_index_build")
+    _lib.count_launch(2)
     return index, total
 
 
@@ -80,4 +82,5 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     a.d_workspace, a.workspace_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
     a.d_stats = stats.data_ptr()
     check(_lib.load().pth_ppo_update(_ctx(params).handle, C.byref(a), current_stream()), "pth_ppo_update")
+    _lib.count_launch()
     return stats
