@@ -1,0 +1,233 @@
+"""PPO model object shaped like stable_baselines3.PPO as the reference uses it
+(trainer.py:107-137, 196-203; agents.py:97-184): same keyword names, `.policy`,
+`.rollout_buffer`, `.n_steps`, `.train()`, `.learn()`, `.save()` / `.load()`.
+
+n_envs == 1: the reference's host-driven flow — one kernel call per decision
+  (pth_policy_forward, B = 1), rows staged on the host and uploaded once per
+  train(); GAE and PPO.train are pth_gae_f32 / pth_ppo_update.
+n_envs  > 1: learn() hands the whole loop to the device engine (VecTrainer ->
+  pth_rollout_run) for the built-in envs.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops, policy as pol, update as up
+from .common.agents import OnPolicyAgent, StaticPolicyAgent
+from .spaces import to_pth_space
+
+
+class DevicePolicy:
+    """ActorCriticPolicy stand-in: parameters live on the device as one flat vector."""
+
+    def __init__(self, space, observation_space, action_space, seed, device, rng_stream):
+        self.space, self.observation_space, self.action_space = space, observation_space, action_space
+        self.device, self.seed, self.rng_stream = device, int(seed or 0), rng_stream
+        self.params = torch.from_numpy(pol.init_flat(space, seed)).to(device)
+        self.calls = 0
+        self._obs_dev = torch.zeros(1, 32, dtype=torch.uint8, device=device)
+        self.act_dim = space.n_heads
+
+    def forward(self, obs, deterministic=False):
+        """obs -> (actions [1, act_dim] numpy, values tensor [1], log_probs tensor [1])."""
+        o = np.zeros((1, 32), np.uint8)
+        flat = np.asarray(obs).reshape(-1)
+        o[0, :flat.size] = flat
+        self._obs_dev.copy_(torch.from_numpy(o))
+        out = ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed,
+                                 rng_stream=self.rng_stream, tick=self.calls & 0xffffffff, slot=0, idx0=0,
+                                 want=("action", "value", "logp"))
+        self.calls += 1
+        act = out["action"].cpu().numpy()[:, :self.act_dim].astype(np.int64)
+        if self.act_dim == 1 and getattr(self.action_space, "shape", ()) == ():
+            act = act.reshape(1)  # Discrete: actions[0] is a scalar, like SB3
+        return act, out["value"], out["logp"]
+
+    def predict_values(self, obs):
+        return self.forward(obs)[1]
+
+    def state_dict(self):
+        return pol.flat_to_state_dict(self.space, self.params.cpu().numpy())
+
+    def load_state_dict(self, sd):
+        self.params.copy_(torch.from_numpy(pol.state_dict_to_flat(self.space, sd)))
+
+
+class HostStagedBuffer:
+    """RolloutBuffer for the N = 1 flow: rows are staged on the host while the env is
+    stepped from Python and uploaded once when GAE / train() run on the device."""
+
+    def __init__(self, n_steps, device):
+        self.T, self.device = n_steps, device
+        self.h = dict(obs=np.zeros((n_steps, 32), np.uint8), actions=np.zeros((n_steps, 4), np.uint8),
+                      rewards=np.zeros(n_steps, np.float32), values=np.zeros(n_steps, np.float32),
+                      logp=np.zeros(n_steps, np.float32), episode_starts=np.zeros(n_steps, np.float32))
+        self.d = {k: torch.zeros(v.shape, dtype=torch.from_numpy(v).dtype, device=device) for k, v in self.h.items()}
+        self.d["advantages"] = torch.zeros(n_steps, 1, device=device)
+        self.d["returns"] = torch.zeros(n_steps, 1, device=device)
+        self.reset()
+
+    def reset(self):
+        self.pos, self.full = 0, False
+
+    def add(self, obs, action, reward, episode_start, value, log_prob):
+        i = self.pos
+        flat = np.asarray(obs).reshape(-1)
+        self.h["obs"][i] = 0
+        self.h["obs"][i, :flat.size] = flat
+        a = np.asarray(action).reshape(-1)
+        self.h["actions"][i] = 0
+        self.h["actions"][i, :a.size] = a
+        self.h["rewards"][i] = reward
+        self.h["episode_starts"][i] = float(episode_start)
+        self.h["values"][i] = float(value.item())
+        self.h["logp"][i] = float(log_prob.item())
+        self.pos += 1
+        self.full = self.pos == self.T
+
+    def add_reward(self, reward):
+        # agents.py:198 `rewards[pos - 1] += reward`; with pos == 0 the reference hits
+        # row -1 of a just-reset buffer, which the next add() overwrites: the reward is lost.
+        if self.pos > 0:
+            self.h["rewards"][self.pos - 1] += np.float32(reward)
+
+    def upload(self):
+        for k, v in self.h.items():
+            self.d[k].copy_(torch.from_numpy(v))
+
+    def compute_returns_and_advantage(self, last_values, dones, gamma=0.99, gae_lambda=0.95):
+        self.upload()
+        T = self.T
+        lv = last_values.reshape(1).to(self.device).float()
+        dn = torch.tensor([float(dones)], device=self.device)
+        ops.gae(self.d["rewards"].view(T, 1), self.d["values"].view(T, 1),
+                self.d["episode_starts"].view(T, 1), lv, dn, gamma, gae_lambda,
+                out=(self.d["advantages"], self.d["returns"]))
+
+
+class PPO:
+    def __init__(self, policy="MlpPolicy", env=None, learning_rate=3e-4, n_steps=2048, batch_size=64,
+                 n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, normalize_advantage=True,
+                 ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, tensorboard_log=None, verbose=0, seed=None,
+                 device="cuda", n_envs=1, n_minibatches=0, _rng_stream=None):
+        if policy != "MlpPolicy":
+            raise ValueError("only 'MlpPolicy' (SB3 default 64-64 tanh towers) is implemented")
+        if not torch.cuda.is_available():
+            raise _lib.PthError("PPO needs a CUDA device: this path has no CPU implementation")
+        self.env, self.device = env, ("cuda" if device in ("auto", "cuda") else device)
+        self.learning_rate, self.n_steps, self.batch_size, self.n_epochs = learning_rate, n_steps, batch_size, n_epochs
+        self.gamma, self.gae_lambda, self.clip_range = gamma, gae_lambda, clip_range
+        self.normalize_advantage, self.ent_coef, self.vf_coef = normalize_advantage, ent_coef, vf_coef
+        self.max_grad_norm, self.verbose, self.seed = max_grad_norm, verbose, seed
+        self.tensorboard_log, self.n_envs, self.n_minibatches = tensorboard_log, int(n_envs), n_minibatches
+        self.observation_space, self.action_space = env.observation_space, env.action_space
+        self.space = to_pth_space(self.observation_space, self.action_space)
+        stream = _rng_stream if _rng_stream is not None else _lib.STREAM_EGO
+        self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, seed, self.device, stream)
+        self.rollout_buffer = HostStagedBuffer(n_steps, self.device)
+        self.adam_m = torch.zeros_like(self.policy.params)
+        self.adam_v = torch.zeros_like(self.policy.params)
+        self.adam_step, self._n_updates, self.num_timesteps = 0, 0, 0
+        self.use_sde, self.sde_sample_freq = False, -1
+        self.logs, self.last_stats = [], None
+        self.ep_info_buffer = None
+        self._ws = None
+        self._last_obs = None
+        self._trainer = None
+
+    # ---------------------------------------------------------------- logging
+    def log(self, record):
+        self.logs.append(record)
+        if self.verbose:
+            print(record)
+
+    # ---------------------------------------------------------------- SB3 PPO.train
+    def train(self):
+        buf, M = self.rollout_buffer, self.rollout_buffer.T
+        if self._ws is None:
+            self._ws = up.UpdateWorkspace(self.space, M, self.batch_size, self.device)
+            self._perm = torch.empty(self.n_epochs, M, dtype=torch.int32, device=self.device)
+        shuffle = _lib.STREAM_SHUFFLE_EGO if self.policy.rng_stream == _lib.STREAM_EGO else _lib.STREAM_SHUFFLE_ALT
+        up.perm_feistel(M, self.n_epochs, self.policy.seed, shuffle, epoch0=self._n_updates, out=self._perm)
+        d = buf.d
+        self.last_stats = up.ppo_update(
+            self.space, self.policy.params, self.adam_m, self.adam_v, self.adam_step, d["obs"], d["actions"],
+            d["logp"], d["advantages"], d["returns"], self._perm, self.batch_size, self._ws,
+            learning_rate=self.learning_rate, clip_range=self.clip_range, ent_coef=self.ent_coef,
+            vf_coef=self.vf_coef, max_grad_norm=self.max_grad_norm, normalize_advantage=self.normalize_advantage)
+        self.adam_step += self.n_epochs * (-(-M // self.batch_size))
+        self._n_updates += self.n_epochs
+
+    # ---------------------------------------------------------------- learn
+    def learn(self, total_timesteps, tb_log_name="PPO", **_):
+        if self.n_envs > 1:
+            return self._learn_on_device(total_timesteps)
+        env, buf = self.env, self.rollout_buffer
+        if self._last_obs is None:
+            self._last_obs = env.reset()
+            self._last_start = True
+        target = self.num_timesteps + total_timesteps
+        while self.num_timesteps < target:
+            buf.reset()
+            for _ in range(self.n_steps):  # collect_rollouts (adap_learn.py:415-455)
+                actions, values, log_probs = self.policy.forward(self._last_obs)
+                new_obs, reward, done, _info = env.step(actions[0])
+                self.num_timesteps += 1
+                buf.add(self._last_obs, actions, reward, self._last_start, values, log_probs)
+                self._last_start = done
+                self._last_obs = env.reset() if done else new_obs  # DummyVecEnv auto-reset
+            last_values = self.policy.predict_values(self._last_obs)
+            buf.compute_returns_and_advantage(last_values, self._last_start, self.gamma, self.gae_lambda)
+            self.train()
+        return self
+
+    def _learn_on_device(self, total_timesteps):
+        from .engine import PPOConfig, VecTrainer
+        kind = getattr(self.env, "device_kind", None)
+        if kind is None:
+            raise _lib.PthError("n_envs > 1 needs a built-in env with a device twin (RPS-v0, LiarsDice-v0)")
+        plist = self.env.partners[0]
+        if len(plist) != 1:
+            raise _lib.PthError("the on-device loop drives exactly one partner per process (one partner per GPU)")
+        partner = plist[0]
+        if self._trainer is None:
+            mk = lambda m: PPOConfig(learning_rate=m.learning_rate, n_steps=m.n_steps, batch_size=m.batch_size,  # noqa: E731
+                                     n_epochs=m.n_epochs, gamma=m.gamma, gae_lambda=m.gae_lambda,
+                                     clip_range=m.clip_range, normalize_advantage=m.normalize_advantage,
+                                     ent_coef=m.ent_coef, vf_coef=m.vf_coef, max_grad_norm=m.max_grad_norm,
+                                     n_minibatches=m.n_minibatches or 32)
+            if isinstance(partner, OnPolicyAgent):
+                mode, alt_cfg = "ppo", mk(partner.model)
+            elif isinstance(partner, StaticPolicyAgent) and partner.policy is self.policy:
+                mode, alt_cfg = "selfplay", None
+            else:
+                raise _lib.PthError("on-device partners: OnPolicyAgent(PPO) or StaticPolicyAgent(ego.policy)")
+            self._trainer = VecTrainer(kind, self.n_envs, mk(self), alt_cfg, seed=self.policy.seed, partner=mode,
+                                       probegostart=getattr(self.env, "probegostart", 0.5), device=self.device)
+            self._trainer.ego.params = self.policy.params          # share storage with the facade objects
+            self._trainer.ego.adam_m, self._trainer.ego.adam_v = self.adam_m, self.adam_v
+            if mode == "ppo":
+                self._trainer.alt.params = partner.model.policy.params
+                self._trainer.alt.adam_m, self._trainer.alt.adam_v = partner.model.adam_m, partner.model.adam_v
+        start = self._trainer.num_timesteps
+        self._trainer.learn(start + total_timesteps)
+        self.num_timesteps = self._trainer.num_timesteps
+        self.last_stats = self._trainer.ego.last_stats
+        return self
+
+    # ---------------------------------------------------------------- checkpoint
+    def save(self, path):
+        torch.save({"policy": self.policy.state_dict(), "adam_m": self.adam_m.cpu(), "adam_v": self.adam_v.cpu(),
+                    "adam_step": self.adam_step, "n_updates": self._n_updates,
+                    "hyper": {k: getattr(self, k) for k in ("learning_rate", "n_steps", "batch_size", "n_epochs", "gamma",
+                                                           "gae_lambda", "clip_range", "ent_coef", "vf_coef",
+                                                           "max_grad_norm", "seed")}}, path)
+
+    @classmethod
+    def load(cls, path, env, **kw):
+        ck = torch.load(path, weights_only=False)
+        m = cls("MlpPolicy", env, **{**ck["hyper"], **kw})
+        m.policy.load_state_dict(ck["policy"])
+        m.adam_m.copy_(ck["adam_m"])
+        m.adam_v.copy_(ck["adam_v"])
+        m.adam_step, m._n_updates = ck["adam_step"], ck["n_updates"]
+        return m
