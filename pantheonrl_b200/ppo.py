@@ -56,8 +56,8 @@ class HostStagedBuffer:
     """RolloutBuffer for the N = 1 flow: rows are staged on the host while the env is
     stepped from Python and uploaded once when GAE / train() run on the device."""
 
-    def __init__(self, n_steps, device):
-        self.T, self.device = n_steps, device
+    def __init__(self, n_steps, device, gamma=0.99, gae_lambda=0.95):
+        self.T, self.device, self.gamma, self.gae_lambda = n_steps, device, gamma, gae_lambda
         self.h = dict(obs=np.zeros((n_steps, 32), np.uint8), actions=np.zeros((n_steps, 4), np.uint8),
                       rewards=np.zeros(n_steps, np.float32), values=np.zeros(n_steps, np.float32),
                       logp=np.zeros(n_steps, np.float32), episode_starts=np.zeros(n_steps, np.float32))
@@ -94,7 +94,9 @@ class HostStagedBuffer:
         for k, v in self.h.items():
             self.d[k].copy_(torch.from_numpy(v))
 
-    def compute_returns_and_advantage(self, last_values, dones, gamma=0.99, gae_lambda=0.95):
+    def compute_returns_and_advantage(self, last_values, dones, gamma=None, gae_lambda=None):
+        gamma = self.gamma if gamma is None else gamma
+        gae_lambda = self.gae_lambda if gae_lambda is None else gae_lambda
         self.upload()
         T = self.T
         lv = last_values.reshape(1).to(self.device).float()
@@ -123,7 +125,7 @@ class PPO:
         self.space = to_pth_space(self.observation_space, self.action_space)
         stream = _rng_stream if _rng_stream is not None else _lib.STREAM_EGO
         self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, seed, self.device, stream)
-        self.rollout_buffer = HostStagedBuffer(n_steps, self.device)
+        self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda)
         self.adam_m = torch.zeros_like(self.policy.params)
         self.adam_v = torch.zeros_like(self.policy.params)
         self.adam_step, self._n_updates, self.num_timesteps = 0, 0, 0

@@ -1,0 +1,242 @@
+"""GPU tests of the host side that keeps the reference's plugin surface:
+MultiAgentEnv / TurnBasedEnv / SimultaneousEnv routing replayed against event
+traces recorded from the reference's own classes (tests/golden), the
+OnPolicyAgent lazy-train protocol, PPO.learn at n_envs = 1 and the hand-over to
+the device engine at n_envs > 1, and a multi-iteration bit-exact cross-check of
+the engine against the oracle pieces."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import rollout as orc
+from oracle import update as oupd
+from pantheonrl_b200 import _lib, ops, update as dupd
+from pantheonrl_b200.common.agents import Agent, OnPolicyAgent, StaticPolicyAgent
+from pantheonrl_b200.common.multiagentenv import PlayerException
+from pantheonrl_b200.engine import PPOConfig, VecTrainer
+from pantheonrl_b200.envs import LiarEnv, RPSEnv, make
+from pantheonrl_b200.ppo import PPO
+
+pytestmark = pytest.mark.gpu
+
+
+class Scripted(Agent):
+    def __init__(self, pid, actions, log):
+        self.pid, self.actions, self.log, self.k = pid, actions, log, 0
+
+    def get_action(self, obs, record=True):
+        a = self.actions[self.k]
+        self.k += 1
+        self.log.append(("act", self.pid, np.asarray(obs.obs).reshape(-1).copy(), np.asarray(a).reshape(-1).copy()))
+        return a
+
+    def update(self, reward, done):
+        self.log.append(("upd", self.pid, float(reward), bool(done)))
+
+
+class ScriptedLiar(LiarEnv):
+    """LiarEnv whose dice / coin come from a recorded list instead of the device RNG."""
+
+    def __init__(self, resets):
+        super().__init__()
+        self.resets, self.r = resets, 0
+
+    def draw_ego_first(self):
+        return bool(self.resets[self.r][0])
+
+    def multi_reset(self, egofirst):
+        info = self.resets[self.r]
+        self.r += 1
+        st = np.zeros((1, 32), np.uint8)
+        st[0, :12] = info[1:13]
+        self.state = torch.from_numpy(st).cuda()
+        hand = info[1:7] if egofirst else info[7:13]
+        return np.concatenate([hand, np.tile([6, 0], 12)]).astype(np.int64)
+
+
+def _replay(env, g, n_partners):
+    log = []
+    pid_of = g["ev_pid"][g["ev_kind"] == 0]
+    acts = g["ev_act"][g["ev_kind"] == 0]
+    for p in range(n_partners):
+        a = [x if x.size > 1 else int(x[0]) for x in acts[pid_of == p]]
+        env.add_partner_agent(Scripted(p, a, log))
+    obs = env.reset()
+    T = g["ego_act"].shape[0]
+    for t in range(T):
+        assert np.array_equal(np.asarray(obs).reshape(-1), g["ego_obs"][t]), t
+        a = g["ego_act"][t]
+        o2, r, d, info = env.step(a if a.size > 1 else int(a[0]))
+        assert r == g["ego_rew"][t] and int(d) == g["ego_done"][t], t
+        assert info["_partnerid"][0] == g["ego_pid"][t]
+        obs = env.reset() if d else o2
+    assert np.array_equal(np.asarray(obs).reshape(-1), g["final_obs"])
+    assert len(log) == len(g["ev_kind"])
+    for i, e in enumerate(log):
+        assert (0 if e[0] == "act" else 1) == g["ev_kind"][i] and e[1] == g["ev_pid"][i], i
+        if e[0] == "act":
+            assert np.array_equal(e[2], g["ev_obs"][i]) and np.array_equal(e[3], g["ev_act"][i]), i
+        else:
+            assert e[2] == g["ev_rew"][i] and int(e[3]) == g["ev_done"][i], i
+
+
+@pytest.mark.parametrize("fname,n_partners", [("routing_liar.npz", 1), ("routing_liar_rr3.npz", 3)])
+def test_turnbased_routing_matches_reference_trace(ctx, golden_dir, fname, n_partners):
+    g = dict(np.load(os.path.join(golden_dir, fname)))
+    _replay(ScriptedLiar(g["reset_info"]), g, n_partners)
+
+
+def test_simultaneous_routing_matches_reference_trace(ctx, golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "routing_rps.npz")))
+    _replay(RPSEnv(), g, 1)
+
+
+def test_player_exceptions_match_the_reference_contract(ctx):
+    env = RPSEnv()
+    with pytest.raises(PlayerException):
+        env.add_partner_agent(Scripted(0, [], []), player_num=0)  # the ego's seat
+    with pytest.raises(PlayerException):
+        env.set_resample_policy("bogus")
+    assert make("LiarsDice-v0").observation_space.nvec.sum() == 270
+
+
+def test_liar_env_device_rng_is_reproducible(ctx):
+    a, b = LiarEnv(seed=3), LiarEnv(seed=3)
+    for _ in range(5):
+        assert a.draw_ego_first() == b.draw_ego_first()
+        oa, ob = a.multi_reset(True), b.multi_reset(True)
+        assert np.array_equal(oa, ob) and sum(a.hands[0]) == 6 and sum(a.hands[1]) == 6
+    st, ef, obs = oracle.liar_reset(1, seed=3, tick=0)
+    c = LiarEnv(seed=3)
+    assert c.draw_ego_first() == bool(ef[0])
+    c.multi_reset(bool(ef[0]))
+    assert np.array_equal(c.state.cpu().numpy()[0, :12], st[0, :12])
+
+
+def test_onpolicy_agent_lazy_train_protocol(ctx):
+    """agents.py:123-184: the partner trains inside the get_action that follows its
+    n_steps-th recorded action, bootstrapping from the last stored value."""
+    env = RPSEnv()
+    model = PPO("MlpPolicy", env, n_steps=8, batch_size=4, n_epochs=2, seed=10, _rng_stream=_lib.STREAM_ALT)
+    agent = OnPolicyAgent(model)
+    from pantheonrl_b200.common.observation import Observation
+    p0 = model.policy.params.clone()
+    rew = [1, -1, 0, 1, 1, -1, 0, 0]
+    for t in range(8):
+        agent.get_action(Observation(np.array([0])))
+        agent.update(0, False)       # first-move hand-off
+        agent.update(rew[t], True)
+    buf = model.rollout_buffer
+    assert buf.pos == 8 and model._n_updates == 0 and torch.equal(model.policy.params, p0)
+    assert np.array_equal(buf.h["rewards"], np.array(rew, np.float32))
+    assert np.array_equal(buf.h["episode_starts"], np.ones(8, np.float32))
+    vals, starts, lps = buf.h["values"].copy(), buf.h["episode_starts"].copy(), buf.h["logp"].copy()
+    agent.get_action(Observation(np.array([0])))          # 9th call: GAE + train + reset, then record row 0
+    assert model._n_updates == 2 and buf.pos == 1 and not torch.equal(model.policy.params, p0)
+    adv, ret = oracle.gae(np.array(rew, np.float32)[:, None], vals[:, None], starts[:, None], vals[-1:], np.ones(1))
+    assert np.array_equal(buf.d["advantages"].cpu().numpy(), adv)
+    agent.update(5.0, False)
+    model.rollout_buffer.reset()
+    agent.update(7.0, True)  # cursor 0: dropped like the reference drops it (agents.py:198)
+    assert model.rollout_buffer.h["rewards"][0] == 5.0
+
+
+def test_ppo_learn_single_env_and_static_partner(ctx, tmp_path):
+    env = LiarEnv(seed=1)
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=32, batch_size=16, n_epochs=2, seed=10,
+                                _rng_stream=_lib.STREAM_ALT))
+    env.add_partner_agent(partner)
+    ego = PPO("MlpPolicy", env, n_steps=32, batch_size=16, n_epochs=2, seed=10)
+    assert torch.equal(ego.policy.params, partner.model.policy.params)  # same seed -> same init (trainer.py:111,198)
+    ego.learn(total_timesteps=96)
+    assert ego.num_timesteps == 96 and ego._n_updates == 6
+    assert partner.model._n_updates >= 2 and partner.num_timesteps >= 40
+    st = ego.last_stats.cpu().numpy()
+    assert np.all(np.isfinite(st)) and bool(torch.isfinite(ego.policy.params).all())
+    # save / load round trip and a FIXED partner built from the loaded policy (trainer.py:140-162)
+    path = str(tmp_path / "ego.pt")
+    ego.save(path)
+    again = PPO.load(path, env)
+    assert torch.equal(again.policy.params, ego.policy.params)
+    env2 = LiarEnv(seed=2)
+    env2.add_partner_agent(StaticPolicyAgent(again.policy))
+    o = env2.reset()
+    for _ in range(20):
+        o, r, d, _ = env2.step(np.array([0, 11]))
+        if d:
+            o = env2.reset()
+
+
+def test_ppo_learn_on_device_matches_engine(ctx):
+    N, T = 256, 16
+    env = LiarEnv()
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4,
+                                _rng_stream=_lib.STREAM_ALT))
+    env.add_partner_agent(partner)
+    ego = PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_envs=N, n_minibatches=4)
+    ego.learn(total_timesteps=N * T * 2)
+    cfg = PPOConfig(n_steps=T, n_epochs=2, n_minibatches=4)
+    tr = VecTrainer("liar", N, cfg, seed=10, partner="ppo")
+    tr.learn(N * T * 2)
+    assert torch.equal(ego.policy.params, tr.ego.params)
+    assert torch.equal(partner.model.policy.params, tr.alt.params)
+    # self-play: partner = StaticPolicyAgent(ego.policy)
+    env = RPSEnv()
+    ego = PPO("MlpPolicy", env, n_steps=8, n_epochs=1, seed=3, n_envs=512, n_minibatches=2)
+    env.add_partner_agent(StaticPolicyAgent(ego.policy))
+    ego.learn(total_timesteps=512 * 8)
+    assert ego._trainer.alt is None and ego.num_timesteps == 512 * 8
+
+
+def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
+    """The north star's trace claim across training: rollout -> GAE -> PPO.train ->
+    rollout with the UPDATED weights, all buffers and parameters equal to the oracle."""
+    N, T, E, NMB, seed = 192, 12, 2, 3, 7
+    cfg = PPOConfig(n_steps=T, n_epochs=E, n_minibatches=NMB)
+    tr = VecTrainer("liar", N, cfg, seed=seed, partner="ppo")
+    osp = oracle.make_space(**oracle.LIAR_SPACE)
+    sp = tr.space
+    pe = tr.ego.params.cpu().numpy().copy()
+    pa = tr.alt.params.cpu().numpy().copy()
+    me, ve, ma, va = (np.zeros_like(pe) for _ in range(4))
+    step_e = step_a = upd_e = upd_a = 0
+    carry = None
+    for it in range(2):
+        tr.iteration()
+        torch.cuda.synchronize()
+        o_ego, o_alt, carry = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=seed, tick0=it * T,
+                                          first_rollout=it == 0, carry=carry)
+        for k in ("obs", "actions", "rewards", "values", "logp", "episode_starts"):
+            assert np.array_equal(getattr(tr.ego_buf, k).cpu().numpy(), o_ego[k]), (it, k)
+        assert np.array_equal(tr.alt_buf.count.cpu().numpy(), o_alt["count"])
+        adv, ret = oracle.gae(o_ego["rewards"], o_ego["values"], o_ego["episode_starts"],
+                              carry["ego_last_value"], carry["ego_last_done"])
+        aadv, aret = oracle.gae_ragged(o_alt["rewards"], o_alt["values"], o_alt["episode_starts"],
+                                       o_alt["count"], carry["alt_last_done"])
+        # ego update
+        idx = oupd.index_build(None, T, N)
+        M = idx.size
+        bs = -(-M // NMB)
+        perm = oupd.perm_feistel(M, E, seed, _lib.STREAM_SHUFFLE_EGO, epoch0=upd_e)
+        G = dupd.update_grid(sp, M, bs)
+        oupd.ppo_update(osp, pe, me, ve, step_e, o_ego["obs"], o_ego["actions"], o_ego["logp"], adv, ret, perm, bs, G,
+                        index=idx)
+        step_e += E * (-(-M // bs))
+        upd_e += E
+        # partner update
+        aidx = oupd.index_build(o_alt["count"], 2 * T, N)
+        M = aidx.size
+        bs = -(-M // NMB)
+        perm = oupd.perm_feistel(M, E, seed, _lib.STREAM_SHUFFLE_ALT, epoch0=upd_a)
+        G = dupd.update_grid(sp, M, bs)
+        oupd.ppo_update(osp, pa, ma, va, step_a, o_alt["obs"], o_alt["actions"], o_alt["logp"], aadv, aret, perm, bs,
+                        G, index=aidx)
+        step_a += E * (-(-M // bs))
+        upd_a += E
+        assert np.array_equal(tr.ego.params.cpu().numpy(), pe), f"ego params differ after iteration {it}"
+        assert np.array_equal(tr.alt.params.cpu().numpy(), pa), f"partner params differ after iteration {it}"
+    st = tr.train_stats()
+    assert np.isfinite(st["train/loss"]) and tr.episode_stats()["ego_steps"] == 2 * N * T
