@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-sample-envs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--ego-update", default="sharded", choices=["sharded", "replicated"])
     return ap.parse_args()
 
 
@@ -195,6 +196,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # the contract is ONE stdout line; NCCL_DEBUG=VERSION would add one
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = {}
     try:
@@ -206,7 +208,7 @@ def run_ours(args):
     # one partner per GPU, envs sharded: rank r owns global envs [r*N, (r+1)*N)
     tr = VecTrainer(args.env, args.n_envs, cfg, seed=10, partner="ppo", device=f"cuda:{local}",
                     env0=rank * args.n_envs, group=dist.group.WORLD if world > 1 else None,
-                    exchange=args.exchange)
+                    exchange=args.exchange, ego_update=args.ego_update)
 
     def barrier():
         if world > 1:
@@ -323,7 +325,8 @@ def run_ours(args):
         "config": {"workload": f"{args.env}-ppo-vs-ppo (BASELINE configs[1] per GPU; one partner per GPU)",
                    "n_envs_per_gpu": args.n_envs, "n_steps": N_STEPS, "n_epochs": N_EPOCHS,
                    "n_minibatches": N_MB, "partners": world, "parallelism": f"dp{world}: envs + one partner per GPU, "
-                   f"ego replicated, 1 all-gather of packed ego transitions per rollout ({args.exchange})", "l2": "no flush: every step regenerates its rollout "
+                   f"ego replicated, 1 all-gather of packed ego transitions per rollout ({args.exchange}), ego update "
+                   f"{args.ego_update if world > 1 else 'local'}", "l2": "no flush: every step regenerates its rollout "
                    "buffers on the device and re-reads 177 KB of weights; working set per step ~90 MB"},
         "phases_ms": ph, "wall_s": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roof, "roofline_dominant": dom, "cpu_baseline": cpu,

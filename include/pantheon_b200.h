@@ -310,6 +310,20 @@ typedef struct pth_update_args {
   float adam_beta1, adam_beta2, adam_eps;
   int32_t normalize_advantage;
   int32_t grid_ctas;        /* 0 = auto (pth_update_grid); tests pin it to compare with the oracle */
+  /* Multi-GPU sharded update (world > 1): every rank holds the SAME sample arrays
+   * (the all-gathered ego stream) and the same perm; tile t of a minibatch is
+   * computed by rank t mod world; after the local ordered reduction each rank
+   * stores its gradient sums into every peer's exchange buffer over NVLink, a
+   * flag barrier in peer memory follows, and all ranks add the per-rank sums in
+   * rank order inside the same persistent kernel — replicas stay bit-identical.
+   * d_peer_xbuf[r] / d_peer_flags[r]: rank r's exchange buffer (>= pth_update_xbuf_bytes)
+   * and flag words (>= 64 uint32, zero-initialised once) mapped in THIS process
+   * (HOST arrays of `world` device pointers). flag_epoch: value of the monotonic
+   * flag counter before this launch (launches add n_epochs * n_minibatches). */
+  int32_t world, rank;
+  void* const* peer_xbuf;
+  void* const* peer_flags;
+  uint32_t flag_epoch;
   void* d_workspace;        /* pth_update_workspace_bytes() */
   int64_t workspace_bytes;
   float* d_stats;           /* [n_epochs*n_minibatch][8]: pg_loss, value_loss, entropy_loss, approx_kl, clip_frac, loss, grad_norm, n */
@@ -321,6 +335,7 @@ int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
  * summed by CTA t mod grid, CTAs are added in ascending order). */
 int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
                     int64_t batch_size);
+int64_t pth_update_xbuf_bytes(const pth_space* sp, int32_t world);
 int pth_ppo_update(pth_ctx* ctx, const pth_update_args* args, void* stream);
 
 /* ------------------------------------------------------------------ */

@@ -161,6 +161,11 @@ class UpdateArgs(C.Structure):
         ("adam_eps", C.c_float),
         ("normalize_advantage", C.c_int32),
         ("grid_ctas", C.c_int32),
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("peer_xbuf", C.POINTER(C.c_void_p)),
+        ("peer_flags", C.POINTER(C.c_void_p)),
+        ("flag_epoch", C.c_uint32),
         ("d_workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
         ("d_stats", C.c_void_p),
@@ -191,6 +196,7 @@ SIGNATURES = {
     "pth_perm_feistel": (C.c_int, [_vp, _vp, _i64, _i32, _u64, _u32, _u32, _vp]),
     "pth_index_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "pth_update_grid": (C.c_int, [_vp, C.POINTER(Space), _i64, _i64]),
+    "pth_update_xbuf_bytes": (_i64, [C.POINTER(Space), _i32]),
     "pth_index_workspace_bytes": (_i64, [_i64]),
     "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
     "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),

@@ -70,6 +70,12 @@ struct UpdParams {
   float* advstat;    // [n_epochs * n_mb][2]
   float* stats;      // [n_epochs * n_mb][8] or NULL
   uint8_t nvec[MAX_SLOTS];
+  // multi-GPU sharded update (world > 1)
+  int world, rank;
+  float* xbuf[8];       // rank r's exchange buffer [2 parities][world][XS] mapped here
+  uint32_t* flags[8];   // rank r's flag words [world]
+  uint32_t flag_epoch;
+  int XS;               // floats per (parity, rank) slot: P + 8 rounded up to 4
 };
 
 // The fixed 128-lane tree of the reduction contract: xor-shuffle tree inside
@@ -88,6 +94,22 @@ __device__ __forceinline__ float block_tree(float x, float* red, int tid) {
 // exactly one thread of one CTA, so tile t+1's add follows tile t's in program
 // order; a fire-and-forget L2 reduction (RED.ADD.F32, IEEE round-to-nearest)
 // gives the same bits as load-add-store without the load round trip.
+// Cross-GPU barrier on flag words in peer memory: CTA 0 tells every rank that
+// this rank's exchange stores for `epoch` are done, then waits for all ranks.
+__device__ __forceinline__ void peer_barrier(const UpdParams& p, uint32_t epoch, int tid) {
+  if (tid < p.world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[tid] + p.rank), "r"(epoch) : "memory");
+    const uint32_t* mine = p.flags[p.rank] + tid;
+    uint32_t v;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (++spins > (1ll << 31)) __trap();  // a peer died: fail loudly instead of hanging the GPU
+    } while ((int32_t)(v - epoch) < 0);
+  }
+}
+
 __device__ __forceinline__ void acc_store(float* g, float v, bool first) {
   if (first)
     *g = v;
@@ -384,14 +406,16 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       const bool norm = p.normalize && B > 1;
       const float mean = __ldcg(p.advstat + 2 * id), stdv = __ldcg(p.advstat + 2 * id + 1);
       const int64_t n_tiles = (B + BT - 1) / BT;
-      const int A = (int)(n_tiles < G ? n_tiles : G);
+      const int W = p.world;
+      const int64_t local_tiles = (n_tiles - p.rank + W - 1) / W;  // tile t belongs to rank t mod W
+      const int A = (int)(local_tiles < G ? local_tiles : G);
 
       __syncthreads();
       load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, NT);
       float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       bool first = true;
 
-      for (int64_t tau = c; tau < n_tiles; tau += G) {
+      for (int64_t tau = p.rank + (int64_t)W * c; tau < n_tiles; tau += (int64_t)W * G) {
         const int64_t t0 = tau * BT;
         const int nb = (int)((B - t0 < BT) ? (B - t0) : BT);
         const bool valid = tid < nb;
@@ -556,21 +580,58 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
 
       // ---- ordered reduction of this CTA's parameter slice + squared-norm partial
       float q = 0.f;
+      const int par = (int)(id & 1);
       for (int i = tid; i < S && tid < BT; i += BT) {  // 128 strided lanes (reduction contract)
         const int pi = c * S + i;
         if (pi < P) {
-          float g = __ldcg(p.part + pi);
-          int cc = 1;
-          for (; cc + 8 <= A; cc += 8) {
-            float t[8];
+          float g = 0.f;
+          if (A > 0) {
+            g = __ldcg(p.part + pi);
+            int cc = 1;
+            for (; cc + 8 <= A; cc += 8) {
+              float t[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p.part + (size_t)(cc + u) * P + pi);
+              for (int u = 0; u < 8; ++u) t[u] = __ldcg(p.part + (size_t)(cc + u) * P + pi);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) g = g + t[u];
+              for (int u = 0; u < 8; ++u) g = g + t[u];
+            }
+            for (; cc < A; ++cc) g = g + __ldcg(p.part + (size_t)cc * P + pi);
           }
-          for (; cc < A; ++cc) g = g + __ldcg(p.part + (size_t)cc * P + pi);
-          p.grad[pi] = g;
-          q = fmaf(g, g, q);
+          if (W == 1) {
+            p.grad[pi] = g;
+            q = fmaf(g, g, q);
+          } else {
+            // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
+            for (int k = 0; k < W; ++k) {
+              const int dst = (p.rank + k) % W;
+              p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
+            }
+          }
+        }
+      }
+      if (W > 1) {
+        if (c == 0 && tid < 5) {
+          float s = 0.f;
+          if (A > 0) {
+            s = __ldcg(p.stat_part + tid);
+            for (int cc = 1; cc < A; ++cc) s = s + __ldcg(p.stat_part + cc * 8 + tid);
+          }
+          for (int k = 0; k < W; ++k)
+            p.xbuf[(p.rank + k) % W][((size_t)par * W + p.rank) * p.XS + P + tid] = s;
+        }
+        __threadfence_system();
+        grid.sync();  // every CTA's exchange stores are issued and fenced
+        if (c == 0) peer_barrier(p, p.flag_epoch + (uint32_t)id + 1u, tid);
+        grid.sync();  // all ranks' sums have landed in the local exchange buffer
+        const float* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS;
+        for (int i = tid; i < S && tid < BT; i += BT) {
+          const int pi = c * S + i;
+          if (pi < P) {
+            float g = __ldcg(xl + pi);
+            for (int r = 1; r < W; ++r) g = g + __ldcg(xl + (size_t)r * p.XS + pi);  // rank order
+            p.grad[pi] = g;
+            q = fmaf(g, g, q);
+          }
         }
       }
       const float sq = block_tree(q, sm.red, tid);
@@ -604,8 +665,15 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       if (c == 0 && tid == 0 && p.stats) {
         float st[5];
         for (int i = 0; i < 5; ++i) {
-          float s = __ldcg(p.stat_part + i);
-          for (int cc = 1; cc < A; ++cc) s = s + __ldcg(p.stat_part + cc * 8 + i);
+          float s;
+          if (W == 1) {
+            s = __ldcg(p.stat_part + i);
+            for (int cc = 1; cc < A; ++cc) s = s + __ldcg(p.stat_part + cc * 8 + i);
+          } else {
+            const float* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
+            s = __ldcg(xl + i);
+            for (int r = 1; r < W; ++r) s = s + __ldcg(xl + (size_t)r * p.XS + i);
+          }
           st[i] = s;
         }
         float* o = p.stats + 8 * id;
@@ -744,9 +812,10 @@ int max_coop_ctas(const pth_ctx* ctx) {
 
 int cap_check_g(const pth_ctx* ctx) { return max_coop_ctas(ctx); }
 
-int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS) {
+int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1) {
   const int64_t eff = BS < M ? BS : M;
   int64_t tiles = (eff + BT - 1) / BT;
+  tiles = (tiles + world - 1) / world;  // a rank computes every world-th tile
   int cap = max_coop_ctas(ctx);
   if (cap < 1) return 0;
   int64_t g = tiles < cap ? tiles : cap;
@@ -754,6 +823,13 @@ int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS) {
 }
 
 }  // namespace
+
+extern "C" int64_t pth_update_xbuf_bytes(const pth_space* sp, int32_t world) {
+  const int64_t P = pth_policy_param_count(sp);
+  if (P < 0 || world < 1 || world > 8) return PTH_EINVAL;
+  const int64_t XS = (P + 8 + 3) / 4 * 4;
+  return 2 * (int64_t)world * XS * (int64_t)sizeof(float);
+}
 
 extern "C" int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
                                int64_t batch_size) {
@@ -798,7 +874,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     pth_set_error("pth_ppo_update: cooperative launch unavailable on this device");
     return PTH_ENOSUP;
   }
-  int G = a->grid_ctas > 0 ? a->grid_ctas : auto_grid(ctx, a->M, a->batch_size);
+  int G = a->grid_ctas > 0 ? a->grid_ctas : auto_grid(ctx, a->M, a->batch_size, a->world > 1 ? a->world : 1);
   PTH_CHECK_ARG(G >= 1 && G <= cap, "grid_ctas exceeds the co-resident CTA capacity");
   const int64_t n_mb = (a->M + a->batch_size - 1) / a->batch_size;
   const WsLayout w = ws_layout(G, p.lo.total, (int64_t)a->n_epochs * n_mb);
@@ -846,6 +922,23 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.stat_part = reinterpret_cast<float*>(ws + w.stat_part);
   p.advstat = reinterpret_cast<float*>(ws + w.advstat);
   p.stats = a->d_stats;
+  p.world = a->world > 1 ? a->world : 1;
+  p.rank = p.world > 1 ? a->rank : 0;
+  p.flag_epoch = a->flag_epoch;
+  p.XS = (p.lo.total + 8 + 3) / 4 * 4;
+  for (int r = 0; r < 8; ++r) {
+    p.xbuf[r] = nullptr;
+    p.flags[r] = nullptr;
+  }
+  if (p.world > 1) {
+    PTH_CHECK_ARG(p.world <= 8 && p.rank >= 0 && p.rank < p.world, "bad world / rank");
+    PTH_CHECK_ARG(a->peer_xbuf && a->peer_flags, "NULL peer pointer arrays");
+    for (int r = 0; r < p.world; ++r) {
+      PTH_CHECK_ARG(a->peer_xbuf[r] && a->peer_flags[r], "NULL peer buffer");
+      p.xbuf[r] = reinterpret_cast<float*>(a->peer_xbuf[r]);
+      p.flags[r] = reinterpret_cast<uint32_t*>(a->peer_flags[r]);
+    }
+  }
 
   void* kargs[] = {(void*)&p};
   PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel, dim3(G), dim3(NT), kargs,

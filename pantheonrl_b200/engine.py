@@ -60,13 +60,18 @@ class Learner:
 
 class VecTrainer:
     def __init__(self, env_kind, n_envs, ego_cfg=None, alt_cfg=None, seed=10, partner="ppo",
-                 probegostart=0.5, device="cuda", env0=0, group=None, exchange="nccl"):
+                 probegostart=0.5, device="cuda", env0=0, group=None, exchange="nccl",
+                 ego_update="sharded"):
         """group: a torch.distributed process group for one-partner-per-GPU sharding
         (SURVEY.md 8e): every rank owns n_envs envs and its own partner, the ego is
         replicated; per rollout the ranks all-gather their packed ego transitions and
         each runs the same deterministic ego update on the full batch.
         exchange: "nccl" (pack kernel + ncclAllGather) or "p2p" (one kernel packs and
-        stores into every rank's gather buffer through NVLink peer mappings)."""
+        stores into every rank's gather buffer through NVLink peer mappings).
+        ego_update: "sharded" — rank r computes every world-th tile of each global
+        minibatch and the per-rank gradient sums are exchanged through peer memory inside
+        the update kernel (added in rank order: replicas stay bit-identical);
+        "replicated" — every rank computes the whole update redundantly."""
         if not torch.cuda.is_available():
             raise _lib.PthError("VecTrainer needs a CUDA device: the hot path has no CPU implementation")
         self.env_kind, self.N, self.seed = env_kind, int(n_envs), int(seed)
@@ -100,13 +105,10 @@ class VecTrainer:
         if self.world == 1:
             self.ego_index, _ = up.index_build(None, T, N, device=device)
         else:
-            # gathered stream: rank r's record (t, n) sits at r*T*N + t*N + n; sample order is
-            # env-major over GLOBAL env ids (SB3 swap_and_flatten), built once (plumbing)
-            r = torch.arange(self.world, device=device, dtype=torch.int64).view(-1, 1, 1)
-            n = torch.arange(N, device=device, dtype=torch.int64).view(1, -1, 1)
-            t = torch.arange(T, device=device, dtype=torch.int64).view(1, 1, -1)
-            self.ego_index = (r * T * N + t * N + n).reshape(-1).to(torch.int32).contiguous()
+            from .dist_util import global_env_major_index
+            self.ego_index = global_env_major_index(self.world, T, N, device)
             self._setup_exchange()
+            self.peers = up.PeerExchange(self.space, group, device) if ego_update == "sharded" else None
         self.ego_M = self.world * T * N
         self.ego_perm = torch.empty(self.ego_cfg.n_epochs, self.ego_M, dtype=torch.int32, device=device)
         self.ego_ws = up.UpdateWorkspace(self.space, self.ego_M, self.ego.batch_size_for(self.ego_M), device)
@@ -170,7 +172,7 @@ class VecTrainer:
             ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_last_done,
                            ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
 
-    def _train_one(self, learner, buf, index, M, perm, ws, stream_id, packed=None):
+    def _train_one(self, learner, buf, index, M, perm, ws, stream_id, packed=None, peers=None):
         cfg = learner.cfg
         up.perm_feistel(M, cfg.n_epochs, self.seed, stream_id, epoch0=learner.n_updates, out=perm)
         bs = learner.batch_size_for(M)
@@ -180,7 +182,7 @@ class VecTrainer:
             arrays, stride = tuple(packed[o:] for o in (0, 32, 36, 40, 44)), _lib.PTH_PACKED_BYTES
         stats = up.ppo_update(
             learner.space, learner.params, learner.adam_m, learner.adam_v, learner.adam_step,
-            *arrays, perm, bs, ws, index=index, rec_stride=stride,
+            *arrays, perm, bs, ws, index=index, rec_stride=stride, peers=peers,
             M=M, learning_rate=cfg.learning_rate, clip_range=cfg.clip_range, ent_coef=cfg.ent_coef,
             vf_coef=cfg.vf_coef, max_grad_norm=cfg.max_grad_norm,
             normalize_advantage=cfg.normalize_advantage)
@@ -196,7 +198,8 @@ class VecTrainer:
             self.exchange_ego()
             packed = self.gather
         self._train_one(self.ego, self.ego_buf, self.ego_index, self.ego_M, self.ego_perm,
-                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO, packed=packed)
+                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO, packed=packed,
+                        peers=getattr(self, "peers", None) if self.world > 1 else None)
         if self.alt is not None:
             a = self.alt_buf
             index, total = up.index_build(a.count, a.Tcap, self.N, device=self.device)

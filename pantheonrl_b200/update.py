@@ -55,7 +55,8 @@ class UpdateWorkspace:
 def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp, advantages,
                returns, perm, batch_size, workspace, index=None, M=None, rec_stride=0,
                learning_rate=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
-               betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None):
+               betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None,
+               peers=None):
     """SB3 PPO.train() over flat sample arrays on the device, in place on
     params / adam_m / adam_v. Returns the stats tensor [n_epochs * n_mb, 8]."""
     n_epochs = perm.shape[0]
@@ -79,8 +80,35 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     a.adam_beta1, a.adam_beta2, a.adam_eps = betas[0], betas[1], eps
     a.normalize_advantage = int(normalize_advantage)
     a.grid_ctas = int(grid_ctas)
+    if peers is not None:  # sharded multi-GPU update: see PeerExchange
+        a.world, a.rank = peers.world, peers.rank
+        a.peer_xbuf, a.peer_flags = peers.xbuf_array, peers.flag_array
+        a.flag_epoch = peers.epoch & 0xffffffff
+        peers.epoch += n_epochs * n_mb
     a.d_workspace, a.workspace_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
     a.d_stats = stats.data_ptr()
     check(_lib.load().pth_ppo_update(_ctx(params).handle, C.byref(a), current_stream()), "pth_ppo_update")
     _lib.count_launch()
     return stats
+
+
+class PeerExchange:
+    """Symmetric-memory (NVLink peer-mapped) exchange buffers + flag words for the
+    sharded multi-GPU update; one per process group, reused by every launch."""
+
+    def __init__(self, space, group, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nbytes = int(_lib.load().pth_update_xbuf_bytes(C.byref(space), self.world))
+        self.xbuf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.flags = symm.empty(64, dtype=torch.int32, device=device)
+        self.xbuf.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize()
+        self.hx = symm.rendezvous(self.xbuf, group)
+        self.hf = symm.rendezvous(self.flags, group)
+        self.xbuf_array = (C.c_void_p * self.world)(*[int(x) for x in self.hx.buffer_ptrs])
+        self.flag_array = (C.c_void_p * self.world)(*[int(x) for x in self.hf.buffer_ptrs])
+        self.epoch = 0
+        dist.barrier(group)
