@@ -89,15 +89,18 @@ struct SmemPolicy {
   float pad_[3];
 };
 
-// COHERENT = true: loads go to L2 (ld.global.cg) — required when the parameters are
-// rewritten by other CTAs between grid-wide barriers inside one kernel (the update).
+// COHERENT = true: the parameters are rewritten by other CTAs between grid-wide
+// barriers inside one kernel (the update).  One-time loads then go to L2
+// (ld.global.cg); the hot first-layer row gathers use ordinary L1-cached loads
+// (NOT the non-coherent ld.global.nc path) and rely on the gpu-scope fence the
+// update kernel executes after its parameter-update barrier to invalidate L1.
 template <bool COHERENT>
 __device__ __forceinline__ float ld_param(const float* p) {
   return COHERENT ? __ldcg(p) : __ldg(p);
 }
 template <bool COHERENT>
 __device__ __forceinline__ float4 ld_param4(const float4* p) {
-  return COHERENT ? __ldcg(p) : __ldg(p);
+  return COHERENT ? *p : __ldg(p);
 }
 
 template <bool COHERENT = false>
@@ -129,32 +132,34 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
 // global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
 // so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
 // ILP.  obs: [BT][32] bytes in shared memory.
-template <bool COHERENT = false, int NTH = NT>
+template <bool COHERENT = false, int NTH = NT, int BTS = BT>
 __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uint8_t* obs_s,
                                                    const float* W,
                                                    const float* bias_s, float* Out, int tid,
                                                    bool apply_tanh = true) {
+  constexpr int LDA = BTS + 4;
   constexpr int GS = NTH / 16;  // samples the CTA covers at a time (16 threads per row)
+  constexpr int UI = (BTS / GS) < 4 ? (BTS / GS) : 4;  // sample groups interleaved for ILP
   const int jq = tid & 15;   // outputs jq*4 .. +3
   const int bs = tid >> 4;   // sample within the group of GS
   const float4 bv = *reinterpret_cast<const float4*>(bias_s + jq * 4);
   const float4* W4 = reinterpret_cast<const float4*>(W);
 #pragma unroll 1
-  for (int g0 = 0; g0 < BT / GS; g0 += 4) {
-    float4 acc[4];
+  for (int g0 = 0; g0 < BTS / GS; g0 += UI) {
+    float4 acc[UI];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = bv;
+    for (int u = 0; u < UI; ++u) acc[u] = bv;
     // slots in blocks of SB: all SB*4 row loads are issued before the adds
     // (the adds themselves stay in ascending slot order per sample).
     constexpr int SB = 6;
     int s0 = 0;
     for (; s0 + SB <= sp.obs_len; s0 += SB) {
-      float4 w[SB][4];
+      float4 w[SB][UI];
 #pragma unroll
       for (int i = 0; i < SB; ++i) {
         const int off = sp.slot_off[s0 + i];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UI; ++u) {
           const int b = (g0 + u) * GS + bs;
           const int f = off + obs_s[b * 32 + s0 + i];
           w[i][u] = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
@@ -163,7 +168,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
 #pragma unroll
       for (int i = 0; i < SB; ++i)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UI; ++u) {
           acc[u].x = acc[u].x + w[i][u].x;
           acc[u].y = acc[u].y + w[i][u].y;
           acc[u].z = acc[u].z + w[i][u].z;
@@ -173,7 +178,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
     for (int s = s0; s < sp.obs_len; ++s) {
       const int off = sp.slot_off[s];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UI; ++u) {
         const int b = (g0 + u) * GS + bs;
         const int f = off + obs_s[b * 32 + s];
         const float4 w = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
@@ -184,7 +189,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UI; ++u) {
       const int b = (g0 + u) * GS + bs;
       float* o = Out + (jq * 4) * LDA + b;
       if (apply_tanh) {
@@ -245,20 +250,23 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
 
 // ---------------------------------------------------------------------------
 // Hidden layer: Out[j][b] = act(bias[j] + sum_{k<64} A[k][b] * W[j][k]).
-// Thread (tx, ty) owns samples {tx*4..+3, 64+tx*4..+3} and the JT outputs
-// j = jj*(NTH/16) + ty.  NTH = 256: per 4 k, 4 LDS.128 of weights + 8 LDS.128
-// of activations feed 128 FFMA per thread.
-template <bool TANH, int NTH = NT>
+// Thread (tx, ty) owns SPT samples (BTS = 128: {tx*4..+3, 64+tx*4..+3}; smaller
+// tiles: tx*4..+3) and the JT outputs j = jj*NY + ty.  BTS = 128, NTH = 256: per
+// 4 k, 4 LDS.128 of weights + 8 LDS.128 of activations feed 128 FFMA per thread.
+template <bool TANH, int NTH = NT, int BTS = BT>
 __device__ __forceinline__ void dense64(const float* A, const float* W, const float* bias,
                                         float* Out, int tid) {
-  constexpr int NY = NTH / 16, JT = HID / NY;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[JT][8];
+  constexpr int LDA = BTS + 4;
+  constexpr int SPT = BTS >= 128 ? 8 : 4;
+  constexpr int TXN = BTS / SPT, NY = NTH / TXN, JT = HID / NY;
+  static_assert(NY * JT == HID && TXN * NY == NTH, "tile mapping must cover 64 outputs x BTS samples");
+  const int tx = tid % TXN, ty = tid / TXN;
+  float acc[JT][SPT];
 #pragma unroll
   for (int jj = 0; jj < JT; ++jj) {
     const float bj = bias[jj * NY + ty];
 #pragma unroll
-    for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = bj;
+    for (int ss = 0; ss < SPT; ++ss) acc[jj][ss] = bj;
   }
 #pragma unroll 2
   for (int k0 = 0; k0 < HID; k0 += 4) {
@@ -268,32 +276,40 @@ __device__ __forceinline__ void dense64(const float* A, const float* W, const fl
       w[jj] = *reinterpret_cast<const float4*>(W + (jj * NY + ty) * LDW + k0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + tx * 4);
-      const float4 a1 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + 64 + tx * 4);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float a[SPT];
+      {
+        const float4 a0 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + tx * 4);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+        if constexpr (SPT == 8) {
+          const float4 a1 = *reinterpret_cast<const float4*>(A + (k0 + kk) * LDA + 64 + tx * 4);
+          a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        }
+      }
 #pragma unroll
       for (int jj = 0; jj < JT; ++jj) {
         const float wk = kk == 0 ? w[jj].x : (kk == 1 ? w[jj].y : (kk == 2 ? w[jj].z : w[jj].w));
 #pragma unroll
-        for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = fmaf(a[ss], wk, acc[jj][ss]);
+        for (int ss = 0; ss < SPT; ++ss) acc[jj][ss] = fmaf(a[ss], wk, acc[jj][ss]);
       }
     }
   }
 #pragma unroll
   for (int jj = 0; jj < JT; ++jj) {
     float* o = Out + (jj * NY + ty) * LDA;
-    float v[8];
+    float v[SPT];
 #pragma unroll
-    for (int ss = 0; ss < 8; ++ss) v[ss] = TANH ? pth_tanhf(acc[jj][ss]) : acc[jj][ss];
+    for (int ss = 0; ss < SPT; ++ss) v[ss] = TANH ? pth_tanhf(acc[jj][ss]) : acc[jj][ss];
     *reinterpret_cast<float4*>(o + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    if constexpr (SPT == 8) *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
 
 // ---------------------------------------------------------------------------
 // Heads, one thread per sample.  The thread pulls its 64 latent activations
 // into registers once; weights are broadcast reads.
+template <int BTS = BT>
 __device__ __forceinline__ void load_column(const float* A, int b, float (&h)[HID]) {
+  constexpr int LDA = BTS + 4;
 #pragma unroll
   for (int k = 0; k < HID; ++k) h[k] = A[k * LDA + b];
 }
@@ -312,16 +328,19 @@ __device__ __forceinline__ float dot64(const float (&h)[HID], const float* w, fl
 }
 
 // logits[l][b] for l < L into Lg (row stride LDA)
+template <int BTS = BT>
 __device__ __forceinline__ void action_head(const float* A, const SmemPolicy& s, int L, float* Lg,
                                             int b) {
+  constexpr int LDA = BTS + 4;
   float h[HID];
-  load_column(A, b, h);
+  load_column<BTS>(A, b, h);
   for (int l = 0; l < L; ++l) Lg[l * LDA + b] = dot64(h, s.w_act + l * LDW, s.b_act[l]);
 }
 
+template <int BTS = BT>
 __device__ __forceinline__ float value_head(const float* A, const SmemPolicy& s, int b) {
   float h[HID];
-  load_column(A, b, h);
+  load_column<BTS>(A, b, h);
   return dot64(h, s.w_val, s.b_val);
 }
 
@@ -334,8 +353,10 @@ struct HeadOut {
   float logp, entropy;
 };
 
+template <int BTS = BT>
 __device__ __forceinline__ HeadOut head_eval(const float* Lg, int off, int n, int b, bool sample,
                                              float u, int action_in, float* probs_out = nullptr) {
+  constexpr int LDA = BTS + 4;
   float m = Lg[off * LDA + b];
   for (int i = 1; i < n; ++i) {
     float z = Lg[(off + i) * LDA + b];
@@ -378,6 +399,7 @@ struct DistOut {
   float logp, entropy;
 };
 
+template <int BTS = BT>
 __device__ __forceinline__ DistOut dist_eval(const SpaceDev& sp, const float* Lg, int b,
                                              bool sample, pth_u4 rnd, uint32_t action_in,
                                              float* probs_out = nullptr) {
@@ -388,7 +410,7 @@ __device__ __forceinline__ DistOut dist_eval(const SpaceDev& sp, const float* Lg
   int off = 0;
   const uint32_t r[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
   for (int h = 0; h < sp.n_heads; ++h) {
-    HeadOut o = head_eval(Lg, off, sp.head_n[h], b, sample, pth_u01(r[h]),
+    HeadOut o = head_eval<BTS>(Lg, off, sp.head_n[h], b, sample, pth_u01(r[h]),
                           (int)((action_in >> (8 * h)) & 0xffu), probs_out);
     d.action |= ((uint32_t)o.action & 0xffu) << (8 * h);
     d.logp = d.logp + o.logp;

@@ -20,13 +20,16 @@ using namespace pthmlp;
 
 namespace {
 
+// RB = envs per CTA: 128 when there are enough envs to give every SM a tile,
+// 32 otherwise (N = 4096 -> 128 CTAs instead of 32).
+template <int RB>
 struct RollSmem {
   SmemPolicy pol_ego;
   SmemPolicy pol_alt;
-  float A[HID * LDA];
-  float Bf[HID * LDA];
-  float Lg[MAXL * LDA];
-  uint32_t obs[BT * 8];
+  float A[HID * (RB + 4)];
+  float Bf[HID * (RB + 4)];
+  float Lg[MAXL * (RB + 4)];
+  uint32_t obs[RB * 8];
   float red[32];
 };
 
@@ -42,31 +45,32 @@ struct FwdOut {
 };
 
 // One CTA-wide forward over the observations currently in sm.obs.
+template <int RB>
 __device__ __forceinline__ FwdOut cta_forward(const RollParams& p, const float* __restrict__ params,
-                                              const SmemPolicy& pol, RollSmem& sm, int tid,
+                                              const SmemPolicy& pol, RollSmem<RB>& sm, int tid,
                                               bool with_policy, pth_u4 rnd) {
   FwdOut o;
   o.action = 0;
   o.logp = 0.f;
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
   __syncthreads();  // obs written by all lanes; previous users of A/Bf/Lg are done
-  const bool lane = tid < BT;  // threads [BT, NT) only help in the tiled layers
+  const bool lane = tid < RB;  // threads [RB, NT) only help in the tiled layers
   if (with_policy) {
-    first_layer_onehot(p.sp, obs_s, params + p.lo.w_pi0, pol.b_pi0, sm.A, tid);
+    first_layer_onehot<false, NT, RB>(p.sp, obs_s, params + p.lo.w_pi0, pol.b_pi0, sm.A, tid);
     __syncthreads();
-    dense64<true>(sm.A, pol.w_pi1, pol.b_pi1, sm.Bf, tid);
+    dense64<true, NT, RB>(sm.A, pol.w_pi1, pol.b_pi1, sm.Bf, tid);
     __syncthreads();
-    if (lane) action_head(sm.Bf, pol, p.sp.L, sm.Lg, tid);
+    if (lane) action_head<RB>(sm.Bf, pol, p.sp.L, sm.Lg, tid);
   }
-  first_layer_onehot(p.sp, obs_s, params + p.lo.w_vf0, pol.b_vf0, sm.A, tid);
+  first_layer_onehot<false, NT, RB>(p.sp, obs_s, params + p.lo.w_vf0, pol.b_vf0, sm.A, tid);
   __syncthreads();
-  dense64<true>(sm.A, pol.w_vf1, pol.b_vf1, sm.Bf, tid);
+  dense64<true, NT, RB>(sm.A, pol.w_vf1, pol.b_vf1, sm.Bf, tid);
   __syncthreads();
   o.value = 0.f;
   if (!lane) return o;
-  o.value = value_head(sm.Bf, pol, tid);
+  o.value = value_head<RB>(sm.Bf, pol, tid);
   if (with_policy) {
-    DistOut d = dist_eval(p.sp, sm.Lg, tid, true, rnd, 0u);
+    DistOut d = dist_eval<RB>(p.sp, sm.Lg, tid, true, rnd, 0u);
     o.action = d.action;
     o.logp = d.logp;
   }
@@ -127,13 +131,13 @@ __device__ __forceinline__ void update_players(EnvRegs& e, float r_ego, float r_
   e.total_alt = e.total_alt + r_alt;
 }
 
-template <int ENV>
+template <int ENV, int RB>
 __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ RollParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RollSmem& sm = *reinterpret_cast<RollSmem*>(smem_raw);
+  RollSmem<RB>& sm = *reinterpret_cast<RollSmem<RB>*>(smem_raw);
   const int tid = threadIdx.x;
-  const bool lane = tid < BT;  // one env per thread in [0, BT); the rest help with the MLP tiles
-  const int64_t n = (int64_t)blockIdx.x * BT + (lane ? tid : 0);
+  const bool lane = tid < RB;  // one env per thread in [0, RB); the rest help with the MLP tiles
+  const int64_t n = (int64_t)blockIdx.x * RB + (lane ? tid : 0);
   const int64_t N = p.a.N;
   const bool valid = lane && n < N;
   const uint64_t genv = (uint64_t)(p.a.env0 + n);
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
         for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
       }
       pth_u4 rnd = pth_philox(p.a.seed, PTH_STREAM_ALT, genv, p.a.tick0, 2u);
-      FwdOut f = cta_forward(p, alt_w, pol_alt, sm, tid, true, rnd);
+      FwdOut f = cta_forward<RB>(p, alt_w, pol_alt, sm, tid, true, rnd);
       if (act_c) {
         alt_record(p, e, n, w, f);
         float re, ra;
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
 #pragma unroll
       for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
     }
-    FwdOut fe = cta_forward(p, ego_w, sm.pol_ego, sm, tid, true,
+    FwdOut fe = cta_forward<RB>(p, ego_w, sm.pol_ego, sm, tid, true,
                             pth_philox(p.a.seed, PTH_STREAM_EGO, genv, g, 0u));
     if (valid) {
       store_obs_row(p.a.ego.d_obs, o, w);
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
     if (ENV == PTH_ENV_RPS) {
       // ================= SimultaneousEnv: partner acts on the same tick
       __syncthreads();
-      FwdOut fa = cta_forward(p, alt_w, pol_alt, sm, tid, true,
+      FwdOut fa = cta_forward<RB>(p, alt_w, pol_alt, sm, tid, true,
                               pth_philox(p.a.seed, PTH_STREAM_ALT, genv, g, 0u));
       if (valid) {
         alt_record(p, e, n, w, fa);
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
 #pragma unroll
           for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
         }
-        FwdOut fa = cta_forward(p, alt_w, pol_alt, sm, tid, true,
+        FwdOut fa = cta_forward<RB>(p, alt_w, pol_alt, sm, tid, true,
                                 pth_philox(p.a.seed, PTH_STREAM_ALT, genv, g, 0u));
         if (act_b) {
           alt_record(p, e, n, w, fa);
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
 #pragma unroll
           for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
         }
-        FwdOut fa = cta_forward(p, alt_w, pol_alt, sm, tid, true,
+        FwdOut fa = cta_forward<RB>(p, alt_w, pol_alt, sm, tid, true,
                                 pth_philox(p.a.seed, PTH_STREAM_ALT, genv, g, 1u));
         if (act_c) {
           alt_record(p, e, n, w, fa);
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
     for (int i = 0; i < 8; ++i) sm.obs[tid * 8 + i] = w[i];
   }
   pth_u4 zero = {0, 0, 0, 0};
-  FwdOut fl = cta_forward(p, ego_w, sm.pol_ego, sm, tid, false, zero);
+  FwdOut fl = cta_forward<RB>(p, ego_w, sm.pol_ego, sm, tid, false, zero);
 
   if (valid) {
     alt_flush(p, e, n);
@@ -382,18 +386,22 @@ extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* st
   }
   p.lo = make_layout(p.sp.F, p.sp.L);
   p.a = *a;
-  const size_t smem = sizeof(RollSmem);
-  const int grid = pth_ceil_div(a->N, BT);
   cudaStream_t st = (cudaStream_t)stream;
+  // 128-env tiles once every SM gets one; 32-env tiles below that (4x more CTAs)
+  const bool small = pth_ceil_div(a->N, 128) < ctx->sm_count;
+#define PTH_ROLL_LAUNCH(ENVK, RBV)                                                              \
+  do {                                                                                          \
+    const size_t smem = sizeof(RollSmem<RBV>);                                                  \
+    PTH_CUDA(cudaFuncSetAttribute(rollout_kernel<ENVK, RBV>,                                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    rollout_kernel<ENVK, RBV><<<pth_ceil_div(a->N, RBV), NT, smem, st>>>(p);                    \
+  } while (0)
   if (a->env_kind == PTH_ENV_RPS) {
-    PTH_CUDA(cudaFuncSetAttribute(rollout_kernel<PTH_ENV_RPS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_kernel<PTH_ENV_RPS><<<grid, NT, smem, st>>>(p);
+    if (small) PTH_ROLL_LAUNCH(PTH_ENV_RPS, 32); else PTH_ROLL_LAUNCH(PTH_ENV_RPS, 128);
   } else {
-    PTH_CUDA(cudaFuncSetAttribute(rollout_kernel<PTH_ENV_LIAR>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rollout_kernel<PTH_ENV_LIAR><<<grid, NT, smem, st>>>(p);
+    if (small) PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 32); else PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 128);
   }
+#undef PTH_ROLL_LAUNCH
   PTH_LAUNCH_CHECK();
   return PTH_OK;
 }

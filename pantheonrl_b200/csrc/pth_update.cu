@@ -588,6 +588,13 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           if (A > 0) {
             g = __ldcg(p.part + pi);
             int cc = 1;
+            for (; cc + 32 <= A; cc += 32) {  // 32 independent L2 loads in flight, adds stay in order
+              float t[32];
+#pragma unroll
+              for (int u = 0; u < 32; ++u) t[u] = __ldcg(p.part + (size_t)(cc + u) * P + pi);
+#pragma unroll
+              for (int u = 0; u < 32; ++u) g = g + t[u];
+            }
             for (; cc + 8 <= A; cc += 8) {
               float t[8];
 #pragma unroll
@@ -687,6 +694,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         o[7] = Bf;
       }
       grid.sync();  // ---------------------------------------------- (3) parameters updated
+      __threadfence();  // invalidate L1: the next minibatch gathers fresh first-layer rows through L1
     }
   }
 }
