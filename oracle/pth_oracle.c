@@ -479,5 +479,6 @@ void orc_policy_forward(const orc_space* sp, const float* params, const void* ob
   }
 }
 
+#include "pth_oracle_overcooked.inc"
 #include "pth_oracle_rollout.inc"
 #include "pth_oracle_update.inc"

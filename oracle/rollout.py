@@ -27,11 +27,16 @@ class OrcRolloutArgs(C.Structure):
         ("seed", C.c_uint64), ("tick0", C.c_uint32), ("probegostart", C.c_float),
         ("first_rollout", C.c_int32),
         ("script_ego_act", C.c_void_p), ("script_alt_act", C.c_void_p), ("script_reset", C.c_void_p),
+        ("oc_layout", C.c_void_p), ("oc_state", C.c_void_p), ("oc_ego_idx", C.c_int32),
     ]
 
 
-def new_buffer(Tcap, N, ragged):
-    b = dict(obs=np.zeros((Tcap, N, 32), np.uint8), actions=np.zeros((Tcap, N, 4), np.uint8),
+OC_STATE_BYTES = 14 + 128 * 4 + 1 + 8 + 1 + 4  # sizeof(orc_oc_state): 540 (t is 4-byte aligned)
+
+
+def new_buffer(Tcap, N, ragged, box=False):
+    obs = np.zeros((Tcap, N, 64), np.float32) if box else np.zeros((Tcap, N, 32), np.uint8)
+    b = dict(obs=obs, actions=np.zeros((Tcap, N, 4), np.uint8),
              rewards=np.zeros((Tcap, N), np.float32), values=np.zeros((Tcap, N), np.float32),
              logp=np.zeros((Tcap, N), np.float32), episode_starts=np.zeros((Tcap, N), np.float32))
     b["count"] = np.zeros(N, np.int32) if ragged else None
@@ -41,7 +46,8 @@ def new_buffer(Tcap, N, ragged):
 def new_carry(N):
     return dict(ego_last_start=np.ones(N, np.float32), alt_last_done=np.ones(N, np.float32),
                 total_rew=np.zeros((2, N), np.float32), flags=np.zeros(N, np.uint8),
-                game_state=np.zeros((N, 32), np.uint8), ego_last_value=np.zeros(N, np.float32),
+                game_state=np.zeros((N, 32), np.uint8), oc_state=np.zeros((N, OC_STATE_BYTES), np.uint8),
+                ego_last_value=np.zeros(N, np.float32),
                 ego_last_done=np.zeros(N, np.float32), ep_stats=np.zeros(4, np.float32))
 
 
@@ -55,13 +61,20 @@ def _cbuf(b):
 
 def rollout(env_kind, space, ego_params, alt_params, N, T, seed=10, tick0=0, env0=0,
             probegostart=0.5, first_rollout=True, partner_records=True, carry=None, ego=None,
-            alt=None, script_ego_act=None, script_alt_act=None, script_reset=None):
+            alt=None, script_ego_act=None, script_alt_act=None, script_reset=None, oc_layout=None,
+            oc_ego_idx=0):
     """Runs one rollout; returns (ego buffer dict, partner buffer dict, carry dict)."""
-    ego = ego or new_buffer(T, N, False)
-    alt = alt or new_buffer(2 * T, N, True)
+    box = env_kind == "overcooked"
+    ego = ego or new_buffer(T, N, False, box)
+    alt = alt or new_buffer(T if box else 2 * T, N, True, box)
     carry = carry or new_carry(N)
     a = OrcRolloutArgs()
-    a.env_kind = {"rps": 0, "liar": 1}[env_kind]
+    a.env_kind = {"rps": 0, "liar": 1, "overcooked": 2}[env_kind]
+    if box:
+        assert oc_layout is not None
+        a.oc_layout = C.addressof(oc_layout)
+        a.oc_state = carry["oc_state"].ctypes.data
+        a.oc_ego_idx = int(oc_ego_idx)
     a.partner_records = int(partner_records)
     a.space = C.pointer(space)
     keep = []
