@@ -105,8 +105,8 @@ def test_layout_tables_cover_every_trainer_layout(golden_dir):
         n += 1
         L = oc.multienv_layout(golden_dir, name)
         assert L.GW * L.GH <= oc.OC_MAX_CELLS
-        # only `mdp_test` has tomato dispensers (featurize_state raises on a held tomato there)
-        assert (sum(r.count("T") for r in d["grid"]) == 0) == (name != "mdp_test"), name
+        # only two layouts have tomato dispensers (featurize_state raises on a held tomato there)
+        assert (sum(r.count("T") for r in d["grid"]) == 0) == (name not in ("mdp_test", "simple_tomato")), name
         feats, *_ = oc.replay(L, np.zeros((1, 2), np.uint8) + 4)
         assert feats.shape == (2, 2, 62) and np.isfinite(feats).all()
     assert n >= 16
