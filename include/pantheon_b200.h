@@ -176,6 +176,73 @@ int pth_env_liar_step(pth_ctx* ctx, pth_liar_state* d_state,
                       uint8_t* d_done, int64_t N, void* stream);
 
 /* ------------------------------------------------------------------ */
+/* a10: Overcooked gridworld behind OvercookedMultiEnv                 */
+/* replaces overcookedgym/overcooked.py:51-98 (multi_step/multi_reset) */
+/* -> overcooked_ai_py/mdp/overcooked_env.py:77-121 (step/reset/done)  */
+/* -> mdp/overcooked_mdp.py:643-846 (get_state_transition) and         */
+/* :1077-1170 (featurize_state), planning/planners.py:250-295          */
+/* (MotionPlanner.min_cost_to_feature with NO_COUNTERS_PARAMS)         */
+/* ------------------------------------------------------------------ */
+
+#define PTH_OC_MAX_CELLS 128    /* width * height (largest reference layout: corridor 14 x 9) */
+#define PTH_OC_MAX_POTS 4
+#define PTH_OC_MAX_COUNTERS 64
+#define PTH_OC_OBS 62           /* featurize_state width (29 + 29 + 2 + 2) */
+#define PTH_OC_ROW 64           /* floats per observation row in the rollout buffers */
+enum { PTH_OC_FLOOR = 0, PTH_OC_COUNTER = 1, PTH_OC_ONION = 2, PTH_OC_POT = 3, PTH_OC_DISH = 4, PTH_OC_SERVE = 5 };
+
+/* One layout + the env constants of OvercookedMultiEnv, plus lookup tables derived from
+ * them.  Fill the first block, call pth_overcooked_layout_init (HOST, no device work),
+ * then copy the struct to device memory and pass that pointer as d_layout.
+ * Onion-only layouts (every layout trainer.py accepts except mdp_test / simple_tomato,
+ * on which the reference's featurize_state itself raises once a tomato is held). */
+typedef struct pth_overcooked_layout {
+  /* ---- inputs */
+  int32_t width, height;
+  int32_t cook_time, num_items, delivery_reward, horizon;   /* layout file + DEFAULT_ENV_PARAMS (overcooked.py:18-20) */
+  int32_t rew_placement_in_pot, rew_dish_pickup, rew_soup_pickup; /* rew_shaping_params (overcooked.py:21-28) */
+  int32_t ego_agent_idx;                                    /* OvercookedMultiEnv(ego_agent_idx=) */
+  int32_t start_x[2], start_y[2];                           /* start_player_positions */
+  uint8_t terrain[PTH_OC_MAX_CELLS];                        /* row-major y*width+x, PTH_OC_* codes */
+  /* ---- derived by pth_overcooked_layout_init */
+  int32_t n_pots, n_counters;
+  uint8_t slot[PTH_OC_MAX_CELLS];        /* counter index of an X cell, pot index of a P cell, 255 otherwise */
+  uint8_t wall[PTH_OC_MAX_CELLS];        /* bit d: the neighbour in direction d (N,S,E,W) is not floor */
+  uint8_t pot_x[PTH_OC_MAX_POTS], pot_y[PTH_OC_MAX_POTS];
+  /* per MotionPlanner node = cell*4 + orientation: */
+  int8_t static_delta[PTH_OC_MAX_CELLS * 4][3][2];  /* (dx, dy) to the closest onion dispenser / dish dispenser / serving cell; (0,0) if none */
+  uint8_t pot_dist[PTH_OC_MAX_CELLS * 4][PTH_OC_MAX_POTS]; /* plan length to pot p's closest valid motion goal; 255 = unreachable */
+} pth_overcooked_layout;
+
+/* HOST: validates the grid and fills the derived tables (BFS over the (position,
+ * orientation) motion graph).  PTH_ENOSUP for tomato layouts / too many cells, pots or counters. */
+int pth_overcooked_layout_init(pth_overcooked_layout* host_layout);
+
+/* Per-env game state, 40 bytes.  Objects on counters: 2 bits per counter slot
+ * (bit in ctr_lo | bit in ctr_hi << 1): 0 none, 1 onion, 2 soup (always a finished
+ * onion soup), 3 dish.  held: same codes.  Pot p: pot_n onions, pot_t cook time. */
+typedef struct pth_overcooked_state {
+  uint64_t ctr_lo, ctr_hi;
+  uint8_t px[2], py[2], po[2], held[2];
+  uint8_t pot_n[PTH_OC_MAX_POTS], pot_t[PTH_OC_MAX_POTS];
+  uint16_t t;
+  uint8_t pad[6];
+} pth_overcooked_state;
+
+/* OvercookedMultiEnv.multi_reset: standard start state; obs out fp32 [N][2][PTH_OC_ROW]
+ * (ego's row first, then the partner's; columns 62, 63 are zero). */
+int pth_env_overcooked_reset(pth_ctx* ctx, const pth_overcooked_layout* d_layout,
+                             pth_overcooked_state* d_state, float* d_obs, int64_t N, void* stream);
+/* OvercookedMultiEnv.multi_step for N envs: actions u8 [N] in Action.INDEX_TO_ACTION
+ * order (N, S, E, W, stay, interact) for the ego and the partner; reward (same for both
+ * agents: sparse + shaped) fp32 [N]; done u8 [N] (horizon).  Envs are NOT auto-reset.
+ * d_obs as above for the next state. */
+int pth_env_overcooked_step(pth_ctx* ctx, const pth_overcooked_layout* d_layout,
+                            pth_overcooked_state* d_state, const uint8_t* d_ego_action,
+                            const uint8_t* d_alt_action, float* d_obs, float* d_reward,
+                            uint8_t* d_done, int64_t N, void* stream);
+
+/* ------------------------------------------------------------------ */
 /* a1 + a2: policy forward + sample + log-prob + value (+ buffer row)  */
 /* replaces util.action_from_policy (util.py:63-81) ->                 */
 /* ActorCriticPolicy.forward and RolloutBuffer.add (agents.py:162-179) */
@@ -215,13 +282,15 @@ int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream)
 /* / update (agents.py:111-203) -> n_step / n_reset                    */
 /* ------------------------------------------------------------------ */
 
-enum { PTH_ENV_RPS = 0, PTH_ENV_LIAR = 1 };
+enum { PTH_ENV_RPS = 0, PTH_ENV_LIAR = 1, PTH_ENV_OVERCOOKED = 2 };
 
-/* rollout buffer of one learner; all arrays [Tcap][N] (row = 32 B obs).
+/* rollout buffer of one learner; all arrays [Tcap][N].  Observation rows: 32 B
+ * (PTH_OBS_ONEHOT: one byte per slot) or PTH_OC_ROW fp32 = 256 B (PTH_OBS_BOX).
  * Ego: Tcap = T, dense (count unused, may be NULL).
- * Partner: Tcap >= 2*T, ragged, count[n] decisions recorded this rollout. */
+ * Partner: Tcap >= 2*T (turn-based) or T (simultaneous), ragged, count[n] decisions
+ * recorded this rollout. */
 typedef struct pth_buffer {
-  uint8_t* d_obs;            /* [Tcap][N][32] */
+  uint8_t* d_obs;            /* [Tcap][N][32] u8, or [Tcap][N][64] fp32 for Box spaces */
   uint8_t* d_actions;        /* [Tcap][N][4]  */
   float* d_rewards;          /* [Tcap][N] */
   float* d_values;           /* [Tcap][N] */
@@ -238,7 +307,7 @@ typedef struct pth_env_carry {
   float* d_alt_last_done;      /* [N] partner _last_episode_starts latch  */
   float* d_total_rew;          /* [2][N] total_rews                       */
   uint8_t* d_flags;            /* [N] bit0 ego_moved, bit1 should_update  */
-  void* d_game_state;          /* PTH_ENV_LIAR: pth_liar_state[N]; RPS: NULL */
+  void* d_game_state;          /* PTH_ENV_LIAR: pth_liar_state[N]; PTH_ENV_OVERCOOKED: pth_overcooked_state[N]; RPS: NULL */
   float* d_ego_last_value;     /* [N] out: V(obs_T) bootstrap for the ego  */
   float* d_ego_last_done;      /* [N] out: done flag after the last tick   */
   float* d_ep_stats;           /* [4] += {episodes, sum ego ep reward, sum ep len, partner decisions} or NULL */
@@ -260,6 +329,7 @@ typedef struct pth_rollout_args {
   uint32_t tick0;              /* global tick of the first tick of this rollout */
   float probegostart;          /* TurnBasedEnv.probegostart */
   int32_t first_rollout;       /* 1: envs are reset before tick 0 (SB3 _setup_learn) */
+  const pth_overcooked_layout* d_layout; /* PTH_ENV_OVERCOOKED: DEVICE copy of an initialised layout; else NULL */
 } pth_rollout_args;
 int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* args, void* stream);
 
@@ -294,8 +364,8 @@ typedef struct pth_update_args {
   int64_t adam_step;        /* optimiser steps already taken */
   /* flat sample arrays indexed by offset = d_index[perm[...]] */
   const uint8_t* d_obs;     /* [*][32] u8 (ONEHOT) ; BOX: fp32 rows via d_obs_f32 */
-  const float* d_obs_f32;   /* [*][obs_stride] or NULL */
-  int64_t obs_stride;
+  const float* d_obs_f32;   /* BOX: [*][obs_stride] fp32 rows (16-byte aligned), else NULL */
+  int64_t obs_stride;       /* BOX: floats per row (multiple of 4, >= obs_len) */
   const uint8_t* d_actions; /* [*][4] */
   const float* d_old_logp;
   const float* d_advantages;

@@ -14,7 +14,10 @@ PTH_MAX_OBS_SLOTS = 64
 PTH_MAX_HEADS = 4
 PTH_HIDDEN = 64
 PTH_OBS_ONEHOT, PTH_OBS_BOX = 0, 1
-PTH_ENV_RPS, PTH_ENV_LIAR = 0, 1
+PTH_ENV_RPS, PTH_ENV_LIAR, PTH_ENV_OVERCOOKED = 0, 1, 2
+PTH_OC_MAX_CELLS, PTH_OC_MAX_POTS, PTH_OC_OBS, PTH_OC_ROW = 128, 4, 62, 64
+PTH_OC_STATE_BYTES = 40
+PTH_OC_FLOOR, PTH_OC_COUNTER, PTH_OC_ONION, PTH_OC_POT, PTH_OC_DISH, PTH_OC_SERVE = range(6)
 PTH_PACKED_BYTES = 48
 
 STREAM_ENV, STREAM_EGO, STREAM_ALT, STREAM_SHUFFLE_EGO, STREAM_SHUFFLE_ALT = 1, 2, 3, 4, 5
@@ -111,6 +114,26 @@ class EnvCarry(C.Structure):
     ]
 
 
+class OvercookedLayout(C.Structure):
+    """pth_overcooked_layout (include/pantheon_b200.h): inputs + tables derived by
+    pth_overcooked_layout_init."""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("cook_time", C.c_int32), ("num_items", C.c_int32), ("delivery_reward", C.c_int32),
+        ("horizon", C.c_int32),
+        ("rew_placement_in_pot", C.c_int32), ("rew_dish_pickup", C.c_int32), ("rew_soup_pickup", C.c_int32),
+        ("ego_agent_idx", C.c_int32),
+        ("start_x", C.c_int32 * 2), ("start_y", C.c_int32 * 2),
+        ("terrain", C.c_uint8 * PTH_OC_MAX_CELLS),
+        ("n_pots", C.c_int32), ("n_counters", C.c_int32),
+        ("slot", C.c_uint8 * PTH_OC_MAX_CELLS),
+        ("wall", C.c_uint8 * PTH_OC_MAX_CELLS),
+        ("pot_x", C.c_uint8 * PTH_OC_MAX_POTS), ("pot_y", C.c_uint8 * PTH_OC_MAX_POTS),
+        ("static_delta", C.c_int8 * (PTH_OC_MAX_CELLS * 4 * 3 * 2)),
+        ("pot_dist", C.c_uint8 * (PTH_OC_MAX_CELLS * 4 * PTH_OC_MAX_POTS)),
+    ]
+
+
 class RolloutArgs(C.Structure):
     _fields_ = [
         ("env_kind", C.c_int32),
@@ -128,6 +151,7 @@ class RolloutArgs(C.Structure):
         ("tick0", C.c_uint32),
         ("probegostart", C.c_float),
         ("first_rollout", C.c_int32),
+        ("d_layout", C.c_void_p),
     ]
 
 
@@ -191,6 +215,9 @@ SIGNATURES = {
     "pth_env_rps_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pth_env_liar_reset": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _u64, _u32, _i64, _f, _vp]),
     "pth_env_liar_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pth_overcooked_layout_init": (C.c_int, [C.POINTER(OvercookedLayout)]),
+    "pth_env_overcooked_reset": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "pth_env_overcooked_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pth_policy_forward": (C.c_int, [_vp, C.POINTER(ForwardArgs), _vp]),
     "pth_rollout_run": (C.c_int, [_vp, C.POINTER(RolloutArgs), _vp]),
     "pth_perm_feistel": (C.c_int, [_vp, _vp, _i64, _i32, _u64, _u32, _u32, _vp]),

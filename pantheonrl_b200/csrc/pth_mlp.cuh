@@ -207,44 +207,58 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
   }
 }
 
-// First layer, Box observations: X[k][b] (k < F) in shared memory, W
-// input-major [F][64] in global memory.  Thread tile 8 samples x 8 outputs.
-template <int NTH = NT>
-__device__ __forceinline__ void first_layer_box(int F, const float* X, const float* __restrict__ W,
+// First layer, Box observations: X[k][b] (k < F) feature-major in shared memory,
+// W input-major [F][64] in global memory (L1/L2 resident).  Same thread tile as
+// dense64: SPT samples x JT contiguous outputs; Out[j][b] = tanh(bias[j] +
+// sum_k fma(X[k][b], W[k][j], .)), k ascending.
+template <bool COHERENT = false, int NTH = NT, int BTS = BT>
+__device__ __forceinline__ void first_layer_box(int F, const float* X, const float* W,
                                                 const float* bias_s, float* Out, int tid) {
-  constexpr int JT = HID / (NTH / 16);  // outputs per thread (8 or 4), contiguous
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[JT][8];
+  constexpr int LDA = BTS + 4;
+  constexpr int SPT = BTS >= 128 ? 8 : 4;
+  constexpr int TXN = BTS / SPT, NY = NTH / TXN, JT = HID / NY;
+  static_assert(NY * JT == HID && TXN * NY == NTH && (JT == 2 || JT == 4), "tile mapping");
+  const int tx = tid % TXN, ty = tid / TXN;
+  float acc[JT][SPT];
 #pragma unroll
   for (int jj = 0; jj < JT; ++jj) {
     const float bj = bias_s[ty * JT + jj];
 #pragma unroll
-    for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = bj;
+    for (int ss = 0; ss < SPT; ++ss) acc[jj][ss] = bj;
   }
+#pragma unroll 2
   for (int k = 0; k < F; ++k) {
-    const float4 a0 = *reinterpret_cast<const float4*>(X + k * LDA + tx * 4);
-    const float4 a1 = *reinterpret_cast<const float4*>(X + k * LDA + 64 + tx * 4);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float a[SPT];
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(X + k * LDA + tx * 4);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+      if constexpr (SPT == 8) {
+        const float4 a1 = *reinterpret_cast<const float4*>(X + k * LDA + 64 + tx * 4);
+        a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      }
+    }
     float w[JT];
-#pragma unroll
-    for (int q = 0; q < JT / 4; ++q) {
-      const float4 wq = __ldg(reinterpret_cast<const float4*>(W + k * HID + ty * JT + 4 * q));
-      w[4 * q + 0] = wq.x; w[4 * q + 1] = wq.y; w[4 * q + 2] = wq.z; w[4 * q + 3] = wq.w;
+    if constexpr (JT == 4) {
+      const float4 wq = ld_param4<COHERENT>(reinterpret_cast<const float4*>(W + k * HID + ty * JT));
+      w[0] = wq.x; w[1] = wq.y; w[2] = wq.z; w[3] = wq.w;
+    } else {
+      const float2* q = reinterpret_cast<const float2*>(W + k * HID + ty * JT);
+      const float2 wq = COHERENT ? *q : __ldg(q);
+      w[0] = wq.x; w[1] = wq.y;
     }
 #pragma unroll
     for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
-      for (int ss = 0; ss < 8; ++ss) acc[jj][ss] = fmaf(a[ss], w[jj], acc[jj][ss]);
+      for (int ss = 0; ss < SPT; ++ss) acc[jj][ss] = fmaf(a[ss], w[jj], acc[jj][ss]);
   }
 #pragma unroll
   for (int jj = 0; jj < JT; ++jj) {
     float* o = Out + (ty * JT + jj) * LDA;
-    float4 v0 = make_float4(pth_tanhf(acc[jj][0]), pth_tanhf(acc[jj][1]), pth_tanhf(acc[jj][2]),
-                            pth_tanhf(acc[jj][3]));
-    float4 v1 = make_float4(pth_tanhf(acc[jj][4]), pth_tanhf(acc[jj][5]), pth_tanhf(acc[jj][6]),
-                            pth_tanhf(acc[jj][7]));
-    *reinterpret_cast<float4*>(o + tx * 4) = v0;
-    *reinterpret_cast<float4*>(o + 64 + tx * 4) = v1;
+    float v[SPT];
+#pragma unroll
+    for (int ss = 0; ss < SPT; ++ss) v[ss] = pth_tanhf(acc[jj][ss]);
+    *reinterpret_cast<float4*>(o + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    if constexpr (SPT == 8) *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
 }
 

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   if (p.sp.obs_kind == PTH_OBS_ONEHOT)
     first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
   else
-    first_layer_box(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
+    first_layer_box<false>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
   __syncthreads();
   dense64<true>(sm.A, sm.pol.w_pi1, sm.pol.b_pi1, sm.Bf, tid);
   __syncthreads();
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   if (p.sp.obs_kind == PTH_OBS_ONEHOT)
     first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
   else
-    first_layer_box(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
+    first_layer_box<false>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
   __syncthreads();
   dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, sm.Bf, tid);
   __syncthreads();

@@ -15,6 +15,7 @@
 // follow oracle/pth_oracle_rollout.inc exactly.
 #include "pth_games.cuh"
 #include "pth_mlp.cuh"
+#include "pth_overcooked.cuh"
 
 using namespace pthmlp;
 
@@ -44,37 +45,51 @@ struct FwdOut {
   float value, logp;
 };
 
-// One CTA-wide forward over the observations currently in sm.obs.
-template <int RB>
-__device__ __forceinline__ FwdOut cta_forward(const RollParams& p, const float* __restrict__ params,
-                                              const SmemPolicy& pol, RollSmem<RB>& sm, int tid,
-                                              bool with_policy, pth_u4 rnd) {
+// One CTA-wide forward over the observations currently staged in shared memory:
+// BOX = false: obs_s = [RB][32] bytes (one-hot slots); BOX = true: obs_s = feature-major
+// fp32 tile X[k][b] (row stride RB + 4).
+template <int RB, bool BOX>
+__device__ __forceinline__ FwdOut cta_forward_t(const RollParams& p, const float* __restrict__ params,
+                                                const SmemPolicy& pol, float* A, float* Bf, float* Lg,
+                                                const void* obs_s, int tid, bool with_policy, pth_u4 rnd) {
   FwdOut o;
   o.action = 0;
   o.logp = 0.f;
-  const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
   __syncthreads();  // obs written by all lanes; previous users of A/Bf/Lg are done
   const bool lane = tid < RB;  // threads [RB, NT) only help in the tiled layers
+  auto first = [&](const float* W, const float* bias) {
+    if constexpr (BOX)
+      first_layer_box<false, NT, RB>(p.sp.F, reinterpret_cast<const float*>(obs_s), W, bias, A, tid);
+    else
+      first_layer_onehot<false, NT, RB>(p.sp, reinterpret_cast<const uint8_t*>(obs_s), W, bias, A, tid);
+  };
   if (with_policy) {
-    first_layer_onehot<false, NT, RB>(p.sp, obs_s, params + p.lo.w_pi0, pol.b_pi0, sm.A, tid);
+    first(params + p.lo.w_pi0, pol.b_pi0);
     __syncthreads();
-    dense64<true, NT, RB>(sm.A, pol.w_pi1, pol.b_pi1, sm.Bf, tid);
+    dense64<true, NT, RB>(A, pol.w_pi1, pol.b_pi1, Bf, tid);
     __syncthreads();
-    if (lane) action_head<RB>(sm.Bf, pol, p.sp.L, sm.Lg, tid);
+    if (lane) action_head<RB>(Bf, pol, p.sp.L, Lg, tid);
   }
-  first_layer_onehot<false, NT, RB>(p.sp, obs_s, params + p.lo.w_vf0, pol.b_vf0, sm.A, tid);
+  first(params + p.lo.w_vf0, pol.b_vf0);
   __syncthreads();
-  dense64<true, NT, RB>(sm.A, pol.w_vf1, pol.b_vf1, sm.Bf, tid);
+  dense64<true, NT, RB>(A, pol.w_vf1, pol.b_vf1, Bf, tid);
   __syncthreads();
   o.value = 0.f;
   if (!lane) return o;
-  o.value = value_head<RB>(sm.Bf, pol, tid);
+  o.value = value_head<RB>(Bf, pol, tid);
   if (with_policy) {
-    DistOut d = dist_eval<RB>(p.sp, sm.Lg, tid, true, rnd, 0u);
+    DistOut d = dist_eval<RB>(p.sp, Lg, tid, true, rnd, 0u);
     o.action = d.action;
     o.logp = d.logp;
   }
   return o;
+}
+
+template <int RB>
+__device__ __forceinline__ FwdOut cta_forward(const RollParams& p, const float* __restrict__ params,
+                                              const SmemPolicy& pol, RollSmem<RB>& sm, int tid,
+                                              bool with_policy, pth_u4 rnd) {
+  return cta_forward_t<RB, false>(p, params, pol, sm.A, sm.Bf, sm.Lg, sm.obs, tid, with_policy, rnd);
 }
 
 struct EnvRegs {
@@ -344,12 +359,184 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
   }
 }
 
+// ---------------------------------------------------------------- Overcooked
+// SimultaneousEnv with per-agent Box observations (overcookedgym/overcooked.py:10-98 behind
+// multiagentenv.py:149-243, 395-409).  Per tick: both agents' feature rows are derived once
+// from the env's registers into two shared-memory tiles (Xe, Xa), stored to the rollout
+// buffers with coalesced 256-byte rows, ego forward on Xe, partner forward on Xa, one joint
+// env step, reward routing, horizon auto-reset.  No env randomness (standard start state).
+template <int RB>
+struct RollSmemOC {
+  SmemPolicy pol_ego;
+  SmemPolicy pol_alt;
+  float A[HID * (RB + 4)];
+  float Bf[HID * (RB + 4)];
+  float Lg[MAXL * (RB + 4)];
+  float Xe[HID * (RB + 4)];
+  float Xa[HID * (RB + 4)];
+  pth_overcooked_layout lay;
+};
+
+// rows of the tile X (feature-major) -> obs rows [row0 + b] of 64 floats, 16 threads per row
+template <int RB>
+__device__ __forceinline__ void store_box_rows(const float* X, float* dst_rows, int64_t row0, int64_t n_valid,
+                                               int tid) {
+  constexpr int LDX = RB + 4;
+  for (int i = tid; i < RB * 16; i += NT) {
+    const int b = i >> 4, k4 = (i & 15) * 4;
+    if (b < n_valid) {
+      const float4 v = make_float4(X[(k4 + 0) * LDX + b], X[(k4 + 1) * LDX + b], X[(k4 + 2) * LDX + b],
+                                   X[(k4 + 3) * LDX + b]);
+      __stcs(reinterpret_cast<float4*>(dst_rows + (row0 + b) * PTH_OC_ROW + k4), v);
+    }
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(NT) rollout_overcooked_kernel(const __grid_constant__ RollParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RollSmemOC<RB>& sm = *reinterpret_cast<RollSmemOC<RB>*>(smem_raw);
+  constexpr int LDX = RB + 4;
+  const int tid = threadIdx.x;
+  const bool lane = tid < RB;
+  const int64_t n0 = (int64_t)blockIdx.x * RB;
+  const int64_t n = n0 + (lane ? tid : 0);
+  const int64_t N = p.a.N;
+  const bool valid = lane && n < N;
+  const int64_t n_valid = (N - n0 < RB) ? (N - n0) : RB;
+  const uint64_t genv = (uint64_t)(p.a.env0 + n);
+  const bool selfplay = p.a.d_alt_params == p.a.d_ego_params;
+  const float* ego_w = p.a.d_ego_params;
+  const float* alt_w = p.a.d_alt_params;
+
+  load_policy(sm.pol_ego, ego_w, p.lo, p.sp.L, tid, NT);
+  if (!selfplay) load_policy(sm.pol_alt, alt_w, p.lo, p.sp.L, tid, NT);
+  const SmemPolicy& pol_alt = selfplay ? sm.pol_ego : sm.pol_alt;
+  {
+    const uint2* src = reinterpret_cast<const uint2*>(p.a.d_layout);
+    uint2* dst = reinterpret_cast<uint2*>(&sm.lay);
+    for (int i = tid; i < (int)(sizeof(pth_overcooked_layout) / 8); i += NT) dst[i] = __ldg(src + i);
+  }
+  for (int i = tid; i < HID * LDX; i += NT) {
+    sm.Xe[i] = 0.f;
+    sm.Xa[i] = 0.f;
+  }
+  __syncthreads();
+  const pth_overcooked_layout& L = sm.lay;
+
+  EnvRegs e;
+  memset(&e, 0, sizeof(e));
+  OcRegs g;
+  oc_reset(L, g);
+  const pth_env_carry& cr = p.a.carry;
+  pth_overcooked_state* gstate = reinterpret_cast<pth_overcooked_state*>(cr.d_game_state);
+  if (valid) {
+    if (p.a.first_rollout) {
+      e.ego_last_start = 1.f;  // SB3 _setup_learn: _last_episode_starts = ones
+      e.alt_last_done = 1.f;   // agents.py:97
+    } else {
+      e.ego_last_start = cr.d_ego_last_start[n];
+      e.alt_last_done = cr.d_alt_last_done[n];
+      e.total_ego = cr.d_total_rew[n];
+      e.total_alt = cr.d_total_rew[N + n];
+      e.flags = cr.d_flags[n];
+      oc_load(gstate + n, g);
+    }
+  }
+  float* ego_rows = reinterpret_cast<float*>(p.a.ego.d_obs);
+  float* alt_rows = reinterpret_cast<float*>(p.a.alt.d_obs);
+
+  for (int64_t t = 0; t < p.a.T; ++t) {
+    const uint32_t gt = p.a.tick0 + (uint32_t)t;
+    const int64_t o = t * N + n;
+    __syncthreads();  // the previous tick's forwards are done with Xe / Xa
+    if (lane) oc_write_obs(L, g, sm.Xe, sm.Xa, LDX, tid);
+    __syncthreads();
+    store_box_rows<RB>(sm.Xe, ego_rows, t * N + n0, n_valid, tid);
+    const bool alt_rec = p.a.partner_records && t < p.a.alt.Tcap;  // simultaneous: one partner row per tick
+    if (alt_rec) store_box_rows<RB>(sm.Xa, alt_rows, t * N + n0, n_valid, tid);
+    // ================= ego decision, partner decision (same tick)
+    FwdOut fe = cta_forward_t<RB, true>(p, ego_w, sm.pol_ego, sm.A, sm.Bf, sm.Lg, sm.Xe, tid, true,
+                                        pth_philox(p.a.seed, PTH_STREAM_EGO, genv, gt, 0u));
+    FwdOut fa = cta_forward_t<RB, true>(p, alt_w, pol_alt, sm.A, sm.Bf, sm.Lg, sm.Xa, tid, true,
+                                        pth_philox(p.a.seed, PTH_STREAM_ALT, genv, gt, 0u));
+    if (valid) {
+      *reinterpret_cast<uint32_t*>(p.a.ego.d_actions + 4 * o) = fe.action;
+      p.a.ego.d_values[o] = fe.value;
+      p.a.ego.d_logp[o] = fe.logp;
+      p.a.ego.d_episode_starts[o] = e.ego_last_start;
+      // partner.get_action bookkeeping (agents.py:172-179) + first-move hand-off (multiagentenv.py:158-160)
+      if (alt_rec) {
+        alt_flush(p, e, n);
+        const int64_t oa = (int64_t)e.alt_count * N + n;
+        *reinterpret_cast<uint32_t*>(p.a.alt.d_actions + 4 * oa) = fa.action;
+        p.a.alt.d_values[oa] = fa.value;
+        p.a.alt.d_logp[oa] = fa.logp;
+        p.a.alt.d_episode_starts[oa] = e.alt_last_done;
+        e.alt_count += 1;
+        e.alt_pending = 0.f;
+      }
+      e.st_alt += 1.f;
+      if (!(e.flags & 2u)) alt_update(e, e.total_alt, false);
+      e.flags |= 2u;
+      // OvercookedMultiEnv.multi_step: joint action in player order, one reward for both
+      const int ea = (int)(fe.action & 0xffu), aa = (int)(fa.action & 0xffu);
+      float rew;
+      const bool done = L.ego_agent_idx == 0 ? oc_step(L, g, ea, aa, rew) : oc_step(L, g, aa, ea, rew);
+      update_players(e, rew, rew, done);
+      const float ego_rew = (e.flags & 1u) ? rew : e.total_ego;
+      e.flags |= 1u;
+      p.a.ego.d_rewards[o] = ego_rew;
+      e.ego_last_start = done ? 1.f : 0.f;
+      e.st_steps += 1.f;
+      if (done) {  // DummyVecEnv auto-reset -> MultiAgentEnv.reset -> multi_reset
+        e.st_eps += 1.f;
+        e.st_rew += e.total_ego;
+        e.flags = 0u;
+        e.total_ego = 0.f;
+        e.total_alt = 0.f;
+        oc_reset(L, g);
+      }
+    }
+  }
+
+  // ---- bootstrap value of the ego's next observation (SB3 predict_values)
+  __syncthreads();
+  if (lane) oc_write_obs(L, g, sm.Xe, sm.Xa, LDX, tid);
+  pth_u4 zero = {0, 0, 0, 0};
+  FwdOut fl = cta_forward_t<RB, true>(p, ego_w, sm.pol_ego, sm.A, sm.Bf, sm.Lg, sm.Xe, tid, false, zero);
+  if (valid) {
+    alt_flush(p, e, n);
+    cr.d_ego_last_value[n] = fl.value;
+    cr.d_ego_last_done[n] = e.ego_last_start;
+    cr.d_ego_last_start[n] = e.ego_last_start;
+    cr.d_alt_last_done[n] = e.alt_last_done;
+    cr.d_total_rew[n] = e.total_ego;
+    cr.d_total_rew[N + n] = e.total_alt;
+    cr.d_flags[n] = (uint8_t)e.flags;
+    oc_store(gstate + n, g);
+    if (p.a.alt.d_count) p.a.alt.d_count[n] = e.alt_count;
+  }
+  if (cr.d_ep_stats) {
+    float v[4] = {e.st_eps, e.st_rew, e.st_steps, e.st_alt};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x = v[i];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+      if ((tid & 31) == 0) atomicAdd(cr.d_ep_stats + i, x);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* stream) {
   PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");
   PTH_CHECK_ARG(a->space && a->d_ego_params && a->d_alt_params, "NULL space/params");
-  PTH_CHECK_ARG(a->env_kind == PTH_ENV_RPS || a->env_kind == PTH_ENV_LIAR, "unknown env_kind");
+  PTH_CHECK_ARG(a->env_kind == PTH_ENV_RPS || a->env_kind == PTH_ENV_LIAR ||
+                    a->env_kind == PTH_ENV_OVERCOOKED,
+                "unknown env_kind");
   PTH_CHECK_ARG(a->N >= 0 && a->T >= 0, "negative size");
   PTH_CHECK_ARG(a->ego.d_obs && a->ego.d_actions && a->ego.d_rewards && a->ego.d_values &&
                     a->ego.d_logp && a->ego.d_episode_starts,
@@ -366,7 +553,7 @@ extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* st
   PTH_CHECK_ARG(c.d_ego_last_start && c.d_alt_last_done && c.d_total_rew && c.d_flags &&
                     c.d_ego_last_value && c.d_ego_last_done,
                 "NULL carry array");
-  PTH_CHECK_ARG(a->env_kind != PTH_ENV_LIAR || c.d_game_state, "NULL game state");
+  PTH_CHECK_ARG(a->env_kind == PTH_ENV_RPS || c.d_game_state, "NULL game state");
   PTH_CHECK_ARG(((uintptr_t)a->ego.d_obs % 16) == 0 &&
                     (!a->partner_records || ((uintptr_t)a->alt.d_obs % 16) == 0) &&
                     ((uintptr_t)c.d_game_state % 16) == 0 && ((uintptr_t)a->d_ego_params % 16) == 0 &&
@@ -374,8 +561,25 @@ extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* st
                 "obs/state/params must be 16-byte aligned");
   if (a->N == 0) return PTH_OK;
   RollParams p;
+  if (a->env_kind == PTH_ENV_OVERCOOKED) {
+    PTH_CHECK_ARG(a->d_layout != nullptr && ((uintptr_t)a->d_layout % 8) == 0, "NULL / misaligned d_layout");
+    if (fill_space(a->space, &p.sp) != 0 || p.sp.obs_kind != PTH_OBS_BOX || p.sp.obs_len != PTH_OC_OBS ||
+        p.sp.n_heads != 1 || p.sp.head_n[0] != 6) {
+      pth_set_error("pth_rollout_run: Overcooked needs Box(62) observations and Discrete(6) actions");
+      return PTH_EINVAL;
+    }
+    p.lo = make_layout(p.sp.F, p.sp.L);
+    p.a = *a;
+    constexpr int RBV = 32;
+    const size_t smem = sizeof(RollSmemOC<RBV>);
+    PTH_CUDA(cudaFuncSetAttribute(rollout_overcooked_kernel<RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    rollout_overcooked_kernel<RBV><<<pth_ceil_div(a->N, RBV), NT, smem, (cudaStream_t)stream>>>(p);
+    PTH_LAUNCH_CHECK();
+    return PTH_OK;
+  }
   if (fill_space(a->space, &p.sp) != 0 || p.sp.obs_kind != PTH_OBS_ONEHOT) {
-    pth_set_error("pth_rollout_run: on-device envs need a one-hot observation space");
+    pth_set_error("pth_rollout_run: RPS / Liar's Dice need a one-hot observation space");
     return PTH_ENOSUP;
   }
   const int want_len = a->env_kind == PTH_ENV_LIAR ? PTH_LIAR_OBS_LEN : 1;

@@ -218,7 +218,9 @@ __device__ __forceinline__ void row_sums(const float* X, int rows, float* gout, 
   acc_store(gout + r, s, first);
 }
 
-// dzT[b][k] = (sum_j fma(W[j][k], Dz[j][b], .)) * (1 - Hact[k][b]^2)
+// dz1[k][b] = (sum_j fma(W[j][k], Dz[j][b], .)) * (1 - Hact[k][b]^2), stored transposed
+// ([b][LDT], one-hot path: the segmented sums walk samples) or feature-major ([k][LDA], Box path)
+template <bool TRANSPOSED>
 __device__ __forceinline__ void backprop64(const float* Dz, const float* W, const float* Hact,
                                            float* outT, int tid) {
   constexpr int KT = HID / (NT / 16);  // outputs per thread, contiguous (4)
@@ -251,9 +253,48 @@ __device__ __forceinline__ void backprop64(const float* Dz, const float* W, cons
     for (int kk = 0; kk < KT; ++kk) {
       const int k = ty * KT + kk;
       const float h = Hact[k * LDA + b];
-      outT[b * LDT + k] = acc[kk][ss] * (1.0f - h * h);
+      outT[TRANSPOSED ? (b * LDT + k) : (k * LDA + b)] = acc[kk][ss] * (1.0f - h * h);
     }
   }
+}
+
+// Box first layer: gW0[k][j] = sum_b fma(Dz1[j][b], X[k][b], .) for k < F, b ascending; the
+// tile of wgrad64 with the result stored input-major (the layout of the first-layer matrices).
+__device__ __forceinline__ void wgrad_first_box(const float* Dz, const float* X, int F, float* gout,
+                                                bool first, int tid) {
+  constexpr int NY = NT / 16, JT = HID / NY;
+  const int kt = tid & 15, jt = tid >> 4;
+  float acc[JT][4];
+#pragma unroll
+  for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) acc[jj][kk] = 0.f;
+#pragma unroll 2
+  for (int b0 = 0; b0 < BT; b0 += 4) {
+    float4 d[JT], h[4];
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj)
+      d[jj] = *reinterpret_cast<const float4*>(Dz + (jt + NY * jj) * LDA + b0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      h[kk] = *reinterpret_cast<const float4*>(X + (kt + 16 * kk) * LDA + b0);
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float a = acc[jj][kk];
+        a = fmaf(d[jj].x, h[kk].x, a);
+        a = fmaf(d[jj].y, h[kk].y, a);
+        a = fmaf(d[jj].z, h[kk].z, a);
+        a = fmaf(d[jj].w, h[kk].w, a);
+        acc[jj][kk] = a;
+      }
+  }
+#pragma unroll
+  for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      if (kt + 16 * kk < F) acc_store(gout + (kt + 16 * kk) * HID + (jt + NY * jj), acc[jj][kk], first);
 }
 
 // Stable counting sort of the tile's nb samples by observed value, one slot per
@@ -332,14 +373,20 @@ __device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* ord
 }
 
 // body of one tower after dz2 (in sm.D1) is known
-__device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, const float* w1_s,
-                                               float* g_w0, float* g_b0, float* g_w1, float* g_b1,
-                                               int nb, bool first, int tid) {
+template <bool BOX>
+__device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, const float* Xs,
+                                               const float* w1_s, float* g_w0, float* g_b0,
+                                               float* g_w1, float* g_b1, int nb, bool first, int tid) {
   __syncthreads();  // D1 complete
   wgrad64(sm.D1, sm.H1, g_w1, first, tid);
   row_sums(sm.D1, HID, g_b1, first, tid, 64);
-  backprop64(sm.D1, w1_s, sm.H1, sm.H2, tid);
-  __syncthreads();  // dz1T complete (in H2)
+  backprop64<!BOX>(sm.D1, w1_s, sm.H1, sm.H2, tid);
+  __syncthreads();  // dz1 complete (in H2)
+  if constexpr (BOX) {
+    row_sums(sm.H2, HID, g_b0, first, tid, NT - HID);
+    wgrad_first_box(sm.H2, Xs, p.sp.F, g_w0, first, tid);
+    return;
+  }
   if (tid >= NT - HID) {
     const int j = tid - (NT - HID);
     float s = 0.f;
@@ -350,9 +397,11 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, 
   segsum_w1(p, sm.order, sm.rcount, sm.H2, g_w0, first, tid);
 }
 
+template <bool BOX>
 __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UpdSmem& sm = *reinterpret_cast<UpdSmem*>(smem_raw);
+  float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(UpdSmem));  // BOX only: X[64][LDA]
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int G = gridDim.x;
@@ -423,27 +472,55 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         uint32_t act = 0;
         float adv = 0.f, oldlp = 0.f, ret = 0.f;
         uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+        float4 xrow[8];  // BOX: 32 of the sample's 64 row floats (threads b and b + 128 share a sample)
+        if constexpr (BOX) {
+          const int b = tid & (BT - 1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b < nb) {
+            const int64_t offb = sample_offset(p, e, i0 + t0 + b);
+            const float4* q = reinterpret_cast<const float4*>(p.obs + offb * p.obs_stride) + (tid >> 7) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xrow[i] = __ldg(q + i);
+          }
+        }
         if (valid) {
           const int64_t off = sample_offset(p, e, i0 + t0 + tid);
-          const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
-          o0 = __ldg(q);
-          o1 = __ldg(q + 1);
+          if constexpr (!BOX) {
+            const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
+            o0 = __ldg(q);
+            o1 = __ldg(q + 1);
+          }
           act = *reinterpret_cast<const uint32_t*>(p.actions + off * p.act_stride);
           adv = *reinterpret_cast<const float*>(p.adv + off * p.f_stride);
           oldlp = *reinterpret_cast<const float*>(p.old_logp + off * p.f_stride);
           ret = *reinterpret_cast<const float*>(p.ret + off * p.f_stride);
         }
         const bool lane = tid < BT;  // threads [0, BT) own one sample each
-        __syncthreads();  // previous tile done with sm.obs / Lg / H2
-        if (lane) {
+        __syncthreads();  // previous tile done with sm.obs / Xs / Lg / H2
+        if constexpr (BOX) {
+          const int b = tid & (BT - 1), k0 = (tid >> 7) * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v[4] = {xrow[i].x, xrow[i].y, xrow[i].z, xrow[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = k0 + 4 * i + j;
+              Xs[k * LDA + b] = k < p.sp.F ? v[j] : 0.f;
+            }
+          }
+        } else if (lane) {
           *reinterpret_cast<uint4*>(&sm.obs[tid * 8]) = o0;
           *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
         }
         __syncthreads();
-        sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid);  // consumed after several barriers
+        if constexpr (!BOX) sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid);  // consumed after several barriers
 
         // ================= policy tower: forward
-        first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
+        if constexpr (BOX)
+          first_layer_box<true>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
+        else
+          first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         __syncthreads();
         dense64<true>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
         __syncthreads();
@@ -525,12 +602,15 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
             sm.D1[k * LDA + tid] = acc[k] * (1.0f - h * h);
           }
         }
-        tower_backward(p, sm, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0, part + p.lo.w_pi1,
-                       part + p.lo.b_pi1, nb, first, tid);
+        tower_backward<BOX>(p, sm, Xs, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
+                            part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid);
 
         // ================= value tower
         __syncthreads();
-        first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
+        if constexpr (BOX)
+          first_layer_box<true>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
+        else
+          first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
         __syncthreads();
         dense64<true>(sm.H1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
         __syncthreads();
@@ -564,8 +644,8 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           for (int b = 0; b < BT; ++b) s = s + sm.Lg[b];
           acc_store(part + p.lo.b_val, s, first);
         }
-        tower_backward(p, sm, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0, part + p.lo.w_vf1,
-                       part + p.lo.b_vf1, nb, first, tid);
+        tower_backward<BOX>(p, sm, Xs, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
+                            part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid);
 
         // ---- tile statistics
         const float ts[5] = {block_tree(s_pl, sm.red, tid), block_tree(s_v, sm.red, tid),
@@ -804,27 +884,29 @@ WsLayout ws_layout(int G, int P, int64_t n_stat) {
   return w;
 }
 
-int max_coop_ctas(const pth_ctx* ctx) {
-  static int cached = -1;
-  if (cached < 0) {
-    cudaFuncSetAttribute(ppo_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(UpdSmem));
+constexpr size_t SMEM_ONEHOT = sizeof(UpdSmem);
+constexpr size_t SMEM_BOX = sizeof(UpdSmem) + sizeof(float) * HID * LDA;
+
+int max_coop_ctas(const pth_ctx* ctx, bool box = false) {
+  static int cached[2] = {-1, -1};
+  if (cached[box] < 0) {
+    const void* fn = box ? (const void*)ppo_update_kernel<true> : (const void*)ppo_update_kernel<false>;
+    const size_t smem = box ? SMEM_BOX : SMEM_ONEHOT;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_update_kernel, NT,
-                                                      sizeof(UpdSmem)) != cudaSuccess)
-      per_sm = 0;
-    cached = per_sm * ctx->sm_count;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem) != cudaSuccess) per_sm = 0;
+    cached[box] = per_sm * ctx->sm_count;
   }
-  return cached;
+  return cached[box];
 }
 
-int cap_check_g(const pth_ctx* ctx) { return max_coop_ctas(ctx); }
+bool space_is_box(const pth_space* sp) { return sp && sp->obs_kind == PTH_OBS_BOX; }
 
-int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1) {
+int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1, bool box = false) {
   const int64_t eff = BS < M ? BS : M;
   int64_t tiles = (eff + BT - 1) / BT;
   tiles = (tiles + world - 1) / world;  // a rank computes every world-th tile
-  int cap = max_coop_ctas(ctx);
+  int cap = max_coop_ctas(ctx, box);
   if (cap < 1) return 0;
   int64_t g = tiles < cap ? tiles : cap;
   return (int)(g < 1 ? 1 : g);
@@ -841,9 +923,8 @@ extern "C" int64_t pth_update_xbuf_bytes(const pth_space* sp, int32_t world) {
 
 extern "C" int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
                                int64_t batch_size) {
-  (void)sp;
   if (!ctx || M <= 0 || batch_size <= 0) return PTH_EINVAL;
-  return auto_grid(ctx, M, batch_size);
+  return auto_grid(ctx, M, batch_size, 1, space_is_box(sp));
 }
 
 extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int64_t M,
@@ -851,7 +932,7 @@ extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_spac
   if (!ctx || !sp || M <= 0 || batch_size <= 0) return PTH_EINVAL;
   const int64_t P = pth_policy_param_count(sp);
   if (P < 0) return PTH_EINVAL;
-  const int cap = max_coop_ctas(ctx);  // worst case grid (tests may pin any G <= cap)
+  const int cap = max_coop_ctas(ctx, space_is_box(sp));  // worst case grid (tests may pin any G <= cap)
   const int64_t n_mb = (M + batch_size - 1) / batch_size;
   return (int64_t)ws_layout(cap > 0 ? cap : 1, (int)P, 64 * n_mb).total;
 }
@@ -859,8 +940,8 @@ extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_spac
 extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stream) {
   PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");
   PTH_CHECK_ARG(a->space && a->d_params && a->d_adam_m && a->d_adam_v, "NULL space/params/adam");
-  PTH_CHECK_ARG(a->d_obs && a->d_actions && a->d_old_logp && a->d_advantages && a->d_returns &&
-                    a->d_perm && a->d_workspace,
+  PTH_CHECK_ARG((a->d_obs || a->d_obs_f32) && a->d_actions && a->d_old_logp && a->d_advantages &&
+                    a->d_returns && a->d_perm && a->d_workspace,
                 "NULL sample array / perm / workspace");
   PTH_CHECK_ARG(a->M > 0 && a->batch_size > 0 && a->n_epochs > 0 && a->n_epochs <= 64,
                 "bad M / batch_size / n_epochs");
@@ -870,19 +951,30 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     pth_set_error("pth_ppo_update: unsupported space");
     return PTH_ENOSUP;
   }
-  if (p.sp.obs_kind != PTH_OBS_ONEHOT) {
-    pth_set_error("pth_ppo_update: Box observations are not supported by this build");
-    return PTH_ENOSUP;
+  const bool box = p.sp.obs_kind == PTH_OBS_BOX;
+  if (box) {
+    if (p.sp.F > HID) {
+      pth_set_error("pth_ppo_update: Box observations wider than 64 are not supported");
+      return PTH_ENOSUP;
+    }
+    PTH_CHECK_ARG(a->d_obs_f32 != nullptr && a->obs_stride == HID && a->rec_stride == 0 && a->world <= 1,
+                  "Box observations: d_obs_f32 rows of 64 floats, separate arrays, single GPU");
+    PTH_CHECK_ARG(((uintptr_t)a->d_obs_f32 % 16) == 0, "obs rows must be 16-byte aligned");
+  } else {
+    PTH_CHECK_ARG(a->d_obs != nullptr, "NULL d_obs");
+    PTH_CHECK_ARG(p.sp.F <= MAX_ROWS, "one-hot feature width above 2048 is not supported");
   }
   p.lo = make_layout(p.sp.F, p.sp.L);
-  for (int i = 0; i < MAX_SLOTS; ++i) p.nvec[i] = i < p.sp.obs_len ? (uint8_t)a->space->obs_nvec[i] : 0;
-  PTH_CHECK_ARG(cap_check_g(ctx) <= 160, "more than 160 co-resident CTAs are not supported");
-  const int cap = max_coop_ctas(ctx);
+  for (int i = 0; i < MAX_SLOTS; ++i)
+    p.nvec[i] = (!box && i < p.sp.obs_len) ? (uint8_t)a->space->obs_nvec[i] : 0;
+  const int cap = max_coop_ctas(ctx, box);
+  PTH_CHECK_ARG(cap <= 160, "more than 160 co-resident CTAs are not supported");
   if (cap < 1 || !ctx->coop_launch) {
     pth_set_error("pth_ppo_update: cooperative launch unavailable on this device");
     return PTH_ENOSUP;
   }
-  int G = a->grid_ctas > 0 ? a->grid_ctas : auto_grid(ctx, a->M, a->batch_size, a->world > 1 ? a->world : 1);
+  int G = a->grid_ctas > 0 ? a->grid_ctas
+                           : auto_grid(ctx, a->M, a->batch_size, a->world > 1 ? a->world : 1, box);
   PTH_CHECK_ARG(G >= 1 && G <= cap, "grid_ctas exceeds the co-resident CTA capacity");
   const int64_t n_mb = (a->M + a->batch_size - 1) / a->batch_size;
   const WsLayout w = ws_layout(G, p.lo.total, (int64_t)a->n_epochs * n_mb);
@@ -893,7 +985,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.params = a->d_params;
   p.adam_m = a->d_adam_m;
   p.adam_v = a->d_adam_v;
-  p.obs = a->d_obs;
+  p.obs = box ? reinterpret_cast<const uint8_t*>(a->d_obs_f32) : a->d_obs;
   p.actions = a->d_actions;
   p.old_logp = reinterpret_cast<const uint8_t*>(a->d_old_logp);
   p.adv = reinterpret_cast<const uint8_t*>(a->d_advantages);
@@ -902,11 +994,11 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     PTH_CHECK_ARG(a->rec_stride % 16 == 0, "rec_stride must be a multiple of 16");
     p.obs_stride = p.act_stride = p.f_stride = a->rec_stride;
   } else {
-    p.obs_stride = 32;
+    p.obs_stride = box ? (int64_t)HID * 4 : 32;
     p.act_stride = 4;
     p.f_stride = 4;
   }
-  PTH_CHECK_ARG(((uintptr_t)a->d_obs % 16) == 0, "obs rows must be 16-byte aligned");
+  PTH_CHECK_ARG(((uintptr_t)p.obs % 16) == 0, "obs rows must be 16-byte aligned");
   p.index = a->d_index;
   p.perm = a->d_perm;
   p.M = a->M;
@@ -949,8 +1041,12 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   }
 
   void* kargs[] = {(void*)&p};
-  PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel, dim3(G), dim3(NT), kargs,
-                                       sizeof(UpdSmem), (cudaStream_t)stream));
+  if (box)
+    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<true>, dim3(G), dim3(NT), kargs, SMEM_BOX,
+                                         (cudaStream_t)stream));
+  else
+    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<false>, dim3(G), dim3(NT), kargs,
+                                         SMEM_ONEHOT, (cudaStream_t)stream));
   return PTH_OK;
 }
 

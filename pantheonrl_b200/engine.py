@@ -61,7 +61,7 @@ class Learner:
 class VecTrainer:
     def __init__(self, env_kind, n_envs, ego_cfg=None, alt_cfg=None, seed=10, partner="ppo",
                  probegostart=0.5, device="cuda", env0=0, group=None, exchange="nccl",
-                 ego_update="sharded"):
+                 ego_update="sharded", layout="simple", ego_agent_idx=0, horizon=None):
         """group: a torch.distributed process group for one-partner-per-GPU sharding
         (SURVEY.md 8e): every rank owns n_envs envs and its own partner, the ego is
         replicated; per rollout the ranks all-gather their packed ego transitions and
@@ -77,6 +77,14 @@ class VecTrainer:
         self.env_kind, self.N, self.seed = env_kind, int(n_envs), int(seed)
         self.device, self.env0, self.probegostart = device, env0, probegostart
         self.space = ro.space_for(env_kind)
+        self.d_layout, box, state_bytes = None, False, 32
+        if env_kind == "overcooked":  # config 4: OvercookedMultiEnv-v0, Box(62) observations
+            from .envs import overcooked as oc
+            if group is not None:
+                raise _lib.PthError("overcooked: the multi-GPU ego exchange packs one-hot records only")
+            self.layout = oc.build_layout(layout, ego_agent_idx, horizon or oc.HORIZON)
+            self.d_layout = oc.layout_to_device(self.layout, device)
+            box, state_bytes = True, _lib.PTH_OC_STATE_BYTES
         self.ego_cfg = ego_cfg or PPOConfig()
         self.alt_cfg = alt_cfg or self.ego_cfg
         self.partner = partner
@@ -89,10 +97,10 @@ class VecTrainer:
         else:
             raise ValueError(partner)
         N, T = self.N, self.T
-        self.ego_buf = ro.Buffer(T, N, False, device)
+        self.ego_buf = ro.Buffer(T, N, False, device, box)
         alt_cap = 2 * T if env_kind == "liar" else T
-        self.alt_buf = ro.Buffer(alt_cap, N, True, device)
-        self.carry = ro.Carry(N, device)
+        self.alt_buf = ro.Buffer(alt_cap, N, True, device, box)
+        self.carry = ro.Carry(N, device, state_bytes)
         self.rollouts = 0
         self.num_timesteps = 0
         self.partner_decisions = 0
@@ -159,7 +167,8 @@ class VecTrainer:
         ro.run_rollout(self.env_kind, self.space, self.ego.params, alt_params, self.ego_buf,
                        self.alt_buf, self.carry, self.T, self.seed, self.rollouts * self.T,
                        env0=self.env0, probegostart=self.probegostart,
-                       first_rollout=self.rollouts == 0, partner_records=self.alt is not None)
+                       first_rollout=self.rollouts == 0, partner_records=self.alt is not None,
+                       d_layout=self.d_layout)
         self.rollouts += 1
         self.num_timesteps += self.N * self.T
 

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import Context, check, current_stream
 
-ENV_KINDS = {"rps": _lib.PTH_ENV_RPS, "liar": _lib.PTH_ENV_LIAR}
+ENV_KINDS = {"rps": _lib.PTH_ENV_RPS, "liar": _lib.PTH_ENV_LIAR, "overcooked": _lib.PTH_ENV_OVERCOOKED}
 
 
 def space_for(env_kind):
@@ -18,16 +18,19 @@ def space_for(env_kind):
         return _lib.Space.onehot([1], [3])
     if env_kind == "liar":
         return _lib.Space.onehot([7] * 6 + [7, 12] * 12, [7, 12])
+    if env_kind == "overcooked":
+        return _lib.Space.box(_lib.PTH_OC_OBS, [6])
     raise ValueError(env_kind)
 
 
 class Buffer:
     """One learner's rollout buffer: arrays [Tcap, N] (time-major, env contiguous)."""
 
-    def __init__(self, Tcap, N, ragged, device):
-        self.Tcap, self.N, self.ragged = Tcap, N, ragged
+    def __init__(self, Tcap, N, ragged, device, box=False):
+        self.Tcap, self.N, self.ragged, self.box = Tcap, N, ragged, box
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)  # noqa: E731
-        self.obs = z(Tcap, N, 32, dt=torch.uint8)
+        # observation rows: 32 bytes (one-hot slots) or 64 fp32 (Box)
+        self.obs = z(Tcap, N, _lib.PTH_OC_ROW) if box else z(Tcap, N, 32, dt=torch.uint8)
         self.actions = z(Tcap, N, 4, dt=torch.uint8)
         self.rewards = z(Tcap, N)
         self.values = z(Tcap, N)
@@ -53,13 +56,13 @@ class Buffer:
 class Carry:
     """Per-env driver state carried across rollouts (MultiAgentEnv fields)."""
 
-    def __init__(self, N, device):
+    def __init__(self, N, device, state_bytes=32):
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)  # noqa: E731
         self.ego_last_start = torch.ones(N, device=device)
         self.alt_last_done = torch.ones(N, device=device)
         self.total_rew = z(2, N)
         self.flags = z(N, dt=torch.uint8)
-        self.game_state = z(N, 32, dt=torch.uint8)
+        self.game_state = z(N, state_bytes, dt=torch.uint8)
         self.ego_last_value = z(N)
         self.ego_last_done = z(N)
         self.ep_stats = z(4)
@@ -73,7 +76,7 @@ class Carry:
 
 
 def run_rollout(env_kind, space, ego_params, alt_params, ego, alt, carry, T, seed, tick0,
-                env0=0, probegostart=0.5, first_rollout=False, partner_records=True):
+                env0=0, probegostart=0.5, first_rollout=False, partner_records=True, d_layout=None):
     """One T-tick rollout of ego.N on-device envs (pth_rollout_run)."""
     a = _lib.RolloutArgs()
     a.env_kind = ENV_KINDS[env_kind]
@@ -89,6 +92,7 @@ def run_rollout(env_kind, space, ego_params, alt_params, ego, alt, carry, T, see
     a.seed, a.tick0 = int(seed), int(tick0) & 0xffffffff
     a.probegostart = float(probegostart)
     a.first_rollout = int(first_rollout)
+    a.d_layout = d_layout.data_ptr() if d_layout is not None else None
     dev = ego_params.device
     ctx = Context.get(dev.index if dev.index is not None else torch.cuda.current_device())
     check(_lib.load().pth_rollout_run(ctx.handle, C.byref(a), current_stream()), "pth_rollout_run")
