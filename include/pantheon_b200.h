@@ -407,6 +407,10 @@ int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
                     int64_t batch_size);
 int64_t pth_update_xbuf_bytes(const pth_space* sp, int32_t world);
 int pth_ppo_update(pth_ctx* ctx, const pth_update_args* args, void* stream);
+/* debug only: when set to a device array of 32 int64 (zeroed by the caller), later
+ * pth_ppo_update launches add CTA 0's per-phase clock64 sums to it (phase list in
+ * csrc/pth_update.cu, PTH_PROF); NULL switches it off again.  Process-wide. */
+int pth_debug_update_profile(void* d_clock_sums);
 
 /* ------------------------------------------------------------------ */
 /* e: multi-GPU exchange staging                                       */

@@ -227,6 +227,7 @@ SIGNATURES = {
     "pth_index_workspace_bytes": (_i64, [_i64]),
     "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
     "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),
+    "pth_debug_update_profile": (C.c_int, [_vp]),
     "pth_pack_transitions": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "pth_pack_allgather_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp]),
 }

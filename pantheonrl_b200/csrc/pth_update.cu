@@ -76,7 +76,18 @@ struct UpdParams {
   uint32_t* flags[8];   // rank r's flag words [world]
   uint32_t flag_epoch;
   int XS;               // floats per (parity, rank) slot: P + 8 rounded up to 4
+  long long* prof;      // debug: per-phase clock64 sums of CTA 0 (pth_debug_update_profile), or NULL
 };
+
+// phase timeline of CTA 0 (thread 0), accumulated over every minibatch of the launch
+#define PTH_PROF(i)                                   \
+  do {                                                \
+    if (p.prof != nullptr && c == 0 && tid == 0) {    \
+      const long long now__ = clock64();              \
+      p.prof[i] += now__ - prof_last;                 \
+      prof_last = now__;                              \
+    }                                                 \
+  } while (0)
 
 // The fixed 128-lane tree of the reduction contract: xor-shuffle tree inside
 // each of the first four warps, then the four warp sums left to right.  Threads
@@ -297,6 +308,49 @@ __device__ __forceinline__ void wgrad_first_box(const float* Dz, const float* X,
       if (kt + 16 * kk < F) acc_store(gout + (kt + 16 * kk) * HID + (jt + NY * jj), acc[jj][kk], first);
 }
 
+// action head for the whole tile with all NT threads: Lg[l][b] = b_act[l] + sum_k fma(H2[k][b],
+// w_act[l][k], .), k ascending (the chain of dot64).  Warp w owns logits w, w + 8, ... (uniform
+// per warp: weight reads are broadcasts); lane owns 4 consecutive samples.
+__device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& pol, int L, float* Lg,
+                                            int tid) {
+  const int tx = tid & 31, ty = tid >> 5;
+  float acc[4][4];
+#pragma unroll
+  for (int ll = 0; ll < 4; ++ll) {
+    const int l = ty + 8 * ll;
+    const float bl = l < L ? pol.b_act[l] : 0.f;
+#pragma unroll
+    for (int ss = 0; ss < 4; ++ss) acc[ll][ss] = bl;
+  }
+#pragma unroll 4
+  for (int k0 = 0; k0 < HID; k0 += 4) {
+    float4 w[4];
+#pragma unroll
+    for (int ll = 0; ll < 4; ++ll) {
+      const int l = ty + 8 * ll;
+      w[ll] = l < L ? *reinterpret_cast<const float4*>(pol.w_act + l * LDW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(Hh + (k0 + kk) * LDA + tx * 4);
+#pragma unroll
+      for (int ll = 0; ll < 4; ++ll) {
+        const float wk = kk == 0 ? w[ll].x : (kk == 1 ? w[ll].y : (kk == 2 ? w[ll].z : w[ll].w));
+        acc[ll][0] = fmaf(a.x, wk, acc[ll][0]);
+        acc[ll][1] = fmaf(a.y, wk, acc[ll][1]);
+        acc[ll][2] = fmaf(a.z, wk, acc[ll][2]);
+        acc[ll][3] = fmaf(a.w, wk, acc[ll][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int ll = 0; ll < 4; ++ll) {
+    const int l = ty + 8 * ll;
+    if (l < L)
+      *reinterpret_cast<float4*>(Lg + l * LDA + tx * 4) = make_float4(acc[ll][0], acc[ll][1], acc[ll][2], acc[ll][3]);
+  }
+}
+
 // Stable counting sort of the tile's nb samples by observed value, one slot per
 // warp at a time: order[s][pos] = sample id, rcount[row] = samples selecting the
 // first-layer row (row = slot_off[s] + value).
@@ -441,6 +495,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
   }
   grid.sync();
 
+  long long prof_last = clock64();
   double b1pow = p.b1pow0, b2pow = p.b2pow0;
   const float omb1 = (float)(1.0 - (double)p.b1), omb2 = (float)(1.0 - (double)p.b2);
   const float clip_lo = 1.0f - p.clip, clip_hi = 1.0f + p.clip;
@@ -459,8 +514,10 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       const int64_t local_tiles = (n_tiles - p.rank + W - 1) / W;  // tile t belongs to rank t mod W
       const int A = (int)(local_tiles < G ? local_tiles : G);
 
+      PTH_PROF(0);  // loop head (prologue on the first pass)
       __syncthreads();
       load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, NT);
+      PTH_PROF(1);  // weights -> smem
       float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       bool first = true;
 
@@ -515,6 +572,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         }
         __syncthreads();
         if constexpr (!BOX) sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid);  // consumed after several barriers
+        PTH_PROF(2);  // gather + slot sort
 
         // ================= policy tower: forward
         if constexpr (BOX)
@@ -522,16 +580,57 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         else
           first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         __syncthreads();
+        PTH_PROF(3);  // pi first layer
         dense64<true>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
         __syncthreads();
+        PTH_PROF(4);  // pi hidden layer
         float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
+        logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
+        __syncthreads();
         if (lane) {
-          action_head(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
-          // ---- per-sample losses and d loss / d logits (own column of Lg)
-          pth_u4 zero = {0, 0, 0, 0};
-          const DistOut dist = dist_eval(p.sp, sm.Lg, tid, false, zero, act);
+          // ---- per-sample losses and d loss / d logits (own column of Lg).  Same values as
+          // dist_eval (pth_mlp.cuh) evaluates, with every exp computed once: the softmax
+          // probabilities are parked in the own column of sm.D1 (free until dz2 is written).
+          float* Pr = sm.D1;
+          float h_m[PTH_MAX_HEADS], h_logS[PTH_MAX_HEADS], h_ent[PTH_MAX_HEADS];
+          float logp = 0.f, entropy = 0.f;
+          {
+            int off = 0;
+#pragma unroll
+            for (int h = 0; h < PTH_MAX_HEADS; ++h) {
+              if (h < p.sp.n_heads) {
+                const int n = p.sp.head_n[h];
+                const int a_h = (int)((act >> (8 * h)) & 0xffu);
+                float mx = sm.Lg[off * LDA + tid];
+                for (int i = 1; i < n; ++i) {
+                  const float z = sm.Lg[(off + i) * LDA + tid];
+                  mx = z > mx ? z : mx;
+                }
+                float Ssum = 0.f;
+                for (int i = 0; i < n; ++i) {
+                  const float ex = pth_expf(sm.Lg[(off + i) * LDA + tid] - mx);
+                  Pr[(off + i) * LDA + tid] = ex;
+                  Ssum = Ssum + ex;
+                }
+                const float logS = pth_logf(Ssum);
+                float ent = 0.f;
+                for (int i = 0; i < n; ++i) {
+                  const float lp = (sm.Lg[(off + i) * LDA + tid] - mx) - logS;
+                  const float pi = Pr[(off + i) * LDA + tid] / Ssum;
+                  Pr[(off + i) * LDA + tid] = pi;
+                  ent = fmaf(-pi, lp, ent);
+                }
+                h_m[h] = mx;
+                h_logS[h] = logS;
+                h_ent[h] = ent;
+                logp = logp + ((sm.Lg[(off + a_h) * LDA + tid] - mx) - logS);
+                entropy = entropy + ent;
+                off += n;
+              }
+            }
+          }
           if (norm) adv = (adv - mean) / (stdv + 1e-8f);
-          const float lr_ = dist.logp - oldlp;
+          const float lr_ = logp - oldlp;
           const float ratio = pth_expf(lr_);
           const float pl1 = adv * ratio;
           const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
@@ -541,41 +640,31 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           const float glp = (valid && gmask) ? -((adv * ratio) * invB) : 0.f;
           const float gH = valid ? -(p.ent_coef * invB) : 0.f;
           s_pl = valid ? fminf(pl1, pl2) : 0.f;
-          s_e = valid ? dist.entropy : 0.f;
+          s_e = valid ? entropy : 0.f;
           s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
           s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
           int off = 0;
-          for (int h = 0; h < p.sp.n_heads; ++h) {
-            const int n = p.sp.head_n[h];
-            const int a_h = (int)((act >> (8 * h)) & 0xffu);
-            float mx = sm.Lg[off * LDA + tid];
-            for (int i = 1; i < n; ++i) {
-              const float z = sm.Lg[(off + i) * LDA + tid];
-              mx = z > mx ? z : mx;
+#pragma unroll
+          for (int h = 0; h < PTH_MAX_HEADS; ++h) {
+            if (h < p.sp.n_heads) {
+              const int n = p.sp.head_n[h];
+              const int a_h = (int)((act >> (8 * h)) & 0xffu);
+              const float mx = h_m[h], logS = h_logS[h], Hh = h_ent[h];
+              for (int i = 0; i < n; ++i) {
+                const float zi = sm.Lg[(off + i) * LDA + tid];
+                const float lp = (zi - mx) - logS;
+                const float pi = Pr[(off + i) * LDA + tid];
+                const float t1 = (i == a_h ? 1.0f : 0.0f) - pi;
+                const float dzv = glp * t1;
+                const float t2 = (gH * pi) * (lp + Hh);
+                sm.Lg[(off + i) * LDA + tid] = dzv - t2;
+              }
+              off += n;
             }
-            float Ssum = 0.f;
-            for (int i = 0; i < n; ++i) Ssum = Ssum + pth_expf(sm.Lg[(off + i) * LDA + tid] - mx);
-            const float logS = pth_logf(Ssum);
-            float Hh = 0.f;
-            for (int i = 0; i < n; ++i) {
-              const float zi = sm.Lg[(off + i) * LDA + tid];
-              const float lp = (zi - mx) - logS;
-              const float pi = pth_expf(zi - mx) / Ssum;
-              Hh = fmaf(-pi, lp, Hh);
-            }
-            for (int i = 0; i < n; ++i) {
-              const float zi = sm.Lg[(off + i) * LDA + tid];
-              const float lp = (zi - mx) - logS;
-              const float pi = pth_expf(zi - mx) / Ssum;
-              const float t1 = (i == a_h ? 1.0f : 0.0f) - pi;
-              const float dzv = glp * t1;
-              const float t2 = (gH * pi) * (lp + Hh);
-              sm.Lg[(off + i) * LDA + tid] = dzv - t2;
-            }
-            off += n;
           }
         }
         __syncthreads();  // dlogits complete
+        PTH_PROF(5);  // action head + losses + dlogits
         // ================= policy tower: backward
         // upper half: head weight / bias gradients; lower half: dz2 of each sample
         if (!lane) {
@@ -602,8 +691,10 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
             sm.D1[k * LDA + tid] = acc[k] * (1.0f - h * h);
           }
         }
+        PTH_PROF(6);  // head wgrad | dz2
         tower_backward<BOX>(p, sm, Xs, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
                             part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid);
+        PTH_PROF(7);  // pi tower backward (wgrad64, backprop64, first-layer gradient)
 
         // ================= value tower
         __syncthreads();
@@ -612,8 +703,10 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         else
           first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
         __syncthreads();
+        PTH_PROF(8);  // vf first layer
         dense64<true>(sm.H1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
         __syncthreads();
+        PTH_PROF(9);  // vf hidden layer
         if (lane) {
           const float v = value_head(sm.H2, sm.pol, tid);
           const float dret = ret - v;
@@ -644,8 +737,10 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           for (int b = 0; b < BT; ++b) s = s + sm.Lg[b];
           acc_store(part + p.lo.b_val, s, first);
         }
+        PTH_PROF(10);  // value head + its gradients
         tower_backward<BOX>(p, sm, Xs, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
                             part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid);
+        PTH_PROF(11);  // vf tower backward
 
         // ---- tile statistics
         const float ts[5] = {block_tree(s_pl, sm.red, tid), block_tree(s_v, sm.red, tid),
@@ -656,15 +751,22 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         first = false;
       }
       if (tid < 5) p.stat_part[c * 8 + tid] = cta_stat[tid];
+      PTH_PROF(12);  // tile statistics
       grid.sync();  // ---------------------------------------------- (1) partials written
+      PTH_PROF(13);  // barrier 1 (includes waiting for the slowest CTA)
 
-      // ---- ordered reduction of this CTA's parameter slice + squared-norm partial
+      // ---- ordered reduction of this CTA's parameter slice + squared-norm partial.
+      // All NT threads fetch (one parameter each per chunk of NT, 32 L2 loads in flight, adds in
+      // CTA order); the squared norm keeps the contract's 128 strided lanes: lane t owns
+      // parameters t, t + 128, ... of the slice, fed through shared memory.
       float q = 0.f;
       const int par = (int)(id & 1);
-      for (int i = tid; i < S && tid < BT; i += BT) {  // 128 strided lanes (reduction contract)
+      float* gs = sm.H1;  // chunk scratch (H1 is free between tiles)
+      for (int i0c = 0; i0c < S; i0c += NT) {
+        const int i = i0c + tid;
         const int pi = c * S + i;
-        if (pi < P) {
-          float g = 0.f;
+        float g = 0.f;
+        if (i < S && pi < P) {
           if (A > 0) {
             g = __ldcg(p.part + pi);
             int cc = 1;
@@ -686,7 +788,6 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           }
           if (W == 1) {
             p.grad[pi] = g;
-            q = fmaf(g, g, q);
           } else {
             // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
             for (int k = 0; k < W; ++k) {
@@ -694,6 +795,42 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
               p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
             }
           }
+        }
+        if (W == 1) {
+          __syncthreads();  // previous chunk's readers are done with gs
+          gs[tid] = g;      // 0 beyond the slice / P: fma(0, 0, q) leaves q unchanged
+          __syncthreads();
+          if (tid < BT) {
+            q = fmaf(gs[tid], gs[tid], q);
+            q = fmaf(gs[tid + BT], gs[tid + BT], q);
+          }
+        }
+      }
+      // loss statistics of the minibatch: one warp of the last CTA fetches every CTA's 5 sums in
+      // one L2 round trip, parks them in shared memory, and 5 lanes add them in CTA order —
+      // off the critical path of the parameter update (read back after barrier 2)
+      if (W == 1 && c == G - 1 && (tid >> 5) == 4) {
+        const int ln = tid & 31;
+        float* sc = sm.Lg;  // [5][160] scratch (free between tiles)
+        float t[5][5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const int cc = r * 32 + ln;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) t[i][r] = cc < A ? __ldcg(p.stat_part + cc * 8 + i) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+#pragma unroll
+          for (int i = 0; i < 5; ++i) sc[i * 160 + r * 32 + ln] = t[i][r];
+        __syncwarp();
+        if (ln < 5) {
+          float s_ = 0.f;
+          if (A > 0) {
+            s_ = sc[ln * 160];
+            for (int cc = 1; cc < A; ++cc) s_ = s_ + sc[ln * 160 + cc];
+          }
+          p.stat_part[G * 8 + ln] = s_;
         }
       }
       if (W > 1) {
@@ -723,7 +860,9 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       }
       const float sq = block_tree(q, sm.red, tid);
       if (tid == 0) p.norm_part[c] = sq;
+      PTH_PROF(14);  // ordered reduction of the slice
       grid.sync();  // ---------------------------------------------- (2) gradient + norm partials
+      PTH_PROF(15);  // barrier 2
 
       __syncthreads();
       for (int cc = tid; cc < G; cc += NT) sm.bc[cc] = __ldcg(p.norm_part + cc);
@@ -754,8 +893,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         for (int i = 0; i < 5; ++i) {
           float s;
           if (W == 1) {
-            s = __ldcg(p.stat_part + i);
-            for (int cc = 1; cc < A; ++cc) s = s + __ldcg(p.stat_part + cc * 8 + i);
+            s = __ldcg(p.stat_part + G * 8 + i);  // summed in CTA order during the reduce phase
           } else {
             const float* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
             s = __ldcg(xl + i);
@@ -773,7 +911,9 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         o[6] = gnorm;
         o[7] = Bf;
       }
+      PTH_PROF(16);  // clip + Adam
       grid.sync();  // ---------------------------------------------- (3) parameters updated
+      PTH_PROF(17);  // barrier 3
       __threadfence();  // invalidate L1: the next minibatch gathers fresh first-layer rows through L1
     }
   }
@@ -878,7 +1018,7 @@ WsLayout ws_layout(int G, int P, int64_t n_stat) {
   w.part = take(sizeof(float) * (size_t)G * P);
   w.grad = take(sizeof(float) * P);
   w.norm_part = take(sizeof(float) * G);
-  w.stat_part = take(sizeof(float) * G * 8);
+  w.stat_part = take(sizeof(float) * (G + 1) * 8);  // + one row: the minibatch sums
   w.advstat = take(sizeof(float) * 2 * n_stat);
   w.total = o;
   return w;
@@ -913,6 +1053,12 @@ int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1, bool box
 }
 
 }  // namespace
+
+static long long* g_prof_buf = nullptr;
+extern "C" int pth_debug_update_profile(void* d_clock_sums) {
+  g_prof_buf = reinterpret_cast<long long*>(d_clock_sums);
+  return PTH_OK;
+}
 
 extern "C" int64_t pth_update_xbuf_bytes(const pth_space* sp, int32_t world) {
   const int64_t P = pth_policy_param_count(sp);
@@ -1022,6 +1168,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.stat_part = reinterpret_cast<float*>(ws + w.stat_part);
   p.advstat = reinterpret_cast<float*>(ws + w.advstat);
   p.stats = a->d_stats;
+  p.prof = g_prof_buf;
   p.world = a->world > 1 ? a->world : 1;
   p.rank = p.world > 1 ? a->rank : 0;
   p.flag_epoch = a->flag_epoch;

@@ -9,9 +9,9 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def run(env, N, T, partner, iters=4, nmb=32, epochs=10):
+def run(env, N, T, partner, iters=4, nmb=32, epochs=10, **kw):
     cfg = PPOConfig(n_steps=T, n_minibatches=nmb, n_epochs=epochs)
-    tr = VecTrainer(env, N, cfg, seed=10, partner=partner)
+    tr = VecTrainer(env, N, cfg, seed=10, partner=partner, **kw)
     out = []
     for it in range(iters):
         e = [ev() for _ in range(4)]
@@ -29,6 +29,8 @@ def run(env, N, T, partner, iters=4, nmb=32, epochs=10):
 
 if __name__ == "__main__":
     run("liar", 4096, 128, "ppo")
+    run("overcooked", 1024, 400, "ppo", layout="simple")
+    run("overcooked", 4096, 400, "ppo", layout="simple", iters=3)
     run("rps", 65536, 128, "selfplay")
     run("rps", 4096, 128, "ppo")
     run("liar", 1, 2048, "ppo", iters=2, nmb=0)
