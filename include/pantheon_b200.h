@@ -274,6 +274,9 @@ typedef struct pth_forward_args {
   float* d_logits;
 } pth_forward_args;
 int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream);
+/* debug / parity only: y[i] = f(x[i]) with the library's exp (which = 0), log (1, positive
+ * normal inputs) or tanh (2) — the polynomial kernels of the numeric contract. */
+int pth_debug_math(pth_ctx* ctx, int which, const float* d_x, float* d_y, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* a1+a2+a3+a7+a8/a9 fused: T-tick rollout with on-device envs         */

@@ -100,7 +100,22 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
     for (int l = 0; l < p.sp.L; ++l) p.logits[b * p.sp.L + l] = sm.Lg[l * LDA + tid];
 }
 
+__global__ void math_kernel(int which, const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = which == 0 ? pth_expf(v) : (which == 1 ? pth_logf(v) : pth_tanhf(v));
+}
+
 }  // namespace
+
+extern "C" int pth_debug_math(pth_ctx* ctx, int which, const float* d_x, float* d_y, int64_t n, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && d_x && d_y && n >= 0 && which >= 0 && which <= 2, "bad argument");
+  if (n == 0) return PTH_OK;
+  math_kernel<<<pth_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(which, d_x, d_y, n);
+  PTH_LAUNCH_CHECK();
+  return PTH_OK;
+}
 
 extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void* stream) {
   PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");

@@ -73,6 +73,40 @@ def test_device_math_matches_oracle_math(ctx):
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
 
 
+def test_device_exp_log_tanh_bit_exact_dense_sweep(ctx):
+    """Every fp32 value in a band of each function's domain (2^22 consecutive bit patterns per
+    band) plus random values: device exp / log / tanh equal the oracle's bit for bit."""
+    lib = _lib.load()
+
+    def dev(which, x):
+        dx = torch.from_numpy(x).cuda()
+        dy = torch.empty_like(dx)
+        _lib.check(lib.pth_debug_math(ctx.handle, which, dx.data_ptr(), dy.data_ptr(), dx.numel(),
+                                      _lib.current_stream()), "pth_debug_math")
+        return dy.cpu().numpy()
+
+    def band(lo, n=1 << 22):
+        start = np.float32(lo).view(np.uint32)
+        return (start + np.arange(n, dtype=np.uint32)).view(np.float32)
+
+    rng = np.random.RandomState(0)
+    for lo in (0.62, 0.999, 2.0, 4.9, 9.99, 1e-3):  # around the branch points and the clamp at 10
+        for sign in (1.0, -1.0):
+            x = (band(lo) * np.float32(sign)).astype(np.float32)
+            assert np.array_equal(dev(2, x), oracle.math_vec("tanh", x)), ("tanh", lo, sign)
+    x = np.concatenate([rng.uniform(-12, 12, 1 << 21), rng.randn(1 << 20) * 1e-2, [0.0, -0.0, 10.0, -10.0, 50.0, 1e30,
+                        -1e30, np.inf, -np.inf]]).astype(np.float32)
+    assert np.array_equal(dev(2, x), oracle.math_vec("tanh", x))
+    for lo in (-87.5, -20.0, -1.0, -1e-3, 1e-3, 0.69, 19.9, 87.9):
+        x = band(abs(lo)) * np.float32(np.sign(lo))
+        assert np.array_equal(dev(0, x), oracle.math_vec("exp", x)), ("exp", lo)
+    x = rng.uniform(-100, 95, 1 << 21).astype(np.float32)
+    assert np.array_equal(dev(0, x), oracle.math_vec("exp", x))
+    for lo in (1.0, 1.41, 7.0, 1e3, 1e-30):
+        x = band(lo)
+        assert np.array_equal(dev(1, x), oracle.math_vec("log", x)), ("log", lo)
+
+
 def test_sampling_is_a_pure_function_of_the_counter(ctx):
     gsp = _lib.Space.onehot([1], [3])
     osp = oracle.make_space(**oracle.RPS_SPACE)
