@@ -430,12 +430,15 @@ __device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* ord
 template <bool BOX>
 __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, const float* Xs,
                                                const float* w1_s, float* g_w0, float* g_b0,
-                                               float* g_w1, float* g_b1, int nb, bool first, int tid) {
+                                               float* g_w1, float* g_b1, int nb, bool first, int tid,
+                                               long long& prof_last, int c, int pbase) {
   __syncthreads();  // D1 complete
   wgrad64(sm.D1, sm.H1, g_w1, first, tid);
   row_sums(sm.D1, HID, g_b1, first, tid, 64);
+  PTH_PROF(pbase + 0);  // wgrad64 + bias sums
   backprop64<!BOX>(sm.D1, w1_s, sm.H1, sm.H2, tid);
   __syncthreads();  // dz1 complete (in H2)
+  PTH_PROF(pbase + 1);  // backprop64
   if constexpr (BOX) {
     row_sums(sm.H2, HID, g_b0, first, tid, NT - HID);
     wgrad_first_box(sm.H2, Xs, p.sp.F, g_w0, first, tid);
@@ -693,7 +696,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         }
         PTH_PROF(6);  // head wgrad | dz2
         tower_backward<BOX>(p, sm, Xs, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
-                            part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid);
+                            part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid, prof_last, c, 18);
         PTH_PROF(7);  // pi tower backward (wgrad64, backprop64, first-layer gradient)
 
         // ================= value tower
@@ -739,7 +742,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         }
         PTH_PROF(10);  // value head + its gradients
         tower_backward<BOX>(p, sm, Xs, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
-                            part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid);
+                            part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid, prof_last, c, 20);
         PTH_PROF(11);  // vf tower backward
 
         // ---- tile statistics

@@ -24,12 +24,14 @@ class DevicePolicy:
         self.device, self.seed, self.rng_stream = device, int(seed or 0), rng_stream
         self.params = torch.from_numpy(pol.init_flat(space, seed)).to(device)
         self.calls = 0
-        self._obs_dev = torch.zeros(1, 32, dtype=torch.uint8, device=device)
+        self.box = space.obs_kind == _lib.PTH_OBS_BOX  # fp32 rows of 64 instead of 32 slot bytes
+        self._obs_dev = (torch.zeros(1, _lib.PTH_OC_ROW, dtype=torch.float32, device=device) if self.box
+                         else torch.zeros(1, 32, dtype=torch.uint8, device=device))
         self.act_dim = space.n_heads
 
     def forward(self, obs, deterministic=False):
         """obs -> (actions [1, act_dim] numpy, values tensor [1], log_probs tensor [1])."""
-        o = np.zeros((1, 32), np.uint8)
+        o = np.zeros((1, _lib.PTH_OC_ROW), np.float32) if self.box else np.zeros((1, 32), np.uint8)
         flat = np.asarray(obs).reshape(-1)
         o[0, :flat.size] = flat
         self._obs_dev.copy_(torch.from_numpy(o))
@@ -56,9 +58,10 @@ class HostStagedBuffer:
     """RolloutBuffer for the N = 1 flow: rows are staged on the host while the env is
     stepped from Python and uploaded once when GAE / train() run on the device."""
 
-    def __init__(self, n_steps, device, gamma=0.99, gae_lambda=0.95):
+    def __init__(self, n_steps, device, gamma=0.99, gae_lambda=0.95, box=False):
         self.T, self.device, self.gamma, self.gae_lambda = n_steps, device, gamma, gae_lambda
-        self.h = dict(obs=np.zeros((n_steps, 32), np.uint8), actions=np.zeros((n_steps, 4), np.uint8),
+        obs = np.zeros((n_steps, _lib.PTH_OC_ROW), np.float32) if box else np.zeros((n_steps, 32), np.uint8)
+        self.h = dict(obs=obs, actions=np.zeros((n_steps, 4), np.uint8),
                       rewards=np.zeros(n_steps, np.float32), values=np.zeros(n_steps, np.float32),
                       logp=np.zeros(n_steps, np.float32), episode_starts=np.zeros(n_steps, np.float32))
         self.d = {k: torch.zeros(v.shape, dtype=torch.from_numpy(v).dtype, device=device) for k, v in self.h.items()}
@@ -125,7 +128,10 @@ class PPO:
         self.space = to_pth_space(self.observation_space, self.action_space)
         stream = _rng_stream if _rng_stream is not None else _lib.STREAM_EGO
         self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, seed, self.device, stream)
-        self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda)
+        if self.space.obs_kind == _lib.PTH_OBS_BOX and self.space.obs_len > _lib.PTH_OC_ROW:
+            raise _lib.PthError("Box observations wider than 64 are not supported")
+        self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda,
+                                               box=self.space.obs_kind == _lib.PTH_OBS_BOX)
         self.adam_m = torch.zeros_like(self.policy.params)
         self.adam_v = torch.zeros_like(self.policy.params)
         self.adam_step, self._n_updates, self.num_timesteps = 0, 0, 0
@@ -186,7 +192,8 @@ class PPO:
         from .engine import PPOConfig, VecTrainer
         kind = getattr(self.env, "device_kind", None)
         if kind is None:
-            raise _lib.PthError("n_envs > 1 needs a built-in env with a device twin (RPS-v0, LiarsDice-v0)")
+            raise _lib.PthError("n_envs > 1 needs a built-in env with a device twin "
+                                "(RPS-v0, LiarsDice-v0, OvercookedMultiEnv-v0)")
         plist = self.env.partners[0]
         if len(plist) != 1:
             raise _lib.PthError("the on-device loop drives exactly one partner per process (one partner per GPU)")
@@ -204,7 +211,9 @@ class PPO:
             else:
                 raise _lib.PthError("on-device partners: OnPolicyAgent(PPO) or StaticPolicyAgent(ego.policy)")
             self._trainer = VecTrainer(kind, self.n_envs, mk(self), alt_cfg, seed=self.policy.seed, partner=mode,
-                                       probegostart=getattr(self.env, "probegostart", 0.5), device=self.device)
+                                       probegostart=getattr(self.env, "probegostart", 0.5), device=self.device,
+                                       **({"layout": self.env.layout_name, "ego_agent_idx": self.env.ego_agent_idx,
+                                           "horizon": self.env.layout.horizon} if kind == "overcooked" else {}))
             self._trainer.ego.params = self.policy.params          # share storage with the facade objects
             self._trainer.ego.adam_m, self._trainer.ego.adam_v = self.adam_m, self.adam_v
             if mode == "ppo":

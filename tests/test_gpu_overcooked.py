@@ -361,3 +361,35 @@ def test_facade_env_steps_on_device(ctx, golden_dir):
         assert r == g["ego_rew"][i] and int(d) == g["ego_done"][i]
         obs = env.reset() if d else o2
     assert np.array_equal(np.array(partner.seen), g["ev_obs"][g["ev_kind"] == 0][:T].astype(np.float64))
+
+
+def test_facade_ppo_learns_host_driven_and_on_device(ctx):
+    """trainer.py-style drop-in: OvercookedMultiEnv + OnPolicyAgent(PPO) partner + ego PPO.learn at N = 1
+    (one kernel call per decision, Box rows staged on the host), and the same objects with n_envs > 1
+    handing the loop to the device engine."""
+    from pantheonrl_b200.common.agents import OnPolicyAgent
+    from pantheonrl_b200.ppo import PPO
+    env = oc.OvercookedMultiEnv("simple")
+    env.layout.horizon = 30
+    env.d_layout = oc.layout_to_device(env.layout)
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=40, batch_size=20, n_epochs=2, seed=10,
+                                _rng_stream=_lib.STREAM_ALT))
+    env.add_partner_agent(partner)
+    ego = PPO("MlpPolicy", env, n_steps=40, batch_size=20, n_epochs=2, seed=10)
+    assert torch.equal(ego.policy.params, partner.model.policy.params)
+    ego.learn(total_timesteps=80)
+    assert ego.num_timesteps == 80 and ego._n_updates == 4 and partner.model._n_updates >= 2
+    assert bool(torch.isfinite(ego.policy.params).all()) and np.all(np.isfinite(ego.last_stats.cpu().numpy()))
+    # n_envs > 1: the device loop, equal to driving VecTrainer directly
+    N, T = 64, 32
+    env = oc.OvercookedMultiEnv("unident_s", ego_agent_idx=1)
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4,
+                                _rng_stream=_lib.STREAM_ALT))
+    env.add_partner_agent(partner)
+    ego = PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_envs=N, n_minibatches=4)
+    ego.learn(total_timesteps=N * T * 2)
+    tr = VecTrainer("overcooked", N, PPOConfig(n_steps=T, n_epochs=2, n_minibatches=4), seed=10, partner="ppo",
+                    layout="unident_s", ego_agent_idx=1)
+    tr.learn(N * T * 2)
+    assert torch.equal(ego.policy.params, tr.ego.params)
+    assert torch.equal(partner.model.policy.params, tr.alt.params)

@@ -8,7 +8,7 @@ from pantheonrl_b200.engine import VecTrainer, PPOConfig
 
 NAMES = ["loop head", "weights->smem", "gather+sort", "pi L0", "pi L1", "head+loss", "head wgrad|dz2",
          "pi tower bwd", "vf L0", "vf L1", "value head", "vf tower bwd", "tile stats", "barrier1",
-         "reduce", "barrier2", "adam", "barrier3"]
+         "reduce", "barrier2", "adam", "barrier3", " pi wgrad64", " pi backprop64", " vf wgrad64", " vf backprop64"]
 
 
 def run(env, N, T, **kw):
