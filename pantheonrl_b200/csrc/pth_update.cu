@@ -759,54 +759,56 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       PTH_PROF(13);  // barrier 1 (includes waiting for the slowest CTA)
 
       // ---- ordered reduction of this CTA's parameter slice + squared-norm partial.
-      // All NT threads fetch (one parameter each per chunk of NT, 32 L2 loads in flight, adds in
-      // CTA order); the squared norm keeps the contract's 128 strided lanes: lane t owns
-      // parameters t, t + 128, ... of the slice, fed through shared memory.
+      // 128 parameters per pass, two threads per parameter: the upper half of the CTA fetches and
+      // adds partials [0, RH) left to right, the lower half fetches partials [RH, A) AT THE SAME TIME
+      // (up to 80 L2 loads in flight per thread, one round trip per pass), picks the running sum up
+      // through shared memory and continues the same left-to-right chain — the order of the
+      // additions is the contract's CTA order.  Lane t < 128 ends up with parameters t, t + 128, ...
+      // of the slice, which is exactly the lane assignment of the squared-norm contract.
       float q = 0.f;
       const int par = (int)(id & 1);
-      float* gs = sm.H1;  // chunk scratch (H1 is free between tiles)
-      for (int i0c = 0; i0c < S; i0c += NT) {
-        const int i = i0c + tid;
-        const int pi = c * S + i;
-        float g = 0.f;
-        if (i < S && pi < P) {
-          if (A > 0) {
-            g = __ldcg(p.part + pi);
-            int cc = 1;
-            for (; cc + 32 <= A; cc += 32) {  // 32 independent L2 loads in flight, adds stay in order
-              float t[32];
+      {
+        constexpr int RH = 80;  // max co-resident CTAs is 160
+        float* gs = sm.H1;      // hand-over scratch (H1 is free between tiles)
+        const int li = tid & (BT - 1);
+        const bool second = tid < BT;
+        const int cc0 = second ? RH : 0;
+        for (int i0c = 0; i0c < S; i0c += BT) {
+          const int i = i0c + li;
+          const int pi = c * S + i;
+          const bool live = i < S && pi < P;
+          float t[RH];
 #pragma unroll
-              for (int u = 0; u < 32; ++u) t[u] = __ldcg(p.part + (size_t)(cc + u) * P + pi);
+          for (int u = 0; u < RH; ++u)
+            t[u] = (live && cc0 + u < A) ? __ldcg(p.part + (size_t)(cc0 + u) * P + pi) : 0.f;
+          float g = 0.f;
+          if (!second) {
+            if (live && A > 0) {
+              g = t[0];
 #pragma unroll
-              for (int u = 0; u < 32; ++u) g = g + t[u];
+              for (int u = 1; u < RH; ++u) g = (u < A) ? g + t[u] : g;
             }
-            for (; cc + 8 <= A; cc += 8) {
-              float t[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) t[u] = __ldcg(p.part + (size_t)(cc + u) * P + pi);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) g = g + t[u];
-            }
-            for (; cc < A; ++cc) g = g + __ldcg(p.part + (size_t)cc * P + pi);
+            gs[li] = g;
           }
-          if (W == 1) {
-            p.grad[pi] = g;
-          } else {
-            // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
-            for (int k = 0; k < W; ++k) {
-              const int dst = (p.rank + k) % W;
-              p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
-            }
-          }
-        }
-        if (W == 1) {
-          __syncthreads();  // previous chunk's readers are done with gs
-          gs[tid] = g;      // 0 beyond the slice / P: fma(0, 0, q) leaves q unchanged
           __syncthreads();
-          if (tid < BT) {
-            q = fmaf(gs[tid], gs[tid], q);
-            q = fmaf(gs[tid + BT], gs[tid + BT], q);
+          if (second) {
+            g = gs[li];
+#pragma unroll
+            for (int u = 0; u < RH; ++u) g = (RH + u < A) ? g + t[u] : g;
+            if (live) {
+              if (W == 1) {
+                p.grad[pi] = g;
+              } else {
+                // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
+                for (int k = 0; k < W; ++k) {
+                  const int dst = (p.rank + k) % W;
+                  p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
+                }
+              }
+            }
+            if (W == 1) q = fmaf(g, g, q);  // g = 0 beyond the slice: q unchanged
           }
+          __syncthreads();  // gs is rewritten by the next pass
         }
       }
       // loss statistics of the minibatch: one warp of the last CTA fetches every CTA's 5 sums in
