@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--env", default="liar", choices=["liar", "rps"])
     ap.add_argument("--n-envs", type=int, default=N_ENVS)
-    ap.add_argument("--cpu-sample-envs", type=int, default=64)
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0 = same env count as the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--ego-update", default="sharded", choices=["sharded", "replicated"])
@@ -82,7 +82,8 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------- CPU arm
-CPU_EPOCHS_TIMED = 2  # of N_EPOCHS: the update time of the sample is scaled by N_EPOCHS / this
+CPU_BUDGET_S = 150.0   # the reference arm stops adding steps after this much wall time
+CPU_EPOCHS_TIMED = 1  # of N_EPOCHS: the update time of the sample is scaled by N_EPOCHS / this
 
 
 def cpu_iteration_rate(env, n_envs, steps, warmup):
@@ -101,31 +102,39 @@ def cpu_iteration_rate(env, n_envs, steps, warmup):
     for _ in range(warmup):
         tr.iteration()
     dec, total, phases = 0, 0.0, {"rollout_s": 0.0, "gae_s": 0.0, "train_s": 0.0}
+    t_begin, done = time.perf_counter(), 0
     for _ in range(steps):
         dec += tr.iteration()
+        done += 1
         t = tr.timing
         total += t["rollout_s"] + t["gae_s"] + t["train_s"] * (N_EPOCHS / CPU_EPOCHS_TIMED)
         for k in phases:
-            phases[k] += t[k] / steps
+            phases[k] += t[k]
+        if time.perf_counter() - t_begin > CPU_BUDGET_S:  # bounded: stop early, report the steps really run
+            break
+    phases = {k: v / done for k, v in phases.items()}
     phases["train_s_scaled_to_10_epochs"] = phases["train_s"] * N_EPOCHS / CPU_EPOCHS_TIMED
-    return dec / total, total / steps, threads, phases
+    return dec / total, total / done, threads, phases, done
 
 
 def cpu_sample_text(args):
     return (f"per step: one train iteration (rollout + GAE + PPO.train of both learners, T={N_STEPS}, "
-            f"{N_MB} minibatches/epoch) at {args.cpu_sample_envs} envs instead of {args.n_envs}; "
-            f"{CPU_EPOCHS_TIMED} of {N_EPOCHS} epochs run, update time scaled x{N_EPOCHS // CPU_EPOCHS_TIMED}; "
-            f"OpenMP C rollout + torch CPU eager update (threads capped at 16: more is slower)")
+            f"{N_MB} minibatches/epoch) at {args.cpu_sample_envs} envs (GPU arm: {args.n_envs}); "
+            f"{CPU_EPOCHS_TIMED} of {N_EPOCHS} epochs run, update time scaled x{N_EPOCHS // CPU_EPOCHS_TIMED} "
+            f"(epochs are identical work); OpenMP C rollout + torch CPU eager update (threads capped at 16: "
+            f"more is slower)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, spi, cores, timing = cpu_iteration_rate(args.env, args.cpu_sample_envs, args.steps, min(args.warmup, 1))
+    args.cpu_sample_envs = args.cpu_sample_envs or args.n_envs
+    rate, spi, cores, timing, done = cpu_iteration_rate(args.env, args.cpu_sample_envs, args.steps, min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": spi * 1e3, "higher_is_better": True,
+        "steps": done, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": spi * 1e3,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.env}-ppo-vs-ppo", "n_envs_per_gpu": args.n_envs, "n_steps": N_STEPS,
                    "n_epochs": N_EPOCHS, "n_minibatches": N_MB},
@@ -139,7 +148,7 @@ def run_reference(args):
 
 def cpu_baseline_subprocess(args):
     """The CPU leg runs in a child with a hard timeout so it can never stall the GPU line."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "0",
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "0",
            "--env", args.env, "--n-envs", str(args.n_envs), "--cpu-sample-envs", str(args.cpu_sample_envs)]
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout.strip().splitlines()
@@ -224,12 +233,13 @@ def run_ours(args):
     marks = []
     launches0 = _lib.LAUNCHES
     decisions = 0
+    # L2 flush between timed steps: 256 MB written (> the 126 MB L2), outside the per-step event brackets
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     with ClockSampler(local) as clk:
         barrier()
         t_wall0 = time.perf_counter()
-        e_start = ev()
-        e_start.record()
         for _ in range(args.steps):
+            flush.fill_(1)
             a, b, c, d = ev(), ev(), ev(), ev()
             a.record()
             tr.collect()
@@ -240,13 +250,11 @@ def run_ours(args):
             d.record()
             marks.append((a, b, c, d))
             decisions += tr.N * tr.T + m_alt
-        e_end = ev()
-        e_end.record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
     clocks = clk.summary()
     launches = _lib.LAUNCHES - launches0
-    ms_total = e_start.elapsed_time(e_end)
+    ms_total = sum(a.elapsed_time(d) for a, b, c, d in marks)  # K steps, device time, flushes excluded
     ph = {"rollout_ms": sum(a.elapsed_time(b) for a, b, c, d in marks) / args.steps,
           "gae_ms": sum(b.elapsed_time(c) for a, b, c, d in marks) / args.steps,
           "update_ms": sum(c.elapsed_time(d) for a, b, c, d in marks) / args.steps}
@@ -326,8 +334,9 @@ def run_ours(args):
                    "n_envs_per_gpu": args.n_envs, "n_steps": N_STEPS, "n_epochs": N_EPOCHS,
                    "n_minibatches": N_MB, "partners": world, "parallelism": f"dp{world}: envs + one partner per GPU, "
                    f"ego replicated, 1 all-gather of packed ego transitions per rollout ({args.exchange}), ego update "
-                   f"{args.ego_update if world > 1 else 'local'}", "l2": "no flush: every step regenerates its rollout "
-                   "buffers on the device and re-reads 177 KB of weights; working set per step ~90 MB"},
+                   f"{args.ego_update if world > 1 else 'local'}", "l2": "flushed between timed steps (256 MB "
+                   "fill outside the per-step CUDA-event brackets); within a step the rollout buffers (~90 MB) are "
+                   "produced and consumed on the device"},
         "phases_ms": ph, "wall_s": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roof, "roofline_dominant": dom, "cpu_baseline": cpu,
     }

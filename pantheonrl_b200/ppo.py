@@ -226,19 +226,44 @@ class PPO:
         return self
 
     # ---------------------------------------------------------------- checkpoint
+    _HYPER = ("learning_rate", "n_steps", "batch_size", "n_epochs", "gamma", "gae_lambda", "clip_range",
+              "normalize_advantage", "ent_coef", "vf_coef", "max_grad_norm", "seed", "n_envs", "verbose",
+              "n_minibatches")
+
     def save(self, path):
-        torch.save({"policy": self.policy.state_dict(), "adam_m": self.adam_m.cpu(), "adam_v": self.adam_v.cpu(),
-                    "adam_step": self.adam_step, "n_updates": self._n_updates,
-                    "hyper": {k: getattr(self, k) for k in ("learning_rate", "n_steps", "batch_size", "n_epochs", "gamma",
-                                                           "gae_lambda", "clip_range", "ent_coef", "vf_coef",
-                                                           "max_grad_norm", "seed")}}, path)
+        """SB3-1.7.0-shaped zip (`data` JSON + policy.pth + policy.optimizer.pth): what
+        trainer.py:419-432 writes and trainer.py:146-151 / PPO.load read."""
+        from . import checkpoint as ck
+        names = [n for n, _ in pol.tensor_shapes(self.space)]
+        return ck.save_zip(
+            path, self.observation_space, self.action_space, {k: getattr(self, k) for k in self._HYPER},
+            self.policy.state_dict(),
+            ck.optimizer_state_dict(names, pol.flat_to_state_dict(self.space, self.adam_m.cpu().numpy()),
+                                    pol.flat_to_state_dict(self.space, self.adam_v.cpu().numpy()),
+                                    self.adam_step, self.learning_rate),
+            {"num_timesteps": self.num_timesteps, "n_updates": self._n_updates, "adam_step": self.adam_step})
 
     @classmethod
-    def load(cls, path, env, **kw):
-        ck = torch.load(path, weights_only=False)
-        m = cls("MlpPolicy", env, **{**ck["hyper"], **kw})
-        m.policy.load_state_dict(ck["policy"])
-        m.adam_m.copy_(ck["adam_m"])
-        m.adam_v.copy_(ck["adam_v"])
-        m.adam_step, m._n_updates = ck["adam_step"], ck["n_updates"]
+    def load(cls, path, env=None, **kw):
+        """PPO.load(path) as trainer.py:149 calls it (no env: the spaces come from the
+        archive) or with an env / keyword overrides like SB3's."""
+        from . import checkpoint as ck
+        c = ck.load_zip(path)
+        if env is None:
+            env = type("_Spaces", (), {"observation_space": c["observation_space"],
+                                       "action_space": c["action_space"]})()
+        m = cls("MlpPolicy", env, **{**c["hyper"], **kw})
+        m.policy.load_state_dict(c["policy"])
+        names = [n for n, _ in pol.tensor_shapes(m.space)]
+        mom_m, mom_v = ck.adam_moments(names, c["optimizer"])
+        if all(v is not None for v in mom_m.values()):
+            m.adam_m.copy_(torch.from_numpy(pol.state_dict_to_flat(m.space, mom_m)))
+            m.adam_v.copy_(torch.from_numpy(pol.state_dict_to_flat(m.space, mom_v)))
+        m.adam_step, m._n_updates = c["counters"]["adam_step"], c["counters"]["n_updates"]
+        m.num_timesteps = c["counters"]["num_timesteps"]
         return m
+
+    def set_env(self, env):
+        """trainer.py:123 (`model.set_env(vec_env)` after a LOAD)."""
+        self.env = env
+        self._last_obs = None
