@@ -207,6 +207,24 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
   }
 }
 
+// tanh applied in place to the NQ float4 a thread has just written itself (no barrier needed),
+// as a rolled loop: the polynomial tanh is ~32 instructions, and 32 inlined copies per layer
+// made the epilogues instruction-fetch bound (ncu: stall_no_inst on every tanh line).
+template <int NQ, typename F>
+__device__ __forceinline__ void tanh_own_quads(float* Out, int tid, F index_of) {
+  (void)tid;
+#pragma unroll 1
+  for (int q = 0; q < NQ; ++q) {
+    float4* o = reinterpret_cast<float4*>(Out + index_of(q));
+    float4 v = *o;
+    v.x = pth_tanhf(v.x);
+    v.y = pth_tanhf(v.y);
+    v.z = pth_tanhf(v.z);
+    v.w = pth_tanhf(v.w);
+    *o = v;
+  }
+}
+
 // First layer, Box observations: X[k][b] (k < F) feature-major in shared memory,
 // W input-major [F][64] in global memory (L1/L2 resident).  Same thread tile as
 // dense64: SPT samples x JT contiguous outputs; Out[j][b] = tanh(bias[j] +
@@ -254,12 +272,11 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
 #pragma unroll
   for (int jj = 0; jj < JT; ++jj) {
     float* o = Out + (ty * JT + jj) * LDA;
-    float v[SPT];
-#pragma unroll
-    for (int ss = 0; ss < SPT; ++ss) v[ss] = pth_tanhf(acc[jj][ss]);
-    *reinterpret_cast<float4*>(o + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    if constexpr (SPT == 8) *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(o + tx * 4) = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+    if constexpr (SPT == 8)
+      *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(acc[jj][4], acc[jj][5], acc[jj][6], acc[jj][7]);
   }
+  tanh_own_quads<JT * (SPT / 4)>(Out, tid, [&](int q) { return (ty * JT + q / (SPT / 4)) * LDA + (q % (SPT / 4)) * 64 + tx * 4; });
 }
 
 // ---------------------------------------------------------------------------
@@ -310,12 +327,12 @@ __device__ __forceinline__ void dense64(const float* A, const float* W, const fl
 #pragma unroll
   for (int jj = 0; jj < JT; ++jj) {
     float* o = Out + (jj * NY + ty) * LDA;
-    float v[SPT];
-#pragma unroll
-    for (int ss = 0; ss < SPT; ++ss) v[ss] = TANH ? pth_tanhf(acc[jj][ss]) : acc[jj][ss];
-    *reinterpret_cast<float4*>(o + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    if constexpr (SPT == 8) *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(o + tx * 4) = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+    if constexpr (SPT == 8)
+      *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(acc[jj][4], acc[jj][5], acc[jj][6], acc[jj][7]);
   }
+  if constexpr (TANH)
+    tanh_own_quads<JT * (SPT / 4)>(Out, tid, [&](int q) { return ((q / (SPT / 4)) * NY + ty) * LDA + (q % (SPT / 4)) * 64 + tx * 4; });
 }
 
 // ---------------------------------------------------------------------------

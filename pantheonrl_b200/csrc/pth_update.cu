@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
   const int c = blockIdx.x;
   const int P = p.lo.total;
   const int64_t n_mb = (p.M + p.BS - 1) / p.BS;
-  float* part = p.part + (size_t)c * P;
+  const int PS = (P + 3) & ~3;  // per-CTA stride of the partial sums: keeps every row 16-byte aligned
+  float* part = p.part + (size_t)c * PS;
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
 
   // ------------------------------------------------ prologue: advantage statistics
@@ -780,7 +781,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           float t[RH];
 #pragma unroll
           for (int u = 0; u < RH; ++u)
-            t[u] = (live && cc0 + u < A) ? __ldcg(p.part + (size_t)(cc0 + u) * P + pi) : 0.f;
+            t[u] = (live && cc0 + u < A) ? __ldcg(p.part + (size_t)(cc0 + u) * PS + pi) : 0.f;
           float g = 0.f;
           if (!second) {
             if (live && A > 0) {
@@ -1020,7 +1021,7 @@ WsLayout ws_layout(int G, int P, int64_t n_stat) {
     o += (bytes + 255) / 256 * 256;
     return r;
   };
-  w.part = take(sizeof(float) * (size_t)G * P);
+  w.part = take(sizeof(float) * (size_t)G * ((P + 3) & ~3));
   w.grad = take(sizeof(float) * P);
   w.norm_part = take(sizeof(float) * G);
   w.stat_part = take(sizeof(float) * (G + 1) * 8);  // + one row: the minibatch sums

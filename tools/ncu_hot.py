@@ -35,3 +35,9 @@ print("total samples", tot)
 for (f, l, src), (n, ins, st) in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
     tops = sorted(st.items(), key=lambda x: -x[1])[:3]
     print(f"{100*n/tot:5.1f}% {f}:{l:>4} inst={ins:>10}  {src}\n         {tops}")
+allst = {}
+for (n, ins, st) in agg.values():
+    for k, v in st.items():
+        allst[k] = allst.get(k, 0) + v
+ts = sum(allst.values())
+print("stall reasons over the kernel:", ", ".join(f"{k[6:]} {100*v/ts:.1f}%" for k, v in sorted(allst.items(), key=lambda x: -x[1])[:10]))

@@ -3,8 +3,12 @@ averaged per minibatch.  usage: python tools/prof_update_phases.py [env N T]"""
 import sys, os
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from pantheonrl_b200 import _lib
+from pantheonrl_b200 import _lib, update as up
 from pantheonrl_b200.engine import VecTrainer, PPOConfig
+
+GRID = int(os.environ.get("PTH_GRID", "0"))  # pin the update grid (0 = auto)
+_orig = up.ppo_update
+up.ppo_update = lambda *a, **k: _orig(*a, **{**k, "grid_ctas": GRID})
 
 NAMES = ["loop head", "weights->smem", "gather+sort", "pi L0", "pi L1", "head+loss", "head wgrad|dz2",
          "pi tower bwd", "vf L0", "vf L1", "value head", "vf tower bwd", "tile stats", "barrier1",
