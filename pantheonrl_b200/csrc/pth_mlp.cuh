@@ -132,7 +132,7 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
 // global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
 // so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
 // ILP.  obs: [BT][32] bytes in shared memory.
-template <bool COHERENT = false, int NTH = NT, int BTS = BT>
+template <bool COHERENT = false, int NTH = NT, int BTS = BT, int SB = 6>
 __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uint8_t* obs_s,
                                                    const float* W,
                                                    const float* bias_s, float* Out, int tid,
@@ -149,9 +149,9 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
     float4 acc[UI];
 #pragma unroll
     for (int u = 0; u < UI; ++u) acc[u] = bv;
-    // slots in blocks of SB: all SB*4 row loads are issued before the adds
+    // slots in blocks of SB (template: 6 at 255 registers per thread, 3 at 128): all SB*4 row
+    // loads are issued before the adds
     // (the adds themselves stay in ascending slot order per sample).
-    constexpr int SB = 6;
     int s0 = 0;
     for (; s0 + SB <= sp.obs_len; s0 += SB) {
       float4 w[SB][UI];

@@ -24,6 +24,11 @@ using namespace pthmlp;
 
 namespace {
 
+// The update CTA runs 512 threads on its 128-sample tile (16 warps = 4 per SM sub-partition,
+// <= 128 registers per thread): every phase is latency bound at this occupancy rather than
+// throughput bound, so twice the warps of the rollout / forward kernels (UNT = 256) pays even
+// though the register tiles get smaller.  Thread tiles only decide WHO computes an output.
+constexpr int UNT = 512;
 constexpr int LDT = 66;  // stride of the transposed dz1 tile [sample][unit] (even: float2 loads)
 constexpr int MAX_SLOTS = 32;
 constexpr int MAX_ROWS = 2048;  // first-layer rows (one-hot feature width) supported by the update
@@ -91,7 +96,7 @@ struct UpdParams {
 
 // The fixed 128-lane tree of the reduction contract: xor-shuffle tree inside
 // each of the first four warps, then the four warp sums left to right.  Threads
-// [128, NT) take part in the barriers only.
+// [128, UNT) take part in the barriers only.
 __device__ __forceinline__ float block_tree(float x, float* red, int tid) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, d);
@@ -134,9 +139,10 @@ __device__ __forceinline__ int64_t sample_offset(const UpdParams& p, int e, int6
 }
 
 // gW[j][k] = sum_b fma(Dz[j][b], Hh[k][b], .)  (64 x 64 outputs, b ascending)
+template <int NTH>
 __device__ __forceinline__ void wgrad64(const float* Dz, const float* Hh, float* gout, bool first,
                                         int tid) {
-  constexpr int NY = NT / 16, JT = HID / NY;
+  constexpr int NY = NTH / 16, JT = HID / NY;
   const int kt = tid & 15, jt = tid >> 4;
   float acc[JT][4];
 #pragma unroll
@@ -231,10 +237,10 @@ __device__ __forceinline__ void row_sums(const float* X, int rows, float* gout, 
 
 // dz1[k][b] = (sum_j fma(W[j][k], Dz[j][b], .)) * (1 - Hact[k][b]^2), stored transposed
 // ([b][LDT], one-hot path: the segmented sums walk samples) or feature-major ([k][LDA], Box path)
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, int NTH>
 __device__ __forceinline__ void backprop64(const float* Dz, const float* W, const float* Hact,
                                            float* outT, int tid) {
-  constexpr int KT = HID / (NT / 16);  // outputs per thread, contiguous (4)
+  constexpr int KT = HID / (NTH / 16);  // outputs per thread, contiguous
   const int tx = tid & 15, ty = tid >> 4;
   float acc[KT][8];
 #pragma unroll
@@ -247,10 +253,15 @@ __device__ __forceinline__ void backprop64(const float* Dz, const float* W, cons
     const float4 a1 = *reinterpret_cast<const float4*>(Dz + j * LDA + 64 + tx * 4);
     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     float w[KT];
+    if constexpr (KT == 2) {
+      const float2 wq = *reinterpret_cast<const float2*>(W + j * LDW + ty * KT);
+      w[0] = wq.x; w[1] = wq.y;
+    } else {
 #pragma unroll
-    for (int q = 0; q < KT / 4; ++q) {
-      const float4 wq = *reinterpret_cast<const float4*>(W + j * LDW + ty * KT + 4 * q);
-      w[4 * q + 0] = wq.x; w[4 * q + 1] = wq.y; w[4 * q + 2] = wq.z; w[4 * q + 3] = wq.w;
+      for (int q = 0; q < KT / 4; ++q) {
+        const float4 wq = *reinterpret_cast<const float4*>(W + j * LDW + ty * KT + 4 * q);
+        w[4 * q + 0] = wq.x; w[4 * q + 1] = wq.y; w[4 * q + 2] = wq.z; w[4 * q + 3] = wq.w;
+      }
     }
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk)
@@ -273,7 +284,7 @@ __device__ __forceinline__ void backprop64(const float* Dz, const float* W, cons
 // tile of wgrad64 with the result stored input-major (the layout of the first-layer matrices).
 __device__ __forceinline__ void wgrad_first_box(const float* Dz, const float* X, int F, float* gout,
                                                 bool first, int tid) {
-  constexpr int NY = NT / 16, JT = HID / NY;
+  constexpr int NY = UNT / 16, JT = HID / NY;
   const int kt = tid & 15, jt = tid >> 4;
   float acc[JT][4];
 #pragma unroll
@@ -308,33 +319,34 @@ __device__ __forceinline__ void wgrad_first_box(const float* Dz, const float* X,
       if (kt + 16 * kk < F) acc_store(gout + (kt + 16 * kk) * HID + (jt + NY * jj), acc[jj][kk], first);
 }
 
-// action head for the whole tile with all NT threads: Lg[l][b] = b_act[l] + sum_k fma(H2[k][b],
-// w_act[l][k], .), k ascending (the chain of dot64).  Warp w owns logits w, w + 8, ... (uniform
+// action head for the whole tile with all UNT threads: Lg[l][b] = b_act[l] + sum_k fma(H2[k][b],
+// w_act[l][k], .), k ascending (the chain of dot64).  Warp w owns logits w, w + NW, ... (uniform
 // per warp: weight reads are broadcasts); lane owns 4 consecutive samples.
 __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& pol, int L, float* Lg,
                                             int tid) {
+  constexpr int NW = UNT / 32, NL = MAXL / NW;  // warps, logits per warp
   const int tx = tid & 31, ty = tid >> 5;
-  float acc[4][4];
+  float acc[NL][4];
 #pragma unroll
-  for (int ll = 0; ll < 4; ++ll) {
-    const int l = ty + 8 * ll;
+  for (int ll = 0; ll < NL; ++ll) {
+    const int l = ty + NW * ll;
     const float bl = l < L ? pol.b_act[l] : 0.f;
 #pragma unroll
     for (int ss = 0; ss < 4; ++ss) acc[ll][ss] = bl;
   }
 #pragma unroll 4
   for (int k0 = 0; k0 < HID; k0 += 4) {
-    float4 w[4];
+    float4 w[NL];
 #pragma unroll
-    for (int ll = 0; ll < 4; ++ll) {
-      const int l = ty + 8 * ll;
+    for (int ll = 0; ll < NL; ++ll) {
+      const int l = ty + NW * ll;
       w[ll] = l < L ? *reinterpret_cast<const float4*>(pol.w_act + l * LDW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(Hh + (k0 + kk) * LDA + tx * 4);
 #pragma unroll
-      for (int ll = 0; ll < 4; ++ll) {
+      for (int ll = 0; ll < NL; ++ll) {
         const float wk = kk == 0 ? w[ll].x : (kk == 1 ? w[ll].y : (kk == 2 ? w[ll].z : w[ll].w));
         acc[ll][0] = fmaf(a.x, wk, acc[ll][0]);
         acc[ll][1] = fmaf(a.y, wk, acc[ll][1]);
@@ -344,8 +356,8 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
     }
   }
 #pragma unroll
-  for (int ll = 0; ll < 4; ++ll) {
-    const int l = ty + 8 * ll;
+  for (int ll = 0; ll < NL; ++ll) {
+    const int l = ty + NW * ll;
     if (l < L)
       *reinterpret_cast<float4*>(Lg + l * LDA + tx * 4) = make_float4(acc[ll][0], acc[ll][1], acc[ll][2], acc[ll][3]);
   }
@@ -357,7 +369,7 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
 __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* obs_s, uint8_t* order,
                                            uint8_t* rcount, int nb, int tid) {
   const int lane = tid & 31, wid = tid >> 5;
-  for (int s = wid; s < p.sp.obs_len; s += NT / 32) {
+  for (int s = wid; s < p.sp.obs_len; s += UNT / 32) {
     int val[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -389,7 +401,7 @@ __device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* ord
                                           const uint8_t* rcount, const float* dzT, float* gW0,
                                           bool first, int tid) {
   const int jp = (tid & 31) * 2, wid = tid >> 5;
-  for (int s = wid; s < p.sp.obs_len; s += NT / 32) {
+  for (int s = wid; s < p.sp.obs_len; s += UNT / 32) {
     const int row0 = p.sp.slot_off[s];
     const int nv = p.nvec[s];
     const uint8_t* ord = order + s * BT;
@@ -426,26 +438,33 @@ __device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* ord
   }
 }
 
-// body of one tower after dz2 (in sm.D1) is known
+// body of one tower after dz2 (in sm.D1) is known; Ha = the tower's first-layer activations.
+// The hidden-layer weight gradient (D1 x Ha^T) and the back-propagation through the hidden layer
+// (W^T x D1) only READ D1 / Ha, so they run side by side: each on one half of the CTA with the
+// large register tiles of a 256-thread group (the 512-thread tiles are shared-memory bound).
 template <bool BOX>
 __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, const float* Xs,
-                                               const float* w1_s, float* g_w0, float* g_b0,
-                                               float* g_w1, float* g_b1, int nb, bool first, int tid,
-                                               long long& prof_last, int c, int pbase) {
+                                               const float* Ha, const float* w1_s, float* g_w0,
+                                               float* g_b0, float* g_w1, float* g_b1, int nb,
+                                               bool first, int tid, long long& prof_last, int c,
+                                               int pbase) {
   __syncthreads();  // D1 complete
-  wgrad64(sm.D1, sm.H1, g_w1, first, tid);
-  row_sums(sm.D1, HID, g_b1, first, tid, 64);
-  PTH_PROF(pbase + 0);  // wgrad64 + bias sums
-  backprop64<!BOX>(sm.D1, w1_s, sm.H1, sm.H2, tid);
+  PTH_PROF(pbase + 0);
+  if (tid < UNT / 2) {
+    backprop64<!BOX, UNT / 2>(sm.D1, w1_s, Ha, sm.H2, tid);
+  } else {
+    wgrad64<UNT / 2>(sm.D1, Ha, g_w1, first, tid - UNT / 2);
+    row_sums(sm.D1, HID, g_b1, first, tid, UNT - HID);
+  }
   __syncthreads();  // dz1 complete (in H2)
-  PTH_PROF(pbase + 1);  // backprop64
+  PTH_PROF(pbase + 1);  // backprop64 | wgrad64 + bias sums
   if constexpr (BOX) {
-    row_sums(sm.H2, HID, g_b0, first, tid, NT - HID);
+    row_sums(sm.H2, HID, g_b0, first, tid, UNT - HID);
     wgrad_first_box(sm.H2, Xs, p.sp.F, g_w0, first, tid);
     return;
   }
-  if (tid >= NT - HID) {
-    const int j = tid - (NT - HID);
+  if (tid >= UNT - HID) {
+    const int j = tid - (UNT - HID);
     float s = 0.f;
     for (int b = 0; b < BT; ++b) s = s + sm.H2[b * LDT + j];
     acc_store(g_b0 + j, s, first);
@@ -455,10 +474,14 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, 
 }
 
 template <bool BOX>
-__global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
+__global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UpdSmem& sm = *reinterpret_cast<UpdSmem*>(smem_raw);
-  float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(UpdSmem));  // BOX only: X[64][LDA]
+  // one more [64][LDA] tile behind the struct.  BOX: the observation rows, feature major (Xs).
+  // One-hot: the value tower's first-layer activations (V1), computed next to the policy
+  // tower's at the start of the tile and kept until the value tower runs.
+  float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(UpdSmem));
+  float* V1 = BOX ? sm.H1 : Xs;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int G = gridDim.x;
@@ -477,7 +500,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
     const int64_t B = (i0 + p.BS <= p.M) ? p.BS : (p.M - i0);
     float mean = 0.f, stdv = 0.f;
     if (p.normalize && B > 1) {
-      // 128 strided lanes (reduction contract), threads [BT, NT) idle here
+      // 128 strided lanes (reduction contract), threads [BT, UNT) idle here
       float s = 0.f;
       if (tid < BT)
         for (int64_t i = tid; i < B; i += BT)
@@ -520,7 +543,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
 
       PTH_PROF(0);  // loop head (prologue on the first pass)
       __syncthreads();
-      load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, NT);
+      load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, UNT);
       PTH_PROF(1);  // weights -> smem
       float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       bool first = true;
@@ -533,36 +556,41 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         uint32_t act = 0;
         float adv = 0.f, oldlp = 0.f, ret = 0.f;
         uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
-        float4 xrow[8];  // BOX: 32 of the sample's 64 row floats (threads b and b + 128 share a sample)
+        constexpr int XQ = 16 / (UNT / BT);  // BOX: float4 of the sample's 64-float row per thread
+        float4 xrow[XQ];                     // (threads b, b + 128, ... share sample b)
         if constexpr (BOX) {
           const int b = tid & (BT - 1);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < XQ; ++i) xrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (b < nb) {
             const int64_t offb = sample_offset(p, e, i0 + t0 + b);
-            const float4* q = reinterpret_cast<const float4*>(p.obs + offb * p.obs_stride) + (tid >> 7) * 8;
+            const float4* q = reinterpret_cast<const float4*>(p.obs + offb * p.obs_stride) + (tid >> 7) * XQ;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xrow[i] = __ldg(q + i);
+            for (int i = 0; i < XQ; ++i) xrow[i] = __ldg(q + i);
           }
         }
-        if (valid) {
-          const int64_t off = sample_offset(p, e, i0 + t0 + tid);
+        const int sb = tid & (BT - 1);  // the sample this thread works on in the per-sample phases
+        const bool svalid = sb < nb;
+        if (svalid) {
+          const int64_t off = sample_offset(p, e, i0 + t0 + sb);
           if constexpr (!BOX) {
-            const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
-            o0 = __ldg(q);
-            o1 = __ldg(q + 1);
+            if (valid) {
+              const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
+              o0 = __ldg(q);
+              o1 = __ldg(q + 1);
+            }
           }
           act = *reinterpret_cast<const uint32_t*>(p.actions + off * p.act_stride);
           adv = *reinterpret_cast<const float*>(p.adv + off * p.f_stride);
           oldlp = *reinterpret_cast<const float*>(p.old_logp + off * p.f_stride);
-          ret = *reinterpret_cast<const float*>(p.ret + off * p.f_stride);
+          if (valid) ret = *reinterpret_cast<const float*>(p.ret + off * p.f_stride);
         }
         const bool lane = tid < BT;  // threads [0, BT) own one sample each
         __syncthreads();  // previous tile done with sm.obs / Xs / Lg / H2
         if constexpr (BOX) {
-          const int b = tid & (BT - 1), k0 = (tid >> 7) * 32;
+          const int b = tid & (BT - 1), k0 = (tid >> 7) * (4 * XQ);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < XQ; ++i) {
             const float v[4] = {xrow[i].x, xrow[i].y, xrow[i].z, xrow[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -579,58 +607,70 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
         PTH_PROF(2);  // gather + slot sort
 
         // ================= policy tower: forward
-        if constexpr (BOX)
-          first_layer_box<true>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
-        else
-          first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
+        if constexpr (BOX) {
+          first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
+        } else {
+          // both towers' first layers (latency-bound row gathers) side by side, one per CTA half
+          if (tid < UNT / 2)
+            first_layer_onehot<true, UNT / 2, BT, 3>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1,
+                                                      tid);
+          else
+            first_layer_onehot<true, UNT / 2, BT, 3>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, V1,
+                                                      tid - UNT / 2);
+        }
         __syncthreads();
-        PTH_PROF(3);  // pi first layer
-        dense64<true>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
+        PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
+        dense64<true, UNT>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
         __syncthreads();
         PTH_PROF(4);  // pi hidden layer
         float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
         logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
         __syncthreads();
-        if (lane) {
-          // ---- per-sample losses and d loss / d logits (own column of Lg).  Same values as
-          // dist_eval (pth_mlp.cuh) evaluates, with every exp computed once: the softmax
-          // probabilities are parked in the own column of sm.D1 (free until dz2 is written).
+        {
+          // ---- per-sample losses and d loss / d logits.  Thread group h (threads [128h, 128h + 128))
+          // evaluates head h of sample sb: same values as dist_eval (pth_mlp.cuh), with every exp
+          // computed once (the softmax probabilities are parked in the sample's column of sm.D1,
+          // free until dz2 is written).  The heads' log-probs / entropies meet in rows 32.. of D1
+          // and every group adds them in head order, as the one-thread-per-sample version did.
+          static_assert(UNT / BT >= PTH_MAX_HEADS, "one thread group per head");
           float* Pr = sm.D1;
-          float h_m[PTH_MAX_HEADS], h_logS[PTH_MAX_HEADS], h_ent[PTH_MAX_HEADS];
+          float* hs = sm.D1 + MAXL * LDA;  // [2 * PTH_MAX_HEADS][LDA] scratch
+          const int hh = tid >> 7;
+          const bool mine = hh < p.sp.n_heads;
+          int off = 0, n = 0, a_h = 0;
+          float mx = 0.f, logS = 0.f, ent = 0.f;
+          if (mine) {
+            for (int h = 0; h < hh; ++h) off += p.sp.head_n[h];
+            n = p.sp.head_n[hh];
+            a_h = (int)((act >> (8 * hh)) & 0xffu);
+            mx = sm.Lg[off * LDA + sb];
+            for (int i = 1; i < n; ++i) {
+              const float z = sm.Lg[(off + i) * LDA + sb];
+              mx = z > mx ? z : mx;
+            }
+            float Ssum = 0.f;
+            for (int i = 0; i < n; ++i) {
+              const float ex = pth_expf(sm.Lg[(off + i) * LDA + sb] - mx);
+              Pr[(off + i) * LDA + sb] = ex;
+              Ssum = Ssum + ex;
+            }
+            logS = pth_logf(Ssum);
+            for (int i = 0; i < n; ++i) {
+              const float lp = (sm.Lg[(off + i) * LDA + sb] - mx) - logS;
+              const float pi = Pr[(off + i) * LDA + sb] / Ssum;
+              Pr[(off + i) * LDA + sb] = pi;
+              ent = fmaf(-pi, lp, ent);
+            }
+            hs[hh * LDA + sb] = (sm.Lg[(off + a_h) * LDA + sb] - mx) - logS;
+            hs[(PTH_MAX_HEADS + hh) * LDA + sb] = ent;
+          }
+          __syncthreads();
           float logp = 0.f, entropy = 0.f;
-          {
-            int off = 0;
 #pragma unroll
-            for (int h = 0; h < PTH_MAX_HEADS; ++h) {
-              if (h < p.sp.n_heads) {
-                const int n = p.sp.head_n[h];
-                const int a_h = (int)((act >> (8 * h)) & 0xffu);
-                float mx = sm.Lg[off * LDA + tid];
-                for (int i = 1; i < n; ++i) {
-                  const float z = sm.Lg[(off + i) * LDA + tid];
-                  mx = z > mx ? z : mx;
-                }
-                float Ssum = 0.f;
-                for (int i = 0; i < n; ++i) {
-                  const float ex = pth_expf(sm.Lg[(off + i) * LDA + tid] - mx);
-                  Pr[(off + i) * LDA + tid] = ex;
-                  Ssum = Ssum + ex;
-                }
-                const float logS = pth_logf(Ssum);
-                float ent = 0.f;
-                for (int i = 0; i < n; ++i) {
-                  const float lp = (sm.Lg[(off + i) * LDA + tid] - mx) - logS;
-                  const float pi = Pr[(off + i) * LDA + tid] / Ssum;
-                  Pr[(off + i) * LDA + tid] = pi;
-                  ent = fmaf(-pi, lp, ent);
-                }
-                h_m[h] = mx;
-                h_logS[h] = logS;
-                h_ent[h] = ent;
-                logp = logp + ((sm.Lg[(off + a_h) * LDA + tid] - mx) - logS);
-                entropy = entropy + ent;
-                off += n;
-              }
+          for (int h = 0; h < PTH_MAX_HEADS; ++h) {
+            if (h < p.sp.n_heads) {
+              logp = logp + hs[h * LDA + sb];
+              entropy = entropy + hs[(PTH_MAX_HEADS + h) * LDA + sb];
             }
           }
           if (norm) adv = (adv - mean) / (stdv + 1e-8f);
@@ -641,48 +681,44 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           const float pl2 = adv * rc;
           const bool inside = ratio >= clip_lo && ratio <= clip_hi;
           const bool gmask = inside || (pl1 < pl2);
-          const float glp = (valid && gmask) ? -((adv * ratio) * invB) : 0.f;
-          const float gH = valid ? -(p.ent_coef * invB) : 0.f;
-          s_pl = valid ? fminf(pl1, pl2) : 0.f;
-          s_e = valid ? entropy : 0.f;
-          s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
-          s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
-          int off = 0;
-#pragma unroll
-          for (int h = 0; h < PTH_MAX_HEADS; ++h) {
-            if (h < p.sp.n_heads) {
-              const int n = p.sp.head_n[h];
-              const int a_h = (int)((act >> (8 * h)) & 0xffu);
-              const float mx = h_m[h], logS = h_logS[h], Hh = h_ent[h];
-              for (int i = 0; i < n; ++i) {
-                const float zi = sm.Lg[(off + i) * LDA + tid];
-                const float lp = (zi - mx) - logS;
-                const float pi = Pr[(off + i) * LDA + tid];
-                const float t1 = (i == a_h ? 1.0f : 0.0f) - pi;
-                const float dzv = glp * t1;
-                const float t2 = (gH * pi) * (lp + Hh);
-                sm.Lg[(off + i) * LDA + tid] = dzv - t2;
-              }
-              off += n;
+          const float glp = (svalid && gmask) ? -((adv * ratio) * invB) : 0.f;
+          const float gH = svalid ? -(p.ent_coef * invB) : 0.f;
+          if (lane) {
+            s_pl = valid ? fminf(pl1, pl2) : 0.f;
+            s_e = valid ? entropy : 0.f;
+            s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
+            s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
+          }
+          if (mine) {
+            for (int i = 0; i < n; ++i) {
+              const float zi = sm.Lg[(off + i) * LDA + sb];
+              const float lp = (zi - mx) - logS;
+              const float pi = Pr[(off + i) * LDA + sb];
+              const float t1 = (i == a_h ? 1.0f : 0.0f) - pi;
+              const float dzv = glp * t1;
+              const float t2 = (gH * pi) * (lp + ent);
+              sm.Lg[(off + i) * LDA + sb] = dzv - t2;
             }
           }
         }
         __syncthreads();  // dlogits complete
         PTH_PROF(5);  // action head + losses + dlogits
         // ================= policy tower: backward
-        // upper half: head weight / bias gradients; lower half: dz2 of each sample
-        if (!lane) {
-          head_wgrad(sm.Lg, sm.H2, p.sp.L, part + p.lo.w_act, first, tid - BT);
-          row_sums(sm.Lg, p.sp.L, part + p.lo.b_act, first, tid, BT + 96);
+        // upper half: head weight / bias gradients; lower half: dz2, two threads per sample
+        // (32 hidden units each; every dz2[k][b] is still one fma chain over the logits, ascending)
+        if (tid >= UNT / 2) {
+          head_wgrad(sm.Lg, sm.H2, p.sp.L, part + p.lo.w_act, first, tid - UNT / 2);
+          row_sums(sm.Lg, p.sp.L, part + p.lo.b_act, first, tid, UNT - MAXL);
         } else {
-          float acc[HID];
+          const int kb = (tid >> 7) * (HID / 2);
+          float acc[HID / 2];
 #pragma unroll
-          for (int k = 0; k < HID; ++k) acc[k] = 0.f;
+          for (int k = 0; k < HID / 2; ++k) acc[k] = 0.f;
           for (int l = 0; l < p.sp.L; ++l) {
-            const float d = sm.Lg[l * LDA + tid];
+            const float d = sm.Lg[l * LDA + sb];
 #pragma unroll
-            for (int k0 = 0; k0 < HID; k0 += 4) {
-              const float4 w = *reinterpret_cast<const float4*>(sm.pol.w_act + l * LDW + k0);
+            for (int k0 = 0; k0 < HID / 2; k0 += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(sm.pol.w_act + l * LDW + kb + k0);
               acc[k0 + 0] = fmaf(w.x, d, acc[k0 + 0]);
               acc[k0 + 1] = fmaf(w.y, d, acc[k0 + 1]);
               acc[k0 + 2] = fmaf(w.z, d, acc[k0 + 2]);
@@ -690,25 +726,24 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
             }
           }
 #pragma unroll
-          for (int k = 0; k < HID; ++k) {
-            const float h = sm.H2[k * LDA + tid];
-            sm.D1[k * LDA + tid] = acc[k] * (1.0f - h * h);
+          for (int k = 0; k < HID / 2; ++k) {
+            const float h = sm.H2[(kb + k) * LDA + sb];
+            sm.D1[(kb + k) * LDA + sb] = acc[k] * (1.0f - h * h);
           }
         }
         PTH_PROF(6);  // head wgrad | dz2
-        tower_backward<BOX>(p, sm, Xs, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
+        tower_backward<BOX>(p, sm, Xs, sm.H1, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
                             part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid, prof_last, c, 18);
         PTH_PROF(7);  // pi tower backward (wgrad64, backprop64, first-layer gradient)
 
         // ================= value tower
         __syncthreads();
-        if constexpr (BOX)
-          first_layer_box<true>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
-        else
-          first_layer_onehot<true>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
-        __syncthreads();
-        PTH_PROF(8);  // vf first layer
-        dense64<true>(sm.H1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
+        if constexpr (BOX) {
+          first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
+          __syncthreads();
+        }
+        PTH_PROF(8);  // vf first layer (one-hot: done with the policy tower's)
+        dense64<true, UNT>(V1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
         __syncthreads();
         PTH_PROF(9);  // vf hidden layer
         if (lane) {
@@ -742,16 +777,29 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           acc_store(part + p.lo.b_val, s, first);
         }
         PTH_PROF(10);  // value head + its gradients
-        tower_backward<BOX>(p, sm, Xs, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
+        tower_backward<BOX>(p, sm, Xs, V1, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
                             part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid, prof_last, c, 20);
         PTH_PROF(11);  // vf tower backward
 
-        // ---- tile statistics
-        const float ts[5] = {block_tree(s_pl, sm.red, tid), block_tree(s_v, sm.red, tid),
-                             block_tree(s_e, sm.red, tid), block_tree(s_kl, sm.red, tid),
-                             block_tree(s_cf, sm.red, tid)};
+        // ---- tile statistics: the five 128-lane trees of the contract in one pass (xor tree inside
+        // each of the first four warps, then the four warp sums left to right)
+        {
+          float sv[5] = {s_pl, s_v, s_e, s_kl, s_cf};
 #pragma unroll
-        for (int i = 0; i < 5; ++i) cta_stat[i] = first ? ts[i] : cta_stat[i] + ts[i];
+          for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) sv[i] = sv[i] + __shfl_xor_sync(0xffffffffu, sv[i], d);
+          __syncthreads();  // sm.bc may still be read (norm partials of the previous minibatch)
+          if ((tid & 31) == 0 && tid < BT)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sm.bc[i * 4 + (tid >> 5)] = sv[i];
+          __syncthreads();
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float ts = ((sm.bc[i * 4] + sm.bc[i * 4 + 1]) + sm.bc[i * 4 + 2]) + sm.bc[i * 4 + 3];
+            cta_stat[i] = first ? ts : cta_stat[i] + ts;
+          }
+        }
         first = false;
       }
       if (tid < 5) p.stat_part[c * 8 + tid] = cta_stat[tid];
@@ -760,20 +808,21 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       PTH_PROF(13);  // barrier 1 (includes waiting for the slowest CTA)
 
       // ---- ordered reduction of this CTA's parameter slice + squared-norm partial.
-      // 128 parameters per pass, two threads per parameter: the upper half of the CTA fetches and
-      // adds partials [0, RH) left to right, the lower half fetches partials [RH, A) AT THE SAME TIME
-      // (up to 80 L2 loads in flight per thread, one round trip per pass), picks the running sum up
-      // through shared memory and continues the same left-to-right chain — the order of the
-      // additions is the contract's CTA order.  Lane t < 128 ends up with parameters t, t + 128, ...
-      // of the slice, which is exactly the lane assignment of the squared-norm contract.
+      // 128 parameters per pass, UNT / 128 threads per parameter: thread group k (threads [128k,
+      // 128k + 128)) fetches RH consecutive partials of its parameter, all groups AT THE SAME TIME
+      // (RH L2 loads in flight per thread, one round trip per pass); the highest group adds
+      // partials [0, RH) left to right, hands the running sum down through shared memory, and so on
+      // until group 0 has added the last ones — the order of the additions is the contract's CTA
+      // order.  Lane t < 128 ends up with parameters t, t + 128, ... of the slice, which is exactly
+      // the lane assignment of the squared-norm contract.
       float q = 0.f;
       const int par = (int)(id & 1);
       {
-        constexpr int RH = 80;  // max co-resident CTAs is 160
-        float* gs = sm.H1;      // hand-over scratch (H1 is free between tiles)
+        constexpr int NG = UNT / BT, RH = 160 / NG;  // max co-resident CTAs is 160
+        float* gs = sm.H1;                           // hand-over scratch (H1 is free between tiles)
         const int li = tid & (BT - 1);
-        const bool second = tid < BT;
-        const int cc0 = second ? RH : 0;
+        const int turn = NG - 1 - (tid >> 7);  // position of this thread's group in the chain
+        const int cc0 = turn * RH;
         for (int i0c = 0; i0c < S; i0c += BT) {
           const int i = i0c + li;
           const int pi = c * S + i;
@@ -783,19 +832,25 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
           for (int u = 0; u < RH; ++u)
             t[u] = (live && cc0 + u < A) ? __ldcg(p.part + (size_t)(cc0 + u) * PS + pi) : 0.f;
           float g = 0.f;
-          if (!second) {
-            if (live && A > 0) {
-              g = t[0];
 #pragma unroll
-              for (int u = 1; u < RH; ++u) g = (u < A) ? g + t[u] : g;
+          for (int ph = 0; ph < NG; ++ph) {
+            if (turn == ph) {
+              if (ph > 0) g = gs[li];
+              if (ph == 0) {
+                if (live && A > 0) {
+                  g = t[0];
+#pragma unroll
+                  for (int u = 1; u < RH; ++u) g = (u < A) ? g + t[u] : g;
+                }
+              } else {
+#pragma unroll
+                for (int u = 0; u < RH; ++u) g = (ph * RH + u < A) ? g + t[u] : g;
+              }
+              if (ph < NG - 1) gs[li] = g;
             }
-            gs[li] = g;
+            if (ph < NG - 1) __syncthreads();
           }
-          __syncthreads();
-          if (second) {
-            g = gs[li];
-#pragma unroll
-            for (int u = 0; u < RH; ++u) g = (RH + u < A) ? g + t[u] : g;
+          if (turn == NG - 1) {  // threads [0, 128): the finished sums
             if (live) {
               if (W == 1) {
                 p.grad[pi] = g;
@@ -871,7 +926,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       PTH_PROF(15);  // barrier 2
 
       __syncthreads();
-      for (int cc = tid; cc < G; cc += NT) sm.bc[cc] = __ldcg(p.norm_part + cc);
+      for (int cc = tid; cc < G; cc += UNT) sm.bc[cc] = __ldcg(p.norm_part + cc);
       __syncthreads();
       float total_sq = sm.bc[0];
       for (int cc = 1; cc < G; ++cc) total_sq = total_sq + sm.bc[cc];
@@ -882,7 +937,7 @@ __global__ void __launch_bounds__(NT) ppo_update_kernel(const __grid_constant__ 
       b2pow *= (double)p.b2;
       const float step_size = (float)((double)p.lr / (1.0 - b1pow));
       const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
-      for (int i = tid; i < S; i += NT) {
+      for (int i = tid; i < S; i += UNT) {
         const int pi = c * S + i;
         if (pi < P) {
           const float g = p.grad[pi] * coef;
@@ -1030,7 +1085,7 @@ WsLayout ws_layout(int G, int P, int64_t n_stat) {
   return w;
 }
 
-constexpr size_t SMEM_ONEHOT = sizeof(UpdSmem);
+constexpr size_t SMEM_ONEHOT = sizeof(UpdSmem) + sizeof(float) * HID * LDA;
 constexpr size_t SMEM_BOX = sizeof(UpdSmem) + sizeof(float) * HID * LDA;
 
 int max_coop_ctas(const pth_ctx* ctx, bool box = false) {
@@ -1040,7 +1095,7 @@ int max_coop_ctas(const pth_ctx* ctx, bool box = false) {
     const size_t smem = box ? SMEM_BOX : SMEM_ONEHOT;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, smem) != cudaSuccess) per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, UNT, smem) != cudaSuccess) per_sm = 0;
     cached[box] = per_sm * ctx->sm_count;
   }
   return cached[box];
@@ -1195,10 +1250,10 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
 
   void* kargs[] = {(void*)&p};
   if (box)
-    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<true>, dim3(G), dim3(NT), kargs, SMEM_BOX,
+    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<true>, dim3(G), dim3(UNT), kargs, SMEM_BOX,
                                          (cudaStream_t)stream));
   else
-    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<false>, dim3(G), dim3(NT), kargs,
+    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<false>, dim3(G), dim3(UNT), kargs,
                                          SMEM_ONEHOT, (cudaStream_t)stream));
   return PTH_OK;
 }
