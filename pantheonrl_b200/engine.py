@@ -61,7 +61,8 @@ class Learner:
 class VecTrainer:
     def __init__(self, env_kind, n_envs, ego_cfg=None, alt_cfg=None, seed=10, partner="ppo",
                  probegostart=0.5, device="cuda", env0=0, group=None, exchange="nccl",
-                 ego_update="sharded", layout="simple", ego_agent_idx=0, horizon=None):
+                 ego_update="sharded", layout="simple", ego_agent_idx=0, horizon=None,
+                 concurrent_updates=True):
         """group: a torch.distributed process group for one-partner-per-GPU sharding
         (SURVEY.md 8e): every rank owns n_envs envs and its own partner, the ego is
         replicated; per rollout the ranks all-gather their packed ego transitions and
@@ -71,11 +72,15 @@ class VecTrainer:
         ego_update: "sharded" — rank r computes every world-th tile of each global
         minibatch and the per-rank gradient sums are exchanged through peer memory inside
         the update kernel (added in rank order: replicas stay bit-identical);
-        "replicated" — every rank computes the whole update redundantly."""
+        "replicated" — every rank computes the whole update redundantly.
+        concurrent_updates: run the partner's update kernel next to the ego's (see train())."""
         if not torch.cuda.is_available():
             raise _lib.PthError("VecTrainer needs a CUDA device: the hot path has no CPU implementation")
         self.env_kind, self.N, self.seed = env_kind, int(n_envs), int(seed)
         self.device, self.env0, self.probegostart = device, env0, probegostart
+        self.concurrent_updates = bool(concurrent_updates)
+        self._side_stream = torch.cuda.Stream(device=device)
+        self.last_grids = (0, 0)
         self.space = ro.space_for(env_kind)
         self.d_layout, box, state_bytes = None, False, 32
         if env_kind == "overcooked":  # config 4: OvercookedMultiEnv-v0, Box(62) observations
@@ -181,7 +186,26 @@ class VecTrainer:
             ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_last_done,
                            ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
 
-    def _train_one(self, learner, buf, index, M, perm, ws, stream_id, packed=None, peers=None):
+    def plan_grids(self, M_ego, M_alt):
+        """CTAs for the two learners' update kernels when they run side by side.
+
+        Each update is one persistent cooperative kernel with one CTA per SM; a minibatch has
+        ceil(batch / 128) tiles (a rank of a sharded ego update computes every world-th one).
+        If both fit on the device at one tile per CTA they simply get their tiles; otherwise
+        every CTA runs k tiles per minibatch and the SMs are split in proportion.  The grid is
+        part of the update's reduction contract, so it is recorded in
+        ``last_grids`` for whoever replays the update on the oracle."""
+        cap = up.update_grid(self.space, 1 << 30, 1 << 30, device=torch.device(self.device).index or 0)
+        tiles = lambda M, bs, w: -(-(-(-min(bs, M) // 128)) // w)  # noqa: E731
+        sharded = self.world > 1 and getattr(self, "peers", None) is not None
+        te = tiles(M_ego, self.ego.batch_size_for(M_ego), self.world if sharded else 1)
+        ta = tiles(M_alt, self.alt.batch_size_for(M_alt), 1)
+        k = max(1, -(-(te + ta) // cap))
+        while -(-te // k) + -(-ta // k) > cap:
+            k += 1
+        return max(1, -(-te // k)), max(1, -(-ta // k))
+
+    def _train_one(self, learner, buf, index, M, perm, ws, stream_id, packed=None, peers=None, grid=0):
         cfg = learner.cfg
         up.perm_feistel(M, cfg.n_epochs, self.seed, stream_id, epoch0=learner.n_updates, out=perm)
         bs = learner.batch_size_for(M)
@@ -194,7 +218,7 @@ class VecTrainer:
             *arrays, perm, bs, ws, index=index, rec_stride=stride, peers=peers,
             M=M, learning_rate=cfg.learning_rate, clip_range=cfg.clip_range, ent_coef=cfg.ent_coef,
             vf_coef=cfg.vf_coef, max_grad_norm=cfg.max_grad_norm,
-            normalize_advantage=cfg.normalize_advantage)
+            normalize_advantage=cfg.normalize_advantage, grid_ctas=grid)
         n_mb = -(-M // bs)
         learner.adam_step += cfg.n_epochs * n_mb
         learner.n_updates += cfg.n_epochs
@@ -202,23 +226,35 @@ class VecTrainer:
         return stats
 
     def train(self):
+        """PPO.train for both learners.  They are independent (own parameters, own buffers, own
+        shuffle streams), so with ``concurrent_updates`` the partner's update kernel runs on a
+        side stream next to the ego's, each on its share of the SMs (plan_grids)."""
         packed = None
         if self.world > 1:
             self.exchange_ego()
             packed = self.gather
-        self._train_one(self.ego, self.ego_buf, self.ego_index, self.ego_M, self.ego_perm,
-                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO, packed=packed,
-                        peers=getattr(self, "peers", None) if self.world > 1 else None)
+        peers = getattr(self, "peers", None) if self.world > 1 else None
+        M = 0
         if self.alt is not None:
             a = self.alt_buf
             index, total = up.index_build(a.count, a.Tcap, self.N, device=self.device)
             M = int(total.item())  # the one host read-back per train(): ragged sample count
             self.partner_decisions += M
-            if M > 0:
-                perm = self.alt_perm_store[: self.alt_cfg.n_epochs * M].view(self.alt_cfg.n_epochs, M)
-                self._train_one(self.alt, a, index, M, perm, self.alt_ws, _lib.STREAM_SHUFFLE_ALT)
-            return M
-        return 0
+        both = self.alt is not None and M > 0
+        g_ego, g_alt = self.plan_grids(self.ego_M, M) if both and self.concurrent_updates else (0, 0)
+        self.last_grids = (g_ego, g_alt)
+        cur = torch.cuda.current_stream()
+        if both:
+            perm = self.alt_perm_store[: self.alt_cfg.n_epochs * M].view(self.alt_cfg.n_epochs, M)
+            side = self._side_stream if self.concurrent_updates else cur
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._train_one(self.alt, a, index, M, perm, self.alt_ws, _lib.STREAM_SHUFFLE_ALT, grid=g_alt)
+        self._train_one(self.ego, self.ego_buf, self.ego_index, self.ego_M, self.ego_perm,
+                        self.ego_ws, _lib.STREAM_SHUFFLE_EGO, packed=packed, peers=peers, grid=g_ego)
+        if both:
+            cur.wait_stream(side)
+        return M
 
     def iteration(self):
         """collect -> GAE -> train for both agents. Returns agent decisions made."""
