@@ -50,6 +50,32 @@ def test_update_bit_exact_vs_oracle(ctx, kw, M, BS, E, grid):
     assert np.array_equal(gp, op), np.abs(gp - op).max()
 
 
+def test_subnormal_partial_sums_follow_red_add_semantics(ctx):
+    """Later tiles of a CTA are added with RED.ADD.F32, which flushes subnormal inputs and
+    results to zero; the oracle restates that.  Advantages of ~1e-33 with vf_coef = ent_coef = 0
+    put the policy-side gradient partials around FLT_MIN: some normal, some subnormal (and there
+    are several tiles per CTA)."""
+    kw = oracle.LIAR_SPACE
+    M, BS, E, grid = 1024, 1024, 1, 2  # 8 tiles on 2 CTAs
+    space = oracle.make_space(**kw)
+    pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=11)
+    params = pol.to_flat().copy()
+    obs, act, old_logp, adv, ret = make_batch(kw, M, seed=11)
+    adv = (adv * np.float32(1e-33)).astype(np.float32)
+    ev = oracle.policy_forward(space, params, obs, action_in=act)
+    old_logp = ev["logp"].astype(np.float32)
+    perm = oupd.perm_feistel(M, E, seed=10, stream=4)
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    hp = dict(ent_coef=0.0, vf_coef=0.0, normalize_advantage=False)
+    gp, gm, gv, gst = run_gpu(kw, params, m, v, 0, obs, act, old_logp, adv, ret, perm, BS, grid, **hp)
+    op, om, ov = params.copy(), m.copy(), v.copy()
+    ost, _ = oupd.ppo_update(space, op, om, ov, 0, obs, act, old_logp, adv, ret, perm, BS, grid, **hp)
+    assert np.array_equal(gm, om) and np.array_equal(gv, ov)
+    assert np.array_equal(gp, op) and np.array_equal(gst, ost)
+    tiny = np.abs(gm[gm != 0])
+    assert tiny.size and tiny.min() < 1e-36  # the regime was reached: first moments are that small
+
+
 def test_update_matches_torch_autograd(ctx):
     kw = oracle.LIAR_SPACE
     M, BS, E = 1500, 512, 2
