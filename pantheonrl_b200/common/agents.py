@@ -51,6 +51,9 @@ class OnPolicyAgent(Agent):
         self._last_episode_starts = [True]
         self.n_steps = 0
         self.values = None
+        # agents.py:102-103: the partner logs through its own SB3-style logger / run directory
+        from ..logger import configure_logger
+        self.model.set_logger(configure_logger(getattr(model, "verbose", 0), tensorboard_log, tb_log_name))
         self.name = tb_log_name
         self.num_timesteps = 0
         self.log_interval = log_interval or (1 if getattr(model, "verbose", 0) else None)
@@ -84,13 +87,20 @@ class OnPolicyAgent(Agent):
             self.model.ep_info_buffer.append({"r": 0, "l": 0})
 
     def _log(self):
-        eps = list(self.model.ep_info_buffer)[:-1]
-        rec = {"name": self.name, "time/iterations": self.iteration,
-               "time/total_timesteps": self.num_timesteps}
-        if eps:
-            rec["rollout/ep_rew_mean"] = float(np.mean([e["r"] for e in eps]))
-            rec["rollout/ep_len_mean"] = float(np.mean([e["l"] for e in eps]))
-        self.model.log(rec)
+        """agents.py:132-153: keys, exclusions and the dump step are the reference's."""
+        from ..logger import safe_mean
+        lg = self.model.logger
+        lg.record("name", self.name, exclude="tensorboard")
+        lg.record("time/iterations", self.iteration, exclude="tensorboard")
+        buf = self.model.ep_info_buffer
+        if len(buf) > 0 and len(buf[0]) > 0:
+            last_exclude = buf.pop()  # the episode still in progress
+            lg.record("rollout/ep_rew_mean", safe_mean(ep["r"] for ep in buf))
+            lg.record("rollout/ep_len_mean", safe_mean(ep["l"] for ep in buf))
+            buf.append(last_exclude)
+        lg.record("time/total_timesteps", self.num_timesteps, exclude="tensorboard")
+        lg.dump(step=self.num_timesteps)
 
     def learn(self, **kwargs):
+        self.model._custom_logger = False  # agents.py:206: let learn() configure its own logger
         self.model.learn(**kwargs)

@@ -8,10 +8,13 @@ n_envs == 1: the reference's host-driven flow — one kernel call per decision
 n_envs  > 1: learn() hands the whole loop to the device engine (VecTrainer ->
   pth_rollout_run) for the built-in envs.
 """
+import time
+from collections import deque
+
 import numpy as np
 import torch
 
-from . import _lib, ops, policy as pol, update as up
+from . import _lib, logger as lg, ops, policy as pol, update as up
 from .common.agents import OnPolicyAgent, StaticPolicyAgent
 from .spaces import to_pth_space
 
@@ -136,17 +139,57 @@ class PPO:
         self.adam_v = torch.zeros_like(self.policy.params)
         self.adam_step, self._n_updates, self.num_timesteps = 0, 0, 0
         self.use_sde, self.sde_sample_freq = False, -1
-        self.logs, self.last_stats = [], None
+        self.last_stats = None
         self.ep_info_buffer = None
+        self._logger, self._custom_logger = lg.Logger(), False
+        self._num_timesteps_at_start, self.start_time, self._iteration = 0, time.time(), 0
         self._ws = None
         self._last_obs = None
         self._trainer = None
 
-    # ---------------------------------------------------------------- logging
-    def log(self, record):
-        self.logs.append(record)
-        if self.verbose:
-            print(record)
+    # ---------------------------------------------------------------- logging (SB3 Logger surface)
+    @property
+    def logger(self):
+        return self._logger
+
+    def set_logger(self, logger):
+        """BaseAlgorithm.set_logger: a logger set by the caller survives learn()."""
+        self._logger, self._custom_logger = logger, True
+
+    def _record_train(self, stats, values, returns, n_updates):
+        """The scalars SB3's PPO.train records (adap_learn.py:354-371): means over all
+        minibatches, the last minibatch's loss, explained variance of the buffer."""
+        if not self._logger.output_formats:
+            return  # nothing would read them: skip the device -> host copy
+        s = stats.cpu().numpy()
+        r = self._logger.record
+        r("train/entropy_loss", float(s[:, 2].mean()))
+        r("train/policy_gradient_loss", float(s[:, 0].mean()))
+        r("train/value_loss", float(s[:, 1].mean()))
+        r("train/approx_kl", float(s[:, 3].mean()))
+        r("train/clip_fraction", float(s[:, 4].mean()))
+        r("train/loss", float(s[-1, 5]))
+        r("train/explained_variance", lg.explained_variance(values, returns))
+        r("train/n_updates", n_updates, exclude="tensorboard")
+        r("train/clip_range", self.clip_range)
+
+    def _record_rollout(self, iteration, ep_rew_mean, ep_len_mean):
+        """OnPolicyAlgorithm.learn's per-iteration record + dump (adap_learn.py:487-500)."""
+        elapsed = max(time.time() - self.start_time, 1e-9)
+        r = self._logger.record
+        r("time/iterations", iteration, exclude="tensorboard")
+        if ep_rew_mean is not None:
+            r("rollout/ep_rew_mean", ep_rew_mean)
+            r("rollout/ep_len_mean", ep_len_mean)
+        r("time/fps", int((self.num_timesteps - self._num_timesteps_at_start) / elapsed))
+        r("time/time_elapsed", int(elapsed), exclude="tensorboard")
+        r("time/total_timesteps", self.num_timesteps, exclude="tensorboard")
+        self._logger.dump(step=self.num_timesteps)
+
+    def _setup_learn(self, tb_log_name):
+        if not self._custom_logger:
+            self._logger = lg.configure_logger(self.verbose, self.tensorboard_log, tb_log_name)
+        self.start_time, self._num_timesteps_at_start = time.time(), self.num_timesteps
 
     # ---------------------------------------------------------------- SB3 PPO.train
     def train(self):
@@ -164,15 +207,20 @@ class PPO:
             vf_coef=self.vf_coef, max_grad_norm=self.max_grad_norm, normalize_advantage=self.normalize_advantage)
         self.adam_step += self.n_epochs * (-(-M // self.batch_size))
         self._n_updates += self.n_epochs
+        self._record_train(self.last_stats, d["values"], d["returns"], self._n_updates)
 
     # ---------------------------------------------------------------- learn
-    def learn(self, total_timesteps, tb_log_name="PPO", **_):
+    def learn(self, total_timesteps, log_interval=1, tb_log_name="PPO", **_):
+        self._setup_learn(tb_log_name)
         if self.n_envs > 1:
-            return self._learn_on_device(total_timesteps)
+            return self._learn_on_device(total_timesteps, log_interval)
         env, buf = self.env, self.rollout_buffer
         if self._last_obs is None:
             self._last_obs = env.reset()
             self._last_start = True
+            self._ep = [0.0, 0]  # Monitor: reward and length of the ego's running episode
+        if self.ep_info_buffer is None:
+            self.ep_info_buffer = deque(maxlen=100)
         target = self.num_timesteps + total_timesteps
         while self.num_timesteps < target:
             buf.reset()
@@ -180,15 +228,25 @@ class PPO:
                 actions, values, log_probs = self.policy.forward(self._last_obs)
                 new_obs, reward, done, _info = env.step(actions[0])
                 self.num_timesteps += 1
+                self._ep[0] += float(reward)
+                self._ep[1] += 1
                 buf.add(self._last_obs, actions, reward, self._last_start, values, log_probs)
                 self._last_start = done
+                if done:
+                    self.ep_info_buffer.append({"r": self._ep[0], "l": self._ep[1]})
+                    self._ep = [0.0, 0]
                 self._last_obs = env.reset() if done else new_obs  # DummyVecEnv auto-reset
             last_values = self.policy.predict_values(self._last_obs)
             buf.compute_returns_and_advantage(last_values, self._last_start, self.gamma, self.gae_lambda)
+            self._iteration += 1
+            if log_interval is not None and self._iteration % log_interval == 0 and self._logger.output_formats:
+                eps = list(self.ep_info_buffer)
+                self._record_rollout(self._iteration, lg.safe_mean(e["r"] for e in eps) if eps else None,
+                                     lg.safe_mean(e["l"] for e in eps) if eps else None)
             self.train()
         return self
 
-    def _learn_on_device(self, total_timesteps):
+    def _learn_on_device(self, total_timesteps, log_interval=1):
         from .engine import PPOConfig, VecTrainer
         kind = getattr(self.env, "device_kind", None)
         if kind is None:
@@ -219,10 +277,37 @@ class PPO:
             if mode == "ppo":
                 self._trainer.alt.params = partner.model.policy.params
                 self._trainer.alt.adam_m, self._trainer.alt.adam_v = partner.model.adam_m, partner.model.adam_v
-        start = self._trainer.num_timesteps
-        self._trainer.learn(start + total_timesteps)
-        self.num_timesteps = self._trainer.num_timesteps
-        self.last_stats = self._trainer.ego.last_stats
+        tr, target = self._trainer, self._trainer.num_timesteps + total_timesteps
+        partner_model = partner.model if isinstance(partner, OnPolicyAgent) else None
+        prev = np.zeros(4)
+        while tr.num_timesteps < target:
+            tr.collect()
+            tr.compute_gae()
+            self.num_timesteps = tr.num_timesteps
+            self._iteration += 1
+            log_now = log_interval is not None and self._iteration % log_interval == 0
+            if log_now and self._logger.output_formats:
+                # episodes finished during this rollout (device counters: episodes, reward sum, length sum)
+                e = tr.carry.ep_stats.cpu().numpy().astype(np.float64)
+                d, prev = e - prev, e
+                n = max(d[0], 1.0)
+                self._record_rollout(self._iteration, float(d[1] / n), float(d[2] / n))
+            tr.train()
+            self._n_updates = tr.ego.n_updates
+            self.adam_step = tr.ego.adam_step
+            self._record_train(tr.ego.last_stats, tr.ego_buf.values, tr.ego_buf.returns, tr.ego.n_updates)
+            if partner_model is not None:
+                partner_model._n_updates, partner_model.adam_step = tr.alt.n_updates, tr.alt.adam_step
+                partner.num_timesteps = tr.partner_decisions
+                if log_now and partner_model.logger.output_formats:
+                    m = tr.alt_buf.count.clamp(max=tr.alt_buf.Tcap)
+                    mask = torch.arange(tr.alt_buf.Tcap, device=m.device)[:, None] < m[None, :]
+                    partner_model._record_train(tr.alt.last_stats, tr.alt_buf.values[mask],
+                                                tr.alt_buf.returns[mask], tr.alt.n_updates)
+                    partner_model.logger.record("name", partner.name, exclude="tensorboard")
+                    partner_model.logger.record("time/total_timesteps", partner.num_timesteps, exclude="tensorboard")
+                    partner_model.logger.dump(step=partner.num_timesteps)
+        self.last_stats = tr.ego.last_stats
         return self
 
     # ---------------------------------------------------------------- checkpoint

@@ -170,6 +170,70 @@ def test_ppo_learn_single_env_and_static_partner(ctx, tmp_path):
             o = env2.reset()
 
 
+def _scalars(run_dir):
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(str(run_dir))
+    acc.Reload()
+    return {t: [(e.step, e.value) for e in acc.Scalars(t)] for t in acc.Tags()["scalars"]}
+
+
+SB3_TRAIN_TAGS = {"train/entropy_loss", "train/policy_gradient_loss", "train/value_loss", "train/approx_kl",
+                  "train/clip_fraction", "train/loss", "train/explained_variance", "train/clip_range"}
+
+
+def test_tensorboard_scalars_and_sb3_zip(ctx, tmp_path):
+    """SURVEY.md 8f-2 / 8f-3 through the facade: the TensorBoard tags / steps SB3 writes for the ego
+    (learn) and for an OnPolicyAgent partner (agents.py:132-153), and an SB3-shaped archive that
+    PPO.load(path) reopens without an env (trainer.py:149)."""
+    tb = tmp_path / "tb"
+    env = RPSEnv()
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=2, seed=10,
+                                _rng_stream=_lib.STREAM_ALT), log_interval=1, tensorboard_log=str(tb),
+                            tb_log_name="partner")
+    env.add_partner_agent(partner)
+    ego = PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=2, seed=10, tensorboard_log=str(tb))
+    ego.learn(total_timesteps=48, tb_log_name="ego")
+    ego.logger.close()
+    partner.model.logger.close()
+    sc = _scalars(tb / "ego_1")
+    assert SB3_TRAIN_TAGS | {"rollout/ep_rew_mean", "rollout/ep_len_mean", "time/fps"} <= set(sc)
+    assert [s for s, _ in sc["rollout/ep_len_mean"]] == [16, 32, 48]  # dumped before each train(), step = timesteps
+    assert all(v == 1.0 for _, v in sc["rollout/ep_len_mean"])        # RPS: every step ends an episode
+    assert [s for s, _ in sc["train/loss"]] == [32, 48]               # train() scalars ride on the next dump
+    stats = ego.last_stats.cpu().numpy()
+    ps = _scalars(tb / "partner_1")
+    assert {"rollout/ep_rew_mean", "rollout/ep_len_mean"} <= set(ps) and [s for s, _ in ps["rollout/ep_rew_mean"]][:2] == [16, 32]
+    assert np.isfinite(stats).all()
+    # SB3-shaped archive, reopened the way trainer.py does for LOAD / FIXED partners
+    import zipfile
+    path = ego.save(str(tmp_path / "ego_model"))
+    assert path.endswith("ego_model.zip")
+    assert {"data", "policy.pth", "policy.optimizer.pth"} <= set(zipfile.ZipFile(path).namelist())
+    again = PPO.load(str(tmp_path / "ego_model"))
+    assert torch.equal(again.policy.params, ego.policy.params) and torch.equal(again.adam_m, ego.adam_m)
+    assert torch.equal(again.adam_v, ego.adam_v)
+    assert (again.adam_step, again._n_updates, again.num_timesteps) == (ego.adam_step, ego._n_updates, 48)
+    assert again.n_steps == 16 and again.observation_space.n == 1 and again.action_space.n == 3
+    env2 = RPSEnv()
+    env2.add_partner_agent(StaticPolicyAgent(again.policy))
+    again.set_env(env2)
+    again.learn(total_timesteps=16)  # training continues from the loaded optimizer state
+    assert again._n_updates == ego._n_updates + 2
+    # device loop (n_envs > 1): same tags, one dump per iteration
+    env3 = LiarEnv()
+    p3 = OnPolicyAgent(PPO("MlpPolicy", env3, n_steps=8, n_epochs=1, seed=1, n_minibatches=2,
+                           _rng_stream=_lib.STREAM_ALT), log_interval=1, tensorboard_log=str(tb), tb_log_name="p3")
+    env3.add_partner_agent(p3)
+    e3 = PPO("MlpPolicy", env3, n_steps=8, n_epochs=1, seed=1, n_envs=256, n_minibatches=2, tensorboard_log=str(tb))
+    e3.learn(total_timesteps=256 * 8 * 2, tb_log_name="vec")
+    e3.logger.close()
+    p3.model.logger.close()
+    v = _scalars(tb / "vec_1")
+    assert SB3_TRAIN_TAGS <= set(v) and [s for s, _ in v["rollout/ep_rew_mean"]] == [2048, 4096]
+    assert all(1.0 <= x <= 13.0 for _, x in v["rollout/ep_len_mean"])
+    assert SB3_TRAIN_TAGS <= set(_scalars(tb / "p3_1"))
+
+
 def test_ppo_learn_on_device_matches_engine(ctx):
     N, T = 256, 16
     env = LiarEnv()
