@@ -359,6 +359,8 @@ int pth_index_build(pth_ctx* ctx, const int32_t* d_count, int64_t T, int64_t N,
                     void* stream);
 int64_t pth_index_workspace_bytes(int64_t N);
 
+#define PTH_UPDATE_FLAG_WORDS 2048 /* per rank: one word per (source rank, CTA) of the sharded update */
+
 typedef struct pth_update_args {
   const pth_space* space;   /* HOST pointer */
   float* d_params;          /* [P] in/out */
@@ -386,11 +388,12 @@ typedef struct pth_update_args {
   /* Multi-GPU sharded update (world > 1): every rank holds the SAME sample arrays
    * (the all-gathered ego stream) and the same perm; tile t of a minibatch is
    * computed by rank t mod world; after the local ordered reduction each rank
-   * stores its gradient sums into every peer's exchange buffer over NVLink, a
-   * flag barrier in peer memory follows, and all ranks add the per-rank sums in
-   * rank order inside the same persistent kernel — replicas stay bit-identical.
+   * stores its gradient sums into every peer's exchange buffer over NVLink, the
+   * CTAs that own a parameter slice hand-shake through flag words in peer memory
+   * (slice c of rank r only meets slice c of the other ranks: no grid-wide barrier),
+   * and all ranks add the per-rank sums in rank order inside the same persistent kernel — replicas stay bit-identical.
    * d_peer_xbuf[r] / d_peer_flags[r]: rank r's exchange buffer (>= pth_update_xbuf_bytes)
-   * and flag words (>= 64 uint32, zero-initialised once) mapped in THIS process
+   * and flag words (PTH_UPDATE_FLAG_WORDS uint32 = [world <= 8][256], zero-initialised once) mapped in THIS process
    * (HOST arrays of `world` device pointers). flag_epoch: value of the monotonic
    * flag counter before this launch (launches add n_epochs * n_minibatches). */
   int32_t world, rank;

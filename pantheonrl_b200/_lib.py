@@ -18,6 +18,7 @@ PTH_ENV_RPS, PTH_ENV_LIAR, PTH_ENV_OVERCOOKED = 0, 1, 2
 PTH_OC_MAX_CELLS, PTH_OC_MAX_POTS, PTH_OC_OBS, PTH_OC_ROW = 128, 4, 62, 64
 PTH_OC_STATE_BYTES = 40
 PTH_OC_FLOOR, PTH_OC_COUNTER, PTH_OC_ONION, PTH_OC_POT, PTH_OC_DISH, PTH_OC_SERVE = range(6)
+PTH_UPDATE_FLAG_WORDS = 2048  # include/pantheon_b200.h
 PTH_PACKED_BYTES = 48
 
 STREAM_ENV, STREAM_EGO, STREAM_ALT, STREAM_SHUFFLE_EGO, STREAM_SHUFFLE_ALT = 1, 2, 3, 4, 5

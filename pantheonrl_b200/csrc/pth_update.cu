@@ -110,13 +110,18 @@ __device__ __forceinline__ float block_tree(float x, float* red, int tid) {
 // exactly one thread of one CTA, so tile t+1's add follows tile t's in program
 // order; a fire-and-forget L2 reduction (RED.ADD.F32, IEEE round-to-nearest)
 // gives the same bits as load-add-store without the load round trip.
-// Cross-GPU barrier on flag words in peer memory: CTA 0 tells every rank that
-// this rank's exchange stores for `epoch` are done, then waits for all ranks.
-__device__ __forceinline__ void peer_barrier(const UpdParams& p, uint32_t epoch, int tid) {
+// Cross-GPU hand-shake per parameter slice.  CTA c of every rank owns slice c of the gradient:
+// after this rank's ordered sums of the slice are stored (and fenced) into every rank's exchange
+// buffer, thread k < world tells rank k "slice c of rank `rank` has landed" and waits until slice c
+// of rank k has landed here.  No grid-wide barrier is involved: a slice only ever meets the same
+// slice of the other ranks.  Flag words: [source rank][PTH_FLAG_STRIDE] per rank, monotonic epochs.
+constexpr int PTH_FLAG_STRIDE = 256;
+__device__ __forceinline__ void peer_slice_handshake(const UpdParams& p, uint32_t epoch, int c, int tid) {
   if (tid < p.world) {
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[tid] + p.rank), "r"(epoch) : "memory");
-    const uint32_t* mine = p.flags[p.rank] + tid;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[tid] + p.rank * PTH_FLAG_STRIDE + c),
+                 "r"(epoch)
+                 : "memory");
+    const uint32_t* mine = p.flags[p.rank] + tid * PTH_FLAG_STRIDE + c;
     uint32_t v;
     long long spins = 0;
     do {
@@ -366,10 +371,11 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
 // Stable counting sort of the tile's nb samples by observed value, one slot per
 // warp at a time: order[s][pos] = sample id, rcount[row] = samples selecting the
 // first-layer row (row = slot_off[s] + value).
+// Slots [s_begin, s_end) are shared out over n_warps warps; `wid` is this warp's index among them.
 __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* obs_s, uint8_t* order,
-                                           uint8_t* rcount, int nb, int tid) {
-  const int lane = tid & 31, wid = tid >> 5;
-  for (int s = wid; s < p.sp.obs_len; s += UNT / 32) {
+                                           uint8_t* rcount, int nb, int lane, int wid, int n_warps,
+                                           int s_begin, int s_end) {
+  for (int s = s_begin + wid; s < s_end; s += n_warps) {
     int val[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -603,7 +609,10 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
         }
         __syncthreads();
-        if constexpr (!BOX) sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid);  // consumed after several barriers
+        // (moving the sort into the shadow of the head phase, onto the warps without a head, was
+        // measured: no gain — it competes with the head warps for issue slots)
+        if constexpr (!BOX)
+          sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
         PTH_PROF(2);  // gather + slot sort
 
         // ================= policy tower: forward
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       // loss statistics of the minibatch: one warp of the last CTA fetches every CTA's 5 sums in
       // one L2 round trip, parks them in shared memory, and 5 lanes add them in CTA order —
       // off the critical path of the parameter update (read back after barrier 2)
-      if (W == 1 && c == G - 1 && (tid >> 5) == 4) {
+      if (c == G - 1 && (tid >> 5) == 4) {
         const int ln = tid & 31;
         float* sc = sm.Lg;  // [5][160] scratch (free between tiles)
         float t[5][5];
@@ -891,32 +900,45 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
             s_ = sc[ln * 160];
             for (int cc = 1; cc < A; ++cc) s_ = s_ + sc[ln * 160 + cc];
           }
-          p.stat_part[G * 8 + ln] = s_;
+          if (W == 1) {
+            p.stat_part[G * 8 + ln] = s_;
+          } else {  // this rank's sums go to every rank's exchange slot, behind the gradient slice
+            for (int k = 0; k < W; ++k)
+              p.xbuf[(p.rank + k) % W][((size_t)par * W + p.rank) * p.XS + P + ln] = s_;
+          }
         }
       }
       if (W > 1) {
-        if (c == 0 && tid < 5) {
-          float s = 0.f;
-          if (A > 0) {
-            s = __ldcg(p.stat_part + tid);
-            for (int cc = 1; cc < A; ++cc) s = s + __ldcg(p.stat_part + cc * 8 + tid);
-          }
-          for (int k = 0; k < W; ++k)
-            p.xbuf[(p.rank + k) % W][((size_t)par * W + p.rank) * p.XS + P + tid] = s;
-        }
         __threadfence_system();
-        grid.sync();  // every CTA's exchange stores are issued and fenced
-        if (c == 0) peer_barrier(p, p.flag_epoch + (uint32_t)id + 1u, tid);
-        grid.sync();  // all ranks' sums have landed in the local exchange buffer
+        __syncthreads();  // this CTA's exchange stores (its slice of this rank's sums) are issued and fenced
+        peer_slice_handshake(p, p.flag_epoch + (uint32_t)id + 1u, c, tid);
+        __syncthreads();  // the slice of every rank has landed in the local exchange buffer
+        // rank-order sum of the slice: one parameter per thread, all ranks' values fetched at once;
+        // the squared-norm lanes (t < 128 owns parameters t, t + 128, ... in ascending order) pick the
+        // sums up from shared memory
         const float* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS;
-        for (int i = tid; i < S && tid < BT; i += BT) {
+        float* gs = sm.H1;
+        for (int i0c = 0; i0c < S; i0c += UNT) {
+          const int i = i0c + tid;
           const int pi = c * S + i;
-          if (pi < P) {
-            float g = __ldcg(xl + pi);
-            for (int r = 1; r < W; ++r) g = g + __ldcg(xl + (size_t)r * p.XS + pi);  // rank order
-            p.grad[pi] = g;
-            q = fmaf(g, g, q);
+          const bool live = i < S && pi < P;
+          float t[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) t[r] = (live && r < W) ? __ldcg(xl + (size_t)r * p.XS + pi) : 0.f;
+          float g = t[0];
+#pragma unroll
+          for (int r = 1; r < 8; ++r) g = r < W ? g + t[r] : g;  // rank order
+          if (live) p.grad[pi] = g;
+          gs[tid] = live ? g : 0.f;
+          __syncthreads();
+          if (tid < BT) {
+#pragma unroll
+            for (int k = 0; k < UNT / BT; ++k) {
+              const float gg = gs[tid + k * BT];
+              q = fmaf(gg, gg, q);
+            }
           }
+          __syncthreads();
         }
       }
       const float sq = block_tree(q, sm.red, tid);

@@ -105,7 +105,7 @@ class PeerExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         nbytes = int(_lib.load().pth_update_xbuf_bytes(C.byref(space), self.world))
         self.xbuf = symm.empty(nbytes, dtype=torch.uint8, device=device)
-        self.flags = symm.empty(64, dtype=torch.int32, device=device)
+        self.flags = symm.empty(_lib.PTH_UPDATE_FLAG_WORDS, dtype=torch.int32, device=device)
         self.xbuf.zero_()
         self.flags.zero_()
         torch.cuda.synchronize()
