@@ -102,18 +102,27 @@ template <bool COHERENT>
 __device__ __forceinline__ float4 ld_param4(const float4* p) {
   return COHERENT ? *p : __ldg(p);
 }
+template <bool COHERENT>
+__device__ __forceinline__ float4 ld_param4_l2(const float4* p) {
+  return COHERENT ? __ldcg(p) : __ldg(p);
+}
 
 template <bool COHERENT = false>
 __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
                                             const Layout& lo, int L, int tid, int nthreads) {
-  for (int i = tid; i < HID * HID; i += nthreads) {
-    int j = i >> 6, k = i & 63;
-    s.w_pi1[j * LDW + k] = ld_param<COHERENT>(p + lo.w_pi1 + i);
-    s.w_vf1[j * LDW + k] = ld_param<COHERENT>(p + lo.w_vf1 + i);
+  // the three matrices as float4 (rows of 64 floats; every tensor starts at a multiple of 4
+  // floats of a 16-byte aligned vector): a handful of independent 16-byte loads per thread
+  const float4* pi1 = reinterpret_cast<const float4*>(p + lo.w_pi1);
+  const float4* vf1 = reinterpret_cast<const float4*>(p + lo.w_vf1);
+  const float4* act = reinterpret_cast<const float4*>(p + lo.w_act);
+  for (int i = tid; i < HID * HID / 4; i += nthreads) {
+    const int j = i >> 4, k = (i & 15) * 4;
+    *reinterpret_cast<float4*>(s.w_pi1 + j * LDW + k) = ld_param4_l2<COHERENT>(pi1 + i);
+    *reinterpret_cast<float4*>(s.w_vf1 + j * LDW + k) = ld_param4_l2<COHERENT>(vf1 + i);
   }
-  for (int i = tid; i < L * HID; i += nthreads) {
-    int j = i >> 6, k = i & 63;
-    s.w_act[j * LDW + k] = ld_param<COHERENT>(p + lo.w_act + i);
+  for (int i = tid; i < L * HID / 4; i += nthreads) {
+    const int j = i >> 4, k = (i & 15) * 4;
+    *reinterpret_cast<float4*>(s.w_act + j * LDW + k) = ld_param4_l2<COHERENT>(act + i);
   }
   for (int i = tid; i < HID; i += nthreads) {
     s.w_val[i] = ld_param<COHERENT>(p + lo.w_val + i);

@@ -507,18 +507,38 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
     float mean = 0.f, stdv = 0.f;
     if (p.normalize && B > 1) {
       // 128 strided lanes (reduction contract), threads [BT, UNT) idle here
-      float s = 0.f;
-      if (tid < BT)
-        for (int64_t i = tid; i < B; i += BT)
-          s = s + *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride);
-      mean = block_tree(s, sm.red, tid) / (float)B;
-      float q = 0.f;
-      if (tid < BT)
-        for (int64_t i = tid; i < B; i += BT) {
-          const float d =
-              *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + i) * p.f_stride) - mean;
-          q = fmaf(d, d, q);
+      // lane t adds elements t, t + 128, ... in that order; 8 of its gathers are in flight at a time
+      float s = 0.f, q = 0.f;
+      if (tid < BT) {
+        for (int64_t i = tid; i < B; i += BT * 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t k = i + (int64_t)u * BT;
+            v[u] = k < B ? *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + k) * p.f_stride) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i + (int64_t)u * BT < B) s = s + v[u];
         }
+      }
+      mean = block_tree(s, sm.red, tid) / (float)B;
+      if (tid < BT) {
+        for (int64_t i = tid; i < B; i += BT * 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t k = i + (int64_t)u * BT;
+            v[u] = k < B ? *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + k) * p.f_stride) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i + (int64_t)u * BT < B) {
+              const float d = v[u] - mean;
+              q = fmaf(d, d, q);
+            }
+        }
+      }
       stdv = sqrtf(block_tree(q, sm.red, tid) / (float)(B - 1));
     }
     if (tid == 0) {
@@ -949,6 +969,16 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
 
       __syncthreads();
       for (int cc = tid; cc < G; cc += UNT) sm.bc[cc] = __ldcg(p.norm_part + cc);
+      // this thread's first parameter of the slice: fetched while the norm is being summed
+      const int pi0 = c * S + tid;
+      const bool own0 = tid < S && pi0 < P;
+      float g0 = 0.f, m0 = 0.f, v0 = 0.f, w0 = 0.f;
+      if (own0) {
+        g0 = p.grad[pi0];
+        m0 = p.adam_m[pi0];
+        v0 = p.adam_v[pi0];
+        w0 = p.params[pi0];
+      }
       __syncthreads();
       float total_sq = sm.bc[0];
       for (int cc = 1; cc < G; ++cc) total_sq = total_sq + sm.bc[cc];
@@ -962,13 +992,14 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       for (int i = tid; i < S; i += UNT) {
         const int pi = c * S + i;
         if (pi < P) {
-          const float g = p.grad[pi] * coef;
-          const float mm = fmaf(omb1, g, p.b1 * p.adam_m[pi]);
-          const float vv = fmaf(omb2 * g, g, p.b2 * p.adam_v[pi]);
+          const bool pre = i == tid && own0;
+          const float g = (pre ? g0 : p.grad[pi]) * coef;
+          const float mm = fmaf(omb1, g, p.b1 * (pre ? m0 : p.adam_m[pi]));
+          const float vv = fmaf(omb2 * g, g, p.b2 * (pre ? v0 : p.adam_v[pi]));
           const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
           p.adam_m[pi] = mm;
           p.adam_v[pi] = vv;
-          p.params[pi] = fmaf(-step_size, mm / denom, p.params[pi]);
+          p.params[pi] = fmaf(-step_size, mm / denom, pre ? w0 : p.params[pi]);
         }
       }
       if (c == 0 && tid == 0 && p.stats) {
@@ -1132,6 +1163,11 @@ int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1, bool box
   int cap = max_coop_ctas(ctx, box);
   if (cap < 1) return 0;
   int64_t g = tiles < cap ? tiles : cap;
+  // Small batches (the reference's own n_envs = 1, batch_size = 64 is ONE tile): CTAs without a
+  // tile still take a slice of the ordered reduction and of Adam, which otherwise one CTA would
+  // walk alone (44 k parameters: ~1 ms per minibatch instead of ~0.1 ms).
+  const int64_t gmin = cap < 96 ? cap : 96;
+  if (g < gmin) g = gmin;
   return (int)(g < 1 ? 1 : g);
 }
 

@@ -200,6 +200,9 @@ class VecTrainer:
         sharded = self.world > 1 and getattr(self, "peers", None) is not None
         te = tiles(M_ego, self.ego.batch_size_for(M_ego), self.world if sharded else 1)
         ta = tiles(M_alt, self.alt.batch_size_for(M_alt), 1)
+        if te + ta <= cap:  # spare SMs still help: their CTAs share the reduction and Adam slices
+            extra = cap - te - ta
+            return te + extra // 2, ta + extra - extra // 2
         k = max(1, -(-(te + ta) // cap))
         while -(-te // k) + -(-ta // k) > cap:
             k += 1

@@ -285,7 +285,7 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
         M = idx.size
         bs = -(-M // NMB)
         perm = oupd.perm_feistel(M, E, seed, _lib.STREAM_SHUFFLE_EGO, epoch0=upd_e)
-        G = dupd.update_grid(sp, M, bs)
+        G = tr.last_grids[0] or dupd.update_grid(sp, M, bs)  # the grid is part of the reduction contract
         oupd.ppo_update(osp, pe, me, ve, step_e, o_ego["obs"], o_ego["actions"], o_ego["logp"], adv, ret, perm, bs, G,
                         index=idx)
         step_e += E * (-(-M // bs))
@@ -295,7 +295,7 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
         M = aidx.size
         bs = -(-M // NMB)
         perm = oupd.perm_feistel(M, E, seed, _lib.STREAM_SHUFFLE_ALT, epoch0=upd_a)
-        G = dupd.update_grid(sp, M, bs)
+        G = tr.last_grids[1] or dupd.update_grid(sp, M, bs)
         oupd.ppo_update(osp, pa, ma, va, step_a, o_alt["obs"], o_alt["actions"], o_alt["logp"], aadv, aret, perm, bs,
                         G, index=aidx)
         step_a += E * (-(-M // bs))

@@ -320,7 +320,7 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx, golden_dir):
             M = idx.size
             bs = -(-M // NMB)
             perm = oupd.perm_feistel(M, E, seed, stream, epoch0=upd[who])
-            G = dupd.update_grid(sp, M, bs)
+            G = tr.last_grids[0 if who == "e" else 1] or dupd.update_grid(sp, M, bs)
             oupd.ppo_update(osp, p, m, v, step[who], buf["obs"], buf["actions"], buf["logp"], a_, r_, perm, bs, G,
                             index=idx)
             step[who] += E * (-(-M // bs))

@@ -123,6 +123,8 @@ def test_auto_grid_and_full_size_run(ctx):
     M, BS = 128 * 4096, 128 * 4096 // 32
     G = dupd.update_grid(sp, M, BS)
     assert 1 <= G <= ctx.sm_count and G == min(ctx.sm_count, BS // 128)
+    # one-tile minibatches (the reference's n_envs = 1, batch_size = 64) still spread reduction + Adam
+    assert dupd.update_grid(sp, 2048, 64) == min(ctx.sm_count, 96)
     pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=1)
     params = torch.from_numpy(pol.to_flat().copy()).cuda()
     p0 = params.clone()
