@@ -837,22 +837,24 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       PTH_PROF(13);  // barrier 1 (includes waiting for the slowest CTA)
 
       // ---- ordered reduction of this CTA's parameter slice + squared-norm partial.
-      // 128 parameters per pass, UNT / 128 threads per parameter: thread group k (threads [128k,
-      // 128k + 128)) fetches RH consecutive partials of its parameter, all groups AT THE SAME TIME
-      // (RH L2 loads in flight per thread, one round trip per pass); the highest group adds
-      // partials [0, RH) left to right, hands the running sum down through shared memory, and so on
-      // until group 0 has added the last ones — the order of the additions is the contract's CTA
-      // order.  Lane t < 128 ends up with parameters t, t + 128, ... of the slice, which is exactly
-      // the lane assignment of the squared-norm contract.
+      // Ordered reduction of this CTA's parameter slice.  A partial sums per parameter (A = CTAs that
+      // had a tile) are fetched RH at a time per thread, all of them in flight at once; with
+      // A <= RH one thread adds a parameter's chain alone (512 parameters per pass), otherwise 2 or
+      // 4 thread groups split the chain, the lower group first, handing the running sum up through
+      // shared memory — the order of the additions is the contract's CTA order.  The finished sums
+      // are parked in shared memory, where the squared-norm lanes (t < 128 owns parameters t,
+      // t + 128, ... of the slice in ascending order) pick them up.
       float q = 0.f;
       const int par = (int)(id & 1);
       {
-        constexpr int NG = UNT / BT, RH = 160 / NG;  // max co-resident CTAs is 160
-        float* gs = sm.H1;                           // hand-over scratch (H1 is free between tiles)
-        const int li = tid & (BT - 1);
-        const int turn = NG - 1 - (tid >> 7);  // position of this thread's group in the chain
-        const int cc0 = turn * RH;
-        for (int i0c = 0; i0c < S; i0c += BT) {
+        constexpr int RH = 64;  // max co-resident CTAs is 160 < 4 * RH
+        const int lg = A <= RH ? 0 : (A <= 2 * RH ? 1 : 2);
+        const int ngp = 1 << lg, PL = UNT >> lg;  // thread groups along the chain, parameters per pass
+        const int grp = tid >> (9 - lg), li = tid & (PL - 1);
+        static_assert(UNT == 512, "group index uses log2(UNT) = 9");
+        const int cc0 = grp * RH;
+        float* gs = sm.H1;  // PL sums (H1 is free between tiles)
+        for (int i0c = 0; i0c < S; i0c += PL) {
           const int i = i0c + li;
           const int pi = c * S + i;
           const bool live = i < S && pi < P;
@@ -861,38 +863,37 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           for (int u = 0; u < RH; ++u)
             t[u] = (live && cc0 + u < A) ? __ldcg(p.part + (size_t)(cc0 + u) * PS + pi) : 0.f;
           float g = 0.f;
+#pragma unroll 1
+          for (int ph = 0; ph < ngp; ++ph) {
+            if (grp == ph) {
+              if (live && cc0 < A) {
+                g = ph == 0 ? t[0] : gs[li] + t[0];
 #pragma unroll
-          for (int ph = 0; ph < NG; ++ph) {
-            if (turn == ph) {
-              if (ph > 0) g = gs[li];
-              if (ph == 0) {
-                if (live && A > 0) {
-                  g = t[0];
-#pragma unroll
-                  for (int u = 1; u < RH; ++u) g = (u < A) ? g + t[u] : g;
-                }
-              } else {
-#pragma unroll
-                for (int u = 0; u < RH; ++u) g = (ph * RH + u < A) ? g + t[u] : g;
-              }
-              if (ph < NG - 1) gs[li] = g;
-            }
-            if (ph < NG - 1) __syncthreads();
-          }
-          if (turn == NG - 1) {  // threads [0, 128): the finished sums
-            if (live) {
-              if (W == 1) {
-                p.grad[pi] = g;
-              } else {
-                // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
-                for (int k = 0; k < W; ++k) {
-                  const int dst = (p.rank + k) % W;
-                  p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
-                }
+                for (int u = 1; u < RH; ++u) g = (cc0 + u < A) ? g + t[u] : g;
+                gs[li] = g;
+              } else if (ph == 0) {
+                gs[li] = 0.f;  // beyond the slice, or no tile at all this minibatch
               }
             }
-            if (W == 1) q = fmaf(g, g, q);  // g = 0 beyond the slice: q unchanged
+            __syncthreads();
           }
+          if (grp == 0 && live) {
+            g = gs[li];
+            if (W == 1) {
+              p.grad[pi] = g;
+            } else {
+              // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
+              for (int k = 0; k < W; ++k) {
+                const int dst = (p.rank + k) % W;
+                p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
+              }
+            }
+          }
+          if (W == 1 && tid < BT)
+            for (int k = 0; k < PL / BT; ++k) {
+              const float gg = gs[tid + k * BT];
+              q = fmaf(gg, gg, q);  // 0 beyond the slice: q unchanged
+            }
           __syncthreads();  // gs is rewritten by the next pass
         }
       }
