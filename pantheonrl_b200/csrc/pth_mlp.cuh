@@ -293,10 +293,11 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
 // Thread (tx, ty) owns SPT samples (BTS = 128: {tx*4..+3, 64+tx*4..+3}; smaller
 // tiles: tx*4..+3) and the JT outputs j = jj*NY + ty.  BTS = 128, NTH = 256: per
 // 4 k, 4 LDS.128 of weights + 8 LDS.128 of activations feed 128 FFMA per thread.
-template <bool TANH, int NTH = NT, int BTS = BT>
+// LDAX: row stride of A / Out when the BTS samples are a column block of a wider tile.
+template <bool TANH, int NTH = NT, int BTS = BT, int LDAX = BTS + 4>
 __device__ __forceinline__ void dense64(const float* A, const float* W, const float* bias,
                                         float* Out, int tid) {
-  constexpr int LDA = BTS + 4;
+  constexpr int LDA = LDAX;
   constexpr int SPT = BTS >= 128 ? 8 : 4;
   constexpr int TXN = BTS / SPT, NY = NTH / TXN, JT = HID / NY;
   static_assert(NY * JT == HID && TXN * NY == NTH, "tile mapping must cover 64 outputs x BTS samples");

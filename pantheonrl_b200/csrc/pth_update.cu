@@ -649,7 +649,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         }
         __syncthreads();
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
-        dense64<true, UNT>(sm.H1, sm.pol.w_pi1, sm.pol.b_pi1, sm.H2, tid);
+        dense64<true, UNT / 2, BT / 2, LDA>(sm.H1 + (tid >> 8) * (BT / 2), sm.pol.w_pi1, sm.pol.b_pi1,
+                                             sm.H2 + (tid >> 8) * (BT / 2), tid & (UNT / 2 - 1));
         __syncthreads();
         PTH_PROF(4);  // pi hidden layer
         float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
@@ -772,7 +773,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           __syncthreads();
         }
         PTH_PROF(8);  // vf first layer (one-hot: done with the policy tower's)
-        dense64<true, UNT>(V1, sm.pol.w_vf1, sm.pol.b_vf1, sm.H2, tid);
+        dense64<true, UNT / 2, BT / 2, LDA>(V1 + (tid >> 8) * (BT / 2), sm.pol.w_vf1, sm.pol.b_vf1,
+                                             sm.H2 + (tid >> 8) * (BT / 2), tid & (UNT / 2 - 1));
         __syncthreads();
         PTH_PROF(9);  // vf hidden layer
         if (lane) {
