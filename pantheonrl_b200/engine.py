@@ -36,6 +36,16 @@ class PPOConfig:
     n_minibatches: int = 0
 
 
+def split_update_grids(cap, ego_tiles, alt_tiles, floor=48):
+    """(ego CTAs, partner CTAs) for two update kernels sharing ``cap`` co-resident CTAs.
+    The ego's share is a function of (cap, ego_tiles) ONLY — see VecTrainer.plan_grids."""
+    even = lambda t, budget: -(-t // -(-t // budget))  # noqa: E731  t tiles in equal rounds within budget
+    ge = max(even(max(ego_tiles, 1), cap // 2), min(cap // 2, floor))
+    if alt_tiles <= 0:
+        return ge, 0
+    return ge, max(even(alt_tiles, cap - ge), min(cap - ge, floor))
+
+
 class Learner:
     """Device state of one PPO learner: parameters, Adam moments, step counters."""
 
@@ -191,22 +201,21 @@ class VecTrainer:
 
         Each update is one persistent cooperative kernel with one CTA per SM; a minibatch has
         ceil(batch / 128) tiles (a rank of a sharded ego update computes every world-th one).
-        If both fit on the device at one tile per CTA they simply get their tiles; otherwise
-        every CTA runs k tiles per minibatch and the SMs are split in proportion.  The grid is
-        part of the update's reduction contract, so it is recorded in
-        ``last_grids`` for whoever replays the update on the oracle."""
+        The ego gets at most half of the SMs, in as few equal rounds of tiles as that allows;
+        the partner gets what is left, the same way.  Spare SMs are handed out too: CTAs without
+        a tile still share the ordered reduction and Adam.
+
+        The grid is part of the update's reduction contract and, for a sharded or
+        replicated ego update, must be THE SAME ON EVERY RANK: the ego's grid therefore depends
+        only on the global ego batch, the world size and the device — never on this rank's
+        (ragged) partner batch.  ``last_grids`` records both for whoever replays the update on
+        the oracle."""
         cap = up.update_grid(self.space, 1 << 30, 1 << 30, device=torch.device(self.device).index or 0)
         tiles = lambda M, bs, w: -(-(-(-min(bs, M) // 128)) // w)  # noqa: E731
         sharded = self.world > 1 and getattr(self, "peers", None) is not None
         te = tiles(M_ego, self.ego.batch_size_for(M_ego), self.world if sharded else 1)
-        ta = tiles(M_alt, self.alt.batch_size_for(M_alt), 1)
-        if te + ta <= cap:  # spare SMs still help: their CTAs share the reduction and Adam slices
-            extra = cap - te - ta
-            return te + extra // 2, ta + extra - extra // 2
-        k = max(1, -(-(te + ta) // cap))
-        while -(-te // k) + -(-ta // k) > cap:
-            k += 1
-        return max(1, -(-te // k)), max(1, -(-ta // k))
+        ta = tiles(M_alt, self.alt.batch_size_for(M_alt), 1) if M_alt > 0 else 0
+        return split_update_grids(cap, te, ta)
 
     def _train_one(self, learner, buf, index, M, perm, ws, stream_id, packed=None, peers=None, grid=0):
         cfg = learner.cfg
@@ -244,7 +253,8 @@ class VecTrainer:
             M = int(total.item())  # the one host read-back per train(): ragged sample count
             self.partner_decisions += M
         both = self.alt is not None and M > 0
-        g_ego, g_alt = self.plan_grids(self.ego_M, M) if both and self.concurrent_updates else (0, 0)
+        planned = self.alt is not None and self.concurrent_updates  # rank-independent (M is not)
+        g_ego, g_alt = self.plan_grids(self.ego_M, M) if planned else (0, 0)
         self.last_grids = (g_ego, g_alt)
         cur = torch.cuda.current_stream()
         if both:

@@ -83,3 +83,17 @@ def test_global_index_layout():
     # rank 0: envs 0,1 ; rank 1: envs 2,3 ; record offset = r*6 + t*2 + n ; order env-major
     assert idx == [0, 2, 4, 1, 3, 5, 6, 8, 10, 7, 9, 11]
     assert dist_util.shard_env0(3, 4096) == 12288
+
+
+def test_update_grid_split_is_rank_independent_for_the_ego():
+    """Replicated / sharded ego updates need the same grid on every rank although the ranks'
+    partner batches differ (ragged): the ego's share may not depend on the partner's tiles."""
+    from pantheonrl_b200.engine import split_update_grids
+    for cap in (148, 132, 16):
+        for te in (1, 6, 64, 128, 129, 1000):
+            shares = {split_update_grids(cap, te, ta) for ta in (0, 1, 7, 128, 129, 130, 257, 5000)}
+            assert len({ge for ge, _ in shares}) == 1, (cap, te, shares)
+            for ge, ga in shares:
+                assert 1 <= ge and ge + ga <= cap and (ga == 0 or ga >= 1)
+    assert split_update_grids(148, 128, 129) == (64, 65)   # BASELINE configs[1]: two rounds each
+    assert split_update_grids(148, 1, 1) == (48, 48)       # n_envs = 1: spare CTAs share reduction + Adam
