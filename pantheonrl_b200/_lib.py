@@ -40,6 +40,9 @@ class Space(C.Structure):
     @classmethod
     def onehot(cls, nvec, heads):
         s = cls()
+        if len(nvec) > len(s.obs_nvec) or len(heads) > len(s.head_n):
+            raise PthError(f"one-hot spaces take at most {len(s.obs_nvec)} observation slots and "
+                           f"{len(s.head_n)} action heads (got {len(nvec)} / {len(heads)})")
         s.obs_kind = PTH_OBS_ONEHOT
         s.obs_len = len(nvec)
         for i, v in enumerate(nvec):

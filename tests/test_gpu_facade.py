@@ -234,6 +234,36 @@ def test_tensorboard_scalars_and_sb3_zip(ctx, tmp_path):
     assert SB3_TRAIN_TAGS <= set(_scalars(tb / "p3_1"))
 
 
+def test_wrappers_around_device_games(ctx, tmp_path):
+    """--framestack / --record of trainer.py:92-100 on the device-backed games: the ego trains on
+    stacked observations while every step is recorded and written in the reference's .npy layout."""
+    from pantheonrl_b200.common import trajsaver, wrappers
+    env = RPSEnv()
+    env.add_partner_agent(OnPolicyAgent(PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=1, seed=10,
+                                            _rng_stream=_lib.STREAM_ALT)))
+    env = wrappers.frame_wrap(env, 3)
+    env = rec = wrappers.recorder_wrap(env)
+    assert env.observation_space.nvec.tolist() == [1, 1, 1]
+    ego = PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=1, seed=10)
+    ego.learn(total_timesteps=32)
+    tr = rec.get_transitions()
+    assert tr.egoobs.shape == (32, 3) and tr.flags.tolist() == [wrappers.DONE] * 32  # RPS: one step per game
+    tr.write_transition(tmp_path / "rps.npy")
+    back = trajsaver.SimultaneousTransitions.read_transition(tmp_path / "rps.npy", env.observation_space,
+                                                             env.action_space)
+    assert np.array_equal(back.egoacts.reshape(-1), tr.egoacts) and set(np.unique(tr.altacts)) <= {0, 1, 2}
+    # turn based, recorded only (a 3-frame Liar observation would be 90 slots: the kernels take 32)
+    lenv = LiarEnv(seed=3)
+    lenv.add_partner_agent(StaticPolicyAgent(PPO("MlpPolicy", lenv, seed=1, _rng_stream=_lib.STREAM_ALT).policy))
+    lrec = wrappers.recorder_wrap(lenv)
+    PPO("MlpPolicy", lrec, n_steps=16, batch_size=8, n_epochs=1, seed=2).learn(total_timesteps=16)
+    lt = lrec.get_transitions()
+    assert len(lt.get_ego_transitions()) == 16 and lt.obs.shape[1] == 30
+    assert len(lt.get_alt_transitions()) == int((lt.flags % 2 == 1).sum()) > 0
+    with pytest.raises(_lib.PthError):
+        PPO("MlpPolicy", wrappers.frame_wrap(LiarEnv(), 3), seed=1)
+
+
 def test_ppo_learn_on_device_matches_engine(ctx):
     N, T = 256, 16
     env = LiarEnv()
