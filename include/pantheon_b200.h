@@ -403,7 +403,17 @@ typedef struct pth_update_args {
   void* d_workspace;        /* pth_update_workspace_bytes() */
   int64_t workspace_bytes;
   float* d_stats;           /* [n_epochs*n_minibatch][8]: pg_loss, value_loss, entropy_loss, approx_kl, clip_frac, loss, grad_norm, n */
+  /* loss_kind PTH_LOSS_BC: behaviour cloning on (obs, action) pairs instead of PPO
+   * (pantheonrl/algos/bc.py:270-315): loss = -mean(log_prob) - ent_coef * mean(entropy)
+   * + l2_weight * sum(theta^2) / 2; old_logp / advantages / returns are not read (pass any
+   * valid pointers), vf_coef should be 0 and max_grad_norm +inf (bc.py does not clip).
+   * stats columns then hold: neglogp, value_loss, -entropy, prob_true_act, 0, loss
+   * (without the l2 term), grad_norm, n. */
+  int32_t loss_kind;
+  float l2_weight;
 } pth_update_args;
+#define PTH_LOSS_PPO 0
+#define PTH_LOSS_BC 1
 int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
                                    int64_t M, int64_t batch_size);
 /* Number of CTAs the persistent cooperative update kernel will run with for

@@ -162,3 +162,34 @@ def ppo_train(policy, obs, actions, old_log_prob, advantages, returns, perms, ba
             stats.append(ppo_minibatch_step(policy, obs[idx], actions[idx], old_log_prob[idx],
                                             advantages[idx], returns[idx], **kw))
     return stats
+
+
+def bc_minibatch_step(policy, optimizer, obs, actions, ent_weight=1e-3, l2_weight=0.0):
+    """One batch of behaviour cloning: BC._calculate_loss + the optimiser step of BC.train
+    (pantheonrl/algos/bc.py:270-315, 345-352)."""
+    _, log_prob, entropy = policy.evaluate_actions(obs, actions)
+    prob_true_act = th.exp(log_prob).mean()
+    log_prob, entropy = log_prob.mean(), entropy.mean()
+    l2_norm = sum(th.sum(th.square(w)) for w in policy.ordered_parameters()) / 2
+    ent_loss = -ent_weight * entropy
+    neglogp = -log_prob
+    loss = neglogp + ent_loss + l2_weight * l2_norm
+    optimizer.zero_grad()
+    loss.backward()
+    grad = policy.flat_grad()
+    optimizer.step()
+    return dict(neglogp=neglogp.item(), loss=loss.item(), entropy=entropy.item(), ent_loss=ent_loss.item(),
+                prob_true_act=prob_true_act.item(), l2_norm=l2_norm.item(), grad=grad)
+
+
+def bc_train(policy, obs, actions, perms, batch_size=32, ent_weight=1e-3, l2_weight=0.0, lr=1e-3, eps=1e-8):
+    """BC.train over epochs of shuffled batches with torch.optim.Adam at its defaults
+    (bc.py:196: optimizer_cls=Adam, no optimizer_kwargs)."""
+    opt = th.optim.Adam(policy.ordered_parameters(), lr=lr, eps=eps)
+    stats, M = [], len(actions)
+    for perm in perms:
+        perm = np.asarray(perm)
+        for s in range(0, M, batch_size):
+            idx = perm[s:s + batch_size]
+            stats.append(bc_minibatch_step(policy, opt, obs[idx], actions[idx], ent_weight, l2_weight))
+    return stats

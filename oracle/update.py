@@ -21,6 +21,7 @@ class OrcUpdateArgs(C.Structure):
         ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
         ("normalize_advantage", C.c_int32), ("grid", C.c_int32), ("world", C.c_int32),
         ("stats", C.c_void_p), ("grad_out", C.c_void_p),
+        ("loss_kind", C.c_int32), ("l2_weight", C.c_float),
     ]
 
 
@@ -44,7 +45,7 @@ def index_build(count, T, N):
 def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp, advantages,
                returns, perm, batch_size, grid, index=None, learning_rate=3e-4, clip_range=0.2,
                ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, betas=(0.9, 0.999), eps=1e-5,
-               normalize_advantage=True, world=1):
+               normalize_advantage=True, world=1, loss_kind=0, l2_weight=0.0):
     """Runs PPO.train on flat sample arrays; params / adam state are updated IN PLACE
     (float32 numpy arrays). Returns (stats [n_epochs*n_mb, 8], last pre-clip gradient)."""
     f32 = lambda x: np.ascontiguousarray(x, np.float32)  # noqa: E731
@@ -76,6 +77,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     a.vf_coef, a.max_grad_norm = vf_coef, max_grad_norm
     a.adam_beta1, a.adam_beta2, a.adam_eps = betas[0], betas[1], eps
     a.normalize_advantage = int(normalize_advantage)
+    a.loss_kind, a.l2_weight = int(loss_kind), float(l2_weight)
     a.grid = int(grid)
     a.world = int(world)
     a.stats, a.grad_out = stats.ctypes.data, grad.ctypes.data

@@ -18,6 +18,7 @@ PTH_ENV_RPS, PTH_ENV_LIAR, PTH_ENV_OVERCOOKED = 0, 1, 2
 PTH_OC_MAX_CELLS, PTH_OC_MAX_POTS, PTH_OC_OBS, PTH_OC_ROW = 128, 4, 62, 64
 PTH_OC_STATE_BYTES = 40
 PTH_OC_FLOOR, PTH_OC_COUNTER, PTH_OC_ONION, PTH_OC_POT, PTH_OC_DISH, PTH_OC_SERVE = range(6)
+PTH_LOSS_PPO, PTH_LOSS_BC = 0, 1
 PTH_UPDATE_FLAG_WORDS = 2048  # include/pantheon_b200.h
 PTH_PACKED_BYTES = 48
 
@@ -197,6 +198,8 @@ class UpdateArgs(C.Structure):
         ("d_workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
         ("d_stats", C.c_void_p),
+        ("loss_kind", C.c_int32),
+        ("l2_weight", C.c_float),
     ]
 
 

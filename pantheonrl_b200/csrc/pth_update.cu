@@ -67,6 +67,8 @@ struct UpdParams {
   int n_epochs;
   float lr, clip, ent_coef, vf_coef, max_norm, b1, b2, eps;
   int normalize;
+  int loss_kind;  // PTH_LOSS_PPO / PTH_LOSS_BC
+  float l2;       // BC: weight of sum(theta^2) / 2
   double b1pow0, b2pow0;
   float* part;       // [G][P]
   float* grad;       // [P]
@@ -703,21 +705,33 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
               entropy = entropy + hs[(PTH_MAX_HEADS + h) * LDA + sb];
             }
           }
-          if (norm) adv = (adv - mean) / (stdv + 1e-8f);
-          const float lr_ = logp - oldlp;
-          const float ratio = pth_expf(lr_);
-          const float pl1 = adv * ratio;
-          const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
-          const float pl2 = adv * rc;
-          const bool inside = ratio >= clip_lo && ratio <= clip_hi;
-          const bool gmask = inside || (pl1 < pl2);
-          const float glp = (svalid && gmask) ? -((adv * ratio) * invB) : 0.f;
+          float glp;
           const float gH = svalid ? -(p.ent_coef * invB) : 0.f;
-          if (lane) {
-            s_pl = valid ? fminf(pl1, pl2) : 0.f;
-            s_e = valid ? entropy : 0.f;
-            s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
-            s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
+          if (p.loss_kind == PTH_LOSS_BC) {
+            // bc.py:297-315: loss = -mean(log_prob) - ent_weight * mean(entropy) (+ l2, in Adam)
+            glp = svalid ? -invB : 0.f;
+            if (lane) {
+              s_pl = valid ? logp : 0.f;            // column 0: neglogp
+              s_e = valid ? entropy : 0.f;
+              s_kl = valid ? pth_expf(logp) : 0.f;  // column 3: prob_true_act
+              s_cf = 0.f;
+            }
+          } else {
+            if (norm) adv = (adv - mean) / (stdv + 1e-8f);
+            const float lr_ = logp - oldlp;
+            const float ratio = pth_expf(lr_);
+            const float pl1 = adv * ratio;
+            const float rc = fminf(fmaxf(ratio, clip_lo), clip_hi);
+            const float pl2 = adv * rc;
+            const bool inside = ratio >= clip_lo && ratio <= clip_hi;
+            const bool gmask = inside || (pl1 < pl2);
+            glp = (svalid && gmask) ? -((adv * ratio) * invB) : 0.f;
+            if (lane) {
+              s_pl = valid ? fminf(pl1, pl2) : 0.f;
+              s_e = valid ? entropy : 0.f;
+              s_kl = valid ? (ratio - 1.0f) - lr_ : 0.f;
+              s_cf = (valid && fabsf(ratio - 1.0f) > p.clip) ? 1.f : 0.f;
+            }
           }
           if (mine) {
             for (int i = 0; i < n; ++i) {
@@ -996,7 +1010,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         const int pi = c * S + i;
         if (pi < P) {
           const bool pre = i == tid && own0;
-          const float g = (pre ? g0 : p.grad[pi]) * coef;
+          float g = (pre ? g0 : p.grad[pi]) * coef;
+          if (p.l2 != 0.f) g = fmaf(p.l2, pre ? w0 : p.params[pi], g);  // d/dtheta of l2 * sum(theta^2) / 2
           const float mm = fmaf(omb1, g, p.b1 * (pre ? m0 : p.adam_m[pi]));
           const float vv = fmaf(omb2 * g, g, p.b2 * (pre ? v0 : p.adam_v[pi]));
           const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
@@ -1281,6 +1296,10 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.b2 = a->adam_beta2;
   p.eps = a->adam_eps;
   p.normalize = a->normalize_advantage;
+  p.loss_kind = a->loss_kind;
+  p.l2 = a->l2_weight;
+  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->loss_kind == PTH_LOSS_BC, "bad loss_kind");
+  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->world <= 1, "behaviour cloning runs on one GPU");
   p.b1pow0 = pow((double)a->adam_beta1, (double)a->adam_step);
   p.b2pow0 = pow((double)a->adam_beta2, (double)a->adam_step);
   unsigned char* ws = reinterpret_cast<unsigned char*>(a->d_workspace);

@@ -56,7 +56,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
                returns, perm, batch_size, workspace, index=None, M=None, rec_stride=0,
                learning_rate=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
                betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None,
-               peers=None):
+               peers=None, loss_kind=0, l2_weight=0.0):
     """SB3 PPO.train() over flat sample arrays on the device, in place on
     params / adam_m / adam_v. Returns the stats tensor [n_epochs * n_mb, 8]."""
     n_epochs = perm.shape[0]
@@ -90,6 +90,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
         peers.epoch += n_epochs * n_mb
     a.d_workspace, a.workspace_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
     a.d_stats = stats.data_ptr()
+    a.loss_kind, a.l2_weight = int(loss_kind), float(l2_weight)
     check(_lib.load().pth_ppo_update(_ctx(params).handle, C.byref(a), current_stream()), "pth_ppo_update")
     _lib.count_launch()
     return stats

@@ -264,6 +264,54 @@ def test_wrappers_around_device_games(ctx, tmp_path):
         PPO("MlpPolicy", wrappers.frame_wrap(LiarEnv(), 3), seed=1)
 
 
+def test_behaviour_cloning_facade(ctx, tmp_path):
+    """pantheonrl/algos/bc.py surface: clone a scripted Liar's Dice partner from recorded transitions
+    (recorder_wrap -> get_alt_transitions -> BC.train), save / reconstruct the policy (trainer.py:152)."""
+    from pantheonrl_b200.bc import BC, BCShell, reconstruct_policy
+    from pantheonrl_b200.common import wrappers
+    from pantheonrl_b200.envs.liar import LiarDefaultAgent
+    lenv = LiarEnv(seed=5)
+    lenv.add_partner_agent(LiarDefaultAgent())
+    rec = wrappers.recorder_wrap(lenv)
+    o = rec.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(400):  # a random ego keeps the games going; the scripted partner is the expert
+        o, r, d, _ = rec.step(np.array([rng.randint(6), rng.randint(12)]))
+        if d:
+            o = rec.reset()
+    expert = rec.get_transitions().get_alt_transitions()
+    assert len(expert) > 100 and expert.obs.shape[1] == 30
+    bc = BC(lenv.observation_space, lenv.action_space, expert_data=expert, seed=1)
+    p0 = bc.policy.params.clone()
+    bc.train(n_epochs=30)
+    per_epoch = -(-len(expert) // BC.DEFAULT_BATCH_SIZE)
+    st = bc.last_stats.cpu().numpy()
+    assert st.shape == (30 * per_epoch, 8) and bc.adam_step == 30 * per_epoch
+    first, last = st[:per_epoch, 0].mean(), st[-per_epoch:, 0].mean()
+    assert last < 0.6 * first, (first, last)                      # neglogp of the expert's actions drops
+    assert st[-per_epoch:, 3].mean() > 2 * st[:per_epoch, 3].mean()  # prob_true_act rises
+    row = bc.stats_row(st[-1])
+    assert row["loss"] == pytest.approx(row["neglogp"] - 1e-3 * row["entropy"])
+    assert not torch.equal(bc.policy.params, p0)
+    bc.train(n_batches=per_epoch + 2)  # one full epoch + the first two batches of another
+    assert bc.last_stats.shape[0] == per_epoch + 2 and bc.batches_done == 31 * per_epoch + 2
+    with pytest.raises(ValueError):
+        bc.train(n_epochs=1, n_batches=1)
+    # the value tower is untouched by BC (vf_coef = 0): Adam sees exact zeros there
+    lay = bc.policy.state_dict()
+    assert torch.equal(lay["value_net.weight"], BC(lenv.observation_space, lenv.action_space, seed=1).policy.state_dict()["value_net.weight"])
+    bc.save_policy(str(tmp_path / "bc_policy.pt"))
+    pol2 = reconstruct_policy(str(tmp_path / "bc_policy.pt"))
+    assert torch.equal(pol2.params, bc.policy.params)
+    env2 = LiarEnv(seed=6)
+    env2.add_partner_agent(StaticPolicyAgent(BCShell(pol2).policy))  # gen_fixed for a BC partner
+    o = env2.reset()
+    for _ in range(10):
+        o, r, d, _ = env2.step(np.array([1, 11]))
+        if d:
+            o = env2.reset()
+
+
 def test_ppo_learn_on_device_matches_engine(ctx):
     N, T = 256, 16
     env = LiarEnv()

@@ -76,6 +76,26 @@ def test_subnormal_partial_sums_follow_red_add_semantics(ctx):
     assert tiny.size and tiny.min() < 1e-36  # the regime was reached: first moments are that small
 
 
+@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE])
+@pytest.mark.parametrize("M,BS,E,grid,l2", [(150, 32, 2, 3, 0.0), (700, 300, 2, 2, 0.01)])
+def test_behaviour_cloning_bit_exact_vs_oracle(ctx, kw, M, BS, E, grid, l2):
+    """loss_kind = PTH_LOSS_BC (pantheonrl/algos/bc.py:270-315): same kernel, supervised loss."""
+    space = oracle.make_space(**kw)
+    pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=M)
+    params = pol.to_flat().copy()
+    obs, act, old_logp, adv, ret = make_batch(kw, M, seed=M + 1)
+    perm = oupd.perm_feistel(M, E, seed=10, stream=4)
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    hp = dict(loss_kind=1, l2_weight=l2, ent_coef=1e-3, vf_coef=0.0, max_grad_norm=float("inf"),
+              learning_rate=1e-3, eps=1e-8, normalize_advantage=False)
+    gp, gm, gv, gst = run_gpu(kw, params, m, v, 0, obs, act, old_logp, adv, ret, perm, BS, grid, **hp)
+    op, om, ov = params.copy(), m.copy(), v.copy()
+    ost, _ = oupd.ppo_update(space, op, om, ov, 0, obs, act, old_logp, adv, ret, perm, BS, grid, **hp)
+    assert np.array_equal(gst, ost), np.abs(gst - ost).max()
+    assert np.array_equal(gm, om) and np.array_equal(gv, ov) and np.array_equal(gp, op)
+    assert np.all(gst[:, 4] == 0) and np.all(np.isfinite(gst))  # (random labels: nothing to learn here)
+
+
 def test_update_matches_torch_autograd(ctx):
     kw = oracle.LIAR_SPACE
     M, BS, E = 1500, 512, 2
