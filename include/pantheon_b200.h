@@ -388,14 +388,16 @@ typedef struct pth_update_args {
   /* Multi-GPU sharded update (world > 1): every rank holds the SAME sample arrays
    * (the all-gathered ego stream) and the same perm; tile t of a minibatch is
    * computed by rank t mod world; after the local ordered reduction each rank
-   * stores its gradient sums into every peer's exchange buffer over NVLink, the
-   * CTAs that own a parameter slice hand-shake through flag words in peer memory
-   * (slice c of rank r only meets slice c of the other ranks: no grid-wide barrier),
-   * and all ranks add the per-rank sums in rank order inside the same persistent kernel — replicas stay bit-identical.
-   * d_peer_xbuf[r] / d_peer_flags[r]: rank r's exchange buffer (>= pth_update_xbuf_bytes)
-   * and flag words (PTH_UPDATE_FLAG_WORDS uint32 = [world <= 8][256], zero-initialised once) mapped in THIS process
-   * (HOST arrays of `world` device pointers). flag_epoch: value of the monotonic
-   * flag counter before this launch (launches add n_epochs * n_minibatches). */
+   * stores its gradient sums into every peer's exchange buffer over NVLink as 8-byte
+   * {value, epoch tag} pairs ("LL" protocol: the reader polls the pair itself until the
+   * tag is the minibatch's epoch — no fence, no flag, no grid-wide barrier; slice c of rank
+   * r only ever meets slice c of the other ranks), and all ranks add the per-rank sums in
+   * rank order inside the same persistent kernel — replicas stay bit-identical.
+   * d_peer_xbuf[r]: rank r's exchange buffer (>= pth_update_xbuf_bytes, zero-initialised
+   * once) mapped in THIS process (HOST array of `world` device pointers).  d_peer_flags[r]:
+   * reserved (PTH_UPDATE_FLAG_WORDS uint32 per rank; not used by the LL protocol).
+   * flag_epoch: value of the monotonic epoch counter before this launch (launches add
+   * n_epochs * n_minibatches; it must be the same on every rank). */
   int32_t world, rank;
   void* const* peer_xbuf;
   void* const* peer_flags;

@@ -79,7 +79,7 @@ struct UpdParams {
   uint8_t nvec[MAX_SLOTS];
   // multi-GPU sharded update (world > 1)
   int world, rank;
-  float* xbuf[8];       // rank r's exchange buffer [2 parities][world][XS] mapped here
+  uint2* xbuf[8];       // rank r's exchange buffer [2 parities][world][XS] of (value bits, epoch tag)
   uint32_t* flags[8];   // rank r's flag words [world]
   uint32_t flag_epoch;
   int XS;               // floats per (parity, rank) slot: P + 8 rounded up to 4
@@ -112,25 +112,30 @@ __device__ __forceinline__ float block_tree(float x, float* red, int tid) {
 // exactly one thread of one CTA, so tile t+1's add follows tile t's in program
 // order; a fire-and-forget L2 reduction (RED.ADD.F32, IEEE round-to-nearest)
 // gives the same bits as load-add-store without the load round trip.
-// Cross-GPU hand-shake per parameter slice.  CTA c of every rank owns slice c of the gradient:
-// after this rank's ordered sums of the slice are stored (and fenced) into every rank's exchange
-// buffer, thread k < world tells rank k "slice c of rank `rank` has landed" and waits until slice c
-// of rank k has landed here.  No grid-wide barrier is involved: a slice only ever meets the same
-// slice of the other ranks.  Flag words: [source rank][PTH_FLAG_STRIDE] per rank, monotonic epochs.
-constexpr int PTH_FLAG_STRIDE = 256;
-__device__ __forceinline__ void peer_slice_handshake(const UpdParams& p, uint32_t epoch, int c, int tid) {
-  if (tid < p.world) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flags[tid] + p.rank * PTH_FLAG_STRIDE + c),
-                 "r"(epoch)
-                 : "memory");
-    const uint32_t* mine = p.flags[p.rank] + tid * PTH_FLAG_STRIDE + c;
-    uint32_t v;
-    long long spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if (++spins > (1ll << 31)) __trap();  // a peer died: fail loudly instead of hanging the GPU
-    } while ((int32_t)(v - epoch) < 0);
+// Cross-GPU exchange of the per-rank gradient sums, "LL" style: every value travels as ONE
+// 8-byte store {value bits, epoch tag} into the peer's exchange buffer (8-byte stores are single
+// NVLink transactions), and the reader polls the pair itself until the tag is this minibatch's
+// epoch.  No fence, no separate flag, no barrier: a parameter slice only ever meets the same
+// slice of the other ranks, and a value is usable the moment it lands.  Buffers are zero
+// initialised once and epochs start at 1; two parities keep a fast rank's next-but-one
+// minibatch off values a slow rank is still reading (it cannot get that far ahead: it needs the
+// slow rank's next values first).
+__device__ __forceinline__ void ll_store(uint2* dst, float v, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(epoch)
+               : "memory");
+}
+__device__ __forceinline__ uint2 ll_peek(const uint2* src) {
+  uint2 r;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(src) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ll_wait(const uint2* src, uint32_t epoch, uint2 first) {
+  long long spins = 0;
+  while (first.y != epoch) {
+    first = ll_peek(src);
+    if (++spins > (1ll << 24)) __trap();  // a peer died: fail loudly instead of hanging the GPU
   }
+  return __uint_as_float(first.x);
 }
 
 __device__ __forceinline__ void acc_store(float* g, float v, bool first) {
@@ -861,7 +866,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       // are parked in shared memory, where the squared-norm lanes (t < 128 owns parameters t,
       // t + 128, ... of the slice in ascending order) pick them up.
       float q = 0.f;
-      const int par = (int)(id & 1);
+      const uint32_t epoch = p.flag_epoch + (uint32_t)id + 1u;  // tag of this minibatch's exchange
+      const int par = (int)(epoch & 1u);  // alternates across launches too (flag_epoch is monotonic)
       {
         constexpr int RH = 64;  // max co-resident CTAs is 160 < 4 * RH
         const int lg = A <= RH ? 0 : (A <= 2 * RH ? 1 : 2);
@@ -901,7 +907,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
               // this rank's ordered sum goes to every rank's exchange slot [par][rank] over NVLink
               for (int k = 0; k < W; ++k) {
                 const int dst = (p.rank + k) % W;
-                p.xbuf[dst][((size_t)par * W + p.rank) * p.XS + pi] = g;
+                ll_store(p.xbuf[dst] + ((size_t)par * W + p.rank) * p.XS + pi, g, epoch);
               }
             }
           }
@@ -941,27 +947,28 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
             p.stat_part[G * 8 + ln] = s_;
           } else {  // this rank's sums go to every rank's exchange slot, behind the gradient slice
             for (int k = 0; k < W; ++k)
-              p.xbuf[(p.rank + k) % W][((size_t)par * W + p.rank) * p.XS + P + ln] = s_;
+              ll_store(p.xbuf[(p.rank + k) % W] + ((size_t)par * W + p.rank) * p.XS + P + ln, s_, epoch);
           }
         }
       }
       if (W > 1) {
-        __threadfence_system();
-        __syncthreads();  // this CTA's exchange stores (its slice of this rank's sums) are issued and fenced
-        peer_slice_handshake(p, p.flag_epoch + (uint32_t)id + 1u, c, tid);
-        __syncthreads();  // the slice of every rank has landed in the local exchange buffer
-        // rank-order sum of the slice: one parameter per thread, all ranks' values fetched at once;
+        // rank-order sum of the slice: one parameter per thread, all ranks' values polled at once;
         // the squared-norm lanes (t < 128 owns parameters t, t + 128, ... in ascending order) pick the
         // sums up from shared memory
-        const float* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS;
+        const uint2* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS;
         float* gs = sm.H1;
         for (int i0c = 0; i0c < S; i0c += UNT) {
           const int i = i0c + tid;
           const int pi = c * S + i;
           const bool live = i < S && pi < P;
+          uint2 raw[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            raw[r] = (live && r < W) ? ll_peek(xl + (size_t)r * p.XS + pi) : make_uint2(0u, epoch);
           float t[8];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) t[r] = (live && r < W) ? __ldcg(xl + (size_t)r * p.XS + pi) : 0.f;
+          for (int r = 0; r < 8; ++r)
+            t[r] = (live && r < W) ? ll_wait(xl + (size_t)r * p.XS + pi, epoch, raw[r]) : 0.f;
           float g = t[0];
 #pragma unroll
           for (int r = 1; r < 8; ++r) g = r < W ? g + t[r] : g;  // rank order
@@ -1027,9 +1034,10 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           if (W == 1) {
             s = __ldcg(p.stat_part + G * 8 + i);  // summed in CTA order during the reduce phase
           } else {
-            const float* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
-            s = __ldcg(xl + i);
-            for (int r = 1; r < W; ++r) s = s + __ldcg(xl + (size_t)r * p.XS + i);
+            const uint2* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
+            s = ll_wait(xl + i, epoch, ll_peek(xl + i));
+            for (int r = 1; r < W; ++r)
+              s = s + ll_wait(xl + (size_t)r * p.XS + i, epoch, ll_peek(xl + (size_t)r * p.XS + i));
           }
           st[i] = s;
         }
@@ -1201,7 +1209,7 @@ extern "C" int64_t pth_update_xbuf_bytes(const pth_space* sp, int32_t world) {
   const int64_t P = pth_policy_param_count(sp);
   if (P < 0 || world < 1 || world > 8) return PTH_EINVAL;
   const int64_t XS = (P + 8 + 3) / 4 * 4;
-  return 2 * (int64_t)world * XS * (int64_t)sizeof(float);
+  return 2 * (int64_t)world * XS * (int64_t)sizeof(uint2);  // (value, epoch tag) pairs
 }
 
 extern "C" int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t M,
@@ -1323,7 +1331,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     PTH_CHECK_ARG(a->peer_xbuf && a->peer_flags, "NULL peer pointer arrays");
     for (int r = 0; r < p.world; ++r) {
       PTH_CHECK_ARG(a->peer_xbuf[r] && a->peer_flags[r], "NULL peer buffer");
-      p.xbuf[r] = reinterpret_cast<float*>(a->peer_xbuf[r]);
+      p.xbuf[r] = reinterpret_cast<uint2*>(a->peer_xbuf[r]);
       p.flags[r] = reinterpret_cast<uint32_t*>(a->peer_flags[r]);
     }
   }
