@@ -5,8 +5,6 @@ the arithmetic (forward + sample, GAE, PPO.train) runs in libpantheon_b200.so.
 from abc import ABC, abstractmethod
 from collections import deque
 
-import numpy as np
-
 
 class Agent(ABC):
     """Base class of everything MultiAgentEnv can call (agents.py:24-51)."""

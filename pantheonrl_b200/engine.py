@@ -11,7 +11,6 @@ Python only sequences kernel launches; every number is computed on the device.
 """
 import dataclasses
 
-import numpy as np
 import torch
 
 from . import _lib, ops, policy, rollout as ro, update as up
