@@ -514,37 +514,38 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
     float mean = 0.f, stdv = 0.f;
     if (p.normalize && B > 1) {
       // 128 strided lanes (reduction contract), threads [BT, UNT) idle here
-      // lane t adds elements t, t + 128, ... in that order; 8 of its gathers are in flight at a time
+      // lane t < 128 adds elements t, t + 128, ... in that order (reduction contract).  The gathers
+      // (permutation -> index -> advantage: three dependent DRAM accesses at large batches) are done by
+      // ALL threads, 16 in flight each, into a shared-memory stage of CH elements; the lanes then add
+      // their elements of the stage in order.
+      constexpr int CH = 8192;  // floats staged per round (fits sm.H1)
+      float* stage = sm.H1;
       float s = 0.f, q = 0.f;
-      if (tid < BT) {
-        for (int64_t i = tid; i < B; i += BT * 8) {
-          float v[8];
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t base = 0; base < B; base += CH) {
+          float v[CH / UNT];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int64_t k = i + (int64_t)u * BT;
+          for (int u = 0; u < CH / UNT; ++u) {
+            const int64_t k = base + tid + (int64_t)u * UNT;
             v[u] = k < B ? *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + k) * p.f_stride) : 0.f;
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (i + (int64_t)u * BT < B) s = s + v[u];
-        }
-      }
-      mean = block_tree(s, sm.red, tid) / (float)B;
-      if (tid < BT) {
-        for (int64_t i = tid; i < B; i += BT * 8) {
-          float v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int64_t k = i + (int64_t)u * BT;
-            v[u] = k < B ? *reinterpret_cast<const float*>(p.adv + sample_offset(p, e, i0 + k) * p.f_stride) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (i + (int64_t)u * BT < B) {
-              const float d = v[u] - mean;
-              q = fmaf(d, d, q);
+          for (int u = 0; u < CH / UNT; ++u) stage[tid + u * UNT] = v[u];
+          __syncthreads();
+          if (tid < BT) {
+            const int n = (int)((B - base < CH) ? (B - base) : CH);
+            if (pass == 0) {
+              for (int j = tid; j < n; j += BT) s = s + stage[j];
+            } else {
+              for (int j = tid; j < n; j += BT) {
+                const float d = stage[j] - mean;
+                q = fmaf(d, d, q);
+              }
             }
+          }
+          __syncthreads();
         }
+        if (pass == 0) mean = block_tree(s, sm.red, tid) / (float)B;
       }
       stdv = sqrtf(block_tree(q, sm.red, tid) / (float)(B - 1));
     }
