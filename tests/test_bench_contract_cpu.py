@@ -1,0 +1,35 @@
+"""bench.py's reference arm runs on the host cores (the oracle port of the reference's path), so its
+JSON contract can be checked without a GPU: one line, the required keys, sane values."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+            "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"}
+
+
+def run(extra, env=None):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-envs", "8"] + extra, capture_output=True, text=True,
+                         timeout=600, env={**os.environ, **(env or {})})
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [ln for ln in out.stdout.splitlines() if ln.strip()]
+
+
+def test_reference_arm_prints_one_json_line():
+    lines = run(["--gpus", "1"])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec (all agents)" and d["unit"] == "agent-steps/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["steps"] == 1 and d["value"] > 0
+    assert d["config"]["workload"] == "liar-ppo-vs-ppo" and d["config"]["n_envs_per_gpu"] == 4096
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "8 envs" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    assert run(["--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
