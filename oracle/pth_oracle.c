@@ -14,10 +14,14 @@
  *
  * PARITY STATUS: the env / routing half is pinned against traces produced by
  * the reference's own Python classes (tests/golden/make_golden.py imports
- * /root/reference).  The SB3 arithmetic half has no reference-owned golden
- * vectors (the reference ships no tests and SB3 is not installable here):
- * "parity unpinned" for that half; it is cross-checked against an independent
- * torch-autograd restatement (oracle/sb3_torch.py).
+ * /root/reference).  PPO.train and GAE are pinned on the reference's own
+ * in-tree copies of the SB3 routines, executed verbatim
+ * (tests/golden/make_golden_sb3_intree.py runs ADAP.train of
+ * pantheonrl/algos/adap/adap_learn.py:229-347 and the GAE loop of
+ * ppo2/runner.py:152-164; tests/test_oracle_sb3_intree.py: <= 5e-6 / 1e-5).
+ * "Parity unpinned" remains for the policy construction / sampling against a
+ * real SB3 + torch 1.13.1 (not installable here); that part is cross-checked
+ * against an independent torch restatement (oracle/sb3_torch.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this file.  Everything is scalar fp32 with a

@@ -2,9 +2,11 @@
 stable-baselines3 1.7.0 RolloutBuffer.compute_returns_and_advantage — the loop
 over reversed(range(buffer_size)) with float32 numpy vectors of length n_envs —
 as called from pantheonrl/common/agents.py:127-130.  Same recurrence in-tree:
-overcookedgym/human_aware_rl/baselines/baselines/ppo2/runner.py:150-165.
-"parity unpinned": SB3 is not vendored and the reference has no golden vectors
-for it; this file and pth_oracle.c are independent restatements of each other.
+overcookedgym/human_aware_rl/baselines/baselines/ppo2/runner.py:152-164.
+SB3 is not vendored; the in-tree loop is executed verbatim by
+tests/golden/make_golden_sb3_intree.py and this file / pth_oracle.c reproduce its
+outputs to 1e-5 (tests/test_oracle_sb3_intree.py; the in-tree loop accumulates in
+float64, SB3's partner path and this file in float32).
 """
 import numpy as np
 

@@ -9,8 +9,10 @@ reference's in-tree near copies:
       pantheonrl/algos/modular/policies.py:84-118, 214-241, 273-290, 364-383
   * PPO.train:  pantheonrl/algos/adap/adap_learn.py:229-347 (minus context loss)
   * collect_rollouts: pantheonrl/algos/adap/adap_learn.py:415-471
-PARITY UNPINNED for this half: the reference holds no golden vectors for it.
-This module is (a) the independent tolerance check of pth_oracle.c's hand-written
+PARITY: ppo_train reproduces the parameters and logged scalars of the reference's own
+ADAP.train (adap_learn.py:229-347, executed verbatim with the context loss off) to 1e-7
+(tests/golden/make_golden_sb3_intree.py, tests/test_oracle_sb3_intree.py).  UNPINNED: policy
+construction / sampling against a real SB3 + torch 1.13.1.  This module is (a) the independent tolerance check of pth_oracle.c's hand-written
 backward pass / Adam and of the CUDA update kernel, and (b) the CPU arm that
 bench.py --impl reference times (torch CPU eager is what SB3 executes).
 """
@@ -105,6 +107,7 @@ class MlpPolicy(nn.Module):
         latent_pi, latent_vf = self.policy_net(x), self.value_net_body(x)
         _, dists = self._dists(latent_pi)
         actions = th.as_tensor(np.asarray(actions)).long()
+        actions = actions.reshape(actions.shape[0], -1)  # Discrete: SB3 passes a flat vector
         log_prob = th.stack([d.log_prob(actions[:, h]) for h, d in enumerate(dists)], dim=1).sum(dim=1)
         entropy = th.stack([d.entropy() for d in dists], dim=1).sum(dim=1)
         return self.value_net(latent_vf), log_prob, entropy

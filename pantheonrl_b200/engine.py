@@ -289,7 +289,8 @@ class VecTrainer:
         learner = learner or self.ego
         s = learner.last_stats.cpu().numpy()
         return {"train/policy_gradient_loss": float(s[:, 0].mean()), "train/value_loss": float(s[:, 1].mean()),
-                "train/entropy_loss": float(s[:, 2].mean()), "train/approx_kl": float(s[:, 3].mean()),
+                "train/entropy_loss": float(s[:, 2].mean()),
+                "train/approx_kl": float(s[-max(1, len(s) // max(1, learner.cfg.n_epochs)):, 3].mean()),  # last epoch (SB3)
                 "train/clip_fraction": float(s[:, 4].mean()), "train/loss": float(s[-1, 5]),
                 "train/n_updates": learner.n_updates}
 

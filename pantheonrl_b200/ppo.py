@@ -166,7 +166,9 @@ class PPO:
         r("train/entropy_loss", float(s[:, 2].mean()))
         r("train/policy_gradient_loss", float(s[:, 0].mean()))
         r("train/value_loss", float(s[:, 1].mean()))
-        r("train/approx_kl", float(s[:, 3].mean()))
+        # SB3 resets approx_kl_divs at the start of every epoch: the logged value is the LAST epoch's mean
+        # (adap_learn.py:250, 357; pinned by tests/test_oracle_sb3_intree.py)
+        r("train/approx_kl", float(s[-max(1, len(s) // max(1, self.n_epochs)):, 3].mean()))
         r("train/clip_fraction", float(s[:, 4].mean()))
         r("train/loss", float(s[-1, 5]))
         r("train/explained_variance", lg.explained_variance(values, returns))
