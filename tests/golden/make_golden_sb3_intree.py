@@ -12,6 +12,8 @@ two SB3 routines on the hot path, and those can be EXECUTED:
   * GAE        -> overcookedgym/human_aware_rl/baselines/baselines/ppo2/runner.py:152-164: the
     bootstrap loop, exec'd from the file's own source lines on float32 arrays.
 
+  * BC         -> pantheonrl/algos/bc.py:270-357 (`BC._calculate_loss`, `BC.train`), run unbound the same way.
+
 Writes sb3_intree.npz: inputs, the parameters / Adam moments / logged scalars after the
 reference's train(), and the advantages / returns of its GAE loop.  tests/test_oracle_sb3_intree.py
 replays them through oracle/sb3_torch.py, oracle/sb3_numpy.py and the C oracle.
@@ -138,8 +140,59 @@ def run_reference_gae(T, N, p_done, seed):
                 returns=ns["mb_returns"])
 
 
+def run_reference_bc(kw, M, E, seed, ent_weight, l2_weight):
+    """BC.train / BC._calculate_loss of pantheonrl/algos/bc.py:270-357, executed unbound on a duck-typed
+    self: batches of BC.DEFAULT_BATCH_SIZE cut from one stored permutation per epoch, torch's default Adam."""
+    stub("stable_baselines3.common.policies", BasePolicy=object)
+    import gym
+    gym.Space = gym.spaces.Space  # only named in bc.py's annotations
+    lg = Data(record=lambda *a, **k: None, dump=lambda *a, **k: None)
+    u = sys.modules["stable_baselines3.common.utils"]
+    u.configure_logger = lambda verbose=0, *a, **k: lg
+    u.get_device = lambda d="auto": th.device("cpu")
+    sb3c = sys.modules["stable_baselines3.common"]
+    sb3c.policies, sb3c.utils = sys.modules["stable_baselines3.common.policies"], u
+    from pantheonrl.algos import bc as ref_bc  # the reference's file, verbatim
+
+    pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=seed)
+    p0 = pol.to_flat().copy()
+    obs, act, _, _, _ = make_batch(kw, M, seed=seed + 1)
+    nslot, nh = len(kw["nvec"]), len(kw["heads"])
+    perms = oupd.perm_feistel(M, E, seed=seed, stream=6)
+    BS = ref_bc.BC.DEFAULT_BATCH_SIZE
+
+    class Loader:
+        def __init__(self):
+            self.epoch = 0
+
+        def __iter__(self):
+            perm = np.asarray(perms[self.epoch])
+            self.epoch += 1
+            for s0 in range(0, M, BS):
+                idx = perm[s0:s0 + BS]
+                yield {"obs": obs[idx][:, :nslot].astype(np.int64), "acts": act[idx][:, :nh].astype(np.int64)}
+
+    pol.parameters = pol.ordered_parameters
+    losses = []
+    me = Data(expert_data_loader=Loader(), policy=pol, device=th.device("cpu"), ent_weight=ent_weight,
+              l2_weight=l2_weight, optimizer=th.optim.Adam(pol.ordered_parameters()))
+
+    def calc(o, a):
+        loss, stats = ref_bc.BC._calculate_loss(me, o, a)
+        losses.append([stats["neglogp"], stats["entropy"], stats["prob_true_act"], stats["loss"], stats["l2_norm"]])
+        return loss, stats
+    me._calculate_loss = calc
+    ref_bc.BC.train(me, n_epochs=E)  # <- the reference's own training loop
+    return dict(p0=p0, obs=obs, act=act, perms=perms, params=pol.to_flat().copy(), stats=np.array(losses, np.float64),
+                hp=np.array([M, BS, E], np.int64), w=np.array([ent_weight, l2_weight], np.float64))
+
+
 def main():
     out = {}
+    for name, kw, M, E, seed, ew, l2 in (("rps", oracle.RPS_SPACE, 100, 2, 3, 1e-3, 0.0),
+                                         ("liar", oracle.LIAR_SPACE, 150, 2, 5, 1e-3, 0.01)):
+        for k, v in run_reference_bc(kw, M, E, seed, ew, l2).items():
+            out[f"bc_{name}_{k}"] = v
     for name, kw, M, BS, E, seed in (("rps", oracle.RPS_SPACE, 300, 64, 3, 7), ("liar", oracle.LIAR_SPACE, 700, 256, 2, 11)):
         for k, v in run_reference_train(kw, M, BS, E, seed).items():
             out[f"train_{name}_{k}"] = v

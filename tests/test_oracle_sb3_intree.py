@@ -73,3 +73,29 @@ def test_gae_matches_the_in_tree_bootstrap_loop(g, case):
     assert np.abs(adv - adv_ref).max() <= 1e-5 and np.abs(ret - ret_ref).max() <= 1e-5
     adv2, ret2 = sb3_numpy.compute_returns_and_advantage(rew, val, start, lv, dn)
     assert np.array_equal(adv2, adv) and np.array_equal(ret2, ret)
+
+
+@pytest.mark.parametrize("name,kw", CASES)
+def test_behaviour_cloning_matches_the_references_bc_train(g, name, kw):
+    """`BC.train` + `BC._calculate_loss` of pantheonrl/algos/bc.py:270-357, executed verbatim by the golden
+    generator, vs the torch restatement and the C oracle's loss_kind = 1 (what PTH_LOSS_BC equals bit for bit)."""
+    pre = f"bc_{name}_"
+    M, BS, E = (int(x) for x in g[pre + "hp"])
+    ent_w, l2 = (float(x) for x in g[pre + "w"])
+    obs, act, perms, p0, want, ref = g[pre + "obs"], g[pre + "act"], g[pre + "perms"], g[pre + "p0"], g[pre + "params"], g[pre + "stats"]
+    nslot, nh = len(kw["nvec"]), len(kw["heads"])
+    pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=0)
+    pol.from_flat(p0)
+    st = sb3_torch.bc_train(pol, obs[:, :nslot], act[:, :nh], perms, BS, ent_weight=ent_w, l2_weight=l2)
+    assert np.abs(pol.to_flat() - want).max() <= 1e-7
+    assert np.allclose([s["neglogp"] for s in st], ref[:, 0], atol=1e-6) and np.allclose([s["loss"] for s in st], ref[:, 3], atol=1e-5)
+    space = oracle.make_space(**kw)
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    z = np.zeros(M, np.float32)
+    cst, _ = oupd.ppo_update(space, p, m, v, 0, obs, act, z, z, z, perms, BS, grid=2, loss_kind=1, l2_weight=l2,
+                             ent_coef=ent_w, vf_coef=0.0, max_grad_norm=float("inf"), learning_rate=1e-3, eps=1e-8,
+                             normalize_advantage=False)
+    assert np.abs(p - want).max() <= 2e-5  # Adam at eps 1e-8 amplifies fp32 summation-order differences of tiny gradients
+    assert np.allclose(cst[:, 0], ref[:, 0], atol=2e-5)          # neglogp
+    assert np.allclose(-cst[:, 2], ref[:, 1], atol=2e-5)         # entropy
+    assert np.allclose(cst[:, 3], ref[:, 2], atol=1e-6)          # prob_true_act
