@@ -112,6 +112,32 @@ class HostStagedBuffer:
                 out=(self.d["advantages"], self.d["returns"]))
 
 
+def collect_rollouts_single_env(algo, env, policy, buf, n_steps):
+    """SB3 ``OnPolicyAlgorithm.collect_rollouts`` for ONE env behind ``DummyVecEnv`` + ``Monitor``
+    (in-tree copy: pantheonrl/algos/adap/adap_learn.py:377-473): every step stores the observation the
+    action was chosen on together with the PREVIOUS step's done flag as ``episode_start``; a finished
+    episode is reset at once and the reset observation is what the next action sees; the rollout
+    bootstraps from the value of the observation AFTER the last step and that step's done flag.
+    ``algo`` carries the state that survives between rollouts (``_last_obs``, ``_last_start``,
+    ``num_timesteps``, the Monitor's running episode ``_ep`` and ``ep_info_buffer``).  Plain host code:
+    pinned against the in-tree copy by tests/test_collect_rollouts_cpu.py with stand-in policy / buffer."""
+    buf.reset()
+    for _ in range(n_steps):
+        actions, values, log_probs = policy.forward(algo._last_obs)
+        new_obs, reward, done, _info = env.step(actions[0])
+        algo.num_timesteps += 1
+        algo._ep[0] += float(reward)
+        algo._ep[1] += 1
+        buf.add(algo._last_obs, actions, reward, algo._last_start, values, log_probs)
+        algo._last_start = done
+        if done:
+            algo.ep_info_buffer.append({"r": algo._ep[0], "l": algo._ep[1]})
+            algo._ep = [0.0, 0]
+        algo._last_obs = env.reset() if done else new_obs  # DummyVecEnv auto-reset
+    last_values = policy.predict_values(algo._last_obs)
+    buf.compute_returns_and_advantage(last_values, algo._last_start)
+
+
 class PPO:
     def __init__(self, policy="MlpPolicy", env=None, learning_rate=3e-4, n_steps=2048, batch_size=64,
                  n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, normalize_advantage=True,
@@ -225,21 +251,7 @@ class PPO:
             self.ep_info_buffer = deque(maxlen=100)
         target = self.num_timesteps + total_timesteps
         while self.num_timesteps < target:
-            buf.reset()
-            for _ in range(self.n_steps):  # collect_rollouts (adap_learn.py:415-455)
-                actions, values, log_probs = self.policy.forward(self._last_obs)
-                new_obs, reward, done, _info = env.step(actions[0])
-                self.num_timesteps += 1
-                self._ep[0] += float(reward)
-                self._ep[1] += 1
-                buf.add(self._last_obs, actions, reward, self._last_start, values, log_probs)
-                self._last_start = done
-                if done:
-                    self.ep_info_buffer.append({"r": self._ep[0], "l": self._ep[1]})
-                    self._ep = [0.0, 0]
-                self._last_obs = env.reset() if done else new_obs  # DummyVecEnv auto-reset
-            last_values = self.policy.predict_values(self._last_obs)
-            buf.compute_returns_and_advantage(last_values, self._last_start, self.gamma, self.gae_lambda)
+            collect_rollouts_single_env(self, env, self.policy, buf, self.n_steps)
             self._iteration += 1
             if log_interval is not None and self._iteration % log_interval == 0 and self._logger.output_formats:
                 eps = list(self.ep_info_buffer)
