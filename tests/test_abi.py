@@ -58,3 +58,22 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert lib.pth_policy_param_count(ctypes.byref(sp)) == 44308
     assert lib.pth_policy_param_count(ctypes.byref(_lib.Space.onehot([1], [3]))) == 8836
     assert lib.pth_policy_param_count(ctypes.byref(_lib.Space.box(62, [6]))) == 16839
+
+
+def test_ctypes_mirrors_have_the_size_gcc_gives_the_header_structs(tmp_path):
+    """The header compiles as plain C, and every ctypes.Structure in _lib.py is as large as the struct it
+    mirrors (a field added on one side only would shift every later argument silently)."""
+    import subprocess
+    from pantheonrl_b200 import _lib
+    pairs = [("pth_space", "Space"), ("pth_update_args", "UpdateArgs"), ("pth_forward_args", "ForwardArgs"),
+             ("pth_rollout_args", "RolloutArgs"), ("pth_buffer", "Buffer"), ("pth_env_carry", "EnvCarry"),
+             ("pth_overcooked_layout", "OvercookedLayout")]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "pantheon_b200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("%zu\\n", sizeof({c}));\n' for c, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    for (c, py), n in zip(pairs, sizes):
+        assert ctypes.sizeof(getattr(_lib, py)) == n, (c, py, n)
