@@ -50,6 +50,26 @@ def test_update_bit_exact_vs_oracle(ctx, kw, M, BS, E, grid):
     assert np.array_equal(gp, op), np.abs(gp - op).max()
 
 
+@pytest.mark.parametrize("grid", [72, 140])
+def test_update_bit_exact_with_many_ctas(ctx, grid):
+    """One tile per CTA on 72 / 140 CTAs: the ordered reduction then splits every parameter's chain
+    over 2 / 4 thread groups (<= 64 partials is the one-group path the small-grid tests cover)."""
+    kw = oracle.RPS_SPACE
+    M = BS = 128 * grid
+    space = oracle.make_space(**kw)
+    pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=grid)
+    params = pol.to_flat().copy()
+    obs, act, old_logp, adv, ret = make_batch(kw, M, seed=grid)
+    ev = oracle.policy_forward(space, params, obs, action_in=act)
+    old_logp = (ev["logp"] + 0.1 * np.random.RandomState(2).randn(M)).astype(np.float32)
+    perm = oupd.perm_feistel(M, 2, seed=10, stream=4)
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    gp, gm, gv, gst = run_gpu(kw, params, m, v, 0, obs, act, old_logp, adv, ret, perm, BS, grid, ent_coef=0.01)
+    op, om, ov = params.copy(), m.copy(), v.copy()
+    ost, _ = oupd.ppo_update(space, op, om, ov, 0, obs, act, old_logp, adv, ret, perm, BS, grid, ent_coef=0.01)
+    assert np.array_equal(gst, ost) and np.array_equal(gm, om) and np.array_equal(gv, ov) and np.array_equal(gp, op)
+
+
 def test_subnormal_partial_sums_follow_red_add_semantics(ctx):
     """Later tiles of a CTA are added with RED.ADD.F32, which flushes subnormal inputs and
     results to zero; the oracle restates that.  Advantages of ~1e-33 with vf_coef = ent_coef = 0
