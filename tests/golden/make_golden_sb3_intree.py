@@ -115,10 +115,8 @@ def run_reference_train(kw, M, BS, E, seed):
                                       ev["value"].astype(np.float32), perms))
     pol.parameters = pol.ordered_parameters  # what clip_grad_norm_ walks
     adap_learn.ADAP.train(algo)  # <- the reference's own code
-    st = pol.optimizer.state
-    m = np.concatenate([st[p]["exp_avg"].detach().numpy().reshape(-1) for p in pol.ordered_parameters()])
     return dict(p0=p0, obs=obs, act=act, old_logp=old_logp, adv=adv, ret=ret, perms=perms,
-                params=pol.to_flat().copy(), adam_m_torch_layout=m, n_updates=np.array(algo._n_updates),
+                params=pol.to_flat().copy(), n_updates=np.array(algo._n_updates),
                 log_keys=np.array(sorted(algo.logger.kv)),
                 log_vals=np.array([float(algo.logger.kv[k]) for k in sorted(algo.logger.kv)], np.float64),
                 hp=np.array([M, BS, E], np.int64))
