@@ -143,3 +143,33 @@ def test_oracle_bc_matches_torch_autograd():
     assert np.allclose(-stats[:, 2], [r["entropy"] for r in ref], atol=1e-5)
     assert np.allclose(stats[:, 3], [r["prob_true_act"] for r in ref], atol=1e-6)
     assert stats[-1, 0] < stats[0, 0]  # it learns: neglogp of the cloned actions goes down
+
+
+def test_uniform_slot_rows_equal_the_bias_gradient_bit_for_bit():
+    """Property behind a round-2 kernel lead: when every sample of a tile holds the same value in
+    a one-hot slot, the first-layer weight-gradient row that value selects is the same ascending chain over the
+    tile's samples as the first-layer bias gradient — in both towers, exactly."""
+    kw = oracle.LIAR_SPACE
+    space = oracle.make_space(**kw)
+    M = 128  # one tile, one minibatch, one CTA
+    pol = sb3_torch.MlpPolicy(nvec=kw["nvec"], heads=kw["heads"], seed=3)
+    params = pol.to_flat().copy()
+    obs, act, old_logp, adv, ret = make_batch(kw, M, seed=8)
+    uniform = {7: 6, 8: 0, 20: 3, 29: 11}  # slot -> the value all samples hold
+    for s, val in uniform.items():
+        obs[:, s] = val
+    perm = np.arange(M, dtype=np.int32)[None]
+    m, v = np.zeros_like(params), np.zeros_like(params)
+    _, grad = oupd.ppo_update(space, params, m, v, 0, obs, act, old_logp, adv, ret, perm, M, grid=1, ent_coef=0.01)
+    F, H = sum(kw["nvec"]), 64
+    off = np.concatenate([[0], np.cumsum(kw["nvec"])])
+    for base_w, base_b in ((0, F * H), (F * H + H + H * H + H, F * H + H + H * H + H + F * H)):  # pi tower, vf tower
+        bias = grad[base_b:base_b + H]
+        assert np.any(bias != 0)
+        for s, val in uniform.items():
+            row = off[s] + val
+            assert np.array_equal(grad[base_w + row * H: base_w + (row + 1) * H], bias), (s, val)
+            for other in range(kw["nvec"][s]):
+                if other != val:
+                    r = off[s] + other
+                    assert not grad[base_w + r * H: base_w + (r + 1) * H].any()
