@@ -148,6 +148,16 @@ class MultiAgentEnv(ABC):
         self._old_ego_obs = ego_obs
         return self.ego_extractor(ego_obs)
 
+    # gym.Env's housekeeping surface, as callers of the reference use it (tester.py:47-58)
+    def close(self):
+        pass
+
+    def render(self, mode="human"):
+        pass
+
+    def seed(self, seed=None):
+        return [seed]
+
     @abstractmethod
     def n_step(self, actions):
         """-> (next players, their observations, rewards of all players, done, info)"""
