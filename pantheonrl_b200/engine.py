@@ -283,6 +283,24 @@ class VecTrainer:
             self.iteration()
         return self
 
+    # ------------------------------------------------------------------ recording
+    def recorded_transitions(self, env=0):
+        """What `recorder_wrap(env)` (pantheonrl/common/wrappers.py:84-232) would hold for env `env` after
+        the LAST rollout, cut out of the rollout buffers on the host (pantheonrl_b200/vec_record.py; pinned
+        against the reference's recorder through the oracle's buffers in tests/test_vec_record_cpu.py).
+        Call it between collect() and the next collect()."""
+        from . import vec_record as vr
+        host = lambda b: {k: getattr(b, k).cpu().numpy() for k in ("obs", "actions", "episode_starts")}  # noqa: E731
+        ego, alt = host(self.ego_buf), host(self.alt_buf)
+        alt["count"] = self.alt_buf.count.cpu().numpy()
+        last_done = float(self.carry.ego_last_done[env].item())
+        if self.env_kind == "liar":
+            return vr.turn_based_transitions(ego, alt, env, last_done)
+        if self.alt is None:
+            raise _lib.PthError("recording needs a recording partner (partner='ppo'): a static partner stores no rows")
+        obs_len, act_len = (1, 1) if self.env_kind == "rps" else (self.space.obs_len, 1)
+        return vr.simultaneous_transitions(ego, alt, env, last_done, obs_len=obs_len, act_len=act_len)
+
     # ------------------------------------------------------------------ logging
     def train_stats(self, learner=None):
         """Mean of the per-minibatch scalars SB3's PPO.train logs (adap_learn.py:354-371)."""
