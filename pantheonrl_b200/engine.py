@@ -295,6 +295,11 @@ class VecTrainer:
         alt["count"] = self.alt_buf.count.cpu().numpy()
         last_done = float(self.carry.ego_last_done[env].item())
         if self.env_kind == "liar":
+            if self.rollouts != 1:
+                # a later rollout may begin after the partner's opening move of the running episode, which sits
+                # in the PREVIOUS partner buffer: the episode counters of the two buffers then differ by one
+                raise _lib.PthError("turn-based recording is cut from a rollout that starts at an episode "
+                                    "boundary: call it after the first collect()")
             return vr.turn_based_transitions(ego, alt, env, last_done)
         if self.alt is None:
             raise _lib.PthError("recording needs a recording partner (partner='ppo'): a static partner stores no rows")
