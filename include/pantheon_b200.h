@@ -290,8 +290,11 @@ enum { PTH_ENV_RPS = 0, PTH_ENV_LIAR = 1, PTH_ENV_OVERCOOKED = 2 };
 /* rollout buffer of one learner; all arrays [Tcap][N].  Observation rows: 32 B
  * (PTH_OBS_ONEHOT: one byte per slot) or PTH_OC_ROW fp32 = 256 B (PTH_OBS_BOX).
  * Ego: Tcap = T, dense (count unused, may be NULL).
- * Partner: Tcap >= 2*T (turn-based) or T (simultaneous), ragged, count[n] decisions
- * recorded this rollout. */
+ * Partner: Tcap >= 2*T + 1 (turn-based) or T (simultaneous), ragged; count[n] = rows of this
+ * rollout that are complete (trainable).  Turn-based games: a row still waiting for the ego's next
+ * move when the rollout ends is not counted; it stays at row count[n], carry flag bit2 is set, and
+ * the next pth_rollout_run on the SAME buffer starts by moving it to row 0 (so no reward is lost at
+ * a rollout boundary; the reference's lazily training partner sees it too, agents.py:126, 198). */
 typedef struct pth_buffer {
   uint8_t* d_obs;            /* [Tcap][N][32] u8, or [Tcap][N][64] fp32 for Box spaces */
   uint8_t* d_actions;        /* [Tcap][N][4]  */
@@ -309,11 +312,15 @@ typedef struct pth_env_carry {
   float* d_ego_last_start;     /* [N] ego _last_episode_starts            */
   float* d_alt_last_done;      /* [N] partner _last_episode_starts latch  */
   float* d_total_rew;          /* [2][N] total_rews                       */
-  uint8_t* d_flags;            /* [N] bit0 ego_moved, bit1 should_update  */
+  uint8_t* d_flags;            /* [N] bit0 ego_moved, bit1 should_update, bit2 open partner row carried */
   void* d_game_state;          /* PTH_ENV_LIAR: pth_liar_state[N]; PTH_ENV_OVERCOOKED: pth_overcooked_state[N]; RPS: NULL */
   float* d_ego_last_value;     /* [N] out: V(obs_T) bootstrap for the ego  */
   float* d_ego_last_done;      /* [N] out: done flag after the last tick   */
   float* d_ep_stats;           /* [4] += {episodes, sum ego ep reward, sum ep len, partner decisions} or NULL */
+  float* d_alt_boot_done;      /* [N] out or NULL: the `dones` argument of the partner's compute_returns_and_advantage
+                                * (agents.py:127-130) for this rollout's closed rows: the partner's done latch, or —
+                                * turn-based games, when the partner's latest row is still open — the
+                                * episode_start stored with that open row */
 } pth_env_carry;
 
 typedef struct pth_rollout_args {

@@ -37,6 +37,8 @@ class CpuTrainer:
         self.alt = (sb3_torch.MlpPolicy(nvec=self.kw["nvec"], heads=self.kw["heads"], seed=seed)
                     if partner == "ppo" else None)
         self.carry = None
+        # one partner buffer for the whole run: a row left open at a rollout's end is carried in it
+        self._alt_buf = orc.new_buffer(orc.alt_capacity(env_kind, n_steps), n_envs, True)
         self.rollouts = 0
         self.n_updates = [0, 0]
         self.nslot, self.nh = len(self.kw["nvec"]), len(self.kw["heads"])
@@ -50,14 +52,14 @@ class CpuTrainer:
         ego, alt, self.carry = orc.rollout(
             self.env_kind, self.space, pe, pa, N=N, T=T, seed=self.seed, tick0=self.rollouts * T,
             first_rollout=self.rollouts == 0, carry=self.carry, partner_records=self.alt is not None,
-            alt=orc.new_buffer(2 * T if self.env_kind == "liar" else T, N, True))
+            alt=self._alt_buf)
         self.rollouts += 1
         t1 = time.perf_counter()
         adv, ret = oracle.gae(ego["rewards"], ego["values"], ego["episode_starts"],
                               self.carry["ego_last_value"], self.carry["ego_last_done"])
         if self.alt is not None:
             aadv, aret = oracle.gae_ragged(alt["rewards"], alt["values"], alt["episode_starts"],
-                                           alt["count"], self.carry["alt_last_done"])
+                                           alt["count"], self.carry["alt_boot_done"])
         t2 = time.perf_counter()
         decisions = N * T
         idx = oupd.index_build(None, T, N)

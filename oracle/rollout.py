@@ -22,7 +22,7 @@ class OrcRolloutArgs(C.Structure):
         ("ego", OrcBuffer), ("alt", OrcBuffer),
         ("ego_last_start", C.c_void_p), ("alt_last_done", C.c_void_p), ("total_rew", C.c_void_p),
         ("flags", C.c_void_p), ("game_state", C.c_void_p), ("ego_last_value", C.c_void_p),
-        ("ego_last_done", C.c_void_p), ("ep_stats", C.c_void_p),
+        ("ego_last_done", C.c_void_p), ("ep_stats", C.c_void_p), ("alt_boot_done", C.c_void_p),
         ("N", C.c_int64), ("T", C.c_int64), ("env0", C.c_int64),
         ("seed", C.c_uint64), ("tick0", C.c_uint32), ("probegostart", C.c_float),
         ("first_rollout", C.c_int32),
@@ -32,6 +32,12 @@ class OrcRolloutArgs(C.Structure):
 
 
 OC_STATE_BYTES = 14 + 128 * 4 + 1 + 8 + 1 + 4  # sizeof(orc_oc_state): 540 (t is 4-byte aligned)
+
+
+def alt_capacity(env_kind, T):
+    """Rows of the partner's buffer: simultaneous games one per tick; Liar's Dice up to two per tick
+    (reply + opening move after a reset) plus the open row carried in from the previous rollout."""
+    return 2 * T + 1 if env_kind == "liar" else T
 
 
 def new_buffer(Tcap, N, ragged, box=False):
@@ -48,7 +54,8 @@ def new_carry(N):
                 total_rew=np.zeros((2, N), np.float32), flags=np.zeros(N, np.uint8),
                 game_state=np.zeros((N, 32), np.uint8), oc_state=np.zeros((N, OC_STATE_BYTES), np.uint8),
                 ego_last_value=np.zeros(N, np.float32),
-                ego_last_done=np.zeros(N, np.float32), ep_stats=np.zeros(4, np.float32))
+                ego_last_done=np.zeros(N, np.float32), ep_stats=np.zeros(4, np.float32),
+                alt_boot_done=np.zeros(N, np.float32))
 
 
 def _cbuf(b):
@@ -66,7 +73,7 @@ def rollout(env_kind, space, ego_params, alt_params, N, T, seed=10, tick0=0, env
     """Runs one rollout; returns (ego buffer dict, partner buffer dict, carry dict)."""
     box = env_kind == "overcooked"
     ego = ego or new_buffer(T, N, False, box)
-    alt = alt or new_buffer(T if box else 2 * T, N, True, box)
+    alt = alt or new_buffer(alt_capacity(env_kind, T), N, True, box)
     carry = carry or new_carry(N)
     a = OrcRolloutArgs()
     a.env_kind = {"rps": 0, "liar": 1, "overcooked": 2}[env_kind]
@@ -85,7 +92,7 @@ def rollout(env_kind, space, ego_params, alt_params, N, T, seed=10, tick0=0, env
             setattr(a, name, p.ctypes.data)
     a.ego, a.alt = _cbuf(ego), _cbuf(alt)
     for k in ("ego_last_start", "alt_last_done", "total_rew", "flags", "game_state",
-              "ego_last_value", "ego_last_done", "ep_stats"):
+              "ego_last_value", "ego_last_done", "ep_stats", "alt_boot_done"):
         setattr(a, k, carry[k].ctypes.data)
     a.N, a.T, a.env0 = N, T, env0
     a.seed, a.tick0, a.probegostart = seed, tick0, probegostart
@@ -96,8 +103,8 @@ def rollout(env_kind, space, ego_params, alt_params, N, T, seed=10, tick0=0, env
             s = np.ascontiguousarray(s, np.uint8)
             keep.append(s)
             setattr(a, name, s.ctypes.data)
-    if alt["count"] is not None:
-        alt["count"][:] = 0
+    if alt["count"] is not None and first_rollout:
+        alt["count"][:] = 0  # later rollouts read count[n]: where the carried open row sits
     lib().orc_rollout(C.byref(a))
     return ego, alt, carry
 

@@ -116,6 +116,7 @@ class EnvCarry(C.Structure):
         ("d_ego_last_value", C.c_void_p),
         ("d_ego_last_done", C.c_void_p),
         ("d_ep_stats", C.c_void_p),
+        ("d_alt_boot_done", C.c_void_p),
     ]
 
 

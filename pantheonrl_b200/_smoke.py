@@ -19,7 +19,7 @@ def run():
     flat = init_flat(sp, seed)
     pe = torch.from_numpy(flat).cuda()
     pa = pe.clone()
-    ego, alt, carry = dev.Buffer(T, N, False, "cuda"), dev.Buffer(2 * T, N, True, "cuda"), dev.Carry(N, "cuda")
+    ego, alt, carry = dev.Buffer(T, N, False, "cuda"), dev.Buffer(dev.alt_capacity("liar", T), N, True, "cuda"), dev.Carry(N, "cuda")
     dev.run_rollout("liar", sp, pe, pa, ego, alt, carry, T, seed, 0, first_rollout=True)
     adv, ret = ops.gae(ego.rewards, ego.values, ego.episode_starts, carry.ego_last_value, carry.ego_last_done)
     index, _ = dupd.index_build(None, T, N)

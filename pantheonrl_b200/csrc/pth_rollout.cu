@@ -97,8 +97,9 @@ struct EnvRegs {
   float total_ego, total_alt;
   float ego_last_start, alt_last_done;
   float alt_pending;   // reward accumulated on the partner's latest row
+  float alt_row_start; // episode_start stored with the partner's latest row
   int alt_count;
-  uint32_t flags;      // bit0 ego_moved, bit1 should_update
+  uint32_t flags;      // bit0 ego_moved, bit1 should_update, bit2 open partner row carried
   float st_eps, st_rew, st_steps, st_alt;
 };
 
@@ -131,6 +132,7 @@ __device__ __forceinline__ void alt_record(const RollParams& p, EnvRegs& e, int6
     p.a.alt.d_values[o] = f.value;
     p.a.alt.d_logp[o] = f.logp;
     p.a.alt.d_episode_starts[o] = e.alt_last_done;
+    e.alt_row_start = e.alt_last_done;
     e.alt_count += 1;
     e.alt_pending = 0.f;
   }
@@ -181,8 +183,30 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
       e.total_ego = cr.d_total_rew[n];
       e.total_alt = cr.d_total_rew[N + n];
       e.flags = cr.d_flags[n];
-      if (ENV == PTH_ENV_LIAR)
+      if (ENV == PTH_ENV_LIAR) {
         liar_load(reinterpret_cast<const pth_liar_state*>(cr.d_game_state) + n, e.liar);
+        if (e.flags & 4u) {
+          // The partner row that was still waiting for the ego's next move when the previous rollout
+          // ended (it sits at row count[n] of the partner's buffer) becomes row 0 of this rollout.
+          if (p.a.partner_records) {
+            const int64_t src = (int64_t)p.a.alt.d_count[n] * N + n;
+            const uint4* q = reinterpret_cast<const uint4*>(p.a.alt.d_obs + src * 32);
+            const uint4 o0 = q[0], o1 = q[1];
+            uint4* d = reinterpret_cast<uint4*>(p.a.alt.d_obs + n * 32);
+            d[0] = o0;
+            d[1] = o1;
+            *reinterpret_cast<uint32_t*>(p.a.alt.d_actions + 4 * n) =
+                *reinterpret_cast<const uint32_t*>(p.a.alt.d_actions + 4 * src);
+            p.a.alt.d_values[n] = p.a.alt.d_values[src];
+            p.a.alt.d_logp[n] = p.a.alt.d_logp[src];
+            e.alt_row_start = p.a.alt.d_episode_starts[src];
+            p.a.alt.d_episode_starts[n] = e.alt_row_start;
+            e.alt_pending = p.a.alt.d_rewards[src];
+            e.alt_count = 1;
+          }
+          e.flags &= ~4u;
+        }
+      }
     }
   }
 
@@ -335,6 +359,15 @@ __global__ void __launch_bounds__(NT) rollout_kernel(const __grid_constant__ Rol
 
   if (valid) {
     alt_flush(p, e, n);
+    float boot_done = e.alt_last_done;
+    if (ENV == PTH_ENV_LIAR && p.a.partner_records && (e.flags & 2u) && e.alt_count > 0) {
+      // turn-based, the partner has moved in the running episode: its latest row still waits for the
+      // ego's next move.  It is left out of this rollout's batch and carried.
+      e.alt_count -= 1;
+      boot_done = e.alt_row_start;
+      e.flags |= 4u;
+    }
+    if (cr.d_alt_boot_done) cr.d_alt_boot_done[n] = boot_done;
     cr.d_ego_last_value[n] = fl.value;
     cr.d_ego_last_done[n] = e.ego_last_start;
     cr.d_ego_last_start[n] = e.ego_last_start;
@@ -507,6 +540,7 @@ __global__ void __launch_bounds__(NT) rollout_overcooked_kernel(const __grid_con
   FwdOut fl = cta_forward_t<RB, true>(p, ego_w, sm.pol_ego, sm.A, sm.Bf, sm.Lg, sm.Xe, tid, false, zero);
   if (valid) {
     alt_flush(p, e, n);
+    if (cr.d_alt_boot_done) cr.d_alt_boot_done[n] = e.alt_last_done;  // simultaneous: no open rows
     cr.d_ego_last_value[n] = fl.value;
     cr.d_ego_last_done[n] = e.ego_last_start;
     cr.d_ego_last_start[n] = e.ego_last_start;
@@ -546,8 +580,8 @@ extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* st
     PTH_CHECK_ARG(a->alt.d_obs && a->alt.d_actions && a->alt.d_rewards && a->alt.d_values &&
                       a->alt.d_logp && a->alt.d_episode_starts && a->alt.d_count,
                   "NULL partner buffer");
-    PTH_CHECK_ARG(a->alt.Tcap >= (a->env_kind == PTH_ENV_LIAR ? 2 * a->T : a->T),
-                  "partner buffer must hold 2*T rows (T for simultaneous envs)");
+    PTH_CHECK_ARG(a->alt.Tcap >= (a->env_kind == PTH_ENV_LIAR ? 2 * a->T + 1 : a->T),
+                  "partner buffer must hold 2*T + 1 rows (T for simultaneous envs)");
   }
   const pth_env_carry& c = a->carry;
   PTH_CHECK_ARG(c.d_ego_last_start && c.d_alt_last_done && c.d_total_rew && c.d_flags &&

@@ -112,10 +112,11 @@ class VecTrainer:
             raise ValueError(partner)
         N, T = self.N, self.T
         self.ego_buf = ro.Buffer(T, N, False, device, box)
-        alt_cap = 2 * T if env_kind == "liar" else T
+        alt_cap = ro.alt_capacity(env_kind, T)
         self.alt_buf = ro.Buffer(alt_cap, N, True, device, box)
         self.carry = ro.Carry(N, device, state_bytes)
         self.rollouts = 0
+        self.tick_base = 0  # global tick of this trainer's first rollout (a resumed model starts past its old ticks)
         self.num_timesteps = 0
         self.partner_decisions = 0
         # dense env-major sample index of the ego buffer (SB3 swap_and_flatten), built once
@@ -179,7 +180,7 @@ class VecTrainer:
     def collect(self):
         alt_params = self.alt.params if self.alt is not None else self.ego.params
         ro.run_rollout(self.env_kind, self.space, self.ego.params, alt_params, self.ego_buf,
-                       self.alt_buf, self.carry, self.T, self.seed, self.rollouts * self.T,
+                       self.alt_buf, self.carry, self.T, self.seed, self.tick_base + self.rollouts * self.T,
                        env0=self.env0, probegostart=self.probegostart,
                        first_rollout=self.rollouts == 0, partner_records=self.alt is not None,
                        d_layout=self.d_layout)
@@ -192,7 +193,7 @@ class VecTrainer:
                 self.carry.ego_last_done, c.gamma, c.gae_lambda, out=(b.advantages, b.returns))
         if self.alt is not None:
             a, ac = self.alt_buf, self.alt_cfg
-            ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_last_done,
+            ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_boot_done,
                            ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
 
     def plan_grids(self, M_ego, M_alt):
@@ -290,9 +291,12 @@ class VecTrainer:
         against the reference's recorder through the oracle's buffers in tests/test_vec_record_cpu.py).
         Call it between collect() and the next collect()."""
         from . import vec_record as vr
+        if self.alt is None:
+            raise _lib.PthError("recording needs a recording partner (partner='ppo'): a static partner stores no rows")
         host = lambda b: {k: getattr(b, k).cpu().numpy() for k in ("obs", "actions", "episode_starts")}  # noqa: E731
         ego, alt = host(self.ego_buf), host(self.alt_buf)
-        alt["count"] = self.alt_buf.count.cpu().numpy()
+        # every recorded partner decision: the complete rows plus the one still open at the rollout's end
+        alt["count"] = self.alt_buf.count.cpu().numpy() + ((self.carry.flags.cpu().numpy() >> 2) & 1)
         last_done = float(self.carry.ego_last_done[env].item())
         if self.env_kind == "liar":
             if self.rollouts != 1:
@@ -301,8 +305,6 @@ class VecTrainer:
                 raise _lib.PthError("turn-based recording is cut from a rollout that starts at an episode "
                                     "boundary: call it after the first collect()")
             return vr.turn_based_transitions(ego, alt, env, last_done)
-        if self.alt is None:
-            raise _lib.PthError("recording needs a recording partner (partner='ppo'): a static partner stores no rows")
         obs_len, act_len = (1, 1) if self.env_kind == "rps" else (self.space.obs_len, 1)
         return vr.simultaneous_transitions(ego, alt, env, last_done, obs_len=obs_len, act_len=act_len)
 

@@ -59,6 +59,9 @@ LAYOUTS = {
 }
 
 LAYOUT_LIST = sorted(LAYOUTS)
+# overcookedgym/overcooked_utils.py:7-13: the names the Overcooked-AI papers use for five layouts
+NAME_TRANSLATION = {"cramped_room": "simple", "asymmetric_advantages": "unident_s", "coordination_ring": "random1",
+                    "forced_coordination": "random0", "counter_circuit": "random3"}
 TERRAIN_CODE = {" ": _lib.PTH_OC_FLOOR, "X": _lib.PTH_OC_COUNTER, "O": _lib.PTH_OC_ONION, "P": _lib.PTH_OC_POT,
                 "D": _lib.PTH_OC_DISH, "S": _lib.PTH_OC_SERVE}
 # OvercookedMultiEnv's constants (overcooked.py:18-28)

@@ -8,6 +8,7 @@ n_envs == 1: the reference's host-driven flow — one kernel call per decision
 n_envs  > 1: learn() hands the whole loop to the device engine (VecTrainer ->
   pth_rollout_run) for the built-in envs.
 """
+import itertools
 import time
 from collections import deque
 
@@ -17,6 +18,23 @@ import torch
 from . import _lib, logger as lg, ops, policy as pol, update as up
 from .common.agents import OnPolicyAgent, StaticPolicyAgent
 from .spaces import to_pth_space
+
+
+# Philox streams of the host-driven (n_envs = 1) flow.  The reference builds the ego and every
+# PPO partner with the SAME seed (trainer.py:111-112, 198-199): same initial weights, but their
+# action samples come from one shared torch generator that keeps advancing, so the two learners
+# never see the same random numbers.  Counter-based Philox has no shared state to advance: every
+# PPO constructed in this process therefore takes the next pair of streams (sampling, shuffle)
+# above the five streams of the device engine.  Construction order defines the streams, so a
+# script run twice gives the same trace.
+FACADE_STREAM0 = 0x100
+_instances = itertools.count()
+
+
+def reset_stream_counter():
+    """Start the per-process PPO instance count again (a fresh run inside one interpreter)."""
+    global _instances
+    _instances = itertools.count()
 
 
 class DevicePolicy:
@@ -142,11 +160,13 @@ class PPO:
     def __init__(self, policy="MlpPolicy", env=None, learning_rate=3e-4, n_steps=2048, batch_size=64,
                  n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, normalize_advantage=True,
                  ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, tensorboard_log=None, verbose=0, seed=None,
-                 device="cuda", n_envs=1, n_minibatches=0, _rng_stream=None):
+                 device="cuda", n_envs=1, n_minibatches=0):
         if policy != "MlpPolicy":
             raise ValueError("only 'MlpPolicy' (SB3 default 64-64 tanh towers) is implemented")
         if not torch.cuda.is_available():
             raise _lib.PthError("PPO needs a CUDA device: this path has no CPU implementation")
+        from .compat import unwrap_env
+        env = unwrap_env(env)  # DummyVecEnv([lambda: Monitor(env)]) -> env (trainer.py:119)
         self.env, self.device = env, ("cuda" if device in ("auto", "cuda") else device)
         self.learning_rate, self.n_steps, self.batch_size, self.n_epochs = learning_rate, n_steps, batch_size, n_epochs
         self.gamma, self.gae_lambda, self.clip_range = gamma, gae_lambda, clip_range
@@ -155,8 +175,12 @@ class PPO:
         self.tensorboard_log, self.n_envs, self.n_minibatches = tensorboard_log, int(n_envs), n_minibatches
         self.observation_space, self.action_space = env.observation_space, env.action_space
         self.space = to_pth_space(self.observation_space, self.action_space)
-        stream = _rng_stream if _rng_stream is not None else _lib.STREAM_EGO
-        self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, seed, self.device, stream)
+        stream = FACADE_STREAM0 + 2 * next(_instances)  # its shuffle stream is stream + 1
+        # seed=None: SB3 leaves the global generators alone, so two unseeded learners differ; here the
+        # effective seed comes from numpy's global stream (np.random.seed(...) still pins a whole run)
+        eff_seed = int(np.random.randint(1, 2 ** 31 - 1)) if seed is None else seed
+        self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, eff_seed, self.device,
+                                   stream)
         if self.space.obs_kind == _lib.PTH_OBS_BOX and self.space.obs_len > _lib.PTH_OC_ROW:
             raise _lib.PthError("Box observations wider than 64 are not supported")
         self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda,
@@ -214,7 +238,12 @@ class PPO:
         r("time/total_timesteps", self.num_timesteps, exclude="tensorboard")
         self._logger.dump(step=self.num_timesteps)
 
-    def _setup_learn(self, tb_log_name):
+    def _setup_learn(self, tb_log_name, reset_num_timesteps=True):
+        """BaseAlgorithm._setup_learn: a learn() call counts its timesteps from 0 unless the caller
+        continues a run with reset_num_timesteps=False (optimizer state and update counters always
+        continue: they belong to the model, not to the call)."""
+        if reset_num_timesteps:
+            self.num_timesteps = 0
         if not self._custom_logger:
             self._logger = lg.configure_logger(self.verbose, self.tensorboard_log, tb_log_name)
         self.start_time, self._num_timesteps_at_start = time.time(), self.num_timesteps
@@ -225,8 +254,8 @@ class PPO:
         if self._ws is None:
             self._ws = up.UpdateWorkspace(self.space, M, self.batch_size, self.device)
             self._perm = torch.empty(self.n_epochs, M, dtype=torch.int32, device=self.device)
-        shuffle = _lib.STREAM_SHUFFLE_EGO if self.policy.rng_stream == _lib.STREAM_EGO else _lib.STREAM_SHUFFLE_ALT
-        up.perm_feistel(M, self.n_epochs, self.policy.seed, shuffle, epoch0=self._n_updates, out=self._perm)
+        up.perm_feistel(M, self.n_epochs, self.policy.seed, self.policy.rng_stream + 1, epoch0=self._n_updates,
+                        out=self._perm)
         d = buf.d
         self.last_stats = up.ppo_update(
             self.space, self.policy.params, self.adam_m, self.adam_v, self.adam_step, d["obs"], d["actions"],
@@ -238,8 +267,11 @@ class PPO:
         self._record_train(self.last_stats, d["values"], d["returns"], self._n_updates)
 
     # ---------------------------------------------------------------- learn
-    def learn(self, total_timesteps, log_interval=1, tb_log_name="PPO", **_):
-        self._setup_learn(tb_log_name)
+    def learn(self, total_timesteps, callback=None, log_interval=1, tb_log_name="PPO", reset_num_timesteps=True,
+              progress_bar=False):
+        if callback is not None or progress_bar:
+            raise NotImplementedError("learn(callback=, progress_bar=) are not supported")
+        self._setup_learn(tb_log_name, reset_num_timesteps)
         if self.n_envs > 1:
             return self._learn_on_device(total_timesteps, log_interval)
         env, buf = self.env, self.rollout_buffer
@@ -278,6 +310,10 @@ class PPO:
                                      n_minibatches=m.n_minibatches or 32)
             if isinstance(partner, OnPolicyAgent):
                 mode, alt_cfg = "ppo", mk(partner.model)
+                if partner.model.n_steps != self.n_steps:
+                    import warnings
+                    warnings.warn("on-device loop: the partner trains at the ego's rollout boundaries; its "
+                                  f"n_steps={partner.model.n_steps} is not used (ego n_steps={self.n_steps})")
             elif isinstance(partner, StaticPolicyAgent) and partner.policy is self.policy:
                 mode, alt_cfg = "selfplay", None
             else:
@@ -288,12 +324,22 @@ class PPO:
                                            "horizon": self.env.layout.horizon} if kind == "overcooked" else {}))
             self._trainer.ego.params = self.policy.params          # share storage with the facade objects
             self._trainer.ego.adam_m, self._trainer.ego.adam_v = self.adam_m, self.adam_v
+            # counters the models bring along (PPO.load, or earlier n_envs = 1 training): Adam's bias
+            # correction and the shuffle keys continue, and the env / sampling streams start at fresh ticks
+            tr0 = self._trainer
+            tr0.ego.adam_step, tr0.ego.n_updates = self.adam_step, self._n_updates
+            tr0.tick_base = (self._n_updates * self.n_steps) & 0xffffffff
             if mode == "ppo":
-                self._trainer.alt.params = partner.model.policy.params
-                self._trainer.alt.adam_m, self._trainer.alt.adam_v = partner.model.adam_m, partner.model.adam_v
-        tr, target = self._trainer, self._trainer.num_timesteps + total_timesteps
+                tr0.alt.params = partner.model.policy.params
+                tr0.alt.adam_m, tr0.alt.adam_v = partner.model.adam_m, partner.model.adam_v
+                tr0.alt.adam_step, tr0.alt.n_updates = partner.model.adam_step, partner.model._n_updates
+                tr0.partner_decisions = partner.num_timesteps
+            self._ep_prev = np.zeros(4)
+        tr = self._trainer
+        tr.num_timesteps = self.num_timesteps
+        target = tr.num_timesteps + total_timesteps
         partner_model = partner.model if isinstance(partner, OnPolicyAgent) else None
-        prev = np.zeros(4)
+        prev = self._ep_prev  # device episode counters are cumulative: keep the last reading across learn() calls
         while tr.num_timesteps < target:
             tr.collect()
             tr.compute_gae()
@@ -304,6 +350,7 @@ class PPO:
                 # episodes finished during this rollout (device counters: episodes, reward sum, length sum)
                 e = tr.carry.ep_stats.cpu().numpy().astype(np.float64)
                 d, prev = e - prev, e
+                self._ep_prev = prev
                 n = max(d[0], 1.0)
                 self._record_rollout(self._iteration, float(d[1] / n), float(d[2] / n))
             tr.train()
@@ -363,6 +410,7 @@ class PPO:
         return m
 
     def set_env(self, env):
-        """trainer.py:123 (`model.set_env(vec_env)` after a LOAD)."""
-        self.env = env
+        """trainer.py:119-123 (`model.set_env(DummyVecEnv([lambda: Monitor(env)]))` after a LOAD)."""
+        from .compat import unwrap_env
+        self.env = unwrap_env(env)
         self._last_obs = None

@@ -23,6 +23,12 @@ def space_for(env_kind):
     raise ValueError(env_kind)
 
 
+def alt_capacity(env_kind, T):
+    """Rows of the partner's buffer: one per tick in simultaneous games; in Liar's Dice up to two per tick
+    (reply + opening move after a reset) plus the open row carried in from the previous rollout."""
+    return 2 * T + 1 if env_kind == "liar" else T
+
+
 class Buffer:
     """One learner's rollout buffer: arrays [Tcap, N] (time-major, env contiguous)."""
 
@@ -66,11 +72,12 @@ class Carry:
         self.ego_last_value = z(N)
         self.ego_last_done = z(N)
         self.ep_stats = z(4)
+        self.alt_boot_done = z(N)
 
     def c_struct(self):
         c = _lib.EnvCarry()
         for k in ("ego_last_start", "alt_last_done", "total_rew", "flags", "game_state",
-                  "ego_last_value", "ego_last_done", "ep_stats"):
+                  "ego_last_value", "ego_last_done", "ep_stats", "alt_boot_done"):
             setattr(c, "d_" + k, getattr(self, k).data_ptr())
         return c
 

@@ -120,7 +120,7 @@ def test_onpolicy_agent_lazy_train_protocol(ctx):
     """agents.py:123-184: the partner trains inside the get_action that follows its
     n_steps-th recorded action, bootstrapping from the last stored value."""
     env = RPSEnv()
-    model = PPO("MlpPolicy", env, n_steps=8, batch_size=4, n_epochs=2, seed=10, _rng_stream=_lib.STREAM_ALT)
+    model = PPO("MlpPolicy", env, n_steps=8, batch_size=4, n_epochs=2, seed=10)
     agent = OnPolicyAgent(model)
     from pantheonrl_b200.common.observation import Observation
     p0 = model.policy.params.clone()
@@ -146,8 +146,7 @@ def test_onpolicy_agent_lazy_train_protocol(ctx):
 
 def test_ppo_learn_single_env_and_static_partner(ctx, tmp_path):
     env = LiarEnv(seed=1)
-    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=32, batch_size=16, n_epochs=2, seed=10,
-                                _rng_stream=_lib.STREAM_ALT))
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=32, batch_size=16, n_epochs=2, seed=10))
     env.add_partner_agent(partner)
     ego = PPO("MlpPolicy", env, n_steps=32, batch_size=16, n_epochs=2, seed=10)
     assert torch.equal(ego.policy.params, partner.model.policy.params)  # same seed -> same init (trainer.py:111,198)
@@ -187,8 +186,7 @@ def test_tensorboard_scalars_and_sb3_zip(ctx, tmp_path):
     PPO.load(path) reopens without an env (trainer.py:149)."""
     tb = tmp_path / "tb"
     env = RPSEnv()
-    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=2, seed=10,
-                                _rng_stream=_lib.STREAM_ALT), log_interval=1, tensorboard_log=str(tb),
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=2, seed=10), log_interval=1, tensorboard_log=str(tb),
                             tb_log_name="partner")
     env.add_partner_agent(partner)
     ego = PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=2, seed=10, tensorboard_log=str(tb))
@@ -221,8 +219,7 @@ def test_tensorboard_scalars_and_sb3_zip(ctx, tmp_path):
     assert again._n_updates == ego._n_updates + 2
     # device loop (n_envs > 1): same tags, one dump per iteration
     env3 = LiarEnv()
-    p3 = OnPolicyAgent(PPO("MlpPolicy", env3, n_steps=8, n_epochs=1, seed=1, n_minibatches=2,
-                           _rng_stream=_lib.STREAM_ALT), log_interval=1, tensorboard_log=str(tb), tb_log_name="p3")
+    p3 = OnPolicyAgent(PPO("MlpPolicy", env3, n_steps=8, n_epochs=1, seed=1, n_minibatches=2), log_interval=1, tensorboard_log=str(tb), tb_log_name="p3")
     env3.add_partner_agent(p3)
     e3 = PPO("MlpPolicy", env3, n_steps=8, n_epochs=1, seed=1, n_envs=256, n_minibatches=2, tensorboard_log=str(tb))
     e3.learn(total_timesteps=256 * 8 * 2, tb_log_name="vec")
@@ -239,8 +236,7 @@ def test_wrappers_around_device_games(ctx, tmp_path):
     stacked observations while every step is recorded and written in the reference's .npy layout."""
     from pantheonrl_b200.common import trajsaver, wrappers
     env = RPSEnv()
-    env.add_partner_agent(OnPolicyAgent(PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=1, seed=10,
-                                            _rng_stream=_lib.STREAM_ALT)))
+    env.add_partner_agent(OnPolicyAgent(PPO("MlpPolicy", env, n_steps=16, batch_size=8, n_epochs=1, seed=10)))
     env = wrappers.frame_wrap(env, 3)
     env = rec = wrappers.recorder_wrap(env)
     assert env.observation_space.nvec.tolist() == [1, 1, 1]
@@ -254,7 +250,7 @@ def test_wrappers_around_device_games(ctx, tmp_path):
     assert np.array_equal(back.egoacts.reshape(-1), tr.egoacts) and set(np.unique(tr.altacts)) <= {0, 1, 2}
     # turn based, recorded only (a 3-frame Liar observation would be 90 slots: the kernels take 32)
     lenv = LiarEnv(seed=3)
-    lenv.add_partner_agent(StaticPolicyAgent(PPO("MlpPolicy", lenv, seed=1, _rng_stream=_lib.STREAM_ALT).policy))
+    lenv.add_partner_agent(StaticPolicyAgent(PPO("MlpPolicy", lenv, seed=1).policy))
     lrec = wrappers.recorder_wrap(lenv)
     PPO("MlpPolicy", lrec, n_steps=16, batch_size=8, n_epochs=1, seed=2).learn(total_timesteps=16)
     lt = lrec.get_transitions()
@@ -315,8 +311,7 @@ def test_behaviour_cloning_facade(ctx, tmp_path):
 def test_ppo_learn_on_device_matches_engine(ctx):
     N, T = 256, 16
     env = LiarEnv()
-    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4,
-                                _rng_stream=_lib.STREAM_ALT))
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4))
     env.add_partner_agent(partner)
     ego = PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_envs=N, n_minibatches=4)
     ego.learn(total_timesteps=N * T * 2)
@@ -333,7 +328,7 @@ def test_ppo_learn_on_device_matches_engine(ctx):
     assert ego._trainer.alt is None and ego.num_timesteps == 512 * 8
 
 
-def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
+def test_engine_three_iterations_bit_exact_vs_oracle(ctx):
     """The north star's trace claim across training: rollout -> GAE -> PPO.train ->
     rollout with the UPDATED weights, all buffers and parameters equal to the oracle."""
     N, T, E, NMB, seed = 192, 12, 2, 3, 7
@@ -346,18 +341,19 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
     me, ve, ma, va = (np.zeros_like(pe) for _ in range(4))
     step_e = step_a = upd_e = upd_a = 0
     carry = None
-    for it in range(2):
+    o_alt = orc.new_buffer(orc.alt_capacity("liar", T), N, True)  # one partner buffer: open rows are carried in it
+    for it in range(3):
         tr.iteration()
         torch.cuda.synchronize()
         o_ego, o_alt, carry = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=seed, tick0=it * T,
-                                          first_rollout=it == 0, carry=carry)
+                                          first_rollout=it == 0, carry=carry, alt=o_alt)
         for k in ("obs", "actions", "rewards", "values", "logp", "episode_starts"):
             assert np.array_equal(getattr(tr.ego_buf, k).cpu().numpy(), o_ego[k]), (it, k)
         assert np.array_equal(tr.alt_buf.count.cpu().numpy(), o_alt["count"])
         adv, ret = oracle.gae(o_ego["rewards"], o_ego["values"], o_ego["episode_starts"],
                               carry["ego_last_value"], carry["ego_last_done"])
         aadv, aret = oracle.gae_ragged(o_alt["rewards"], o_alt["values"], o_alt["episode_starts"],
-                                       o_alt["count"], carry["alt_last_done"])
+                                       o_alt["count"], carry["alt_boot_done"])
         # ego update
         idx = oupd.index_build(None, T, N)
         M = idx.size
@@ -369,7 +365,7 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
         step_e += E * (-(-M // bs))
         upd_e += E
         # partner update
-        aidx = oupd.index_build(o_alt["count"], 2 * T, N)
+        aidx = oupd.index_build(o_alt["count"], orc.alt_capacity("liar", T), N)
         M = aidx.size
         bs = -(-M // NMB)
         perm = oupd.perm_feistel(M, E, seed, _lib.STREAM_SHUFFLE_ALT, epoch0=upd_a)
@@ -381,4 +377,45 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx):
         assert np.array_equal(tr.ego.params.cpu().numpy(), pe), f"ego params differ after iteration {it}"
         assert np.array_equal(tr.alt.params.cpu().numpy(), pa), f"partner params differ after iteration {it}"
     st = tr.train_stats()
-    assert np.isfinite(st["train/loss"]) and tr.episode_stats()["ego_steps"] == 2 * N * T
+    assert np.isfinite(st["train/loss"]) and tr.episode_stats()["ego_steps"] == 3 * N * T
+
+
+def test_load_then_learn_on_device_continues_counters(ctx, tmp_path):
+    """PPO.load followed by learn() with n_envs > 1: the device trainer takes over the loaded Adam step
+    count (bias correction), update counter (shuffle keys) and starts its env / sampling streams at fresh
+    ticks, for the ego and for the partner."""
+    N, T = 128, 8
+    env = LiarEnv()
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4))
+    env.add_partner_agent(partner)
+    ego = PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_envs=N, n_minibatches=4)
+    ego.learn(total_timesteps=N * T)
+    first_perm = ego._trainer.ego_perm.clone()
+    ego.save(str(tmp_path / "ego"))
+    partner.model.save(str(tmp_path / "alt"))
+    env2 = LiarEnv()
+    partner2 = OnPolicyAgent(PPO.load(str(tmp_path / "alt"), env2))
+    env2.add_partner_agent(partner2)
+    ego2 = PPO.load(str(tmp_path / "ego"), env2)
+    assert (ego2.adam_step, ego2._n_updates, ego2.n_envs) == (ego.adam_step, 2, N) and ego.adam_step == 8
+    assert partner2.model.adam_step == partner.model.adam_step > 0
+    ego2.learn(total_timesteps=N * T)
+    tr = ego2._trainer
+    assert tr.tick_base == 2 * T and (tr.ego.adam_step, tr.ego.n_updates) == (16, 4)
+    assert (ego2.adam_step, ego2._n_updates, ego2.num_timesteps) == (16, 4, N * T)
+    assert partner2.model._n_updates == 4 and partner2.model.adam_step == tr.alt.adam_step > partner.model.adam_step
+    assert not torch.equal(tr.ego_perm, first_perm)  # epochs 2, 3 of the shuffle stream, not 0, 1 again
+    # the same continuation driven by hand: a fresh VecTrainer given the saved state and counters
+    cfg = PPOConfig(n_steps=T, n_epochs=2, n_minibatches=4)
+    ref = VecTrainer("liar", N, cfg, seed=10, partner="ppo")
+    ref.ego.params.copy_(ego.policy.params)
+    ref.ego.adam_m.copy_(ego.adam_m)
+    ref.ego.adam_v.copy_(ego.adam_v)
+    ref.alt.params.copy_(partner.model.policy.params)
+    ref.alt.adam_m.copy_(partner.model.adam_m)
+    ref.alt.adam_v.copy_(partner.model.adam_v)
+    ref.ego.adam_step, ref.ego.n_updates = ego.adam_step, 2
+    ref.alt.adam_step, ref.alt.n_updates = partner.model.adam_step, 2
+    ref.tick_base = 2 * T
+    ref.iteration()
+    assert torch.equal(ref.ego.params, ego2.policy.params) and torch.equal(ref.alt.params, partner2.model.policy.params)

@@ -312,7 +312,7 @@ def test_engine_two_iterations_bit_exact_vs_oracle(ctx, golden_dir):
         adv, ret = oracle.gae(o_ego["rewards"], o_ego["values"], o_ego["episode_starts"],
                               carry["ego_last_value"], carry["ego_last_done"])
         aadv, aret = oracle.gae_ragged(o_alt["rewards"], o_alt["values"], o_alt["episode_starts"],
-                                       o_alt["count"], carry["alt_last_done"])
+                                       o_alt["count"], carry["alt_boot_done"])
         for who, p, m, v, buf, a_, r_, stream, cnt in (
                 ("e", pe, me, ve, o_ego, adv, ret, _lib.STREAM_SHUFFLE_EGO, None),
                 ("a", pa, ma, va, o_alt, aadv, aret, _lib.STREAM_SHUFFLE_ALT, o_alt["count"])):
@@ -372,8 +372,7 @@ def test_facade_ppo_learns_host_driven_and_on_device(ctx):
     env = oc.OvercookedMultiEnv("simple")
     env.layout.horizon = 30
     env.d_layout = oc.layout_to_device(env.layout)
-    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=40, batch_size=20, n_epochs=2, seed=10,
-                                _rng_stream=_lib.STREAM_ALT))
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=40, batch_size=20, n_epochs=2, seed=10))
     env.add_partner_agent(partner)
     ego = PPO("MlpPolicy", env, n_steps=40, batch_size=20, n_epochs=2, seed=10)
     assert torch.equal(ego.policy.params, partner.model.policy.params)
@@ -383,8 +382,7 @@ def test_facade_ppo_learns_host_driven_and_on_device(ctx):
     # n_envs > 1: the device loop, equal to driving VecTrainer directly
     N, T = 64, 32
     env = oc.OvercookedMultiEnv("unident_s", ego_agent_idx=1)
-    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4,
-                                _rng_stream=_lib.STREAM_ALT))
+    partner = OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_minibatches=4))
     env.add_partner_agent(partner)
     ego = PPO("MlpPolicy", env, n_steps=T, n_epochs=2, seed=10, n_envs=N, n_minibatches=4)
     ego.learn(total_timesteps=N * T * 2)

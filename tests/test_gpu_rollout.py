@@ -16,12 +16,12 @@ KW = {"rps": oracle.RPS_SPACE, "liar": oracle.LIAR_SPACE}
 
 
 def _gpu_rollout(env_kind, pe, pa, N, T, seed, tick0=0, env0=0, first=True, carry=None, selfplay=False,
-                 records=True, probegostart=0.5):
+                 records=True, probegostart=0.5, alt=None):
     sp = dev.space_for(env_kind)
     d_pe = torch.from_numpy(pe).cuda()
     d_pa = d_pe if selfplay else torch.from_numpy(pa).cuda()
     ego = dev.Buffer(T, N, False, "cuda")
-    alt = dev.Buffer(2 * T if env_kind == "liar" else T, N, True, "cuda")
+    alt = alt or dev.Buffer(dev.alt_capacity(env_kind, T), N, True, "cuda")
     carry = carry or dev.Carry(N, "cuda")
     dev.run_rollout(env_kind, sp, d_pe, d_pa, ego, alt, carry, T, seed, tick0, env0=env0,
                     first_rollout=first, partner_records=records, probegostart=probegostart)
@@ -32,7 +32,8 @@ def _gpu_rollout(env_kind, pe, pa, N, T, seed, tick0=0, env0=0, first=True, carr
 def _compare(ego, alt, carry, o_ego, o_alt, o_carry, records=True):
     for k in ("obs", "actions", "rewards", "values", "logp", "episode_starts"):
         assert np.array_equal(getattr(ego, k).cpu().numpy(), o_ego[k]), f"ego {k}"
-    for k in ("ego_last_start", "alt_last_done", "total_rew", "flags", "ego_last_value", "ego_last_done"):
+    for k in ("ego_last_start", "alt_last_done", "total_rew", "flags", "ego_last_value", "ego_last_done",
+              "alt_boot_done"):
         assert np.array_equal(getattr(carry, k).cpu().numpy(), o_carry[k]), f"carry {k}"
     assert np.array_equal(carry.game_state.cpu().numpy()[:, :25], o_carry["game_state"][:, :25])
     assert np.array_equal(carry.ep_stats.cpu().numpy(), o_carry["ep_stats"])
@@ -40,7 +41,8 @@ def _compare(ego, alt, carry, o_ego, o_alt, o_carry, records=True):
         cnt = alt.count.cpu().numpy()
         assert np.array_equal(cnt, o_alt["count"])
         Tc = min(alt.Tcap, o_alt["obs"].shape[0])
-        mask = np.arange(Tc)[:, None] < cnt[None, :]
+        # complete rows + the row left open for the next rollout (flags bit2), which sits at row count[n]
+        mask = np.arange(Tc)[:, None] < (cnt + ((o_carry["flags"] >> 2) & 1))[None, :]
         for k in ("obs", "actions", "rewards", "values", "logp", "episode_starts"):
             g = getattr(alt, k).cpu().numpy()[:Tc]
             w = o_alt[k][:Tc]
@@ -54,7 +56,7 @@ def test_rollout_bit_exact_vs_oracle(ctx, env_kind, N, T):
     pe = rand_params(osp, seed=1, scale=0.3)
     pa = rand_params(osp, seed=2, scale=0.3)
     o = orc.rollout(env_kind, osp, pe, pa, N=N, T=T, seed=10, tick0=5, env0=7,
-                    alt=orc.new_buffer(2 * T if env_kind == "liar" else T, N, True))
+                    alt=orc.new_buffer(orc.alt_capacity(env_kind, T), N, True))
     g = _gpu_rollout(env_kind, pe, pa, N, T, seed=10, tick0=5, env0=7)
     _compare(*g, *o)
 
@@ -67,9 +69,18 @@ def test_rollout_carry_across_rollouts(ctx):
     o1 = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=2)
     g1 = _gpu_rollout("liar", pe, pa, N, T, seed=2)
     _compare(*g1, *o1)
-    o2 = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=2, tick0=T, first_rollout=False, carry=o1[2])
-    g2 = _gpu_rollout("liar", pe, pa, N, T, seed=2, tick0=T, first=False, carry=g1[2])
+    open1 = (o1[2]["flags"] >> 2) & 1
+    assert 0 < open1.sum() < N  # some partner rows wait for the ego's next move: carried, not dropped
+    # the same partner buffer goes into the next rollout (the open row is in it, at row count[n])
+    o2 = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=2, tick0=T, first_rollout=False, carry=o1[2], alt=o1[1])
+    g2 = _gpu_rollout("liar", pe, pa, N, T, seed=2, tick0=T, first=False, carry=g1[2], alt=g1[1])
     _compare(*g2, *o2)
+    # the boundary case of the partner's reward: a carried row finished by the ego's first move
+    r0 = g2[1].rewards[0].cpu().numpy()
+    assert np.any((open1 == 1) & (r0 != 0))
+    o3 = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=2, tick0=2 * T, first_rollout=False, carry=o2[2], alt=o2[1])
+    g3 = _gpu_rollout("liar", pe, pa, N, T, seed=2, tick0=2 * T, first=False, carry=g2[2], alt=g2[1])
+    _compare(*g3, *o3)
 
 
 def test_selfplay_static_partner(ctx):
@@ -115,8 +126,8 @@ def test_full_size_rollout_properties(ctx):
     assert int(cnt.min()) >= 1 and int(cnt.max()) <= 2 * T
     st = carry.ep_stats.cpu().numpy()
     assert st[2] == N * T and st[3] == int(cnt.sum()) and st[0] == int((nxt == 1).sum())
-    # zero-sum up to rewards that landed on a cursor-0 partner (lost, agents.py:198)
-    mask = torch.arange(2 * T, device="cuda")[:, None] < cnt[None, :]
+    # zero-sum up to the rewards on rows still open at the end (carried into the next rollout)
+    mask = torch.arange(alt.Tcap, device="cuda")[:, None] < cnt[None, :]
     assert abs(float(r.sum()) + float((alt.rewards * mask).sum())) <= N
     # a strided sample of envs replayed on the oracle
     idx = np.arange(0, N, 257)

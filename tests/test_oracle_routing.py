@@ -45,7 +45,12 @@ def test_scripted_rollout_reproduces_reference_trace(golden_dir, env_kind, fname
     assert carry["ego_last_done"][0] == float(g["ego_done"][-1])
     # ---- what the partner (OnPolicyAgent) stored
     K = len(rows)
-    assert alt["count"][0] == K
+    # a turn-based trace that ends while the partner waits for the ego's next move leaves its last row
+    # open: not counted, flagged, kept at row count[n] for the next rollout
+    is_open = int(carry["flags"][0] >> 2) & 1
+    assert alt["count"][0] + is_open == K
+    if env_kind == "rps":
+        assert not is_open
     assert np.array_equal(alt["obs"][:K, 0, :nobs], np.array([r["obs"] for r in rows]))
     assert np.array_equal(alt["rewards"][:K, 0], np.array([r["rew"] for r in rows], np.float32))
     assert np.array_equal(alt["episode_starts"][:K, 0], np.array([r["start"] for r in rows], np.float32))
@@ -64,8 +69,10 @@ def test_scripted_rollout_reproduces_reference_trace(golden_dir, env_kind, fname
 
 
 def test_rollout_split_equals_one_long_rollout():
-    """Carry state across rollout boundaries: 2 x 32 ticks == 64 ticks for the
-    ego; the partner's ragged buffer restarts per rollout."""
+    """Carry state across rollout boundaries: 2 x 32 ticks == 64 ticks for the ego AND for the
+    partner: a partner row still waiting for the ego's next move when the first rollout ends is carried
+    into the second one as its row 0, so no reward is lost at the boundary (the closed rows of the two
+    short rollouts, put end to end, are the closed rows of the long one — rewards included)."""
     space = oracle.make_space(**oracle.LIAR_SPACE)
     P = oracle.param_count(space)
     pe = (np.random.RandomState(0).randn(P) * 0.3).astype(np.float32)
@@ -74,15 +81,25 @@ def test_rollout_split_equals_one_long_rollout():
     e_all, a_all, c_all = orc.rollout("liar", space, pe, pa, N=N, T=64, seed=3)
     e1, a1, c1 = orc.rollout("liar", space, pe, pa, N=N, T=32, seed=3)
     cnt1 = a1["count"].copy()
+    open1 = (c1["flags"] >> 2) & 1
+    assert 0 < open1.sum() < N and np.all(c1["alt_last_done"][open1 == 1] == 0)
+    a1 = {k: v.copy() for k, v in a1.items()}
+    a2 = {k: v.copy() for k, v in a1.items()}  # the SAME buffer goes into the next rollout (the open row is in it)
     e2, a2, c2 = orc.rollout("liar", space, pe, pa, N=N, T=32, seed=3, tick0=32, first_rollout=False,
-                             carry=c1)
+                             carry=c1, alt=a2)
+    # the boundary case itself: a carried row that the ego's first move of the next rollout finishes with the
+    # game's only reward (+-1) — the reward the per-rollout restart of the partner's buffer used to lose
+    carried_terminal = [n for n in range(N) if open1[n] and a2["rewards"][0, n] != 0]
+    assert carried_terminal and all(a2["episode_starts"][1, n] == 1 for n in carried_terminal if a2["count"][n] > 1)
+    assert np.array_equal(c2["alt_boot_done"], c_all["alt_boot_done"])
+    assert np.array_equal(c2["flags"], c_all["flags"])
     for k in ("obs", "actions", "rewards", "values", "logp", "episode_starts"):
         assert np.array_equal(np.concatenate([e1[k], e2[k]]), e_all[k]), k
     assert np.array_equal(c2["ego_last_value"], c_all["ego_last_value"])
     assert np.array_equal(cnt1 + a2["count"], a_all["count"])
     for n in range(N):
-        k1, k2 = cnt1[n], a2["count"][n]
-        for k in ("obs", "actions", "values", "logp", "episode_starts"):
+        k1, k2 = cnt1[n], a2["count"][n] + ((c2["flags"][n] >> 2) & 1)  # closed rows + the open one, if any
+        for k in ("obs", "actions", "values", "logp", "episode_starts", "rewards"):
             assert np.array_equal(a_all[k][:k1, n], a1[k][:k1, n])
             assert np.array_equal(a_all[k][k1:k1 + k2, n], a2[k][:k2, n])
 

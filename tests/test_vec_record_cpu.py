@@ -38,6 +38,7 @@ def test_turn_based_recording_from_buffers_matches_the_reference_recorder():
     space = oracle.make_space(**oracle.LIAR_SPACE)
     ego, alt, carry = orc.rollout("liar", space, None, None, N=1, T=T, script_ego_act=ego_act, script_alt_act=alt_act,
                                   script_reset=g["liar_rf_resets"].astype(np.uint8), alt=orc.new_buffer(3 * T, 1, True))
+    alt["count"] = alt["count"] + ((carry["flags"] >> 2) & 1)  # + the partner row left open at the end, if any
     tr = vr.turn_based_transitions(ego, alt, 0, carry["ego_last_done"][0])
     assert isinstance(tr, TurnBasedTransitions)
     assert np.array_equal(tr.obs, g["liar_rf_rec_obs"]) and np.array_equal(tr.acts, g["liar_rf_rec_acts"])
