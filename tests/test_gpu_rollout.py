@@ -125,7 +125,9 @@ def test_full_size_rollout_properties(ctx):
     cnt = alt.count
     assert int(cnt.min()) >= 1 and int(cnt.max()) <= 2 * T
     st = carry.ep_stats.cpu().numpy()
-    assert st[2] == N * T and st[3] == int(cnt.sum()) and st[0] == int((nxt == 1).sum())
+    n_open = int(((carry.flags >> 2) & 1).sum())  # partner rows still waiting for the ego's next move
+    assert 0 < n_open < N
+    assert st[2] == N * T and st[3] == int(cnt.sum()) + n_open and st[0] == int((nxt == 1).sum())
     # zero-sum up to the rewards on rows still open at the end (carried into the next rollout)
     mask = torch.arange(alt.Tcap, device="cuda")[:, None] < cnt[None, :]
     assert abs(float(r.sum()) + float((alt.rewards * mask).sum())) <= N
