@@ -9,9 +9,18 @@ A "step" is one full train iteration of BASELINE.json configs[1]
 (LiarsDice-v0 PPO-vs-PPO, 4096 on-device envs per GPU, n_steps=128, 10 epochs x
 32 minibatches, SB3 default hyper-parameters): rollout of both agents + GAE +
 PPO.train of both learners.  metric = agent decisions (ego + partner) per second.
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line on stdout (rank 0).
+
+Both arms print the same `config` dict and use the same warm-up rule.  The CPU arm's step is a
+bounded sample of the workload (`cpu_baseline.sample` says which): fewer envs, the SAME
+minibatch size, all epochs really run — nothing is extrapolated.
+
+At N = 1 the line also carries `configs`: the other BASELINE.json configurations measured in the
+same run (facade N = 1 through PPO.learn, RPS self-play at 65 536 envs, Overcooked at 1024 envs),
+each with the CPU port's number beside it.
 """
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -24,8 +33,24 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec (all agents)"
 UNIT = "agent-steps/s"
-N_ENVS, N_STEPS, N_EPOCHS, N_MB = 4096, 128, 10, 32
-FWD_FLOPS = {"liar": 88064, "rps": 17152}  # dense-convention forward FLOPs per sample
+N_EPOCHS, N_MB = 10, 32
+FWD_FLOPS = {"liar": 88064, "rps": 17152, "overcooked": 33152}  # dense forward FLOPs per sample
+
+# BASELINE.json configs.  cpu_*: the bounded sample the CPU port runs per step — fewer envs and
+# proportionally fewer minibatches, so that the minibatch size (what torch-eager's efficiency
+# depends on) is the full workload's.
+WORKLOADS = {
+    "liar": dict(baseline="configs[1]", env="liar", n_envs=4096, n_steps=128, partner="ppo",
+                 name="LiarsDice-v0 PPO-vs-PPO, 4096 vectorised envs", cpu_envs=1024, cpu_mb=8),
+    "rps_selfplay": dict(baseline="configs[2]", env="rps", n_envs=65536, n_steps=128, partner="selfplay",
+                         name="RPS-v0 self-play, 65536 vectorised envs, 64-64 MLP", cpu_envs=8192, cpu_mb=4),
+    "overcooked": dict(baseline="configs[3]", env="overcooked", n_envs=1024, n_steps=400, partner="ppo",
+                       name="OvercookedMultiEnv-v0 layout=simple PPO-vs-PPO, 1024 envs (env on device)",
+                       cpu_envs=128, cpu_mb=4),
+    "rps_single": dict(baseline="configs[0]", env="rps", n_envs=1, n_steps=2048, partner="ppo",
+                       name="RPS-v0 PPO-vs-PPO seed=10, 2 agents, 1 env (trainer.py shape: n_steps 2048, batch 64)",
+                       cpu_envs=1, cpu_mb=0),
+}
 
 
 def parse():
@@ -34,13 +59,32 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--env", default="liar", choices=["liar", "rps"])
-    ap.add_argument("--n-envs", type=int, default=N_ENVS)
-    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0 = same env count as the GPU arm")
+    ap.add_argument("--workload", default="liar", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--partners", type=int, default=0,
+                    help="partner learners in total (default: one per GPU); more than --gpus puts several on a GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--ego-update", default="sharded", choices=["sharded", "replicated"])
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)  # timing rule: at least 3 warm-up steps (both arms)
+    return a
+
+
+def make_config(args, world):
+    """The `config` dict: identical in both arms."""
+    w = WORKLOADS[args.workload]
+    n_envs = args.n_envs or w["n_envs"]
+    partners = args.partners or world
+    cfg = {"workload": f"{w['name']} (BASELINE {w['baseline']}; per GPU)", "n_envs_per_gpu": n_envs,
+           "n_steps": w["n_steps"], "n_epochs": N_EPOCHS, "n_minibatches": N_MB, "partners": partners if w["partner"] == "ppo" else 0,
+           "parallelism": (f"dp{world}: envs sharded, {partners} partner learner(s) over {world} GPU(s), ego replicated, "
+                           f"1 all-gather of packed ego transitions per rollout ({args.exchange}), ego update "
+                           f"{args.ego_update if world > 1 else 'local'}"),
+           "l2": "flushed between timed steps (256 MB fill outside the per-step CUDA-event brackets); within a step the "
+                 "rollout buffers (~90 MB) are produced and consumed on the device"}
+    return cfg
 
 
 # ----------------------------------------------------------------------- clocks
@@ -82,85 +126,87 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------- CPU arm
-CPU_BUDGET_S = 150.0   # the reference arm stops adding steps after this much wall time
-CPU_EPOCHS_TIMED = 1  # of N_EPOCHS: the update time of the sample is scaled by N_EPOCHS / this
-
-
-def cpu_iteration_rate(env, n_envs, steps, warmup):
-    """agent-steps/s of the oracle port (oracle/cpu_trainer.py) on the host cores.
-
-    Bounded sample of the GPU arm's step: the same iteration (T = 128, 32 minibatches
-    per epoch, both learners) at n_envs envs, with CPU_EPOCHS_TIMED of the 10 epochs
-    actually run and the update time scaled up to 10 (epochs are identical work)."""
+def cpu_rate(workload, steps, warmup):
+    """agent-steps/s of the oracle port (oracle/cpu_trainer.py: OpenMP C rollout + torch CPU eager
+    update, the op sequence SB3 executes) on the host cores.  Every step runs ALL epochs."""
     import torch
     from oracle.cpu_trainer import CpuTrainer
+    w = WORKLOADS[workload]
     cores = os.cpu_count() or 1
-    # torch CPU eager over-subscribes badly on tiny ops: cap its intra-op pool
-    threads = min(cores, 16)
+    threads = min(cores, 16)  # torch CPU eager over-subscribes on these op sizes: more threads is slower
     torch.set_num_threads(threads)
-    tr = CpuTrainer(env, n_envs, n_steps=N_STEPS, n_epochs=CPU_EPOCHS_TIMED, n_minibatches=N_MB, seed=10)
+    tr = CpuTrainer(w["env"], w["cpu_envs"], n_steps=w["n_steps"], n_epochs=N_EPOCHS, n_minibatches=w["cpu_mb"],
+                    batch_size=64, seed=10, partner=w["partner"])
     for _ in range(warmup):
         tr.iteration()
     dec, total, phases = 0, 0.0, {"rollout_s": 0.0, "gae_s": 0.0, "train_s": 0.0}
-    t_begin, done = time.perf_counter(), 0
     for _ in range(steps):
+        t0 = time.perf_counter()
         dec += tr.iteration()
-        done += 1
-        t = tr.timing
-        total += t["rollout_s"] + t["gae_s"] + t["train_s"] * (N_EPOCHS / CPU_EPOCHS_TIMED)
+        total += time.perf_counter() - t0
         for k in phases:
-            phases[k] += t[k]
-        if time.perf_counter() - t_begin > CPU_BUDGET_S:  # bounded: stop early, report the steps really run
-            break
-    phases = {k: v / done for k, v in phases.items()}
-    phases["train_s_scaled_to_10_epochs"] = phases["train_s"] * N_EPOCHS / CPU_EPOCHS_TIMED
-    return dec / total, total / done, threads, phases, done
-
-
-def cpu_sample_text(args):
-    return (f"per step: one train iteration (rollout + GAE + PPO.train of both learners, T={N_STEPS}, "
-            f"{N_MB} minibatches/epoch) at {args.cpu_sample_envs} envs (GPU arm: {args.n_envs}); "
-            f"{CPU_EPOCHS_TIMED} of {N_EPOCHS} epochs run, update time scaled x{N_EPOCHS // CPU_EPOCHS_TIMED} "
-            f"(epochs are identical work); OpenMP C rollout + torch CPU eager update (threads capped at 16: "
-            f"more is slower)")
+            phases[k] += tr.timing[k] / steps
+    mb = f"{w['cpu_mb']} minibatches" if w["cpu_mb"] else "batch_size 64"
+    sample = (f"per step: one full train iteration (rollout + GAE + PPO.train of every learner, T={w['n_steps']}, "
+              f"all {N_EPOCHS} epochs run) at {w['cpu_envs']} envs x {mb} per epoch "
+              f"(GPU arm: {w['n_envs']} envs x {N_MB} minibatches; same minibatch size); "
+              f"OpenMP C rollout + torch CPU eager update, {threads} torch threads")
+    return dict(value=dec / total, unit=UNIT, cores=threads, kind="port", sample=sample, phase_seconds=phases,
+                host_cpus=cores, steps=steps, warmup=warmup, s_per_step=total / steps)
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    args.cpu_sample_envs = args.cpu_sample_envs or args.n_envs
-    rate, spi, cores, timing, done = cpu_iteration_rate(args.env, args.cpu_sample_envs, args.steps, min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cpu = cpu_rate(args.workload, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": done, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": spi * 1e3,
-        "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.env}-ppo-vs-ppo", "n_envs_per_gpu": args.n_envs, "n_steps": N_STEPS,
-                   "n_epochs": N_EPOCHS, "n_minibatches": N_MB},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": cpu_sample_text(args), "phase_seconds": timing,
-                         "host_cpus": os.cpu_count()},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["s_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": make_config(args, world), "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_subprocess(args):
+def cpu_baseline_subprocess(workload, steps=3, warmup=1, timeout=300):
     """The CPU leg runs in a child with a hard timeout so it can never stall the GPU line."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "0",
-           "--env", args.env, "--n-envs", str(args.n_envs), "--cpu-sample-envs", str(args.cpu_sample_envs)]
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload]
+    # parse() raises warm-up to 3 for the arms proper; the in-line baseline is a short sample
+    env = dict(os.environ, PTH_BENCH_CPU_LEG=f"{steps},{warmup}")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout.strip().splitlines()
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env).stdout.strip().splitlines()
         return json.loads(out[-1])["cpu_baseline"]
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": UNIT, "cores": None, "kind": "port",
-                "sample": f"CPU leg failed or exceeded 240 s: {type(e).__name__}"}
+                "sample": f"CPU leg failed or exceeded {timeout} s: {type(e).__name__}"}
 
 
 # ----------------------------------------------------------------------- GPU arm
+def ncu_dram_bytes(path, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of `kernel` from a committed
+    `ncu --csv --page raw` export; None if the file or the columns are missing."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        rows = list(csv.reader(open(path, newline="")))
+        head = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+        names, units = rows[head], rows[head + 1]
+        k, rd, wr = names.index("Kernel Name"), names.index("dram__bytes_read.sum"), names.index("dram__bytes_write.sum")
+        vals = [float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
+                for r in rows[head + 2:] if len(r) > max(k, rd, wr) and kernel in r[k]]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+GAE_NCU_CSV = os.path.join("profiles", "gae_r02_raw.csv")
+
+
 def gae_roofline(torch, ops, peaks):
-    """GAE kernel at BASELINE configs[2] size; inputs (2.7 GB) exceed the 126 MB L2."""
+    """GAE kernel at BASELINE configs[2]'s roofline size; inputs (2.7 GB) exceed the 126 MB L2."""
     T, N = 2048, 65536
     g = torch.Generator(device="cuda").manual_seed(0)
     rew = torch.randint(-1, 2, (T, N), generator=g, device="cuda").float()
@@ -188,10 +234,92 @@ def gae_roofline(torch, ops, peaks):
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     del rew, val, start, adv, ret
     torch.cuda.empty_cache()
+    traffic = ncu_dram_bytes(os.path.join(ROOT, GAE_NCU_CSV), "gae_tma_kernel")
     return {"kernel": "gae_tma_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "peak_source": src, "shape": [T, N], "bytes_per_launch": nbytes,
-            "ms_per_launch": ms, "traffic": 2.69e9,
-            "traffic_source": "profiles/gae_r01.md (ncu dram__bytes_read+write per launch)"}
+            "ms_per_launch": ms, "traffic": traffic,
+            "traffic_source": f"{GAE_NCU_CSV}: ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at this shape"
+                              if traffic else f"{GAE_NCU_CSV} not found"}
+
+
+def ffma_peak(torch, _lib, device):
+    """FP32 FFMA rate measured in this run (pth_debug_ffma_peak): the bound of the MLP kernels."""
+    lib, ctx = _lib.load(), _lib.Context.get(device)
+    ctas, iters = ctx.sm_count * 2 * 4, 1 << 15
+    sink = torch.empty(ctas * 1024, dtype=torch.float32, device="cuda")
+    best = None
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.pth_debug_ffma_peak(ctx.handle, sink.data_ptr(), ctas, iters, _lib.current_stream()),
+                   "pth_debug_ffma_peak")
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * ctas * 1024 * iters * 8 / (best / 1e3) / 1e12
+
+
+def timed_iterations(torch, tr, steps, barrier, flush=None):
+    """K iterations with CUDA events on the launching stream -> (ms total, phase means, decisions)."""
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    marks, decisions = [], 0
+    for _ in range(steps):
+        if flush is not None:
+            flush.fill_(1)
+        a, b, c, d = ev(), ev(), ev(), ev()
+        a.record()
+        tr.collect()
+        b.record()
+        tr.compute_gae()
+        c.record()
+        m_alt = tr.train()
+        d.record()
+        marks.append((a, b, c, d))
+        decisions += tr.N * tr.T + (m_alt if tr.alt is not None else tr.N * tr.T)
+    barrier()
+    ms_total = sum(a.elapsed_time(d) for a, b, c, d in marks)
+    ph = {"rollout_ms": sum(a.elapsed_time(b) for a, b, c, d in marks) / steps,
+          "gae_ms": sum(b.elapsed_time(c) for a, b, c, d in marks) / steps,
+          "update_ms": sum(c.elapsed_time(d) for a, b, c, d in marks) / steps}
+    return ms_total, ph, decisions
+
+
+def extra_config(torch, name, flush):
+    """One of the other BASELINE configs on this GPU: 3 warm-up + 5 timed iterations."""
+    from pantheonrl_b200.engine import PPOConfig, VecTrainer
+    w = WORKLOADS[name]
+    out = {"baseline": w["baseline"], "workload": w["name"], "unit": UNIT}
+    sync = torch.cuda.synchronize
+    if name == "rps_single":
+        # the reference's own shape through the facade: PPO('MlpPolicy', env, seed=10).learn(...)
+        from pantheonrl_b200.common.agents import OnPolicyAgent
+        from pantheonrl_b200.envs import RPSEnv
+        from pantheonrl_b200.ppo import PPO
+        env = RPSEnv()
+        env.add_partner_agent(OnPolicyAgent(PPO("MlpPolicy", env, seed=10)))
+        ego = PPO("MlpPolicy", env, seed=10)
+        ego.learn(total_timesteps=2048)
+        sync()
+        t0 = time.perf_counter()
+        ego.learn(total_timesteps=3 * 2048)
+        sync()
+        dt = time.perf_counter() - t0
+        out.update(value=2 * 3 * 2048 / dt, ms_per_step=dt / 3 * 1e3, steps=3, warmup=1,
+                   api="PPO.learn (n_envs = 1): MultiAgentEnv.step -> OnPolicyAgent.get_action/update per decision, "
+                       "one kernel call per forward, wall clock around learn()")
+        return out
+    kw = {"layout": "simple"} if w["env"] == "overcooked" else {}
+    tr = VecTrainer(w["env"], w["n_envs"], PPOConfig(n_steps=w["n_steps"], n_epochs=N_EPOCHS, n_minibatches=N_MB),
+                    seed=10, partner=w["partner"], **kw)
+    for _ in range(3):
+        tr.iteration()
+    sync()
+    ms, ph, dec = timed_iterations(torch, tr, 5, sync, flush)
+    out.update(value=dec / (ms / 1e3), ms_per_step=ms / 5, steps=5, warmup=3, phases_ms=ph)
+    del tr
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -205,7 +333,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # the contract is ONE stdout line; NCCL_DEBUG=VERSION would add one
+        # the contract is ONE stdout line: whatever NCCL logs (NCCL_DEBUG is the caller's choice) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = {}
     try:
@@ -213,51 +342,42 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
 
-    cfg = PPOConfig(n_steps=N_STEPS, n_epochs=N_EPOCHS, n_minibatches=N_MB)
-    # one partner per GPU, envs sharded: rank r owns global envs [r*N, (r+1)*N)
-    tr = VecTrainer(args.env, args.n_envs, cfg, seed=10, partner="ppo", device=f"cuda:{local}",
-                    env0=rank * args.n_envs, group=dist.group.WORLD if world > 1 else None,
-                    exchange=args.exchange, ego_update=args.ego_update)
+    w = WORKLOADS[args.workload]
+    if args.workload == "rps_single":
+        raise SystemExit("rps_single is measured as an extra config of the default run (facade, N = 1)")
+    n_envs = args.n_envs or w["n_envs"]
+    cfg = PPOConfig(n_steps=w["n_steps"], n_epochs=N_EPOCHS, n_minibatches=N_MB)
+    kw = {"layout": "simple"} if w["env"] == "overcooked" else {}
+    partners = args.partners or world
+    if partners % world:
+        raise SystemExit("--partners must be a multiple of --gpus")
+    if partners // world > 1:
+        kw["partners_per_gpu"] = partners // world
+    # envs sharded: rank r owns global envs [r*N, (r+1)*N) and its partner learner(s)
+    tr = VecTrainer(w["env"], n_envs, cfg, seed=10, partner=w["partner"], device=f"cuda:{local}",
+                    env0=rank * n_envs, group=dist.group.WORLD if world > 1 else None,
+                    exchange=args.exchange, ego_update=args.ego_update, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         tr.iteration()
     barrier()
 
     # ---- timed region: K iterations, device timing, phases on the launching stream
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    marks = []
     launches0 = _lib.LAUNCHES
-    decisions = 0
     # L2 flush between timed steps: 256 MB written (> the 126 MB L2), outside the per-step event brackets
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     with ClockSampler(local) as clk:
         barrier()
         t_wall0 = time.perf_counter()
-        for _ in range(args.steps):
-            flush.fill_(1)
-            a, b, c, d = ev(), ev(), ev(), ev()
-            a.record()
-            tr.collect()
-            b.record()
-            tr.compute_gae()
-            c.record()
-            m_alt = tr.train()
-            d.record()
-            marks.append((a, b, c, d))
-            decisions += tr.N * tr.T + m_alt
-        barrier()
+        ms_total, ph, decisions = timed_iterations(torch, tr, args.steps, barrier, flush)
         t_wall = time.perf_counter() - t_wall0
     clocks = clk.summary()
     launches = _lib.LAUNCHES - launches0
-    ms_total = sum(a.elapsed_time(d) for a, b, c, d in marks)  # K steps, device time, flushes excluded
-    ph = {"rollout_ms": sum(a.elapsed_time(b) for a, b, c, d in marks) / args.steps,
-          "gae_ms": sum(b.elapsed_time(c) for a, b, c, d in marks) / args.steps,
-          "update_ms": sum(c.elapsed_time(d) for a, b, c, d in marks) / args.steps}
 
     # max over ranks of the device time; sum of decisions
     if world > 1:
@@ -270,27 +390,27 @@ def run_ours(args):
     value = decisions / (ms_total / 1e3)
 
     # ---- e2e: same iterations through the public API with HOST-resident learner state:
-    # every step uploads both learners' parameters + Adam moments from pinned host
+    # every step uploads every learner's parameters + Adam moments from pinned host
     # memory, runs the iteration, downloads the updated state and the logged scalars.
-    host = {}
-    for name, L in (("ego", tr.ego), ("alt", tr.alt)):
-        host[name] = [t.cpu().pin_memory() for t in (L.params, L.adam_m, L.adam_v)]
+    learners = tr.learners()
+    host = [[t.cpu().pin_memory() for t in (L.params, L.adam_m, L.adam_v)] for L in learners]
     stats_host = torch.empty_like(tr.ego.last_stats, device="cpu").pin_memory()
-    h2d = sum(t.numel() * 4 for v in host.values() for t in v)
-    d2h = h2d + stats_host.numel() * 4 * 2 + 16
+    h2d = sum(t.numel() * 4 for v in host for t in v)
+    d2h = h2d + stats_host.numel() * 4 * len(learners) + 16
     barrier()
     t0 = time.perf_counter()
     e2e_dec = 0
     for _ in range(args.steps):
-        for name, L in (("ego", tr.ego), ("alt", tr.alt)):
-            for dst, src in zip((L.params, L.adam_m, L.adam_v), host[name]):
+        for L, hs in zip(learners, host):
+            for dst, src in zip((L.params, L.adam_m, L.adam_v), hs):
                 dst.copy_(src, non_blocking=True)
         e2e_dec += tr.iteration()
-        for name, L in (("ego", tr.ego), ("alt", tr.alt)):
-            for src, dst in zip((L.params, L.adam_m, L.adam_v), host[name]):
+        for L, hs in zip(learners, host):
+            for src, dst in zip((L.params, L.adam_m, L.adam_v), hs):
                 dst.copy_(src, non_blocking=True)
         stats_host.copy_(tr.ego.last_stats, non_blocking=True)
-        _ = tr.alt.last_stats.cpu()
+        for L in learners[1:]:
+            _ = L.last_stats.cpu()
         _ = tr.carry.ep_stats.cpu()
         torch.cuda.synchronize()
     barrier()
@@ -310,35 +430,47 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- rooflines (rank 0, N = 1 only for the standalone GAE measurement)
+    # ---- rooflines (rank 0, N = 1 only for the standalone GAE / FFMA measurements)
     roof = gae_roofline(torch, ops, peaks) if world == 1 else None
-    M_ego = tr.N * tr.T
-    flops = 3 * FWD_FLOPS[args.env] * N_EPOCHS * (M_ego + decisions / args.steps / world - M_ego)
+    flops = 3 * FWD_FLOPS[w["env"]] * N_EPOCHS * decisions / args.steps / world  # this GPU's learners, per step
     sm_mhz = clocks.get("sm_mhz") or 1500.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-    dom = {"kernel": "ppo_update_kernel (x2 learners)", "bound": "fp32-ffma (not hbm/tensor: parity mode is fp32 CUDA-core math)",
+    if world == 1:
+        fp32_peak = ffma_peak(torch, _lib, local)
+        peak_src = "measured in this run: pth_debug_ffma_peak (register-resident FFMA chains, all SMs, best of 6)"
+    else:
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        peak_src = "148 SMs x 128 FFMA/clk x 2 x median SM clock under load (N > 1: not re-measured)"
+    dom = {"kernel": "ppo_update_kernel (all learners of this GPU)",
+           "bound": "fp32-ffma (not hbm/tensor: parity mode is fp32 CUDA-core math)",
            "achieved": flops / (ph["update_ms"] / 1e3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-           "frac": flops / (ph["update_ms"] / 1e3) / 1e12 / fp32_peak,
-           "peak_source": "148 SMs x 128 FFMA/clk x 2 x median SM clock under load",
+           "frac": flops / (ph["update_ms"] / 1e3) / 1e12 / fp32_peak, "peak_source": peak_src,
            "flops_convention": "dense: 3 x forward FLOPs per sample per epoch (SURVEY.md 8d)"}
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_subprocess(args)
+    cpu, extra = None, None
+    if world == 1:
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline_subprocess(args.workload)
+        if not args.no_extra_configs and args.workload == "liar" and not args.n_envs and not args.partners:
+            del tr
+            torch.cuda.empty_cache()
+            extra = []
+            for name in ("rps_single", "rps_selfplay", "overcooked"):
+                try:
+                    e = extra_config(torch, name, flush)
+                    if not args.no_cpu_baseline:
+                        c = cpu_baseline_subprocess(name, steps=2, warmup=1, timeout=200)
+                        e["cpu_port"] = {k: c.get(k) for k in ("value", "cores", "sample", "s_per_step")}
+                except Exception as ex:  # noqa: BLE001
+                    e = {"baseline": WORKLOADS[name]["baseline"], "error": f"{type(ex).__name__}: {ex}"}
+                extra.append(e)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.env}-ppo-vs-ppo (BASELINE configs[1] per GPU; one partner per GPU)",
-                   "n_envs_per_gpu": args.n_envs, "n_steps": N_STEPS, "n_epochs": N_EPOCHS,
-                   "n_minibatches": N_MB, "partners": world, "parallelism": f"dp{world}: envs + one partner per GPU, "
-                   f"ego replicated, 1 all-gather of packed ego transitions per rollout ({args.exchange}), ego update "
-                   f"{args.ego_update if world > 1 else 'local'}", "l2": "flushed between timed steps (256 MB "
-                   "fill outside the per-step CUDA-event brackets); within a step the rollout buffers (~90 MB) are "
-                   "produced and consumed on the device"},
+        "config": make_config(args, world),
         "phases_ms": ph, "wall_s": t_wall, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roof, "roofline_dominant": dom, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_dominant": dom, "cpu_baseline": cpu, "configs": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -348,6 +480,9 @@ def run_ours(args):
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
+        leg = os.environ.get("PTH_BENCH_CPU_LEG")  # in-line cpu_baseline of our arm: a short sample
+        if leg:
+            a.steps, a.warmup = (int(x) for x in leg.split(","))
         run_reference(a)
     else:
         run_ours(a)

@@ -277,6 +277,11 @@ int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream)
 /* debug / parity only: y[i] = f(x[i]) with the library's exp (which = 0), log (1, positive
  * normal inputs) or tanh (2) — the polynomial kernels of the numeric contract. */
 int pth_debug_math(pth_ctx* ctx, int which, const float* d_x, float* d_y, int64_t n, void* stream);
+/* measurement only: the FP32 FFMA rate the MLP kernels are bounded by (forward and
+ * update are FP32-compute bound).  One launch of `ctas` x 1024 threads, each running 8 independent
+ * register-resident fmaf chains for `iters` rounds: ctas * 1024 * iters * 8 FFMA = 2x that in FLOP.
+ * The caller times it with CUDA events on `stream`; d_sink [ctas * 1024] floats keeps the chains live. */
+int pth_debug_ffma_peak(pth_ctx* ctx, float* d_sink, int32_t ctas, int32_t iters, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* a1+a2+a3+a7+a8/a9 fused: T-tick rollout with on-device envs         */

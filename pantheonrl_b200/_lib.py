@@ -228,6 +228,7 @@ SIGNATURES = {
     "pth_env_overcooked_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "pth_policy_forward": (C.c_int, [_vp, C.POINTER(ForwardArgs), _vp]),
     "pth_debug_math": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
+    "pth_debug_ffma_peak": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "pth_rollout_run": (C.c_int, [_vp, C.POINTER(RolloutArgs), _vp]),
     "pth_perm_feistel": (C.c_int, [_vp, _vp, _i64, _i32, _u64, _u32, _u32, _vp]),
     "pth_index_build": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -6,6 +6,23 @@
 
 static thread_local char g_err[512] = "";
 
+// FP32 FFMA peak probe (pth_debug_ffma_peak): 8 independent chains per thread hide the 4-cycle FFMA
+// latency with 32 warps per SM; nothing but FFMA in the loop body.
+__global__ void __launch_bounds__(1024) ffma_peak_kernel(float* sink, int iters) {
+  const float t = (float)threadIdx.x * 1e-6f;
+  float a0 = t, a1 = t + 1.f, a2 = t + 2.f, a3 = t + 3.f, a4 = t + 4.f, a5 = t + 5.f, a6 = t + 6.f, a7 = t + 7.f;
+  const float m = 0.999f + t, c = 1e-3f;
+#pragma unroll 1
+  for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 void pth_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -60,6 +77,14 @@ int pth_sync_debug(pth_ctx* ctx, void* stream) {
   PTH_CHECK_ARG(ctx != nullptr, "ctx is NULL");
   PTH_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   PTH_CUDA(cudaGetLastError());
+  return PTH_OK;
+}
+
+int pth_debug_ffma_peak(pth_ctx* ctx, float* d_sink, int32_t ctas, int32_t iters, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && d_sink != nullptr && ctas > 0 && iters > 0 && iters % 8 == 0,
+                "NULL ctx / sink, or iters not a positive multiple of 8");
+  ffma_peak_kernel<<<ctas, 1024, 0, (cudaStream_t)stream>>>(d_sink, iters);
+  PTH_LAUNCH_CHECK();
   return PTH_OK;
 }
 

@@ -176,6 +176,10 @@ class VecTrainer:
             dist.all_gather_into_tensor(self.gather, self.packed, group=self.group)
         _lib.count_launch()
 
+    def learners(self):
+        """Every learner whose state this trainer owns: the ego first, then the partner(s)."""
+        return [self.ego] + ([self.alt] if self.alt is not None else [])
+
     # ------------------------------------------------------------------ phases
     def collect(self):
         alt_params = self.alt.params if self.alt is not None else self.ego.params
