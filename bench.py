@@ -481,8 +481,11 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         leg = os.environ.get("PTH_BENCH_CPU_LEG")  # in-line cpu_baseline of our arm: a short sample
-        if leg:
-            a.steps, a.warmup = (int(x) for x in leg.split(","))
+        if leg:  # "steps,warmup[,envs]" (envs: the contract test's tiny sample)
+            leg = [int(x) for x in leg.split(",")]
+            a.steps, a.warmup = leg[:2]
+            if len(leg) > 2:
+                WORKLOADS[a.workload].update(cpu_envs=leg[2], cpu_mb=1)
         run_reference(a)
     else:
         run_ours(a)

@@ -371,7 +371,7 @@ int pth_index_build(pth_ctx* ctx, const int32_t* d_count, int64_t T, int64_t N,
                     void* stream);
 int64_t pth_index_workspace_bytes(int64_t N);
 
-#define PTH_UPDATE_FLAG_WORDS 2048 /* per rank: one word per (source rank, CTA) of the sharded update */
+#define PTH_UPDATE_FLAG_WORDS 16384 /* per rank: 4 uint32 per minibatch of a sharded launch ({mean, tag}, {std, tag}) */
 
 typedef struct pth_update_args {
   const pth_space* space;   /* HOST pointer */
@@ -407,7 +407,10 @@ typedef struct pth_update_args {
    * rank order inside the same persistent kernel — replicas stay bit-identical.
    * d_peer_xbuf[r]: rank r's exchange buffer (>= pth_update_xbuf_bytes, zero-initialised
    * once) mapped in THIS process (HOST array of `world` device pointers).  d_peer_flags[r]:
-   * reserved (PTH_UPDATE_FLAG_WORDS uint32 per rank; not used by the LL protocol).
+   * rank r's advantage-statistics exchange (PTH_UPDATE_FLAG_WORDS uint32, zero-initialised once):
+   * the per-minibatch {mean, std} of the advantages are computed by ONE rank each (minibatch id mod
+   * world) and stored into every rank's array as {value, launch tag} pairs, so a launch may hold at
+   * most PTH_UPDATE_FLAG_WORDS / 4 minibatches (n_epochs * n_minibatches) when world > 1.
    * flag_epoch: value of the monotonic epoch counter before this launch (launches add
    * n_epochs * n_minibatches; it must be the same on every rank). */
   int32_t world, rank;
@@ -446,26 +449,41 @@ int pth_debug_update_profile(void* d_clock_sums);
 /* e: multi-GPU exchange staging                                       */
 /* ------------------------------------------------------------------ */
 
-/* Pack one rank's ego transitions [T][N] into a contiguous record stream
- * (48 B / sample: obs 32, action 4, old_logp 4, advantage 4, return 4) for a
- * single all-gather per rollout. */
-#define PTH_PACKED_BYTES 48
-int pth_pack_transitions(pth_ctx* ctx, const uint8_t* d_obs,
+/* Pack one rank's ego transitions [T][N] into a contiguous record stream for a single all-gather
+ * per rollout.  Record = observation row (obs_bytes: 32 for one-hot rows,
+ * 4 * PTH_OC_ROW = 256 for Box rows) | action 4 | old_logp 4 | advantage 4 | return 4. */
+#define PTH_PACKED_BYTES 48       /* one-hot spaces */
+#define PTH_PACKED_BYTES_BOX 272  /* Box spaces     */
+int pth_pack_transitions(pth_ctx* ctx, const uint8_t* d_obs, int32_t obs_bytes,
                          const uint8_t* d_actions, const float* d_logp,
                          const float* d_advantages, const float* d_returns,
                          int64_t count, uint8_t* d_packed, void* stream);
 /* Same, but stores each record straight into every peer's gather buffer
- * (peer pointers mapped by the caller via CUDA IPC): pack + all-gather in one
- * kernel over NVLink, no intermediate staging. d_peer_bufs: DEVICE array of
+ * (peer pointers mapped by the caller via CUDA IPC / symmetric memory): pack + all-gather in
+ * one kernel over NVLink, no intermediate staging. d_peer_bufs: DEVICE array of
  * world pointers; records land at rank*count. */
-int pth_pack_allgather_p2p(pth_ctx* ctx, const uint8_t* d_obs,
+int pth_pack_allgather_p2p(pth_ctx* ctx, const uint8_t* d_obs, int32_t obs_bytes,
                            const uint8_t* d_actions, const float* d_logp,
                            const float* d_advantages, const float* d_returns,
                            int64_t count, uint8_t* const* d_peer_bufs,
                            int32_t world, int32_t rank, void* stream);
-/* The update reads a packed stream directly: point d_obs / d_actions /
- * d_old_logp / d_advantages / d_returns at offsets 0 / 32 / 36 / 40 / 44 of the
- * first record and set rec_stride = PTH_PACKED_BYTES. */
+/* The NCCL leg of the exchange inside the library (SURVEY.md 8b minimum export set), for hosts that
+ * have no collective library of their own.  NCCL is bound at run time (dlopen of libnccl.so.2; a
+ * process that already loaded one — PyTorch's — shares it); PTH_ENOSUP if it is not there.
+ *   pth_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId and hands it to the other ranks
+ *                       by whatever channel the host has (file, socket, MPI, torch.distributed);
+ *   pth_comm_init     : every rank joins (collective; one communicator per pth_ctx);
+ *   pth_allgather_transitions: ncclAllGather of `bytes_per_rank` packed bytes from every rank into
+ *                       d_gathered [world * bytes_per_rank] (rank r's records at r * bytes_per_rank),
+ *                       enqueued on `stream`.  This is the ONE collective of the path per rollout. */
+int pth_comm_unique_id(void* out128);
+int pth_comm_init(pth_ctx* ctx, const void* unique_id128, int32_t world, int32_t rank);
+int pth_comm_destroy(pth_ctx* ctx);
+int pth_allgather_transitions(pth_ctx* ctx, const uint8_t* d_packed, int64_t bytes_per_rank,
+                              uint8_t* d_gathered, void* stream);
+/* The update reads a packed stream directly: point d_obs (Box: d_obs_f32) / d_actions /
+ * d_old_logp / d_advantages / d_returns at offsets 0 / B / B+4 / B+8 / B+12 of the
+ * first record (B = obs_bytes) and set rec_stride = B + 16. */
 
 #ifdef __cplusplus
 }

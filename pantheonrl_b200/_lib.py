@@ -19,8 +19,8 @@ PTH_OC_MAX_CELLS, PTH_OC_MAX_POTS, PTH_OC_OBS, PTH_OC_ROW = 128, 4, 62, 64
 PTH_OC_STATE_BYTES = 40
 PTH_OC_FLOOR, PTH_OC_COUNTER, PTH_OC_ONION, PTH_OC_POT, PTH_OC_DISH, PTH_OC_SERVE = range(6)
 PTH_LOSS_PPO, PTH_LOSS_BC = 0, 1
-PTH_UPDATE_FLAG_WORDS = 2048  # include/pantheon_b200.h
-PTH_PACKED_BYTES = 48
+PTH_UPDATE_FLAG_WORDS = 16384  # include/pantheon_b200.h
+PTH_PACKED_BYTES, PTH_PACKED_BYTES_BOX = 48, 272
 
 STREAM_ENV, STREAM_EGO, STREAM_ALT, STREAM_SHUFFLE_EGO, STREAM_SHUFFLE_ALT = 1, 2, 3, 4, 5
 
@@ -238,8 +238,12 @@ SIGNATURES = {
     "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
     "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),
     "pth_debug_update_profile": (C.c_int, [_vp]),
-    "pth_pack_transitions": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "pth_pack_allgather_p2p": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp]),
+    "pth_pack_transitions": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "pth_pack_allgather_p2p": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp]),
+    "pth_comm_unique_id": (C.c_int, [_vp]),
+    "pth_comm_init": (C.c_int, [_vp, _vp, _i32, _i32]),
+    "pth_comm_destroy": (C.c_int, [_vp]),
+    "pth_allgather_transitions": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None
@@ -287,6 +291,7 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.sm_count = lib.pth_ctx_sm_count(h)
+        self.has_comm = False  # pth_comm_init done on this context
 
     @classmethod
     def get(cls, device=0):

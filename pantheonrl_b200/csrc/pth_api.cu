@@ -67,7 +67,10 @@ int pth_ctx_create(int device, pth_ctx** out) {
 }
 
 int pth_ctx_destroy(pth_ctx* ctx) {
-  if (ctx) free(ctx);
+  if (ctx) {
+    pth_comm_destroy(ctx);
+    free(ctx);
+  }
   return PTH_OK;
 }
 

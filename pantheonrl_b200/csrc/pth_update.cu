@@ -80,7 +80,7 @@ struct UpdParams {
   // multi-GPU sharded update (world > 1)
   int world, rank;
   uint2* xbuf[8];       // rank r's exchange buffer [2 parities][world][XS] of (value bits, epoch tag)
-  uint32_t* flags[8];   // rank r's flag words [world]
+  uint2* advx[8];       // rank r's advantage-statistics exchange [n_epochs * n_mb][2] of (value bits, launch tag)
   uint32_t flag_epoch;
   int XS;               // floats per (parity, rank) slot: P + 8 rounded up to 4
   long long* prof;      // debug: per-phase clock64 sums of CTA 0 (pth_debug_update_profile), or NULL
@@ -541,7 +541,13 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
 
   // ------------------------------------------------ prologue: advantage statistics
-  for (int64_t id = c; id < (int64_t)p.n_epochs * n_mb; id += G) {
+  // One whole CTA per minibatch id (the lane order of the contract does not depend on WHICH CTA).
+  // Multi-GPU: every rank holds the same gathered stream, so rank r computes the ids congruent to
+  // r (mod world) only — 1 / world of the gathers (three dependent DRAM accesses per sample once
+  // the stream outgrows L2) — and stores {mean, std} into every rank's exchange array as
+  // {value, launch tag} pairs; readers poll the pair at the head of the minibatch.
+  const uint32_t adv_tag = p.flag_epoch + 1u;
+  for (int64_t id = p.rank + (int64_t)p.world * c; id < (int64_t)p.n_epochs * n_mb; id += (int64_t)p.world * G) {
     const int e = (int)(id / n_mb);
     const int64_t m = id % n_mb;
     const int64_t i0 = m * p.BS;
@@ -584,9 +590,13 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       }
       stdv = sqrtf(block_tree(q, sm.red, tid) / (float)(B - 1));
     }
-    if (tid == 0) {
-      p.advstat[2 * id] = mean;
-      p.advstat[2 * id + 1] = stdv;
+    if (p.world == 1) {
+      if (tid == 0) {
+        p.advstat[2 * id] = mean;
+        p.advstat[2 * id + 1] = stdv;
+      }
+    } else if (tid < 2 * p.world) {
+      ll_store(p.advx[tid >> 1] + 2 * id + (tid & 1), (tid & 1) ? stdv : mean, adv_tag);
     }
   }
   grid.sync();
@@ -604,9 +614,19 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       const int64_t B = (i0 + p.BS <= p.M) ? p.BS : (p.M - i0);
       const float Bf = (float)B, invB = 1.0f / Bf;
       const bool norm = p.normalize && B > 1;
-      const float mean = __ldcg(p.advstat + 2 * id), stdv = __ldcg(p.advstat + 2 * id + 1);
-      const int64_t n_tiles = (B + BT - 1) / BT;
       const int W = p.world;
+      float mean, stdv;
+      if (W == 1) {
+        mean = __ldcg(p.advstat + 2 * id);
+        stdv = __ldcg(p.advstat + 2 * id + 1);
+      } else {
+        // computed by rank id mod W (prologue); every thread polls the two pairs (same address: one
+        // L2 transaction per warp)
+        const uint2* ax = p.advx[p.rank] + 2 * id;
+        mean = ll_wait(ax, adv_tag, ll_peek(ax));
+        stdv = ll_wait(ax + 1, adv_tag, ll_peek(ax + 1));
+      }
+      const int64_t n_tiles = (B + BT - 1) / BT;
       const int64_t local_tiles = (n_tiles - p.rank + W - 1) / W;  // tile t belongs to rank t mod W
       const int A = (int)(local_tiles < G ? local_tiles : G);
 
@@ -1284,8 +1304,8 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
       pth_set_error("pth_ppo_update: Box observations wider than 64 are not supported");
       return PTH_ENOSUP;
     }
-    PTH_CHECK_ARG(a->d_obs_f32 != nullptr && a->obs_stride == HID && a->rec_stride == 0 && a->world <= 1,
-                  "Box observations: d_obs_f32 rows of 64 floats, separate arrays, single GPU");
+    PTH_CHECK_ARG(a->d_obs_f32 != nullptr && a->obs_stride == HID,
+                  "Box observations: d_obs_f32 rows of 64 floats");
     PTH_CHECK_ARG(((uintptr_t)a->d_obs_f32 % 16) == 0, "obs rows must be 16-byte aligned");
   } else {
     PTH_CHECK_ARG(a->d_obs != nullptr, "NULL d_obs");
@@ -1360,7 +1380,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.XS = (p.lo.total + 8 + 3) / 4 * 4;
   for (int r = 0; r < 8; ++r) {
     p.xbuf[r] = nullptr;
-    p.flags[r] = nullptr;
+    p.advx[r] = nullptr;
   }
   if (p.world > 1) {
     PTH_CHECK_ARG(p.world <= 8 && p.rank >= 0 && p.rank < p.world, "bad world / rank");
@@ -1368,8 +1388,10 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     for (int r = 0; r < p.world; ++r) {
       PTH_CHECK_ARG(a->peer_xbuf[r] && a->peer_flags[r], "NULL peer buffer");
       p.xbuf[r] = reinterpret_cast<uint2*>(a->peer_xbuf[r]);
-      p.flags[r] = reinterpret_cast<uint32_t*>(a->peer_flags[r]);
+      p.advx[r] = reinterpret_cast<uint2*>(a->peer_flags[r]);
     }
+    PTH_CHECK_ARG((int64_t)a->n_epochs * n_mb * 4 <= PTH_UPDATE_FLAG_WORDS,
+                  "sharded update: more minibatches per launch than the advantage-statistics exchange holds");
   }
 
   void* kargs[] = {(void*)&p};

@@ -94,8 +94,6 @@ class VecTrainer:
         self.d_layout, box, state_bytes = None, False, 32
         if env_kind == "overcooked":  # config 4: OvercookedMultiEnv-v0, Box(62) observations
             from .envs import overcooked as oc
-            if group is not None:
-                raise _lib.PthError("overcooked: the multi-GPU ego exchange packs one-hot records only")
             self.layout = oc.build_layout(layout, ego_agent_idx, horizon or oc.HORIZON)
             self.d_layout = oc.layout_to_device(self.layout, device)
             box, state_bytes = True, _lib.PTH_OC_STATE_BYTES
@@ -111,6 +109,9 @@ class VecTrainer:
         else:
             raise ValueError(partner)
         N, T = self.N, self.T
+        # exchange record: observation row | action 4 | logp 4 | advantage 4 | return 4
+        self.obs_bytes = 4 * _lib.PTH_OC_ROW if box else 32
+        self.rec_bytes = self.obs_bytes + 16
         self.ego_buf = ro.Buffer(T, N, False, device, box)
         alt_cap = ro.alt_capacity(env_kind, T)
         self.alt_buf = ro.Buffer(alt_cap, N, True, device, box)
@@ -144,7 +145,8 @@ class VecTrainer:
     def _setup_exchange(self):
         import torch.distributed as dist
         count = self.T * self.N
-        nbytes = self.world * count * _lib.PTH_PACKED_BYTES
+        nbytes = self.world * count * self.rec_bytes
+        lib, ctx = _lib.load(), _lib.Context.get(torch.device(self.device).index or 0)
         if self.exchange == "p2p":
             import torch.distributed._symmetric_memory as symm
             self.gather = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -152,8 +154,29 @@ class VecTrainer:
             self.peer_ptrs = torch.tensor(list(self.symm.buffer_ptrs), dtype=torch.int64, device=self.device)
         else:
             self.gather = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self.packed = torch.empty(count * _lib.PTH_PACKED_BYTES, dtype=torch.uint8, device=self.device)
+            self.packed = torch.empty(count * self.rec_bytes, dtype=torch.uint8, device=self.device)
+            if self.exchange == "nccl" and not ctx.has_comm:
+                # the library's own NCCL communicator (pth_comm_init): torch.distributed only carries
+                # the 128-byte unique id from rank 0 to the others
+                import ctypes as C
+                uid = (C.c_uint8 * 128)()
+                if self.rank == 0:
+                    _lib.check(lib.pth_comm_unique_id(uid), "pth_comm_unique_id")
+                box = [bytes(uid)]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0), group=self.group)
+                uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+                _lib.check(lib.pth_comm_init(ctx.handle, uid, self.world, self.rank), "pth_comm_init")
+                ctx.has_comm = True
         dist.barrier(self.group)
+
+    def pack_into(self, out):
+        """This rank's ego transitions of the last rollout as exchange records (pth_pack_transitions)."""
+        b, count = self.ego_buf, self.T * self.N
+        lib, ctx = _lib.load(), _lib.Context.get(torch.device(self.device).index or 0)
+        _lib.check(lib.pth_pack_transitions(ctx.handle, b.obs.data_ptr(), self.obs_bytes, b.actions.data_ptr(),
+                                            b.logp.data_ptr(), b.advantages.data_ptr(), b.returns.data_ptr(),
+                                            count, out.data_ptr(), _lib.current_stream()), "pth_pack_transitions")
+        _lib.count_launch()
 
     def exchange_ego(self):
         """All-gather this rollout's ego transitions (one exchange per rollout)."""
@@ -162,19 +185,21 @@ class VecTrainer:
         lib, ctx = _lib.load(), _lib.Context.get(torch.device(self.device).index or 0)
         if self.exchange == "p2p":
             self.symm.barrier()  # peers finished reading the previous rollout's records
-            _lib.check(lib.pth_pack_allgather_p2p(ctx.handle, b.obs.data_ptr(), b.actions.data_ptr(),
+            _lib.check(lib.pth_pack_allgather_p2p(ctx.handle, b.obs.data_ptr(), self.obs_bytes, b.actions.data_ptr(),
                                                   b.logp.data_ptr(), b.advantages.data_ptr(),
                                                   b.returns.data_ptr(), count, self.peer_ptrs.data_ptr(),
                                                   self.world, self.rank, _lib.current_stream()),
                        "pth_pack_allgather_p2p")
+            _lib.count_launch()
             self.symm.barrier()  # every rank's stores have landed
-        else:
-            _lib.check(lib.pth_pack_transitions(ctx.handle, b.obs.data_ptr(), b.actions.data_ptr(),
-                                                b.logp.data_ptr(), b.advantages.data_ptr(),
-                                                b.returns.data_ptr(), count, self.packed.data_ptr(),
-                                                _lib.current_stream()), "pth_pack_transitions")
+            return
+        self.pack_into(self.packed)
+        if self.exchange == "nccl":  # ncclAllGather on the library's communicator, same stream
+            _lib.check(lib.pth_allgather_transitions(ctx.handle, self.packed.data_ptr(), self.packed.numel(),
+                                                     self.gather.data_ptr(), _lib.current_stream()),
+                       "pth_allgather_transitions")
+        else:  # "torch": the same collective through torch.distributed
             dist.all_gather_into_tensor(self.gather, self.packed, group=self.group)
-        _lib.count_launch()
 
     def learners(self):
         """Every learner whose state this trainer owns: the ego first, then the partner(s)."""
@@ -228,7 +253,10 @@ class VecTrainer:
         if packed is None:
             arrays, stride = (buf.obs, buf.actions, buf.logp, buf.advantages, buf.returns), 0
         else:  # read the all-gathered 48-byte records in place
-            arrays, stride = tuple(packed[o:] for o in (0, 32, 36, 40, 44)), _lib.PTH_PACKED_BYTES
+            ob = self.obs_bytes
+            arrays, stride = tuple(packed[o:] for o in (0, ob, ob + 4, ob + 8, ob + 12)), self.rec_bytes
+            if self.ego_buf.box:  # the kernel takes fp32 rows: same bytes, viewed as floats (272 % 4 == 0)
+                arrays = (arrays[0].view(torch.float32).view(-1, self.rec_bytes // 4)[:, :_lib.PTH_OC_ROW],) + arrays[1:]
         stats = up.ppo_update(
             learner.space, learner.params, learner.adam_m, learner.adam_v, learner.adam_step,
             *arrays, perm, bs, ws, index=index, rec_stride=stride, peers=peers,
@@ -245,10 +273,6 @@ class VecTrainer:
         """PPO.train for both learners.  They are independent (own parameters, own buffers, own
         shuffle streams), so with ``concurrent_updates`` the partner's update kernel runs on a
         side stream next to the ego's, each on its share of the SMs (plan_grids)."""
-        packed = None
-        if self.world > 1:
-            self.exchange_ego()
-            packed = self.gather
         peers = getattr(self, "peers", None) if self.world > 1 else None
         M = 0
         if self.alt is not None:
@@ -267,6 +291,12 @@ class VecTrainer:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 self._train_one(self.alt, a, index, M, perm, self.alt_ws, _lib.STREAM_SHUFFLE_ALT, grid=g_alt)
+        packed = None
+        if self.world > 1:
+            # after the partner's launch: its update needs nothing from the other ranks and runs
+            # on its share of the SMs while the ego transitions are exchanged
+            self.exchange_ego()
+            packed = self.gather
         self._train_one(self.ego, self.ego_buf, self.ego_index, self.ego_M, self.ego_perm,
                         self.ego_ws, _lib.STREAM_SHUFFLE_EGO, packed=packed, peers=peers, grid=g_ego)
         if both:

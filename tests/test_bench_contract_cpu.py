@@ -11,9 +11,10 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 
 
 def run(extra, env=None):
+    # PTH_BENCH_CPU_LEG = "steps,warmup,envs": one step of an 8-env sample instead of the arm's real size
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--cpu-sample-envs", "8"] + extra, capture_output=True, text=True,
-                         timeout=600, env={**os.environ, **(env or {})})
+                          "--warmup", "0"] + extra, capture_output=True, text=True,
+                         timeout=600, env={**os.environ, "PTH_BENCH_CPU_LEG": "1,0,8", **(env or {})})
     assert out.returncode == 0, out.stderr[-2000:]
     return [ln for ln in out.stdout.splitlines() if ln.strip()]
 
@@ -25,9 +26,10 @@ def test_reference_arm_prints_one_json_line():
     assert REQUIRED <= set(d), REQUIRED - set(d)
     assert d["impl"] == "reference" and d["metric"] == "env-steps/sec (all agents)" and d["unit"] == "agent-steps/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["steps"] == 1 and d["value"] > 0
-    assert d["config"]["workload"] == "liar-ppo-vs-ppo" and d["config"]["n_envs_per_gpu"] == 4096
+    assert d["config"]["workload"].startswith("LiarsDice-v0 PPO-vs-PPO") and d["config"]["n_envs_per_gpu"] == 4096
+    assert d["config"]["n_epochs"] == 10 and "all 10 epochs run" in d["cpu_baseline"]["sample"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "8 envs" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "at 8 envs" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -419,3 +419,38 @@ def test_load_then_learn_on_device_continues_counters(ctx, tmp_path):
     ref.tick_base = 2 * T
     ref.iteration()
     assert torch.equal(ref.ego.params, ego2.policy.params) and torch.equal(ref.alt.params, partner2.model.policy.params)
+
+
+def test_recorded_transitions_from_the_device_buffers(ctx):
+    """VecTrainer.recorded_transitions (device -> host copies + vec_record) gives, for any env of the
+    engine, the transitions cut from the ORACLE's buffers of the same rollout — which
+    tests/test_vec_record_cpu.py pins byte for byte on the reference's own recorder."""
+    from pantheonrl_b200 import vec_record as vr
+    N, T, seed = 96, 20, 5
+    cfg = PPOConfig(n_steps=T, n_epochs=1, n_minibatches=2)
+    tr = VecTrainer("liar", N, cfg, seed=seed, partner="ppo")
+    pe, pa = tr.ego.params.cpu().numpy().copy(), tr.alt.params.cpu().numpy().copy()
+    tr.collect()
+    osp = oracle.make_space(**oracle.LIAR_SPACE)
+    o_ego, o_alt, carry = orc.rollout("liar", osp, pe, pa, N=N, T=T, seed=seed)
+    o_alt = dict(o_alt, count=o_alt["count"] + ((carry["flags"] >> 2) & 1))  # + the row left open at the end
+    for env in (0, 41, N - 1):
+        got = tr.recorded_transitions(env)
+        want = vr.turn_based_transitions(o_ego, o_alt, env, carry["ego_last_done"][env])
+        assert np.array_equal(got.obs, want.obs) and np.array_equal(got.acts, want.acts)
+        assert np.array_equal(got.flags, want.flags) and len(got.get_ego_transitions()) == T
+    tr.collect()
+    with pytest.raises(_lib.PthError):
+        tr.recorded_transitions(0)  # a later turn-based rollout may start inside an episode
+    # simultaneous game: any rollout
+    tr = VecTrainer("rps", N, cfg, seed=seed, partner="ppo")
+    pe, pa = tr.ego.params.cpu().numpy().copy(), tr.alt.params.cpu().numpy().copy()
+    tr.collect()
+    rsp = oracle.make_space(**oracle.RPS_SPACE)
+    o_ego, o_alt, carry = orc.rollout("rps", rsp, pe, pa, N=N, T=T, seed=seed)
+    got = tr.recorded_transitions(7)
+    want = vr.simultaneous_transitions(o_ego, o_alt, 7, carry["ego_last_done"][7], obs_len=1)
+    for name in ("egoobs", "egoacts", "altobs", "altacts", "flags"):
+        assert np.array_equal(getattr(got, name), getattr(want, name)), name
+    with pytest.raises(_lib.PthError):  # ADVICE r1: a static partner stores no rows — also for Liar's Dice
+        VecTrainer("liar", 8, cfg, seed=1, partner="selfplay").recorded_transitions(0)
