@@ -345,7 +345,12 @@ static void split_params(const orc_space* sp, const float* p, orc_params* q) {
 
 /* features: SB3 preprocess_obs (one-hot concat) — Appendix A2.  A linear layer
  * is evaluated as acc = bias; for k ascending: acc = fma(x_k, w[j][k], acc).
- * With x in {0,1} this equals adding the selected columns in ascending order.
+ * One-hot first layers add the selected rows slot by slot in DESCENDING slot order
+ * (x in {0,1}: an exact product, so only the order of the additions is a choice).  Descending,
+ * because the games pad their observations at the END (Liar's Dice: empty history pairs): the
+ * chain then begins with rows that are the same for most samples of a tile, and the update
+ * kernel evaluates that common beginning once per tile instead of once per sample
+ * (same additions, same bits).
  * Storage: the two first-layer matrices are kept input-major [F][64] (the
  * transpose of torch's nn.Linear.weight); every other tensor is [out][in]. */
 static void first_layer(const orc_space* sp, const void* obs_row, const float* w, const float* b,
@@ -354,10 +359,10 @@ static void first_layer(const orc_space* sp, const void* obs_row, const float* w
     const uint8_t* o = (const uint8_t*)obs_row;
     for (int j = 0; j < H; ++j) {
       float acc = b[j];
-      int off = 0;
-      for (int s = 0; s < sp->obs_len; ++s) {
+      int off = F;
+      for (int s = sp->obs_len - 1; s >= 0; --s) {
+        off -= sp->obs_nvec[s];
         acc = acc + w[(off + o[s]) * H + j];
-        off += sp->obs_nvec[s];
       }
       out[j] = acc;
     }

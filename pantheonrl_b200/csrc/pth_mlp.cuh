@@ -8,7 +8,7 @@
 // in-tree at pantheonrl/algos/modular/policies.py:273-290, 364-383).
 //
 // Numeric contract: every linear output is acc = bias; for k ascending:
-// acc = fma(x_k, w_jk, acc).  Thread tiles only change WHO computes an output,
+// acc = fma(x_k, w_jk, acc); one-hot first layers add their selected rows in descending slot order.  Thread tiles only change WHO computes an output,
 // never the order of its additions.
 #pragma once
 #include "pth_common.cuh"
@@ -137,7 +137,8 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
 
 // ---------------------------------------------------------------------------
 // First layer, one-hot observations: Out[j][b] = tanh(bias[j] + sum_s W[f_s][j]),
-// f_s = slot_off[s] + obs[b][s], slots ascending.  W is input-major [F][64] in
+// f_s = slot_off[s] + obs[b][s], slots DESCENDING (numeric contract, DESIGN.md 3: the chain then
+// begins with the padded trailing slots, which the update kernel evaluates once per tile).  W is input-major [F][64] in
 // global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
 // so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
 // ILP.  obs: [BT][32] bytes in shared memory.
@@ -160,17 +161,17 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
     for (int u = 0; u < UI; ++u) acc[u] = bv;
     // slots in blocks of SB (template: 6 at 255 registers per thread, 3 at 128): all SB*4 row
     // loads are issued before the adds
-    // (the adds themselves stay in ascending slot order per sample).
-    int s0 = 0;
-    for (; s0 + SB <= sp.obs_len; s0 += SB) {
+    // (the adds themselves stay in descending slot order per sample).
+    int s0 = sp.obs_len - 1;
+    for (; s0 - SB + 1 >= 0; s0 -= SB) {
       float4 w[SB][UI];
 #pragma unroll
       for (int i = 0; i < SB; ++i) {
-        const int off = sp.slot_off[s0 + i];
+        const int off = sp.slot_off[s0 - i];
 #pragma unroll
         for (int u = 0; u < UI; ++u) {
           const int b = (g0 + u) * GS + bs;
-          const int f = off + obs_s[b * 32 + s0 + i];
+          const int f = off + obs_s[b * 32 + s0 - i];
           w[i][u] = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
         }
       }
@@ -184,7 +185,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
           acc[u].w = acc[u].w + w[i][u].w;
         }
     }
-    for (int s = s0; s < sp.obs_len; ++s) {
+    for (int s = s0; s >= 0; --s) {
       const int off = sp.slot_off[s];
 #pragma unroll
       for (int u = 0; u < UI; ++u) {

@@ -47,6 +47,15 @@ struct UpdSmem {
   uint8_t rcount[MAX_ROWS];
   float red[8];
   float bc[160];  // broadcast scratch (norm partials)
+  // Common beginnings of the first-layer chains (one-hot): the layer adds its rows in descending
+  // slot order, and most samples of a tile agree on the trailing slots (padding).  With d_s the
+  // MODE of slot s over the tile, pchain[t][j] = bias + row(S-1, d_{S-1}) + ... + row(j, d_j) for
+  // tower t; a sample that agrees with the mode on every slot >= jb starts from pchain[t][jb] and
+  // adds only its slots jb-1 .. 0 — the same additions in the same order, hence the same bits.
+  float pchain[2][(MAX_SLOTS + 1) * HID];
+  uint8_t dmode[MAX_SLOTS];  // mode value per slot (0 beyond obs_len)
+  uint8_t jb[BT];            // per sample: slots [0, jb) are its own
+  uint8_t sorted[BT];        // samples in ascending jb (balances the warps of the first layer)
 };
 
 struct UpdParams {
@@ -380,8 +389,8 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
 // first-layer row (row = slot_off[s] + value).
 // Slots [s_begin, s_end) are shared out over n_warps warps; `wid` is this warp's index among them.
 __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* obs_s, uint8_t* order,
-                                           uint8_t* rcount, int nb, int lane, int wid, int n_warps,
-                                           int s_begin, int s_end) {
+                                           uint8_t* rcount, uint8_t* dmode, int nb, int lane, int wid,
+                                           int n_warps, int s_begin, int s_end) {
   for (int s = s_begin + wid; s < s_end; s += n_warps) {
     int val[4];
 #pragma unroll
@@ -389,7 +398,7 @@ __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* ob
       const int b = lane + 32 * r;
       val[r] = b < nb ? (int)obs_s[b * 32 + s] : -1;
     }
-    int base = 0;
+    int base = 0, best = -1, mode = 0;
     const int nv = p.nvec[s];
     const int row0 = p.sp.slot_off[s];
     for (int v = 0; v < nv; ++v) {
@@ -401,53 +410,184 @@ __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* ob
           order[s * BT + base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * r);
         base += __popc(m);
       }
+      if (base - before > best) {  // ties: the smallest value
+        best = base - before;
+        mode = v;
+      }
       if (lane == 0) rcount[row0 + v] = (uint8_t)(base - before);
+    }
+    if (lane == 0) dmode[s] = (uint8_t)mode;
+  }
+}
+
+// Once per tile, after sort_slots (dmode known) and a barrier: warp WJ finds every sample's jb (the
+// slots [jb, S) agree with the mode) and counting-sorts the samples by it; warp WP builds both towers'
+// common chain beginnings pchain[t][j], j = S .. 0 (lane = tower x 16 float4 column groups).
+constexpr int WJ = 4, WP = 5;
+__device__ __forceinline__ void chain_setup(const UpdParams& p, UpdSmem& sm, int nb, int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+  const int S = p.sp.obs_len;
+  if (wid == WJ) {
+    const uint32_t* dm = reinterpret_cast<const uint32_t*>(sm.dmode);
+    int jbv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int b = lane + 32 * r;
+      int j = 0;
+      if (b < nb) {
+#pragma unroll
+        for (int w = 7; w >= 0; --w) {
+          const uint32_t x = sm.obs[b * 8 + w] ^ dm[w];
+          if (j == 0 && x != 0u) j = 4 * w + 4 - (__clz((int)x) >> 3);
+        }
+      }
+      jbv[r] = j;
+      sm.jb[b] = (uint8_t)j;
+    }
+    int base = 0;
+    for (int k = 0; k <= S; ++k) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned m = __ballot_sync(0xffffffffu, jbv[r] == k);
+        if (jbv[r] == k) sm.sorted[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * r);
+        base += __popc(m);
+      }
+    }
+  } else if (wid == WP) {
+    const int t = lane >> 4, jq = lane & 15;
+    const float4* W4 = reinterpret_cast<const float4*>(p.params + (t ? p.lo.w_vf0 : p.lo.w_pi0));
+    float4 acc = *reinterpret_cast<const float4*>((t ? sm.pol.b_vf0 : sm.pol.b_pi0) + jq * 4);
+    float* P = sm.pchain[t];
+    *reinterpret_cast<float4*>(P + S * HID + jq * 4) = acc;
+    constexpr int PB = 6;  // row loads in flight
+    for (int s0 = S - 1; s0 >= 0; s0 -= PB) {
+      float4 w[PB];
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        const int sl = s0 - i;
+        if (sl >= 0) w[i] = ld_param4<true>(W4 + (p.sp.slot_off[sl] + sm.dmode[sl]) * (HID / 4) + jq);
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        const int sl = s0 - i;
+        if (sl >= 0) {
+          acc.x = acc.x + w[i].x;
+          acc.y = acc.y + w[i].y;
+          acc.z = acc.z + w[i].z;
+          acc.w = acc.w + w[i].w;
+          *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
+        }
+      }
     }
   }
 }
 
-// first-layer (one-hot) weight gradient: gW0[f][j] = sum over the samples whose
-// slot value selects row f of dz1T[b][j], b ascending (stable sort), as one
-// register chain per (row, column pair) — no read-modify-write through memory.
-// Thread = column pair (32 lanes) x slot subset (one warp each).
-//
-// PTH_UNIFORM_SLOTS (off by default: written at the end of round 1 without GPU time left to
-// validate it): when all nb samples of the tile hold ONE value in a slot, the row
-// that value selects is the ascending chain over all samples — the first-layer BIAS gradient, bit
-// for bit (the bias chain also runs over the trailing invalid samples, whose dz1 is +0.0: adding
-// +0.0 never changes a sum that started from +0.0) — so the row is copied from `bsum` and the
-// walk skipped.  Measured on oracle rollouts: 16.6 of Liar's 30 slots per tile.
-__device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* order,
-                                          const uint8_t* rcount, const float* dzT, float* gW0,
-                                          bool first, int tid, const float* bsum = nullptr, int nb = 0) {
-  const int jp = (tid & 31) * 2, wid = tid >> 5;
-  for (int s = wid; s < p.sp.obs_len; s += UNT / 32) {
-    const int row0 = p.sp.slot_off[s];
-    const int nv = p.nvec[s];
-#ifdef PTH_UNIFORM_SLOTS
-    if (bsum != nullptr && nb > 0) {
-      int uni = -1;
-      for (int v = 0; v < nv; ++v)
-        if (rcount[row0 + v] == nb) uni = v;
-      if (uni >= 0) {
-        const float2 b2 = *reinterpret_cast<const float2*>(bsum + jp);
-        for (int v = 0; v < nv; ++v) {
-          float* g = gW0 + (row0 + v) * HID + jp;
-          if (first) {
-            *reinterpret_cast<float2*>(g) = v == uni ? b2 : make_float2(0.f, 0.f);
-          } else if (v == uni) {
-            acc_store(g, b2.x, false);
-            acc_store(g + 1, b2.y, false);
-          }
+// First layer of one tower for the whole tile on NTH threads: Out[j][b] = tanh(bias[j] + rows in
+// descending slot order).  16 threads cover a row with float4 loads; a thread group works on 4
+// samples at a time that are NEIGHBOURS in the jb order, one quartet from the short end of the
+// order and one from the long end (equal work for every warp).  All four start from the chain
+// beginning of the quartet's LARGEST jb: a sample with a smaller jb agrees with the mode on the
+// slots in between, so its own rows there ARE the mode's rows — no predication, same additions.
+template <int NTH>
+__device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdSmem& sm, const uint8_t* obs_s,
+                                                  const float* W, const float* P, float* Out, int tid) {
+  static_assert(NTH / 16 * 8 == BT, "16 thread groups x 2 quartets cover the tile");
+  const int jq = tid & 15, bs = tid >> 4;
+  const float4* W4 = reinterpret_cast<const float4*>(W) + jq;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int pos0 = half == 0 ? bs * 4 : BT - 4 - bs * 4;
+    const uchar4 bq = *reinterpret_cast<const uchar4*>(sm.sorted + pos0);
+    const int b[4] = {bq.x, bq.y, bq.z, bq.w};
+    int jmax = sm.jb[b[0]];
+#pragma unroll
+    for (int u = 1; u < 4; ++u) {
+      const int j = sm.jb[b[u]];
+      jmax = j > jmax ? j : jmax;
+    }
+    float4 acc[4];
+    acc[0] = *reinterpret_cast<const float4*>(P + jmax * HID + jq * 4);
+#pragma unroll
+    for (int u = 1; u < 4; ++u) acc[u] = acc[0];
+    constexpr int SB = 3;  // slots per block: all SB * 4 row loads are issued before the adds
+    int s0 = jmax - 1;
+    for (; s0 - SB + 1 >= 0; s0 -= SB) {
+      float4 w[SB][4];
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        const int off = p.sp.slot_off[s0 - i];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[i][u] = ld_param4<true>(W4 + (off + obs_s[b[u] * 32 + s0 - i]) * (HID / 4));
+      }
+#pragma unroll
+      for (int i = 0; i < SB; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u].x = acc[u].x + w[i][u].x;
+          acc[u].y = acc[u].y + w[i][u].y;
+          acc[u].z = acc[u].z + w[i][u].z;
+          acc[u].w = acc[u].w + w[i][u].w;
         }
-        continue;
+    }
+    for (; s0 >= 0; --s0) {
+      const int off = p.sp.slot_off[s0];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 w = ld_param4<true>(W4 + (off + obs_s[b[u] * 32 + s0]) * (HID / 4));
+        acc[u].x = acc[u].x + w.x;
+        acc[u].y = acc[u].y + w.y;
+        acc[u].z = acc[u].z + w.z;
+        acc[u].w = acc[u].w + w.w;
       }
     }
-#endif
-    const uint8_t* ord = order + s * BT;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float* o = Out + (jq * 4) * LDA + b[u];
+      o[0 * LDA] = acc[u].x;
+      o[1 * LDA] = acc[u].y;
+      o[2 * LDA] = acc[u].z;
+      o[3 * LDA] = acc[u].w;
+    }
+    // tanh in place on the 16 values this thread has just written, as a rolled loop (32 inlined
+    // copies of the polynomial made the layer instruction-fetch bound, profiles/update_r01b.md)
+#pragma unroll 1
+    for (int q = 0; q < 16; ++q) {
+      float* o = Out + (jq * 4 + (q & 3)) * LDA + sm.sorted[pos0 + (q >> 2)];
+      *o = pth_tanhf(*o);
+    }
+  }
+}
+
+// first-layer (one-hot) weight gradient, one slot per warp at a time, lane = column pair.  Per slot
+// the row of every value EXCEPT the mode is the ascending register chain over the samples selecting
+// it (stable sort: no read-modify-write through memory); the mode's row is the tile's first-layer
+// bias gradient (`bsum`, the chain over all samples) minus the sum of the slot's other rows in
+// ascending value order (the reduction contract, oracle/pth_oracle_update.inc).  Only the samples
+// that differ from the mode are walked: in these games ~17 % of the (slot, sample) pairs.
+// Slots are shared out over warps [0, NWS); the caller's barrier separates the walk (phase 0:
+// rows of the other values, their sum kept in registers) from the mode rows (phase 1: bsum ready).
+constexpr int NWS = UNT / 32 - 2;  // the last two warps compute the bias chains meanwhile
+constexpr int SLOTS_PER_WARP = (MAX_SLOTS + NWS - 1) / NWS;
+__device__ __forceinline__ void segsum_w1_walk(const UpdParams& p, const UpdSmem& sm, const float* dzT,
+                                               float* gW0, bool first, int tid, float2 (&csum)[SLOTS_PER_WARP]) {
+  const int jp = (tid & 31) * 2, wid = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < SLOTS_PER_WARP; ++q) {
+    csum[q] = make_float2(0.f, 0.f);
+    const int s = wid + q * NWS;
+    if (wid >= NWS || s >= p.sp.obs_len) continue;
+    const int row0 = p.sp.slot_off[s];
+    const int nv = p.nvec[s];
+    const int mode = sm.dmode[s];
+    const uint8_t* ord = sm.order + s * BT;
     int pos = 0;
+    float c0 = 0.f, c1 = 0.f;
     for (int v = 0; v < nv; ++v) {
-      const int cnt = rcount[row0 + v];
+      const int cnt = sm.rcount[row0 + v];
+      if (v == mode) {
+        pos += cnt;
+        continue;
+      }
       float a0 = 0.f, a1 = 0.f;
       int i = 0;
       for (; i + 4 <= cnt; i += 4) {
@@ -467,6 +607,8 @@ __device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* ord
         a1 = a1 + d.y;
       }
       pos += cnt;
+      c0 = c0 + a0;
+      c1 = c1 + a1;
       float* g = gW0 + (row0 + v) * HID + jp;
       if (first) {
         *reinterpret_cast<float2*>(g) = make_float2(a0, a1);
@@ -474,6 +616,26 @@ __device__ __forceinline__ void segsum_w1(const UpdParams& p, const uint8_t* ord
         acc_store(g, a0, false);
         acc_store(g + 1, a1, false);
       }
+    }
+    csum[q] = make_float2(c0, c1);
+  }
+}
+__device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const UpdSmem& sm, const float* bsum,
+                                               float* gW0, bool first, int tid,
+                                               const float2 (&csum)[SLOTS_PER_WARP]) {
+  const int jp = (tid & 31) * 2, wid = tid >> 5;
+  const float2 b2 = *reinterpret_cast<const float2*>(bsum + jp);
+#pragma unroll
+  for (int q = 0; q < SLOTS_PER_WARP; ++q) {
+    const int s = wid + q * NWS;
+    if (wid >= NWS || s >= p.sp.obs_len) continue;
+    float* g = gW0 + (p.sp.slot_off[s] + sm.dmode[s]) * HID + jp;
+    const float g0 = b2.x - csum[q].x, g1 = b2.y - csum[q].y;
+    if (first) {
+      *reinterpret_cast<float2*>(g) = make_float2(g0, g1);
+    } else {
+      acc_store(g, g0, false);
+      acc_store(g + 1, g1, false);
     }
   }
 }
@@ -503,22 +665,18 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, 
     wgrad_first_box(sm.H2, Xs, p.sp.F, g_w0, first, tid);
     return;
   }
-  if (tid >= UNT - HID) {
+  (void)nb;
+  float2 csum[SLOTS_PER_WARP];
+  if (tid >= UNT - HID) {  // warps NWS, NWS + 1: the bias chains, next to the other warps' walks
     const int j = tid - (UNT - HID);
     float s = 0.f;
     for (int b = 0; b < BT; ++b) s = s + sm.H2[b * LDT + j];
     acc_store(g_b0 + j, s, first);
-#ifdef PTH_UNIFORM_SLOTS
     sm.bc[j] = s;  // bc is free during the tower's backward pass
-#endif
   }
-#ifdef PTH_UNIFORM_SLOTS
-  __syncthreads();
-  segsum_w1(p, sm.order, sm.rcount, sm.H2, g_w0, first, tid, sm.bc, nb);
-#else
-  (void)nb;
-  segsum_w1(p, sm.order, sm.rcount, sm.H2, g_w0, first, tid);
-#endif
+  segsum_w1_walk(p, sm, sm.H2, g_w0, first, tid, csum);
+  __syncthreads();  // bias chains complete
+  segsum_w1_mode(p, sm, sm.bc, g_w0, first, tid, csum);
 }
 
 template <bool BOX>
@@ -539,6 +697,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
   const int PS = (P + 3) & ~3;  // per-CTA stride of the partial sums: keeps every row 16-byte aligned
   float* part = p.part + (size_t)c * PS;
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
+  if (tid < MAX_SLOTS) sm.dmode[tid] = 0;  // slots beyond obs_len compare equal (observation rows are zero padded)
 
   // ------------------------------------------------ prologue: advantage statistics
   // One whole CTA per minibatch id (the lane order of the contract does not depend on WHICH CTA).
@@ -695,8 +854,13 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         // (moving the sort into the shadow of the head phase, onto the warps without a head, was
         // measured: no gain — it competes with the head warps for issue slots)
         if constexpr (!BOX)
-          sort_slots(p, obs_s, sm.order, sm.rcount, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
-        PTH_PROF(2);  // gather + slot sort
+          sort_slots(p, obs_s, sm.order, sm.rcount, sm.dmode, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
+        if constexpr (!BOX) {
+          __syncthreads();  // dmode / rcount complete
+          chain_setup(p, sm, nb, tid);
+          __syncthreads();
+        }
+        PTH_PROF(2);  // gather + slot sort + chain beginnings
 
         // ================= policy tower: forward
         if constexpr (BOX) {
@@ -704,11 +868,9 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         } else {
           // both towers' first layers (latency-bound row gathers) side by side, one per CTA half
           if (tid < UNT / 2)
-            first_layer_onehot<true, UNT / 2, BT, 3>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1,
-                                                      tid);
+            first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_pi0, sm.pchain[0], sm.H1, tid);
           else
-            first_layer_onehot<true, UNT / 2, BT, 3>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, V1,
-                                                      tid - UNT / 2);
+            first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_vf0, sm.pchain[1], V1, tid - UNT / 2);
         }
         __syncthreads();
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
