@@ -31,7 +31,8 @@ namespace {
 constexpr int UNT = 512;
 constexpr int LDT = 66;  // stride of the transposed dz1 tile [sample][unit] (even: float2 loads)
 constexpr int MAX_SLOTS = 32;
-constexpr int MAX_ROWS = 2048;  // first-layer rows (one-hot feature width) supported by the update
+constexpr int MAX_ROWS = 1024;  // first-layer rows (one-hot feature width) supported by the update
+constexpr int STAGE_ROWS = 160;  // first-layer rows per tower staged in shared memory per tile
 
 struct UpdSmem {
   SmemPolicy pol;
@@ -55,8 +56,15 @@ struct UpdSmem {
   float pchain[2][(MAX_SLOTS + 1) * HID];
   uint8_t dmode[MAX_SLOTS];  // mode value per slot (0 beyond obs_len)
   uint8_t jb[BT];            // per sample: slots [0, jb) are its own
-  uint8_t sorted[BT];        // samples in ascending jb (balances the warps of the first layer)
+  // The rows of the two first-layer matrices that this tile's samples select (~92 of Liar's 270)
+  // are staged in shared memory once per tile (in H2 | D1 | Lg, free until the hidden layer runs):
+  // without it every (sample, slot) pair pulls 256 bytes from L2 and the layer is bound by the
+  // L2 -> SM bandwidth (1.9 MB per tile before, 0.5 MB with the chain beginnings, 47 KB staged).
+  // rowmap[row] = staged position, 0xFF = not staged (more than STAGE_ROWS rows touched: global load).
+  uint8_t rowmap[MAX_ROWS];
 };
+static_assert(STAGE_ROWS * 2 * HID <= (2 * HID + MAXL) * LDA, "stage fits in H2 | D1 | Lg");
+static_assert(STAGE_ROWS < 255, "rowmap is one byte per row");
 
 struct UpdParams {
   SpaceDev sp;
@@ -420,91 +428,95 @@ __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* ob
   }
 }
 
-// Once per tile, after sort_slots (dmode known) and a barrier: warp WJ finds every sample's jb (the
-// slots [jb, S) agree with the mode) and counting-sorts the samples by it; warp WP builds both towers'
-// common chain beginnings pchain[t][j], j = S .. 0 (lane = tower x 16 float4 column groups).
-constexpr int WJ = 4, WP = 5;
-__device__ __forceinline__ void chain_setup(const UpdParams& p, UpdSmem& sm, int nb, int tid) {
+// Per-tile set-up of the one-hot first layers, after sort_slots (rcount / dmode known) and a barrier.
+//  step 0: warp 0 numbers the rows some sample selects (rowmap); threads [128, 256) find every
+//          sample's jb (its slots [jb, S) agree with the mode)
+//  step 1: all threads copy the numbered rows of both matrices into the stage
+//  step 2: one warp builds both towers' common chain beginnings pchain[t][j], j = S .. 0
+//          (lane = tower x 16 float4 column groups; 30 dependent adds from shared memory)
+// The caller puts a barrier after every step.
+__device__ __forceinline__ float4 row_load(const UpdSmem& sm, const float* stage, const float4* W4, int t,
+                                           int row, int jq) {
+  const int m = sm.rowmap[row];
+  if (m != 0xFF) return *(reinterpret_cast<const float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID) + jq);
+  return ld_param4<true>(W4 + row * (HID / 4) + jq);
+}
+__device__ __forceinline__ void chain_setup0(const UpdParams& p, UpdSmem& sm, int nb, int tid) {
   const int lane = tid & 31, wid = tid >> 5;
-  const int S = p.sp.obs_len;
-  if (wid == WJ) {
-    const uint32_t* dm = reinterpret_cast<const uint32_t*>(sm.dmode);
-    int jbv[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int b = lane + 32 * r;
-      int j = 0;
-      if (b < nb) {
-#pragma unroll
-        for (int w = 7; w >= 0; --w) {
-          const uint32_t x = sm.obs[b * 8 + w] ^ dm[w];
-          if (j == 0 && x != 0u) j = 4 * w + 4 - (__clz((int)x) >> 3);
-        }
-      }
-      jbv[r] = j;
-      sm.jb[b] = (uint8_t)j;
-    }
+  if (wid == 0) {
     int base = 0;
-    for (int k = 0; k <= S; ++k) {
+    for (int r0 = 0; r0 < p.sp.F; r0 += 32) {
+      const int r = r0 + lane;
+      const bool hit = r < p.sp.F && sm.rcount[r] > 0;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (r < p.sp.F) sm.rowmap[r] = (hit && pos < STAGE_ROWS) ? (uint8_t)pos : (uint8_t)0xFF;
+      base += __popc(m);
+    }
+  } else if (tid >= BT && tid < 2 * BT) {
+    const int b = tid - BT;
+    const uint32_t* dm = reinterpret_cast<const uint32_t*>(sm.dmode);
+    int j = 0;
+    if (b < nb) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const unsigned m = __ballot_sync(0xffffffffu, jbv[r] == k);
-        if (jbv[r] == k) sm.sorted[base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * r);
-        base += __popc(m);
+      for (int w = 7; w >= 0; --w) {
+        const uint32_t x = sm.obs[b * 8 + w] ^ dm[w];
+        if (j == 0 && x != 0u) j = 4 * w + 4 - (__clz((int)x) >> 3);
       }
     }
-  } else if (wid == WP) {
-    const int t = lane >> 4, jq = lane & 15;
-    const float4* W4 = reinterpret_cast<const float4*>(p.params + (t ? p.lo.w_vf0 : p.lo.w_pi0));
-    float4 acc = *reinterpret_cast<const float4*>((t ? sm.pol.b_vf0 : sm.pol.b_pi0) + jq * 4);
-    float* P = sm.pchain[t];
-    *reinterpret_cast<float4*>(P + S * HID + jq * 4) = acc;
-    constexpr int PB = 6;  // row loads in flight
-    for (int s0 = S - 1; s0 >= 0; s0 -= PB) {
-      float4 w[PB];
-#pragma unroll
-      for (int i = 0; i < PB; ++i) {
-        const int sl = s0 - i;
-        if (sl >= 0) w[i] = ld_param4<true>(W4 + (p.sp.slot_off[sl] + sm.dmode[sl]) * (HID / 4) + jq);
-      }
-#pragma unroll
-      for (int i = 0; i < PB; ++i) {
-        const int sl = s0 - i;
-        if (sl >= 0) {
-          acc.x = acc.x + w[i].x;
-          acc.y = acc.y + w[i].y;
-          acc.z = acc.z + w[i].z;
-          acc.w = acc.w + w[i].w;
-          *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
-        }
-      }
-    }
+    sm.jb[b] = (uint8_t)j;
+  }
+}
+__device__ __forceinline__ void chain_setup1(const UpdParams& p, UpdSmem& sm, float* stage, int tid) {
+  const float4* Wp = reinterpret_cast<const float4*>(p.params + p.lo.w_pi0);
+  const float4* Wv = reinterpret_cast<const float4*>(p.params + p.lo.w_vf0);
+  const int n = p.sp.F * 32;  // (row, tower, float4 column group)
+  for (int i = tid; i < n; i += UNT) {
+    const int r = i >> 5, t = (i >> 4) & 1, jq = i & 15;
+    const int m = sm.rowmap[r];
+    if (m != 0xFF)
+      *reinterpret_cast<float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID + jq * 4) =
+          ld_param4_l2<true>((t ? Wv : Wp) + r * (HID / 4) + jq);
+  }
+}
+__device__ __forceinline__ void chain_setup2(const UpdParams& p, UpdSmem& sm, const float* stage, int tid) {
+  if ((tid >> 5) != 0) return;
+  const int lane = tid & 31;
+  const int S = p.sp.obs_len;
+  const int t = lane >> 4, jq = lane & 15;
+  const float4* W4 = reinterpret_cast<const float4*>(p.params + (t ? p.lo.w_vf0 : p.lo.w_pi0));
+  float4 acc = *reinterpret_cast<const float4*>((t ? sm.pol.b_vf0 : sm.pol.b_pi0) + jq * 4);
+  float* P = sm.pchain[t];
+  *reinterpret_cast<float4*>(P + S * HID + jq * 4) = acc;
+  for (int sl = S - 1; sl >= 0; --sl) {
+    const float4 w = row_load(sm, stage, W4, t, p.sp.slot_off[sl] + sm.dmode[sl], jq);
+    acc.x = acc.x + w.x;
+    acc.y = acc.y + w.y;
+    acc.z = acc.z + w.z;
+    acc.w = acc.w + w.w;
+    *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
   }
 }
 
 // First layer of one tower for the whole tile on NTH threads: Out[j][b] = tanh(bias[j] + rows in
-// descending slot order).  16 threads cover a row with float4 loads; a thread group works on 4
-// samples at a time that are NEIGHBOURS in the jb order, one quartet from the short end of the
-// order and one from the long end (equal work for every warp).  All four start from the chain
-// beginning of the quartet's LARGEST jb: a sample with a smaller jb agrees with the mode on the
-// slots in between, so its own rows there ARE the mode's rows — no predication, same additions.
+// descending slot order).  16 threads cover a row with float4 loads (from the stage); a thread
+// group works on 4 samples at a time.  All four start from the chain beginning of the quartet's
+// LARGEST jb: a sample with a smaller jb agrees with the mode on the slots in between, so its
+// own rows there ARE the mode's rows — no predication, same additions.
 template <int NTH>
 __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdSmem& sm, const uint8_t* obs_s,
-                                                  const float* W, const float* P, float* Out, int tid) {
+                                                  const float* W, const float* stage, int t, const float* P,
+                                                  float* Out, int tid) {
   static_assert(NTH / 16 * 8 == BT, "16 thread groups x 2 quartets cover the tile");
   const int jq = tid & 15, bs = tid >> 4;
-  const float4* W4 = reinterpret_cast<const float4*>(W) + jq;
+  const float4* W4 = reinterpret_cast<const float4*>(W);
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    const int pos0 = half == 0 ? bs * 4 : BT - 4 - bs * 4;
-    const uchar4 bq = *reinterpret_cast<const uchar4*>(sm.sorted + pos0);
-    const int b[4] = {bq.x, bq.y, bq.z, bq.w};
-    int jmax = sm.jb[b[0]];
-#pragma unroll
-    for (int u = 1; u < 4; ++u) {
-      const int j = sm.jb[b[u]];
-      jmax = j > jmax ? j : jmax;
-    }
+    const int b0 = half * (BT / 2) + bs * 4;  // samples b0 .. b0 + 3
+    const uchar4 jq4 = *reinterpret_cast<const uchar4*>(sm.jb + b0);
+    int jmax = jq4.x > jq4.y ? jq4.x : jq4.y;
+    jmax = jq4.z > jmax ? jq4.z : jmax;
+    jmax = jq4.w > jmax ? jq4.w : jmax;
     float4 acc[4];
     acc[0] = *reinterpret_cast<const float4*>(P + jmax * HID + jq * 4);
 #pragma unroll
@@ -517,7 +529,7 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdS
       for (int i = 0; i < SB; ++i) {
         const int off = p.sp.slot_off[s0 - i];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[i][u] = ld_param4<true>(W4 + (off + obs_s[b[u] * 32 + s0 - i]) * (HID / 4));
+        for (int u = 0; u < 4; ++u) w[i][u] = row_load(sm, stage, W4, t, off + obs_s[(b0 + u) * 32 + s0 - i], jq);
       }
 #pragma unroll
       for (int i = 0; i < SB; ++i)
@@ -533,28 +545,25 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdS
       const int off = p.sp.slot_off[s0];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float4 w = ld_param4<true>(W4 + (off + obs_s[b[u] * 32 + s0]) * (HID / 4));
+        const float4 w = row_load(sm, stage, W4, t, off + obs_s[(b0 + u) * 32 + s0], jq);
         acc[u].x = acc[u].x + w.x;
         acc[u].y = acc[u].y + w.y;
         acc[u].z = acc[u].z + w.z;
         acc[u].w = acc[u].w + w.w;
       }
     }
+    // the thread owns 4 consecutive samples x 4 outputs: one float4 per output row
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float* o = Out + (jq * 4) * LDA + b[u];
-      o[0 * LDA] = acc[u].x;
-      o[1 * LDA] = acc[u].y;
-      o[2 * LDA] = acc[u].z;
-      o[3 * LDA] = acc[u].w;
+    for (int c = 0; c < 4; ++c) {
+      const float v[4] = {c == 0 ? acc[0].x : c == 1 ? acc[0].y : c == 2 ? acc[0].z : acc[0].w,
+                          c == 0 ? acc[1].x : c == 1 ? acc[1].y : c == 2 ? acc[1].z : acc[1].w,
+                          c == 0 ? acc[2].x : c == 1 ? acc[2].y : c == 2 ? acc[2].z : acc[2].w,
+                          c == 0 ? acc[3].x : c == 1 ? acc[3].y : c == 2 ? acc[3].z : acc[3].w};
+      *reinterpret_cast<float4*>(Out + (jq * 4 + c) * LDA + b0) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    // tanh in place on the 16 values this thread has just written, as a rolled loop (32 inlined
-    // copies of the polynomial made the layer instruction-fetch bound, profiles/update_r01b.md)
-#pragma unroll 1
-    for (int q = 0; q < 16; ++q) {
-      float* o = Out + (jq * 4 + (q & 3)) * LDA + sm.sorted[pos0 + (q >> 2)];
-      *o = pth_tanhf(*o);
-    }
+    // tanh in place on what this thread has just written, as a rolled loop (32 inlined copies of
+    // the polynomial made the layer instruction-fetch bound, profiles/update_r01b.md)
+    tanh_own_quads<4>(Out, tid, [&](int q) { return (jq * 4 + q) * LDA + b0; });
   }
 }
 
@@ -857,7 +866,11 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           sort_slots(p, obs_s, sm.order, sm.rcount, sm.dmode, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
         if constexpr (!BOX) {
           __syncthreads();  // dmode / rcount complete
-          chain_setup(p, sm, nb, tid);
+          chain_setup0(p, sm, nb, tid);
+          __syncthreads();
+          chain_setup1(p, sm, sm.H2, tid);
+          __syncthreads();
+          chain_setup2(p, sm, sm.H2, tid);
           __syncthreads();
         }
         PTH_PROF(2);  // gather + slot sort + chain beginnings
@@ -868,9 +881,10 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         } else {
           // both towers' first layers (latency-bound row gathers) side by side, one per CTA half
           if (tid < UNT / 2)
-            first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_pi0, sm.pchain[0], sm.H1, tid);
+            first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_pi0, sm.H2, 0, sm.pchain[0], sm.H1, tid);
           else
-            first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_vf0, sm.pchain[1], V1, tid - UNT / 2);
+            first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_vf0, sm.H2, 1, sm.pchain[1], V1,
+                                       tid - UNT / 2);
         }
         __syncthreads();
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
@@ -1471,7 +1485,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     PTH_CHECK_ARG(((uintptr_t)a->d_obs_f32 % 16) == 0, "obs rows must be 16-byte aligned");
   } else {
     PTH_CHECK_ARG(a->d_obs != nullptr, "NULL d_obs");
-    PTH_CHECK_ARG(p.sp.F <= MAX_ROWS, "one-hot feature width above 2048 is not supported");
+    PTH_CHECK_ARG(p.sp.F <= MAX_ROWS, "one-hot feature width above 1024 is not supported");
   }
   p.lo = make_layout(p.sp.F, p.sp.L);
   for (int i = 0; i < MAX_SLOTS; ++i)
