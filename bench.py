@@ -326,7 +326,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pantheonrl_b200 import _lib, ops
-    from pantheonrl_b200.engine import PPOConfig, VecTrainer
+    from pantheonrl_b200.engine import PPOConfig
+    from pantheonrl_b200.partner_set import make_trainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -354,9 +355,9 @@ def run_ours(args):
     if partners // world > 1:
         kw["partners_per_gpu"] = partners // world
     # envs sharded: rank r owns global envs [r*N, (r+1)*N) and its partner learner(s)
-    tr = VecTrainer(w["env"], n_envs, cfg, seed=10, partner=w["partner"], device=f"cuda:{local}",
-                    env0=rank * n_envs, group=dist.group.WORLD if world > 1 else None,
-                    exchange=args.exchange, ego_update=args.ego_update, **kw)
+    tr = make_trainer(w["env"], n_envs, cfg, seed=10, partner=w["partner"], device=f"cuda:{local}",
+                      env0=rank * n_envs, group=dist.group.WORLD if world > 1 else None,
+                      exchange=args.exchange, ego_update=args.ego_update, **kw)
 
     def barrier():
         if world > 1:

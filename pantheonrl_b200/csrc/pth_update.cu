@@ -62,6 +62,10 @@ struct UpdSmem {
   // L2 -> SM bandwidth (1.9 MB per tile before, 0.5 MB with the chain beginnings, 47 KB staged).
   // rowmap[row] = staged position, 0xFF = not staged (more than STAGE_ROWS rows touched: global load).
   uint8_t rowmap[MAX_ROWS];
+  uint16_t staged_rows[STAGE_ROWS];  // inverse of rowmap
+  uint8_t rowpos[BT * 32];           // per (sample, slot): staged position of the row it selects (both towers)
+  uint8_t modepos[MAX_SLOTS];        // per slot: staged position of the mode's row
+  int n_staged;
 };
 static_assert(STAGE_ROWS * 2 * HID <= (2 * HID + MAXL) * LDA, "stage fits in H2 | D1 | Lg");
 static_assert(STAGE_ROWS < 255, "rowmap is one byte per row");
@@ -429,18 +433,14 @@ __device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* ob
 }
 
 // Per-tile set-up of the one-hot first layers, after sort_slots (rcount / dmode known) and a barrier.
-//  step 0: warp 0 numbers the rows some sample selects (rowmap); threads [128, 256) find every
-//          sample's jb (its slots [jb, S) agree with the mode)
-//  step 1: all threads copy the numbered rows of both matrices into the stage
+//  step 0: warp 0 numbers the rows some sample selects (rowmap, staged_rows); threads [128, 256)
+//          find every sample's jb (its slots [jb, S) agree with the mode)
+//  step 1: all threads copy the numbered rows of both matrices into the stage (all loads of a
+//          thread in flight together) and translate every (sample, slot) into its row's staged
+//          position once for both towers (rowpos; modepos for the modes)
 //  step 2: one warp builds both towers' common chain beginnings pchain[t][j], j = S .. 0
-//          (lane = tower x 16 float4 column groups; 30 dependent adds from shared memory)
+//          (lane = tower x 16 float4 column groups; dependent adds over rows in shared memory)
 // The caller puts a barrier after every step.
-__device__ __forceinline__ float4 row_load(const UpdSmem& sm, const float* stage, const float4* W4, int t,
-                                           int row, int jq) {
-  const int m = sm.rowmap[row];
-  if (m != 0xFF) return *(reinterpret_cast<const float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID) + jq);
-  return ld_param4<true>(W4 + row * (HID / 4) + jq);
-}
 __device__ __forceinline__ void chain_setup0(const UpdParams& p, UpdSmem& sm, int nb, int tid) {
   const int lane = tid & 31, wid = tid >> 5;
   if (wid == 0) {
@@ -450,9 +450,12 @@ __device__ __forceinline__ void chain_setup0(const UpdParams& p, UpdSmem& sm, in
       const bool hit = r < p.sp.F && sm.rcount[r] > 0;
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       const int pos = base + __popc(m & ((1u << lane) - 1u));
-      if (r < p.sp.F) sm.rowmap[r] = (hit && pos < STAGE_ROWS) ? (uint8_t)pos : (uint8_t)0xFF;
+      const bool staged = hit && pos < STAGE_ROWS;
+      if (r < p.sp.F) sm.rowmap[r] = staged ? (uint8_t)pos : (uint8_t)0xFF;
+      if (staged) sm.staged_rows[pos] = (uint16_t)r;
       base += __popc(m);
     }
+    if (lane == 0) sm.n_staged = base < STAGE_ROWS ? base : STAGE_ROWS;
   } else if (tid >= BT && tid < 2 * BT) {
     const int b = tid - BT;
     const uint32_t* dm = reinterpret_cast<const uint32_t*>(sm.dmode);
@@ -470,14 +473,36 @@ __device__ __forceinline__ void chain_setup0(const UpdParams& p, UpdSmem& sm, in
 __device__ __forceinline__ void chain_setup1(const UpdParams& p, UpdSmem& sm, float* stage, int tid) {
   const float4* Wp = reinterpret_cast<const float4*>(p.params + p.lo.w_pi0);
   const float4* Wv = reinterpret_cast<const float4*>(p.params + p.lo.w_vf0);
-  const int n = p.sp.F * 32;  // (row, tower, float4 column group)
-  for (int i = tid; i < n; i += UNT) {
-    const int r = i >> 5, t = (i >> 4) & 1, jq = i & 15;
-    const int m = sm.rowmap[r];
-    if (m != 0xFF)
-      *reinterpret_cast<float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID + jq * 4) =
-          ld_param4_l2<true>((t ? Wv : Wp) + r * (HID / 4) + jq);
+  const int n = sm.n_staged * 32;  // (staged row, tower, float4 column group)
+  constexpr int CB = 4;            // loads in flight per thread
+  for (int i0 = tid; i0 < n; i0 += CB * UNT) {
+    float4 v[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const int i = min(i0 + c * UNT, n - 1);  // clamped: the load is unconditional, the store is not
+      const int m = i >> 5, t = (i >> 4) & 1, jq = i & 15;
+      v[c] = ld_param4_l2<true>((t ? Wv : Wp) + (int)sm.staged_rows[m] * (HID / 4) + jq);
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      const int i = i0 + c * UNT;
+      if (i < n) {
+        const int m = i >> 5, t = (i >> 4) & 1, jq = i & 15;
+        *reinterpret_cast<float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID + jq * 4) = v[c];
+      }
+    }
   }
+  const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
+  for (int i = tid; i < BT * 32; i += UNT) {
+    const int sl = i & 31;
+    if (sl < p.sp.obs_len) sm.rowpos[i] = sm.rowmap[p.sp.slot_off[sl] + obs_s[i]];
+  }
+  if (tid < p.sp.obs_len) sm.modepos[tid] = sm.rowmap[p.sp.slot_off[tid] + sm.dmode[tid]];
+}
+// row of tower t at staged position m (m == 0xFF: not staged, read it from global memory)
+__device__ __forceinline__ float4 row_load(const float* stage, const float4* W4, int t, int m, int row, int jq) {
+  if (m != 0xFF) return *(reinterpret_cast<const float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID) + jq);
+  return ld_param4<true>(W4 + row * (HID / 4) + jq);
 }
 __device__ __forceinline__ void chain_setup2(const UpdParams& p, UpdSmem& sm, const float* stage, int tid) {
   if ((tid >> 5) != 0) return;
@@ -488,13 +513,25 @@ __device__ __forceinline__ void chain_setup2(const UpdParams& p, UpdSmem& sm, co
   float4 acc = *reinterpret_cast<const float4*>((t ? sm.pol.b_vf0 : sm.pol.b_pi0) + jq * 4);
   float* P = sm.pchain[t];
   *reinterpret_cast<float4*>(P + S * HID + jq * 4) = acc;
-  for (int sl = S - 1; sl >= 0; --sl) {
-    const float4 w = row_load(sm, stage, W4, t, p.sp.slot_off[sl] + sm.dmode[sl], jq);
-    acc.x = acc.x + w.x;
-    acc.y = acc.y + w.y;
-    acc.z = acc.z + w.z;
-    acc.w = acc.w + w.w;
-    *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
+  constexpr int PB = 6;  // row loads issued together
+  for (int s0 = S - 1; s0 >= 0; s0 -= PB) {
+    float4 w[PB];
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      const int sl = max(s0 - i, 0);  // clamped: loaded anyway, added only if s0 - i >= 0
+      w[i] = row_load(stage, W4, t, sm.modepos[sl], p.sp.slot_off[sl] + sm.dmode[sl], jq);
+    }
+#pragma unroll
+    for (int i = 0; i < PB; ++i) {
+      const int sl = s0 - i;
+      if (sl >= 0) {
+        acc.x = acc.x + w[i].x;
+        acc.y = acc.y + w[i].y;
+        acc.z = acc.z + w[i].z;
+        acc.w = acc.w + w[i].w;
+        *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
+      }
+    }
   }
 }
 
@@ -510,6 +547,10 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdS
   static_assert(NTH / 16 * 8 == BT, "16 thread groups x 2 quartets cover the tile");
   const int jq = tid & 15, bs = tid >> 4;
   const float4* W4 = reinterpret_cast<const float4*>(W);
+  auto row = [&](int b, int sl) {
+    const int m = sm.rowpos[b * 32 + sl];
+    return row_load(stage, W4, t, m, m != 0xFF ? 0 : p.sp.slot_off[sl] + obs_s[b * 32 + sl], jq);
+  };
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     const int b0 = half * (BT / 2) + bs * 4;  // samples b0 .. b0 + 3
@@ -526,11 +567,9 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdS
     for (; s0 - SB + 1 >= 0; s0 -= SB) {
       float4 w[SB][4];
 #pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        const int off = p.sp.slot_off[s0 - i];
+      for (int i = 0; i < SB; ++i)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[i][u] = row_load(sm, stage, W4, t, off + obs_s[(b0 + u) * 32 + s0 - i], jq);
-      }
+        for (int u = 0; u < 4; ++u) w[i][u] = row(b0 + u, s0 - i);
 #pragma unroll
       for (int i = 0; i < SB; ++i)
 #pragma unroll
@@ -542,10 +581,9 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdS
         }
     }
     for (; s0 >= 0; --s0) {
-      const int off = p.sp.slot_off[s0];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float4 w = row_load(sm, stage, W4, t, off + obs_s[(b0 + u) * 32 + s0], jq);
+        const float4 w = row(b0 + u, s0);
         acc[u].x = acc[u].x + w.x;
         acc[u].y = acc[u].y + w.y;
         acc[u].z = acc[u].z + w.z;

@@ -299,8 +299,10 @@ class PPO:
             raise _lib.PthError("n_envs > 1 needs a built-in env with a device twin "
                                 "(RPS-v0, LiarsDice-v0, OvercookedMultiEnv-v0)")
         plist = self.env.partners[0]
-        if len(plist) != 1:
-            raise _lib.PthError("the on-device loop drives exactly one partner per process (one partner per GPU)")
+        if len(plist) < 1:
+            raise _lib.PthError("the on-device loop needs a partner: env.add_partner_agent(...)")
+        if len(plist) > 1:
+            return self._learn_on_device_partner_set(total_timesteps, log_interval, plist, kind)
         partner = plist[0]
         if self._trainer is None:
             mk = lambda m: PPOConfig(learning_rate=m.learning_rate, n_steps=m.n_steps, batch_size=m.batch_size,  # noqa: E731
@@ -368,6 +370,56 @@ class PPO:
                     partner_model.logger.record("name", partner.name, exclude="tensorboard")
                     partner_model.logger.record("time/total_timesteps", partner.num_timesteps, exclude="tensorboard")
                     partner_model.logger.dump(step=partner.num_timesteps)
+        self.last_stats = tr.ego.last_stats
+        return self
+
+    def _learn_on_device_partner_set(self, total_timesteps, log_interval, plist, kind):
+        """Several partners added to the env (trainer.py:216-228): the device engine pairs each with its
+        own share of the envs (partner_set.PartnerSetTrainer) instead of drawing one per episode."""
+        from .engine import PPOConfig
+        from .partner_set import PartnerSetTrainer
+        if not all(isinstance(a, OnPolicyAgent) for a in plist):
+            raise _lib.PthError("on-device partner sets are made of OnPolicyAgent(PPO) learners")
+        if self.n_envs % len(plist):
+            raise _lib.PthError(f"n_envs={self.n_envs} must be a multiple of the {len(plist)} partners")
+        if self._trainer is None:
+            mk = lambda m: PPOConfig(learning_rate=m.learning_rate, n_steps=m.n_steps, batch_size=m.batch_size,  # noqa: E731
+                                     n_epochs=m.n_epochs, gamma=m.gamma, gae_lambda=m.gae_lambda,
+                                     clip_range=m.clip_range, normalize_advantage=m.normalize_advantage,
+                                     ent_coef=m.ent_coef, vf_coef=m.vf_coef, max_grad_norm=m.max_grad_norm,
+                                     n_minibatches=m.n_minibatches or 32)
+            tr = PartnerSetTrainer(kind, self.n_envs, mk(self), mk(plist[0].model), partners_per_gpu=len(plist),
+                                   seed=self.policy.seed, probegostart=getattr(self.env, "probegostart", 0.5),
+                                   device=self.device,
+                                   **({"layout": self.env.layout_name, "ego_agent_idx": self.env.ego_agent_idx,
+                                       "horizon": self.env.layout.horizon} if kind == "overcooked" else {}))
+            tr.ego.params, tr.ego.adam_m, tr.ego.adam_v = self.policy.params, self.adam_m, self.adam_v
+            tr.ego.adam_step, tr.ego.n_updates = self.adam_step, self._n_updates
+            tr.tick_base = (self._n_updates * self.n_steps) & 0xffffffff
+            for ln, agent in zip(tr.lanes, plist):
+                m = agent.model
+                ln.learner.params, ln.learner.adam_m, ln.learner.adam_v = m.policy.params, m.adam_m, m.adam_v
+                ln.learner.adam_step, ln.learner.n_updates = m.adam_step, m._n_updates
+            self._trainer, self._ep_prev = tr, np.zeros(4)
+        tr = self._trainer
+        tr.num_timesteps = self.num_timesteps
+        target = tr.num_timesteps + total_timesteps
+        while tr.num_timesteps < target:
+            tr.collect()
+            tr.compute_gae()
+            self.num_timesteps = tr.num_timesteps
+            self._iteration += 1
+            if log_interval is not None and self._iteration % log_interval == 0 and self._logger.output_formats:
+                e = tr.carry.ep_stats.cpu().numpy().astype(np.float64)
+                d, self._ep_prev = e - self._ep_prev, e
+                n = max(d[0], 1.0)
+                self._record_rollout(self._iteration, float(d[1] / n), float(d[2] / n))
+            tr.train()
+            self._n_updates, self.adam_step = tr.ego.n_updates, tr.ego.adam_step
+            self._record_train(tr.ego.last_stats, tr.ego_buf.values, tr.ego_buf.returns, tr.ego.n_updates)
+            for ln, agent in zip(tr.lanes, plist):
+                agent.model._n_updates, agent.model.adam_step = ln.learner.n_updates, ln.learner.adam_step
+                agent.num_timesteps += ln.M
         self.last_stats = tr.ego.last_stats
         return self
 

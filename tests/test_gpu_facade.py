@@ -454,3 +454,74 @@ def test_recorded_transitions_from_the_device_buffers(ctx):
         assert np.array_equal(getattr(got, name), getattr(want, name)), name
     with pytest.raises(_lib.PthError):  # a static partner stores no rows — also for Liar's Dice
         VecTrainer("liar", 8, cfg, seed=1, partner="selfplay").recorded_transitions(0)
+
+
+def test_partner_set_three_partners_on_one_gpu_bit_exact_vs_oracle(ctx):
+    """Several partner learners per GPU (the reference's partner set, trainer.py:216-228): envs cut into
+    one group per partner, one ego update over all groups, P partner updates — every buffer and every
+    parameter equal to the oracle pieces run group by group with the same global env ids."""
+    from pantheonrl_b200.dist_util import global_env_major_index
+    from pantheonrl_b200.partner_set import PartnerSetTrainer
+    P, Ng, T, E, NMB, seed = 3, 64, 10, 2, 3, 11
+    N = P * Ng
+    cfg = PPOConfig(n_steps=T, n_epochs=E, n_minibatches=NMB)
+    tr = PartnerSetTrainer("liar", N, cfg, partners_per_gpu=P, seed=seed)
+    osp, sp = oracle.make_space(**oracle.LIAR_SPACE), tr.space
+    pe = tr.ego.params.cpu().numpy().copy()
+    pas = [ln.learner.params.cpu().numpy().copy() for ln in tr.lanes]
+    me, ve = np.zeros_like(pe), np.zeros_like(pe)
+    mas, vas = [np.zeros_like(pe) for _ in range(P)], [np.zeros_like(pe) for _ in range(P)]
+    step_e = upd_e = 0
+    step_a, carries = [0] * P, [None] * P
+    o_alts = [orc.new_buffer(orc.alt_capacity("liar", T), Ng, True) for _ in range(P)]
+    idx = global_env_major_index(P, T, Ng).numpy()
+    for it in range(2):
+        tr.iteration()
+        torch.cuda.synchronize()
+        cat = {k: [] for k in ("obs", "actions", "logp", "adv", "ret")}
+        parts = []
+        for p in range(P):
+            o_ego, o_alts[p], carries[p] = orc.rollout("liar", osp, pe, pas[p], N=Ng, T=T, seed=seed, tick0=it * T,
+                                                       env0=p * Ng, first_rollout=it == 0, carry=carries[p],
+                                                       alt=o_alts[p])
+            ln = tr.lanes[p]
+            for k in ("obs", "actions", "rewards", "values", "logp", "episode_starts"):
+                assert np.array_equal(getattr(ln.ego_view, k).cpu().numpy(), o_ego[k]), (it, p, k)
+            assert np.array_equal(ln.buf.count.cpu().numpy(), o_alts[p]["count"])
+            adv, ret = oracle.gae(o_ego["rewards"], o_ego["values"], o_ego["episode_starts"],
+                                  carries[p]["ego_last_value"], carries[p]["ego_last_done"])
+            for k, v in (("obs", o_ego["obs"]), ("actions", o_ego["actions"]), ("logp", o_ego["logp"]),
+                         ("adv", adv), ("ret", ret)):
+                cat[k].append(v.reshape(T * Ng, -1) if v.ndim == 3 else v.reshape(T * Ng))
+            parts.append((o_alts[p], carries[p]))
+        cat = {k: np.concatenate(v) for k, v in cat.items()}
+        M = idx.size
+        bs = -(-M // NMB)
+        perm = oupd.perm_feistel(M, E, seed, _lib.STREAM_SHUFFLE_EGO, epoch0=upd_e)
+        oupd.ppo_update(osp, pe, me, ve, step_e, cat["obs"], cat["actions"], cat["logp"], cat["adv"], cat["ret"], perm,
+                        bs, tr.last_grids[0], index=idx)
+        step_e += E * (-(-M // bs))
+        assert np.array_equal(tr.ego.params.cpu().numpy(), pe), f"ego params differ after iteration {it}"
+        for p, (o_alt, carry) in enumerate(parts):
+            aadv, aret = oracle.gae_ragged(o_alt["rewards"], o_alt["values"], o_alt["episode_starts"], o_alt["count"],
+                                           carry["alt_boot_done"])
+            aidx = oupd.index_build(o_alt["count"], orc.alt_capacity("liar", T), Ng)
+            Ma = aidx.size
+            bsa = -(-Ma // NMB)
+            aperm = oupd.perm_feistel(Ma, E, seed, tr.lanes[p].shuffle_stream, epoch0=upd_e)
+            oupd.ppo_update(osp, pas[p], mas[p], vas[p], step_a[p], o_alt["obs"], o_alt["actions"], o_alt["logp"],
+                            aadv, aret, aperm, bsa, tr.last_grids[1 + p], index=aidx)
+            step_a[p] += E * (-(-Ma // bsa))
+            assert np.array_equal(tr.lanes[p].learner.params.cpu().numpy(), pas[p]), (it, p)
+        upd_e += E
+    assert not np.array_equal(pas[0], pas[1]) and tr.episode_stats()["ego_steps"] == 2 * N * T
+    # the facade: three OnPolicyAgent partners added to one env -> the same trainer
+    env = LiarEnv()
+    agents = [OnPolicyAgent(PPO("MlpPolicy", env, n_steps=T, n_epochs=E, seed=seed, n_minibatches=NMB)) for _ in range(P)]
+    for a in agents:
+        env.add_partner_agent(a)
+    ego = PPO("MlpPolicy", env, n_steps=T, n_epochs=E, seed=seed, n_envs=N, n_minibatches=NMB)
+    ego.learn(total_timesteps=2 * N * T)
+    assert np.array_equal(ego.policy.params.cpu().numpy(), pe)
+    for p in range(P):
+        assert np.array_equal(agents[p].model.policy.params.cpu().numpy(), pas[p])
