@@ -272,6 +272,13 @@ typedef struct pth_forward_args {
   float* d_logp;
   float* d_entropy;
   float* d_logits;
+  /* Reference-RNG compatibility (N = 1 facade): when sampling and d_race != NULL, head h picks
+   * argmax_i (p_i / q_i) over its own logits, q = d_race[b][L] exponential(1) draws supplied by the
+   * host — exactly what torch.multinomial(probs, 1) computes from its generator
+   * (Categorical.sample, the reference's sampling path: util.py:63-81 -> SB3 forward), so a host that
+   * draws q from torch's generator in the reference's order reproduces the reference's action stream
+   * whenever the logits agree.  NULL: inverse-CDF sampling on the Philox stream (default). */
+  const float* d_race;
 } pth_forward_args;
 int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream);
 /* debug / parity only: y[i] = f(x[i]) with the library's exp (which = 0), log (1, positive

@@ -90,6 +90,7 @@ class ForwardArgs(C.Structure):
         ("d_logp", C.c_void_p),
         ("d_entropy", C.c_void_p),
         ("d_logits", C.c_void_p),
+        ("d_race", C.c_void_p),
     ]
 
 

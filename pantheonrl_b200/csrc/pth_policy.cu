@@ -34,6 +34,7 @@ struct FwdParams {
   float* logp;
   float* entropy;
   float* logits;
+  const float* race;
 };
 
 __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constant__ FwdParams p) {
@@ -83,13 +84,43 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   const float v = value_head(sm.Bf, sm.pol, tid);
 
   // ---- distribution
-  const bool sample = p.action_in == nullptr;
+  bool sample = p.action_in == nullptr;
   pth_u4 rnd = {0, 0, 0, 0};
   uint32_t ain = 0;
-  if (sample)
+  if (sample && p.race != nullptr) {
+    // exponential race per head (torch.multinomial's single-sample path): argmax_i p_i / q_i,
+    // first maximum wins; p_i as dist_eval computes it (exp(z_i - max) / S)
+    if (live) {
+      const float* q = p.race + b * p.sp.L;
+      int off = 0;
+      for (int h = 0; h < p.sp.n_heads; ++h) {
+        const int n = p.sp.head_n[h];
+        float m = sm.Lg[off * LDA + tid];
+        for (int i = 1; i < n; ++i) {
+          const float z = sm.Lg[(off + i) * LDA + tid];
+          m = z > m ? z : m;
+        }
+        float S = 0.f;
+        for (int i = 0; i < n; ++i) S = S + pth_expf(sm.Lg[(off + i) * LDA + tid] - m);
+        float best = -1.0f;
+        int a = 0;
+        for (int i = 0; i < n; ++i) {
+          const float r = (pth_expf(sm.Lg[(off + i) * LDA + tid] - m) / S) / q[off + i];
+          if (r > best) {
+            best = r;
+            a = i;
+          }
+        }
+        ain |= ((uint32_t)a & 0xffu) << (8 * h);
+        off += n;
+      }
+    }
+    sample = false;
+  } else if (sample) {
     rnd = pth_philox(p.seed, p.rng_stream, (uint64_t)(p.idx0 + b), p.tick, p.slot);
-  else if (live)
+  } else if (live) {
     ain = *reinterpret_cast<const uint32_t*>(p.action_in + 4 * b);
+  }
   DistOut d = dist_eval(p.sp, sm.Lg, tid, sample, rnd, ain);
   if (!live) return;
   if (p.action) *reinterpret_cast<uint32_t*>(p.action + 4 * b) = d.action;
@@ -150,6 +181,7 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   p.logp = a->d_logp;
   p.entropy = a->d_entropy;
   p.logits = a->d_logits;
+  p.race = a->d_race;
   size_t smem = sizeof(FwdSmem) + (p.sp.obs_kind == PTH_OBS_BOX ? sizeof(float) * HID * LDA : 0);
   PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));

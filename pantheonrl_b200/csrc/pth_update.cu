@@ -34,7 +34,7 @@ constexpr int MAX_SLOTS = 32;
 constexpr int MAX_ROWS = 1024;  // first-layer rows (one-hot feature width) supported by the update
 constexpr int STAGE_ROWS = 160;  // first-layer rows per tower staged in shared memory per tile
 
-struct UpdSmem {
+struct alignas(16) UpdSmem {
   SmemPolicy pol;
   float H1[HID * LDA];
   float H2[HID * LDA];  // later: dz1 transposed [sample][LDT]

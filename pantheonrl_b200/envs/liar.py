@@ -17,6 +17,16 @@ ACTION_SPACE = MultiDiscrete([N_SIDES + 1, 2 * N_DICE])
 OBS_SPACE = MultiDiscrete([N_DICE + 1] * N_SIDES + [N_SIDES + 1, 2 * N_DICE] * MAX_MOVES)
 
 
+def reference_hands(np_random):
+    """Both players' dice as the reference rolls them (liar.py:22-26 `randRoll`, called for the ego and
+    then for the partner, liar.py:98-99): per hand six `randint(6)` draws, returned as 2 x 6 face counts."""
+    hands = []
+    for _ in range(2):
+        dice = [np_random.randint(N_SIDES) for _ in range(N_DICE)]
+        hands += [dice.count(f) for f in range(N_SIDES)]
+    return np.array(hands, np.uint8)
+
+
 class LiarDefaultAgent(Agent):
     """Scripted partner: bids its most frequent face, calls when the bid exceeds it."""
 
@@ -35,20 +45,35 @@ class LiarDefaultAgent(Agent):
 class LiarEnv(TurnBasedEnv):
     device_kind = "liar"
 
-    def __init__(self, probegostart=0.5, seed=0, device="cuda"):
+    def __init__(self, probegostart=0.5, seed=0, device="cuda", rng=None):
+        """rng: "philox" (device streams) or "reference" (np.random, in the reference's draw order);
+        default: pantheonrl_b200.rng_mode.get_rng_mode()."""
         super().__init__(probegostart=probegostart)
+        from ..rng_mode import get_rng_mode
         self.observation_space, self.action_space = OBS_SPACE, ACTION_SPACE
         self.device, self.seed = device, int(seed)
+        self.rng = rng or get_rng_mode()
         self.episodes = 0
-        self.state = torch.zeros(1, 32, dtype=torch.uint8, device=device)
+        self.state = None  # device record, created by the first reset
 
     # who starts: the coin of the device reset at this episode's counter
     def draw_ego_first(self):
+        if self.rng == "reference":
+            return np.random.rand() < self.probegostart  # multiagentenv.py:325
         _, ego_first, _ = ops.liar_reset(1, self.seed, self.episodes, probegostart=self.probegostart,
                                          device=self.device)
         return bool(ego_first.item())
 
     def multi_reset(self, egofirst):
+        if self.rng == "reference":
+            # liar.py:22-26, 97-100: six np.random.randint(6) per hand, the ego's hand first
+            hands = reference_hands(np.random)
+            st = np.zeros((1, 32), np.uint8)
+            st[0, :12] = hands
+            self.state = torch.from_numpy(st).to(self.device)
+            self.episodes += 1
+            return np.concatenate([hands[:6] if egofirst else hands[6:], np.tile([N_SIDES, 0], MAX_MOVES)]
+                                  ).astype(np.int64)
         # same (seed, episode) counter -> same dice; the coin is forced to the caller's choice
         state, _, obs = ops.liar_reset(1, self.seed, self.episodes, probegostart=1.0 if egofirst else 0.0,
                                        device=self.device)

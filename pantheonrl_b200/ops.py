@@ -115,7 +115,7 @@ def liar_step(state, is_ego, action):
 
 # ----------------------------------------------------------------------- policy
 def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=0, slot=0, idx0=0,
-                   action_in=None, want=("action", "value", "logp", "entropy", "logits")):
+                   action_in=None, want=("action", "value", "logp", "entropy", "logits"), race=None):
     """ActorCriticPolicy.forward (sampling) or evaluate_actions (action_in given).
 
     obs: [B, stride] uint8 (one-hot spaces) or float32 (Box). Returns a dict of
@@ -155,6 +155,11 @@ def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=
     a.d_logp = out["logp"].data_ptr() if "logp" in out else None
     a.d_entropy = out["entropy"].data_ptr() if "entropy" in out else None
     a.d_logits = out["logits"].data_ptr() if "logits" in out else None
+    if race is not None:  # exponential(1) draws [B, L] from the host's generator (reference-RNG compatibility)
+        _need(race, torch.float32, "race")
+        if tuple(race.shape) != (B, L):
+            raise ValueError("race must be [B, L]")
+        a.d_race = race.data_ptr()
     check(_lib.load().pth_policy_forward(_ctx(obs).handle, C.byref(a), current_stream()),
           "pth_policy_forward")
     _lib.count_launch()

@@ -40,25 +40,34 @@ def reset_stream_counter():
 class DevicePolicy:
     """ActorCriticPolicy stand-in: parameters live on the device as one flat vector."""
 
-    def __init__(self, space, observation_space, action_space, seed, device, rng_stream):
+    def __init__(self, space, observation_space, action_space, seed, device, rng_stream, rng="philox"):
         self.space, self.observation_space, self.action_space = space, observation_space, action_space
-        self.device, self.seed, self.rng_stream = device, int(seed or 0), rng_stream
-        self.params = torch.from_numpy(pol.init_flat(space, seed)).to(device)
+        self.device, self.seed, self.rng_stream, self.rng = device, int(seed or 0), rng_stream, rng
+        self.params = torch.from_numpy(pol.init_flat(space, seed)).to(device)  # seed None: no re-seeding
         self.calls = 0
         self.box = space.obs_kind == _lib.PTH_OBS_BOX  # fp32 rows of 64 instead of 32 slot bytes
         self._obs_dev = (torch.zeros(1, _lib.PTH_OC_ROW, dtype=torch.float32, device=device) if self.box
                          else torch.zeros(1, 32, dtype=torch.uint8, device=device))
         self.act_dim = space.n_heads
 
-    def forward(self, obs, deterministic=False):
-        """obs -> (actions [1, act_dim] numpy, values tensor [1], log_probs tensor [1])."""
+    def _stage_obs(self, obs):
         o = np.zeros((1, _lib.PTH_OC_ROW), np.float32) if self.box else np.zeros((1, 32), np.uint8)
         flat = np.asarray(obs).reshape(-1)
         o[0, :flat.size] = flat
         self._obs_dev.copy_(torch.from_numpy(o))
+
+    def forward(self, obs, deterministic=False):
+        """obs -> (actions [1, act_dim] numpy, values tensor [1], log_probs tensor [1])."""
+        self._stage_obs(obs)
+        race = None
+        if self.rng == "reference":
+            # what Categorical.sample() draws from torch's default generator: torch.multinomial(probs, 1)
+            # fills a tensor like probs with exponential_(1) and takes argmax(probs / q); one head after
+            # the other (SB3 MultiCategoricalDistribution.sample)
+            race = torch.cat([torch.empty(1, n).exponential_(1) for n in self.space.heads], dim=1).to(self.device)
         out = ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed,
                                  rng_stream=self.rng_stream, tick=self.calls & 0xffffffff, slot=0, idx0=0,
-                                 want=("action", "value", "logp"))
+                                 want=("action", "value", "logp"), race=race)
         self.calls += 1
         act = out["action"].cpu().numpy()[:, :self.act_dim].astype(np.int64)
         if self.act_dim == 1 and getattr(self.action_space, "shape", ()) == ():
@@ -66,7 +75,10 @@ class DevicePolicy:
         return act, out["value"], out["logp"]
 
     def predict_values(self, obs):
-        return self.forward(obs)[1]
+        """ActorCriticPolicy.predict_values: the value tower only — no sample is drawn."""
+        self._stage_obs(obs)
+        dummy = torch.zeros(1, 4, dtype=torch.uint8, device=self.device)
+        return ops.policy_forward(self.space, self.params, self._obs_dev, action_in=dummy, want=("value",))["value"]
 
     def state_dict(self):
         return pol.flat_to_state_dict(self.space, self.params.cpu().numpy())
@@ -160,7 +172,7 @@ class PPO:
     def __init__(self, policy="MlpPolicy", env=None, learning_rate=3e-4, n_steps=2048, batch_size=64,
                  n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, normalize_advantage=True,
                  ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, tensorboard_log=None, verbose=0, seed=None,
-                 device="cuda", n_envs=1, n_minibatches=0):
+                 device="cuda", n_envs=1, n_minibatches=0, rng=None):
         if policy != "MlpPolicy":
             raise ValueError("only 'MlpPolicy' (SB3 default 64-64 tanh towers) is implemented")
         if not torch.cuda.is_available():
@@ -175,12 +187,25 @@ class PPO:
         self.tensorboard_log, self.n_envs, self.n_minibatches = tensorboard_log, int(n_envs), n_minibatches
         self.observation_space, self.action_space = env.observation_space, env.action_space
         self.space = to_pth_space(self.observation_space, self.action_space)
+        from .rng_mode import get_rng_mode
+        self.rng = rng or get_rng_mode()
+        if self.rng == "reference" and seed is not None:
+            # SB3 set_random_seed(seed) (BaseAlgorithm._setup_model): every constructor re-seeds all three
+            # global generators (torch is re-seeded by init_flat below, which then draws the weights)
+            import random
+            random.seed(seed)
+            np.random.seed(seed)
         stream = FACADE_STREAM0 + 2 * next(_instances)  # its shuffle stream is stream + 1
         # seed=None: SB3 leaves the global generators alone, so two unseeded learners differ; here the
         # effective seed comes from numpy's global stream (np.random.seed(...) still pins a whole run)
-        eff_seed = int(np.random.randint(1, 2 ** 31 - 1)) if seed is None else seed
+        if seed is not None:
+            eff_seed = seed
+        elif self.rng == "reference":
+            eff_seed = None  # no generator is touched: the weights come from torch's current state
+        else:
+            eff_seed = int(np.random.randint(1, 2 ** 31 - 1))
         self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, eff_seed, self.device,
-                                   stream)
+                                   stream, self.rng)
         if self.space.obs_kind == _lib.PTH_OBS_BOX and self.space.obs_len > _lib.PTH_OC_ROW:
             raise _lib.PthError("Box observations wider than 64 are not supported")
         self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda,
@@ -254,8 +279,12 @@ class PPO:
         if self._ws is None:
             self._ws = up.UpdateWorkspace(self.space, M, self.batch_size, self.device)
             self._perm = torch.empty(self.n_epochs, M, dtype=torch.int32, device=self.device)
-        up.perm_feistel(M, self.n_epochs, self.policy.seed, self.policy.rng_stream + 1, epoch0=self._n_updates,
-                        out=self._perm)
+        if self.rng == "reference":  # SB3 RolloutBuffer.get: one np.random.permutation per epoch
+            self._perm.copy_(torch.from_numpy(np.stack([np.random.permutation(M) for _ in range(self.n_epochs)])
+                                              .astype(np.int32)))
+        else:
+            up.perm_feistel(M, self.n_epochs, self.policy.seed, self.policy.rng_stream + 1, epoch0=self._n_updates,
+                            out=self._perm)
         d = buf.d
         self.last_stats = up.ppo_update(
             self.space, self.policy.params, self.adam_m, self.adam_v, self.adam_step, d["obs"], d["actions"],
