@@ -13,6 +13,8 @@
 // tick runs up to three CTA-wide batched forwards (ego; partner reply; partner
 // opening move after an auto-reset) with lane masks.  Event order and RNG slots
 // follow oracle/pth_oracle_rollout.inc exactly.
+#include <stdlib.h>
+
 #include "pth_games.cuh"
 #include "pth_mlp.cuh"
 #include "pth_overcooked.cuh"
@@ -634,10 +636,13 @@ extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* st
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     rollout_kernel<ENVK, RBV><<<pth_ceil_div(a->N, RBV), NT, smem, st>>>(p);                    \
   } while (0)
+  // 16-env tiles (101 KB of shared memory: two CTAs per SM, 16 warps to hide the row-gather latency)
+  // while 32-env tiles would leave SMs with a single CTA
+  const bool tiny = pth_ceil_div(a->N, 32) < 2 * ctx->sm_count && !getenv("PTH_ROLLOUT_RB32");
   if (a->env_kind == PTH_ENV_RPS) {
-    if (small) PTH_ROLL_LAUNCH(PTH_ENV_RPS, 32); else PTH_ROLL_LAUNCH(PTH_ENV_RPS, 128);
+    if (tiny) PTH_ROLL_LAUNCH(PTH_ENV_RPS, 16); else if (small) PTH_ROLL_LAUNCH(PTH_ENV_RPS, 32); else PTH_ROLL_LAUNCH(PTH_ENV_RPS, 128);
   } else {
-    if (small) PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 32); else PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 128);
+    if (tiny) PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 16); else if (small) PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 32); else PTH_ROLL_LAUNCH(PTH_ENV_LIAR, 128);
   }
 #undef PTH_ROLL_LAUNCH
   PTH_LAUNCH_CHECK();

@@ -898,20 +898,23 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
         }
         __syncthreads();
+        PTH_PROF(2);  // sample gather
         // (moving the sort into the shadow of the head phase, onto the warps without a head, was
         // measured: no gain — it competes with the head warps for issue slots)
-        if constexpr (!BOX)
-          sort_slots(p, obs_s, sm.order, sm.rcount, sm.dmode, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
         if constexpr (!BOX) {
+          sort_slots(p, obs_s, sm.order, sm.rcount, sm.dmode, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
           __syncthreads();  // dmode / rcount complete
+          PTH_PROF(22);  // slot sort
           chain_setup0(p, sm, nb, tid);
           __syncthreads();
+          PTH_PROF(23);  // row numbering | jb
           chain_setup1(p, sm, sm.H2, tid);
           __syncthreads();
+          PTH_PROF(24);  // stage copy + row positions
           chain_setup2(p, sm, sm.H2, tid);
           __syncthreads();
+          PTH_PROF(25);  // chain beginnings
         }
-        PTH_PROF(2);  // gather + slot sort + chain beginnings
 
         // ================= policy tower: forward
         if constexpr (BOX) {

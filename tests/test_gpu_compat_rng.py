@@ -54,7 +54,8 @@ def test_race_sampling_equals_torch_multinomial(ctx, make_env):
     model = PPO("MlpPolicy", env, seed=10, rng="reference")
     model.policy.params.mul_(40.0)  # far from uniform: the argmax is not decided by the noise alone
     rs = np.random.RandomState(0)
-    nvec = getattr(env.observation_space, "nvec", np.array([env.observation_space.n]))
+    sp = env.observation_space
+    nvec = sp.nvec if hasattr(sp, "nvec") else np.array([sp.n])
     torch.manual_seed(77)
     seen = set()
     for k in range(300):

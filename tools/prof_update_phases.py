@@ -10,9 +10,10 @@ GRID = int(os.environ.get("PTH_GRID", "0"))  # pin the update grid (0 = auto)
 _orig = up.ppo_update
 up.ppo_update = lambda *a, **k: _orig(*a, **{**k, "grid_ctas": GRID})
 
-NAMES = ["loop head", "weights->smem", "gather+sort", "pi L0", "pi L1", "head+loss", "head wgrad|dz2",
+NAMES = ["loop head", "weights->smem", "gather", "pi L0", "pi L1", "head+loss", "head wgrad|dz2",
          "pi tower bwd", "vf L0", "vf L1", "value head", "vf tower bwd", "tile stats", "barrier1",
-         "reduce", "barrier2", "adam", "barrier3", " pi wgrad64", " pi backprop64", " vf wgrad64", " vf backprop64"]
+         "reduce", "barrier2", "adam", "barrier3", " pi wgrad64", " pi backprop64", " vf wgrad64", " vf backprop64", "slot sort", "rows|jb", "stage copy",
+         "chain begin"]
 
 
 def run(env, N, T, **kw):
