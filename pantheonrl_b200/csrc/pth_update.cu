@@ -64,7 +64,6 @@ struct alignas(16) UpdSmem {
   uint8_t rowmap[MAX_ROWS];
   uint16_t staged_rows[STAGE_ROWS];  // inverse of rowmap
   uint8_t rowpos[BT * 32];           // per (sample, slot): staged position of the row it selects (both towers)
-  uint8_t modepos[MAX_SLOTS];        // per slot: staged position of the mode's row
   int n_staged;
 };
 static_assert(STAGE_ROWS * 2 * HID <= (2 * HID + MAXL) * LDA, "stage fits in H2 | D1 | Lg");
@@ -396,96 +395,160 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
   }
 }
 
-// Stable counting sort of the tile's nb samples by observed value, one slot per
-// warp at a time: order[s][pos] = sample id, rcount[row] = samples selecting the
-// first-layer row (row = slot_off[s] + value).
-// Slots [s_begin, s_end) are shared out over n_warps warps; `wid` is this warp's index among them.
-__device__ __forceinline__ void sort_slots(const UpdParams& p, const uint8_t* obs_s, uint8_t* order,
-                                           uint8_t* rcount, uint8_t* dmode, int nb, int lane, int wid,
-                                           int n_warps, int s_begin, int s_end) {
-  for (int s = s_begin + wid; s < s_end; s += n_warps) {
+// Stable counting sort of the tile's nb samples by observed value, one slot per warp at a time:
+// order[s][pos] = sample id, rcount[row] = samples selecting the first-layer row (row = slot_off[s]
+// + value), dmode[s] = the slot's mode (ties: the smallest value), and every selected row gets a
+// position in the shared-memory stage (rowmap / staged_rows; positions are handed out with one
+// shared-memory atomic per slot — WHICH position a row gets changes no result).
+// nvec <= 32 (every space of the built-in games): one MATCH.ANY per 32 samples groups equal values,
+// lane v owns value v's count, a warp scan turns counts into start positions.  Larger nvec: one
+// ballot per value.  Per-warp scratch (64 ints) lives in sm.rowpos, which is written after the sort.
+__device__ __forceinline__ void sort_slots(const UpdParams& p, UpdSmem& sm, const uint8_t* obs_s, int nb,
+                                           int lane, int wid, int n_warps) {
+  int* hist = reinterpret_cast<int*>(sm.rowpos) + wid * 64;
+  int* cur = hist + 32;
+  const unsigned lt = (1u << lane) - 1u;
+  uint8_t* order = sm.order;
+  for (int s = wid; s < p.sp.obs_len; s += n_warps) {
     int val[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int b = lane + 32 * r;
       val[r] = b < nb ? (int)obs_s[b * 32 + s] : -1;
     }
-    int base = 0, best = -1, mode = 0;
     const int nv = p.nvec[s];
     const int row0 = p.sp.slot_off[s];
-    for (int v = 0; v < nv; ++v) {
-      const int before = base;
+    int mode = 0;
+    if (nv <= 32) {
+      hist[lane] = 0;
+      __syncwarp();
+      unsigned m[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) m[r] = __match_any_sync(0xffffffffu, val[r]);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const unsigned m = __ballot_sync(0xffffffffu, val[r] == v);
-        if (val[r] == v)
-          order[s * BT + base + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane + 32 * r);
-        base += __popc(m);
+        if (val[r] >= 0 && (m[r] & lt) == 0u) hist[val[r]] += __popc(m[r]);  // the group's lowest lane
+        __syncwarp();
       }
-      if (base - before > best) {  // ties: the smallest value
-        best = base - before;
-        mode = v;
+      const int cnt = hist[lane];
+      int x = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
       }
-      if (lane == 0) rcount[row0 + v] = (uint8_t)(base - before);
+      cur[lane] = x - cnt;  // first position of value `lane`
+      if (lane < nv) sm.rcount[row0 + lane] = (uint8_t)cnt;
+      mode = 63 - (__reduce_max_sync(0xffffffffu, lane < nv ? cnt * 64 + (63 - lane) : -1) & 63);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (val[r] >= 0) order[s * BT + cur[val[r]] + __popc(m[r] & lt)] = (uint8_t)(lane + 32 * r);
+        __syncwarp();
+        if (val[r] >= 0 && (m[r] & lt) == 0u) cur[val[r]] += __popc(m[r]);
+        __syncwarp();
+      }
+    } else {
+      int base = 0, best = -1;
+      for (int v = 0; v < nv; ++v) {
+        const int before = base;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const unsigned mm = __ballot_sync(0xffffffffu, val[r] == v);
+          if (val[r] == v) order[s * BT + base + __popc(mm & lt)] = (uint8_t)(lane + 32 * r);
+          base += __popc(mm);
+        }
+        if (base - before > best) {  // ties: the smallest value
+          best = base - before;
+          mode = v;
+        }
+        if (lane == 0) sm.rcount[row0 + v] = (uint8_t)(base - before);
+      }
+      __syncwarp();
     }
-    if (lane == 0) dmode[s] = (uint8_t)mode;
+    if (lane == 0) sm.dmode[s] = (uint8_t)mode;
+    // stage positions of the rows this slot's samples select
+    for (int v0 = 0; v0 < nv; v0 += 32) {
+      const int v = v0 + lane;
+      const bool hit = v < nv && sm.rcount[row0 + v] > 0;
+      const unsigned t = __ballot_sync(0xffffffffu, hit);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&sm.n_staged, __popc(t));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(t & lt);
+      const bool staged = hit && pos < STAGE_ROWS;
+      if (v < nv) sm.rowmap[row0 + v] = staged ? (uint8_t)pos : (uint8_t)0xFF;
+      if (staged) sm.staged_rows[pos] = (uint16_t)(row0 + v);
+    }
+    __syncwarp();
   }
 }
 
-// Per-tile set-up of the one-hot first layers, after sort_slots (rcount / dmode known) and a barrier.
-//  step 0: warp 0 numbers the rows some sample selects (rowmap, staged_rows); threads [128, 256)
-//          find every sample's jb (its slots [jb, S) agree with the mode)
-//  step 1: all threads copy the numbered rows of both matrices into the stage (all loads of a
-//          thread in flight together) and translate every (sample, slot) into its row's staged
-//          position once for both towers (rowpos; modepos for the modes)
-//  step 2: one warp builds both towers' common chain beginnings pchain[t][j], j = S .. 0
-//          (lane = tower x 16 float4 column groups; dependent adds over rows in shared memory)
-// The caller puts a barrier after every step.
-__device__ __forceinline__ void chain_setup0(const UpdParams& p, UpdSmem& sm, int nb, int tid) {
-  const int lane = tid & 31, wid = tid >> 5;
-  if (wid == 0) {
-    int base = 0;
-    for (int r0 = 0; r0 < p.sp.F; r0 += 32) {
-      const int r = r0 + lane;
-      const bool hit = r < p.sp.F && sm.rcount[r] > 0;
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      const int pos = base + __popc(m & ((1u << lane) - 1u));
-      const bool staged = hit && pos < STAGE_ROWS;
-      if (r < p.sp.F) sm.rowmap[r] = staged ? (uint8_t)pos : (uint8_t)0xFF;
-      if (staged) sm.staged_rows[pos] = (uint16_t)r;
-      base += __popc(m);
+// Per-tile set-up of the one-hot first layers, after sort_slots and a barrier, in ONE step:
+//  * the last warp builds both towers' common chain beginnings pchain[t][j], j = S .. 0 (lane = tower
+//    x 16 float4 column groups; the mode rows come straight from L2, ten in flight);
+//  * the other warps find every sample's jb (its slots [jb, S) agree with the mode), copy the
+//    numbered rows of both matrices into the stage (all loads of a thread in flight together) and
+//    translate every (sample, slot) into its row's staged position, once for both towers (rowpos).
+constexpr int NTC = UNT - 32;  // threads of the copy part
+__device__ __forceinline__ void chain_setup(const UpdParams& p, UpdSmem& sm, float* stage, int nb, int tid) {
+  const int S = p.sp.obs_len;
+  if (tid >= NTC) {
+    const int lane = tid & 31;
+    const int t = lane >> 4, jq = lane & 15;
+    const float4* W4 = reinterpret_cast<const float4*>(p.params + (t ? p.lo.w_vf0 : p.lo.w_pi0));
+    float4 acc = *reinterpret_cast<const float4*>((t ? sm.pol.b_vf0 : sm.pol.b_pi0) + jq * 4);
+    float* P = sm.pchain[t];
+    *reinterpret_cast<float4*>(P + S * HID + jq * 4) = acc;
+    constexpr int PB = 10;  // row loads issued together
+    for (int s0 = S - 1; s0 >= 0; s0 -= PB) {
+      float4 w[PB];
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        const int sl = max(s0 - i, 0);  // clamped: loaded anyway, added only if s0 - i >= 0
+        w[i] = ld_param4_l2<true>(W4 + (p.sp.slot_off[sl] + sm.dmode[sl]) * (HID / 4) + jq);
+      }
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        const int sl = s0 - i;
+        if (sl >= 0) {
+          acc.x = acc.x + w[i].x;
+          acc.y = acc.y + w[i].y;
+          acc.z = acc.z + w[i].z;
+          acc.w = acc.w + w[i].w;
+          *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
+        }
+      }
     }
-    if (lane == 0) sm.n_staged = base < STAGE_ROWS ? base : STAGE_ROWS;
-  } else if (tid >= BT && tid < 2 * BT) {
-    const int b = tid - BT;
+    return;
+  }
+  if (tid < BT) {
     const uint32_t* dm = reinterpret_cast<const uint32_t*>(sm.dmode);
     int j = 0;
-    if (b < nb) {
+    if (tid < nb) {
 #pragma unroll
       for (int w = 7; w >= 0; --w) {
-        const uint32_t x = sm.obs[b * 8 + w] ^ dm[w];
+        const uint32_t x = sm.obs[tid * 8 + w] ^ dm[w];
         if (j == 0 && x != 0u) j = 4 * w + 4 - (__clz((int)x) >> 3);
       }
     }
-    sm.jb[b] = (uint8_t)j;
+    sm.jb[tid] = (uint8_t)j;
   }
-}
-__device__ __forceinline__ void chain_setup1(const UpdParams& p, UpdSmem& sm, float* stage, int tid) {
   const float4* Wp = reinterpret_cast<const float4*>(p.params + p.lo.w_pi0);
   const float4* Wv = reinterpret_cast<const float4*>(p.params + p.lo.w_vf0);
-  const int n = sm.n_staged * 32;  // (staged row, tower, float4 column group)
-  constexpr int CB = 4;            // loads in flight per thread
-  for (int i0 = tid; i0 < n; i0 += CB * UNT) {
+  const int n = (sm.n_staged < STAGE_ROWS ? sm.n_staged : STAGE_ROWS) * 32;  // (staged row, tower, float4 group)
+  constexpr int CB = 4;  // loads in flight per thread
+  for (int i0 = tid; i0 < n; i0 += CB * NTC) {
     float4 v[CB];
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
-      const int i = min(i0 + c * UNT, n - 1);  // clamped: the load is unconditional, the store is not
+      const int i = min(i0 + c * NTC, n - 1);  // clamped: the load is unconditional, the store is not
       const int m = i >> 5, t = (i >> 4) & 1, jq = i & 15;
       v[c] = ld_param4_l2<true>((t ? Wv : Wp) + (int)sm.staged_rows[m] * (HID / 4) + jq);
     }
 #pragma unroll
     for (int c = 0; c < CB; ++c) {
-      const int i = i0 + c * UNT;
+      const int i = i0 + c * NTC;
       if (i < n) {
         const int m = i >> 5, t = (i >> 4) & 1, jq = i & 15;
         *reinterpret_cast<float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID + jq * 4) = v[c];
@@ -493,48 +556,16 @@ __device__ __forceinline__ void chain_setup1(const UpdParams& p, UpdSmem& sm, fl
     }
   }
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
-  for (int i = tid; i < BT * 32; i += UNT) {
+  for (int i = tid; i < BT * 32; i += NTC) {
     const int sl = i & 31;
-    if (sl < p.sp.obs_len) sm.rowpos[i] = sm.rowmap[p.sp.slot_off[sl] + obs_s[i]];
+    if (sl < S) sm.rowpos[i] = sm.rowmap[p.sp.slot_off[sl] + obs_s[i]];
   }
-  if (tid < p.sp.obs_len) sm.modepos[tid] = sm.rowmap[p.sp.slot_off[tid] + sm.dmode[tid]];
 }
 // row of tower t at staged position m (m == 0xFF: not staged, read it from global memory)
 __device__ __forceinline__ float4 row_load(const float* stage, const float4* W4, int t, int m, int row, int jq) {
   if (m != 0xFF) return *(reinterpret_cast<const float4*>(stage + ((size_t)(t * STAGE_ROWS + m)) * HID) + jq);
   return ld_param4<true>(W4 + row * (HID / 4) + jq);
 }
-__device__ __forceinline__ void chain_setup2(const UpdParams& p, UpdSmem& sm, const float* stage, int tid) {
-  if ((tid >> 5) != 0) return;
-  const int lane = tid & 31;
-  const int S = p.sp.obs_len;
-  const int t = lane >> 4, jq = lane & 15;
-  const float4* W4 = reinterpret_cast<const float4*>(p.params + (t ? p.lo.w_vf0 : p.lo.w_pi0));
-  float4 acc = *reinterpret_cast<const float4*>((t ? sm.pol.b_vf0 : sm.pol.b_pi0) + jq * 4);
-  float* P = sm.pchain[t];
-  *reinterpret_cast<float4*>(P + S * HID + jq * 4) = acc;
-  constexpr int PB = 6;  // row loads issued together
-  for (int s0 = S - 1; s0 >= 0; s0 -= PB) {
-    float4 w[PB];
-#pragma unroll
-    for (int i = 0; i < PB; ++i) {
-      const int sl = max(s0 - i, 0);  // clamped: loaded anyway, added only if s0 - i >= 0
-      w[i] = row_load(stage, W4, t, sm.modepos[sl], p.sp.slot_off[sl] + sm.dmode[sl], jq);
-    }
-#pragma unroll
-    for (int i = 0; i < PB; ++i) {
-      const int sl = s0 - i;
-      if (sl >= 0) {
-        acc.x = acc.x + w[i].x;
-        acc.y = acc.y + w[i].y;
-        acc.z = acc.z + w[i].z;
-        acc.w = acc.w + w[i].w;
-        *reinterpret_cast<float4*>(P + sl * HID + jq * 4) = acc;
-      }
-    }
-  }
-}
-
 // First layer of one tower for the whole tile on NTH threads: Out[j][b] = tanh(bias[j] + rows in
 // descending slot order).  16 threads cover a row with float4 loads (from the stage); a thread
 // group works on 4 samples at a time.  All four start from the chain beginning of the quartet's
@@ -896,24 +927,19 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         } else if (lane) {
           *reinterpret_cast<uint4*>(&sm.obs[tid * 8]) = o0;
           *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
+          if (tid == 0) sm.n_staged = 0;
         }
         __syncthreads();
         PTH_PROF(2);  // sample gather
         // (moving the sort into the shadow of the head phase, onto the warps without a head, was
         // measured: no gain — it competes with the head warps for issue slots)
         if constexpr (!BOX) {
-          sort_slots(p, obs_s, sm.order, sm.rcount, sm.dmode, nb, tid & 31, tid >> 5, UNT / 32, 0, p.sp.obs_len);
-          __syncthreads();  // dmode / rcount complete
-          PTH_PROF(22);  // slot sort
-          chain_setup0(p, sm, nb, tid);
+          sort_slots(p, sm, obs_s, nb, tid & 31, tid >> 5, UNT / 32);
+          __syncthreads();  // order / rcount / dmode / rowmap complete; the sort's scratch (rowpos) is free
+          PTH_PROF(22);  // slot sort + row numbering
+          chain_setup(p, sm, sm.H2, nb, tid);
           __syncthreads();
-          PTH_PROF(23);  // row numbering | jb
-          chain_setup1(p, sm, sm.H2, tid);
-          __syncthreads();
-          PTH_PROF(24);  // stage copy + row positions
-          chain_setup2(p, sm, sm.H2, tid);
-          __syncthreads();
-          PTH_PROF(25);  // chain beginnings
+          PTH_PROF(23);  // jb, stage copy, row positions | chain beginnings
         }
 
         // ================= policy tower: forward

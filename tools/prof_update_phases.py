@@ -12,8 +12,7 @@ up.ppo_update = lambda *a, **k: _orig(*a, **{**k, "grid_ctas": GRID})
 
 NAMES = ["loop head", "weights->smem", "gather", "pi L0", "pi L1", "head+loss", "head wgrad|dz2",
          "pi tower bwd", "vf L0", "vf L1", "value head", "vf tower bwd", "tile stats", "barrier1",
-         "reduce", "barrier2", "adam", "barrier3", " pi wgrad64", " pi backprop64", " vf wgrad64", " vf backprop64", "slot sort", "rows|jb", "stage copy",
-         "chain begin"]
+         "reduce", "barrier2", "adam", "barrier3", " pi wgrad64", " pi backprop64", " vf wgrad64", " vf backprop64", "slot sort+rows", "setup"]
 
 
 def run(env, N, T, **kw):

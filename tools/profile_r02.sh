@@ -1,0 +1,17 @@
+#!/bin/bash
+# ncu evidence of round 2 (run under gpurun on ONE GPU).  Reports land in gpurun_out/.
+set -x
+cd "$(dirname "$0")/.."
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-configs > gpurun_out/launches_r02.out 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ppo_update -s 2 -c 1 -o gpurun_out/upd_r02 -f \
+    python tools/prof_iter.py liar 4096 128 1 > gpurun_out/upd_r02.out 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 1 -c 1 -o gpurun_out/roll_r02 -f \
+    python tools/prof_iter.py liar 4096 128 1 > gpurun_out/roll_r02.out 2>&1
+ncu --set full --clock-control none -k regex:gae_tma -c 1 -o gpurun_out/gae_r02 -f \
+    python tools/prof_gae.py > gpurun_out/gae_r02.out 2>&1
+ncu --set full --clock-control none -k 'regex:policy_forward|pack_kernel|gae_ragged' -s 2 -c 12 -o gpurun_out/misc_r02 -f \
+    python tools/prof_misc.py > gpurun_out/misc_r02.out 2>&1
+ncu --set full --clock-control none -k 'regex:rollout_overcooked|ppo_update' -s 2 -c 2 -o gpurun_out/oc_r02 -f \
+    python tools/prof_iter.py overcooked 1024 400 1 > gpurun_out/oc_r02.out 2>&1
+ls -la gpurun_out/*.ncu-rep
