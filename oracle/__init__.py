@@ -19,7 +19,7 @@ class OrcSpace(C.Structure):
     _fields_ = [
         ("obs_kind", C.c_int32),
         ("obs_len", C.c_int32),
-        ("obs_nvec", C.c_int32 * 64),
+        ("obs_nvec", C.c_int32 * 96),
         ("n_heads", C.c_int32),
         ("head_n", C.c_int32 * 4),
     ]
@@ -42,6 +42,7 @@ def make_space(nvec=None, heads=(3,), box_dim=None):
 RPS_SPACE = dict(nvec=[1], heads=[3])
 LIAR_NVEC = [7] * 6 + [7, 12] * 12
 LIAR_SPACE = dict(nvec=LIAR_NVEC, heads=[7, 12])
+LIAR3_SPACE = dict(nvec=LIAR_NVEC * 3, heads=[7, 12])  # frame_wrap(LiarEnv(), 3): 90 slots, rows of 96 bytes
 
 
 def lib():

@@ -34,7 +34,7 @@
 #include <string.h>
 
 #define H 64
-#define MAX_SLOTS 64
+#define MAX_SLOTS 96
 #define MAX_HEADS 4
 
 typedef struct {

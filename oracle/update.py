@@ -54,7 +54,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     if space.obs_kind == 1:  # Box rows of 64 floats
         obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 64)
     else:
-        obs = np.ascontiguousarray(obs, np.uint8).reshape(-1, 32)
+        obs = np.ascontiguousarray(obs, np.uint8).reshape(-1, 32 if space.obs_len <= 32 else 96)
     actions = np.ascontiguousarray(actions, np.uint8).reshape(-1, 4)
     old_logp, advantages, returns = f32(old_logp).reshape(-1), f32(advantages).reshape(-1), f32(returns).reshape(-1)
     perm = np.ascontiguousarray(perm, np.int32)

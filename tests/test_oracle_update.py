@@ -13,7 +13,12 @@ from test_oracle_cpu import rand_liar_obs
 
 def make_batch(kw, M, seed=0):
     rng = np.random.RandomState(seed)
-    obs = rand_liar_obs(M, seed) if len(kw["nvec"]) == 30 else np.zeros((M, 32), np.uint8)
+    if len(kw["nvec"]) == 90:  # three stacked Liar's Dice frames in a 96-byte row
+        obs = np.zeros((M, 96), np.uint8)
+        for f in range(3):
+            obs[:, 30 * f:30 * f + 30] = rand_liar_obs(M, seed + 17 * f)[:, :30]
+    else:
+        obs = rand_liar_obs(M, seed) if len(kw["nvec"]) == 30 else np.zeros((M, 32), np.uint8)
     act = np.zeros((M, 4), np.uint8)
     for h, n in enumerate(kw["heads"]):
         act[:, h] = rng.randint(n, size=M)
@@ -23,7 +28,7 @@ def make_batch(kw, M, seed=0):
     return obs, act, old_logp, adv, ret
 
 
-@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE])
+@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE, oracle.LIAR3_SPACE])
 @pytest.mark.parametrize("ent_coef", [0.0, 0.01])
 def test_single_minibatch_gradient_and_step_match_torch_autograd(kw, ent_coef):
     M = 300  # 3 tiles, the last one ragged
