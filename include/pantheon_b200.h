@@ -62,7 +62,10 @@ int pth_sync_debug(pth_ctx* ctx, void* stream);
 /* Spaces and policy parameter layout                                  */
 /* ------------------------------------------------------------------ */
 
-#define PTH_MAX_OBS_SLOTS 64
+#define PTH_MAX_OBS_SLOTS 96
+/* bytes of a one-hot observation row in rollout buffers / update inputs: one byte per slot, padded to
+ * 32, or to 96 for spaces with more than 32 slots (frame-stacked observations, wrappers.py:233-349) */
+#define PTH_OBS_ROW_BYTES(obs_len) ((obs_len) <= 32 ? 32 : 96)
 #define PTH_MAX_HEADS 4
 #define PTH_HIDDEN 64 /* SB3 MlpPolicy default: pi=[64,64], vf=[64,64], tanh */
 

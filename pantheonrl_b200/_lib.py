@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpantheon_b200.so")
 
-PTH_MAX_OBS_SLOTS = 64
+PTH_MAX_OBS_SLOTS = 96
 PTH_MAX_HEADS = 4
 PTH_HIDDEN = 64
 PTH_OBS_ONEHOT, PTH_OBS_BOX = 0, 1
@@ -62,6 +62,11 @@ class Space(C.Structure):
         for i, v in enumerate(heads):
             s.head_n[i] = int(v)
         return s
+
+    @property
+    def row_bytes(self):
+        """Bytes of one observation row: PTH_OBS_ROW_BYTES for one-hot spaces, 64 fp32 for Box spaces."""
+        return 4 * PTH_OC_ROW if self.obs_kind == PTH_OBS_BOX else (32 if self.obs_len <= 32 else 96)
 
     @property
     def nvec(self):

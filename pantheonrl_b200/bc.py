@@ -69,7 +69,7 @@ class BC:
         if M == 0:
             raise ValueError("no expert transitions")
         box = self.space.obs_kind == _lib.PTH_OBS_BOX
-        obs = np.zeros((M, _lib.PTH_OC_ROW), np.float32) if box else np.zeros((M, 32), np.uint8)
+        obs = np.zeros((M, _lib.PTH_OC_ROW), np.float32) if box else np.zeros((M, self.space.row_bytes), np.uint8)
         flat = np.asarray(expert_data.obs).reshape(M, -1)
         obs[:, :flat.shape[1]] = flat
         acts = np.zeros((M, 4), np.uint8)

@@ -67,7 +67,7 @@ inline int fill_space(const pth_space* sp, SpaceDev* d) {
   d->L = L;
   for (int h = 0; h < sp->n_heads; ++h) d->head_n[h] = sp->head_n[h];
   if (sp->obs_kind == PTH_OBS_ONEHOT) {
-    if (sp->obs_len > 32) return -1;  // obs rows are 32 bytes
+    if (sp->obs_len > PTH_MAX_OBS_SLOTS) return -1;  // obs rows are 32 or 96 bytes
     int off = 0;
     for (int s = 0; s < sp->obs_len; ++s) {
       d->slot_off[s] = (int16_t)off;
@@ -141,8 +141,8 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
 // begins with the padded trailing slots, which the update kernel evaluates once per tile).  W is input-major [F][64] in
 // global memory (L1/L2 resident).  16 threads cover one row with float4 loads,
 // so the CTA works on 8 samples at a time; 4 sample groups are interleaved for
-// ILP.  obs: [BT][32] bytes in shared memory.
-template <bool COHERENT = false, int NTH = NT, int BTS = BT, int SB = 6>
+// ILP.  obs: [BT][OW] bytes in shared memory (OW = 32, or 96 for spaces with more than 32 slots).
+template <bool COHERENT = false, int NTH = NT, int BTS = BT, int SB = 6, int OW = 32>
 __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uint8_t* obs_s,
                                                    const float* W,
                                                    const float* bias_s, float* Out, int tid,
@@ -171,7 +171,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
 #pragma unroll
         for (int u = 0; u < UI; ++u) {
           const int b = (g0 + u) * GS + bs;
-          const int f = off + obs_s[b * 32 + s0 - i];
+          const int f = off + obs_s[b * OW + s0 - i];
           w[i][u] = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
         }
       }
@@ -190,7 +190,7 @@ __device__ __forceinline__ void first_layer_onehot(const SpaceDev& sp, const uin
 #pragma unroll
       for (int u = 0; u < UI; ++u) {
         const int b = (g0 + u) * GS + bs;
-        const int f = off + obs_s[b * 32 + s];
+        const int f = off + obs_s[b * OW + s];
         const float4 w = ld_param4<COHERENT>(W4 + f * (HID / 4) + jq);
         acc[u].x = acc[u].x + w.x;
         acc[u].y = acc[u].y + w.y;

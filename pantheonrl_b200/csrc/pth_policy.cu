@@ -15,7 +15,8 @@ struct FwdSmem {
   float Bf[HID * LDA];
   float Lg[MAXL * LDA];
   uint8_t obs[BT * 32];
-  // Box observations only: X[F][LDA] follows (F <= 64)
+  // Box observations only: X[F][LDA] follows (F <= 64); wide one-hot rows (more than 32 slots):
+  // the [BT][96] byte tile follows instead of `obs`
 };
 
 struct FwdParams {
@@ -37,10 +38,12 @@ struct FwdParams {
   const float* race;
 };
 
+template <int OW>
 __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constant__ FwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
   float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem));
+  uint8_t* obs_s = OW == 32 ? sm.obs : smem_raw + sizeof(FwdSmem);
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * BT;
   const int64_t b = b0 + tid;
@@ -51,10 +54,10 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   if (lane) {
     if (p.sp.obs_kind == PTH_OBS_ONEHOT) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.obs);
-      for (int s = 0; s < 32; ++s) {
+      for (int s = 0; s < OW; ++s) {
         uint8_t v = 0;
         if (live && s < p.sp.obs_len) v = src[b * p.obs_stride + s];
-        sm.obs[tid * 32 + s] = v;
+        obs_s[tid * OW + s] = v;
       }
     } else {
       const float* src = reinterpret_cast<const float*>(p.obs);
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
 
   // ---- policy tower
   if (p.sp.obs_kind == PTH_OBS_ONEHOT)
-    first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
+    first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
   else
     first_layer_box<false>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
   __syncthreads();
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   if (lane) action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
   // ---- value tower (A is free again)
   if (p.sp.obs_kind == PTH_OBS_ONEHOT)
-    first_layer_onehot(p.sp, sm.obs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
+    first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
   else
     first_layer_box<false>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
   __syncthreads();
@@ -182,10 +185,15 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   p.entropy = a->d_entropy;
   p.logits = a->d_logits;
   p.race = a->d_race;
-  size_t smem = sizeof(FwdSmem) + (p.sp.obs_kind == PTH_OBS_BOX ? sizeof(float) * HID * LDA : 0);
-  PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  policy_forward_kernel<<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);
+  const bool wide = p.sp.obs_kind == PTH_OBS_ONEHOT && p.sp.obs_len > 32;
+  size_t smem = sizeof(FwdSmem) + (p.sp.obs_kind == PTH_OBS_BOX ? sizeof(float) * HID * LDA : 0) + (wide ? BT * 96 : 0);
+  if (wide) {
+    PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    policy_forward_kernel<96><<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    policy_forward_kernel<32><<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);
+  }
   PTH_LAUNCH_CHECK();
   return PTH_OK;
 }

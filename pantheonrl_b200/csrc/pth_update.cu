@@ -30,21 +30,27 @@ namespace {
 // though the register tiles get smaller.  Thread tiles only decide WHO computes an output.
 constexpr int UNT = 512;
 constexpr int LDT = 66;  // stride of the transposed dz1 tile [sample][unit] (even: float2 loads)
-constexpr int MAX_SLOTS = 32;
+constexpr int MAX_SLOTS = PTH_MAX_OBS_SLOTS;  // 96: widest one-hot row
 constexpr int MAX_ROWS = 1024;  // first-layer rows (one-hot feature width) supported by the update
 constexpr int STAGE_ROWS = 160;  // first-layer rows per tower staged in shared memory per tile
 
-struct alignas(16) UpdSmem {
+// WIDE: one-hot spaces with more than 32 slots (frame-stacked observations, rows of 96 bytes).  They
+// only occur in the host-driven n_envs = 1 flow, so the wide kernel keeps the plain first layer
+// (every row gathered per sample) and spends the shared memory on the wider tiles instead of on
+// the row stage and the chain beginnings.
+template <bool WIDE>
+struct alignas(16) UpdSmemT {
+  static constexpr int OW = WIDE ? 96 : 32;  // bytes per observation row = slots supported
   SmemPolicy pol;
   float H1[HID * LDA];
   float H2[HID * LDA];  // later: dz1 transposed [sample][LDT]
   float D1[HID * LDA];  // dz2
   float Lg[MAXL * LDA]; // logits -> dlogits -> first-layer gradient chunk
-  uint32_t obs[BT * 8];
+  uint32_t obs[BT * OW / 4];
   // per slot: the tile's samples stably sorted by observed value, and per
   // first-layer row the number of samples selecting it (built once per tile,
   // used by both towers)
-  uint8_t order[MAX_SLOTS * BT];
+  uint8_t order[OW * BT];
   uint8_t rcount[MAX_ROWS];
   float red[8];
   float bc[160];  // broadcast scratch (norm partials)
@@ -53,8 +59,8 @@ struct alignas(16) UpdSmem {
   // MODE of slot s over the tile, pchain[t][j] = bias + row(S-1, d_{S-1}) + ... + row(j, d_j) for
   // tower t; a sample that agrees with the mode on every slot >= jb starts from pchain[t][jb] and
   // adds only its slots jb-1 .. 0 — the same additions in the same order, hence the same bits.
-  float pchain[2][(MAX_SLOTS + 1) * HID];
-  uint8_t dmode[MAX_SLOTS];  // mode value per slot (0 beyond obs_len)
+  float pchain[2][WIDE ? 4 : (32 + 1) * HID];
+  uint8_t dmode[OW];    // mode value per slot (0 beyond obs_len)
   uint8_t jb[BT];            // per sample: slots [0, jb) are its own
   // The rows of the two first-layer matrices that this tile's samples select (~92 of Liar's 270)
   // are staged in shared memory once per tile (in H2 | D1 | Lg, free until the hidden layer runs):
@@ -403,8 +409,10 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
 // nvec <= 32 (every space of the built-in games): one MATCH.ANY per 32 samples groups equal values,
 // lane v owns value v's count, a warp scan turns counts into start positions.  Larger nvec: one
 // ballot per value.  Per-warp scratch (64 ints) lives in sm.rowpos, which is written after the sort.
-__device__ __forceinline__ void sort_slots(const UpdParams& p, UpdSmem& sm, const uint8_t* obs_s, int nb,
+template <class SM>
+__device__ __forceinline__ void sort_slots(const UpdParams& p, SM& sm, const uint8_t* obs_s, int nb,
                                            int lane, int wid, int n_warps) {
+  constexpr int OW = SM::OW;
   int* hist = reinterpret_cast<int*>(sm.rowpos) + wid * 64;
   int* cur = hist + 32;
   const unsigned lt = (1u << lane) - 1u;
@@ -414,7 +422,7 @@ __device__ __forceinline__ void sort_slots(const UpdParams& p, UpdSmem& sm, cons
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int b = lane + 32 * r;
-      val[r] = b < nb ? (int)obs_s[b * 32 + s] : -1;
+      val[r] = b < nb ? (int)obs_s[b * OW + s] : -1;
     }
     const int nv = p.nvec[s];
     const int row0 = p.sp.slot_off[s];
@@ -491,7 +499,8 @@ __device__ __forceinline__ void sort_slots(const UpdParams& p, UpdSmem& sm, cons
 //    numbered rows of both matrices into the stage (all loads of a thread in flight together) and
 //    translate every (sample, slot) into its row's staged position, once for both towers (rowpos).
 constexpr int NTC = UNT - 32;  // threads of the copy part
-__device__ __forceinline__ void chain_setup(const UpdParams& p, UpdSmem& sm, float* stage, int nb, int tid) {
+template <class SM>
+__device__ __forceinline__ void chain_setup(const UpdParams& p, SM& sm, float* stage, int nb, int tid) {
   const int S = p.sp.obs_len;
   if (tid >= NTC) {
     const int lane = tid & 31;
@@ -571,8 +580,8 @@ __device__ __forceinline__ float4 row_load(const float* stage, const float4* W4,
 // group works on 4 samples at a time.  All four start from the chain beginning of the quartet's
 // LARGEST jb: a sample with a smaller jb agrees with the mode on the slots in between, so its
 // own rows there ARE the mode's rows — no predication, same additions.
-template <int NTH>
-__device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdSmem& sm, const uint8_t* obs_s,
+template <int NTH, class SM>
+__device__ __forceinline__ void first_layer_chain(const UpdParams& p, const SM& sm, const uint8_t* obs_s,
                                                   const float* W, const float* stage, int t, const float* P,
                                                   float* Out, int tid) {
   static_assert(NTH / 16 * 8 == BT, "16 thread groups x 2 quartets cover the tile");
@@ -645,8 +654,8 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const UpdS
 // Slots are shared out over warps [0, NWS); the caller's barrier separates the walk (phase 0:
 // rows of the other values, their sum kept in registers) from the mode rows (phase 1: bsum ready).
 constexpr int NWS = UNT / 32 - 2;  // the last two warps compute the bias chains meanwhile
-constexpr int SLOTS_PER_WARP = (MAX_SLOTS + NWS - 1) / NWS;
-__device__ __forceinline__ void segsum_w1_walk(const UpdParams& p, const UpdSmem& sm, const float* dzT,
+template <class SM, int SLOTS_PER_WARP>
+__device__ __forceinline__ void segsum_w1_walk(const UpdParams& p, const SM& sm, const float* dzT,
                                                float* gW0, bool first, int tid, float2 (&csum)[SLOTS_PER_WARP]) {
   const int jp = (tid & 31) * 2, wid = tid >> 5;
 #pragma unroll
@@ -698,7 +707,8 @@ __device__ __forceinline__ void segsum_w1_walk(const UpdParams& p, const UpdSmem
     csum[q] = make_float2(c0, c1);
   }
 }
-__device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const UpdSmem& sm, const float* bsum,
+template <class SM, int SLOTS_PER_WARP>
+__device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const SM& sm, const float* bsum,
                                                float* gW0, bool first, int tid,
                                                const float2 (&csum)[SLOTS_PER_WARP]) {
   const int jp = (tid & 31) * 2, wid = tid >> 5;
@@ -722,8 +732,8 @@ __device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const UpdSmem
 // The hidden-layer weight gradient (D1 x Ha^T) and the back-propagation through the hidden layer
 // (W^T x D1) only READ D1 / Ha, so they run side by side: each on one half of the CTA with the
 // large register tiles of a 256-thread group (the 512-thread tiles are shared-memory bound).
-template <bool BOX>
-__device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, const float* Xs,
+template <bool BOX, class SM>
+__device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const float* Xs,
                                                const float* Ha, const float* w1_s, float* g_w0,
                                                float* g_b0, float* g_w1, float* g_b1, int nb,
                                                bool first, int tid, long long& prof_last, int c,
@@ -744,6 +754,7 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, 
     return;
   }
   (void)nb;
+  constexpr int SLOTS_PER_WARP = (SM::OW + NWS - 1) / NWS;
   float2 csum[SLOTS_PER_WARP];
   if (tid >= UNT - HID) {  // warps NWS, NWS + 1: the bias chains, next to the other warps' walks
     const int j = tid - (UNT - HID);
@@ -757,8 +768,11 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, UpdSmem& sm, 
   segsum_w1_mode(p, sm, sm.bc, g_w0, first, tid, csum);
 }
 
-template <bool BOX>
+template <bool BOX, bool WIDE = false>
 __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
+  static_assert(!(BOX && WIDE), "wide rows are a one-hot notion");
+  using UpdSmem = UpdSmemT<WIDE>;
+  constexpr int OW = UpdSmem::OW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UpdSmem& sm = *reinterpret_cast<UpdSmem*>(smem_raw);
   // one more [64][LDA] tile behind the struct.  BOX: the observation rows, feature major (Xs).
@@ -775,7 +789,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
   const int PS = (P + 3) & ~3;  // per-CTA stride of the partial sums: keeps every row 16-byte aligned
   float* part = p.part + (size_t)c * PS;
   const uint8_t* obs_s = reinterpret_cast<const uint8_t*>(sm.obs);
-  if (tid < MAX_SLOTS) sm.dmode[tid] = 0;  // slots beyond obs_len compare equal (observation rows are zero padded)
+  if (tid < OW) sm.dmode[tid] = 0;  // slots beyond obs_len compare equal (observation rows are zero padded)
 
   // ------------------------------------------------ prologue: advantage statistics
   // One whole CTA per minibatch id (the lane order of the contract does not depend on WHICH CTA).
@@ -881,7 +895,10 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         // ---- gather this thread's sample
         uint32_t act = 0;
         float adv = 0.f, oldlp = 0.f, ret = 0.f;
-        uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+        constexpr int OQ = OW / 16;  // uint4 per observation row
+        uint4 orow[OQ];
+#pragma unroll
+        for (int i = 0; i < OQ; ++i) orow[i] = make_uint4(0, 0, 0, 0);
         constexpr int XQ = 16 / (UNT / BT);  // BOX: float4 of the sample's 64-float row per thread
         float4 xrow[XQ];                     // (threads b, b + 128, ... share sample b)
         if constexpr (BOX) {
@@ -902,8 +919,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           if constexpr (!BOX) {
             if (valid) {
               const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
-              o0 = __ldg(q);
-              o1 = __ldg(q + 1);
+#pragma unroll
+              for (int i = 0; i < OQ; ++i) orow[i] = __ldg(q + i);
             }
           }
           act = *reinterpret_cast<const uint32_t*>(p.actions + off * p.act_stride);
@@ -925,8 +942,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
             }
           }
         } else if (lane) {
-          *reinterpret_cast<uint4*>(&sm.obs[tid * 8]) = o0;
-          *reinterpret_cast<uint4*>(&sm.obs[tid * 8 + 4]) = o1;
+#pragma unroll
+          for (int i = 0; i < OQ; ++i) *reinterpret_cast<uint4*>(&sm.obs[tid * (OW / 4) + 4 * i]) = orow[i];
           if (tid == 0) sm.n_staged = 0;
         }
         __syncthreads();
@@ -937,8 +954,10 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           sort_slots(p, sm, obs_s, nb, tid & 31, tid >> 5, UNT / 32);
           __syncthreads();  // order / rcount / dmode / rowmap complete; the sort's scratch (rowpos) is free
           PTH_PROF(22);  // slot sort + row numbering
-          chain_setup(p, sm, sm.H2, nb, tid);
-          __syncthreads();
+          if constexpr (!WIDE) {
+            chain_setup(p, sm, sm.H2, nb, tid);
+            __syncthreads();
+          }
           PTH_PROF(23);  // jb, stage copy, row positions | chain beginnings
         }
 
@@ -947,11 +966,19 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         } else {
           // both towers' first layers (latency-bound row gathers) side by side, one per CTA half
-          if (tid < UNT / 2)
+          if constexpr (WIDE) {
+            if (tid < UNT / 2)
+              first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1,
+                                                            tid);
+            else
+              first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, V1,
+                                                            tid - UNT / 2);
+          } else if (tid < UNT / 2) {
             first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_pi0, sm.H2, 0, sm.pchain[0], sm.H1, tid);
-          else
+          } else {
             first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_vf0, sm.H2, 1, sm.pchain[1], V1,
                                        tid - UNT / 2);
+          }
         }
         __syncthreads();
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
@@ -1463,25 +1490,37 @@ WsLayout ws_layout(int G, int P, int64_t n_stat) {
   return w;
 }
 
-constexpr size_t SMEM_ONEHOT = sizeof(UpdSmem) + sizeof(float) * HID * LDA;
-constexpr size_t SMEM_BOX = sizeof(UpdSmem) + sizeof(float) * HID * LDA;
+constexpr size_t SMEM_ONEHOT = sizeof(UpdSmemT<false>) + sizeof(float) * HID * LDA;
+constexpr size_t SMEM_BOX = sizeof(UpdSmemT<false>) + sizeof(float) * HID * LDA;
+constexpr size_t SMEM_WIDE = sizeof(UpdSmemT<true>) + sizeof(float) * HID * LDA;
+static_assert(SMEM_ONEHOT <= 227 * 1024 && SMEM_WIDE <= 227 * 1024, "one CTA per SM: 227 KB of shared memory");
 
-int max_coop_ctas(const pth_ctx* ctx, bool box = false) {
-  static int cached[2] = {-1, -1};
-  if (cached[box] < 0) {
-    const void* fn = box ? (const void*)ppo_update_kernel<true> : (const void*)ppo_update_kernel<false>;
-    const size_t smem = box ? SMEM_BOX : SMEM_ONEHOT;
+// kernel variant: 0 one-hot rows of 32 bytes, 1 Box rows, 2 one-hot rows of 96 bytes
+const void* update_fn(int kind) {
+  return kind == 1 ? (const void*)ppo_update_kernel<true, false>
+                   : (kind == 2 ? (const void*)ppo_update_kernel<false, true> : (const void*)ppo_update_kernel<false, false>);
+}
+size_t update_smem(int kind) { return kind == 1 ? SMEM_BOX : (kind == 2 ? SMEM_WIDE : SMEM_ONEHOT); }
+
+int max_coop_ctas(const pth_ctx* ctx, int kind = 0) {
+  static int cached[3] = {-1, -1, -1};
+  if (cached[kind] < 0) {
+    const void* fn = update_fn(kind);
+    const size_t smem = update_smem(kind);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, UNT, smem) != cudaSuccess) per_sm = 0;
-    cached[box] = per_sm * ctx->sm_count;
+    cached[kind] = per_sm * ctx->sm_count;
   }
-  return cached[box];
+  return cached[kind];
 }
 
-bool space_is_box(const pth_space* sp) { return sp && sp->obs_kind == PTH_OBS_BOX; }
+int space_is_box(const pth_space* sp) {  // the kernel variant of a space
+  if (sp && sp->obs_kind == PTH_OBS_BOX) return 1;
+  return sp && sp->obs_len > 32 ? 2 : 0;
+}
 
-int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1, bool box = false) {
+int auto_grid(const pth_ctx* ctx, int64_t M, int64_t BS, int world = 1, int box = 0) {
   const int64_t eff = BS < M ? BS : M;
   int64_t tiles = (eff + BT - 1) / BT;
   tiles = (tiles + world - 1) / world;  // a rank computes every world-th tile
@@ -1557,14 +1596,15 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.lo = make_layout(p.sp.F, p.sp.L);
   for (int i = 0; i < MAX_SLOTS; ++i)
     p.nvec[i] = (!box && i < p.sp.obs_len) ? (uint8_t)a->space->obs_nvec[i] : 0;
-  const int cap = max_coop_ctas(ctx, box);
+  const int kind = box ? 1 : (p.sp.obs_len > 32 ? 2 : 0);
+  const int cap = max_coop_ctas(ctx, kind);
   PTH_CHECK_ARG(cap <= 160, "more than 160 co-resident CTAs are not supported");
   if (cap < 1 || !ctx->coop_launch) {
     pth_set_error("pth_ppo_update: cooperative launch unavailable on this device");
     return PTH_ENOSUP;
   }
   int G = a->grid_ctas > 0 ? a->grid_ctas
-                           : auto_grid(ctx, a->M, a->batch_size, a->world > 1 ? a->world : 1, box);
+                           : auto_grid(ctx, a->M, a->batch_size, a->world > 1 ? a->world : 1, kind);
   PTH_CHECK_ARG(G >= 1 && G <= cap, "grid_ctas exceeds the co-resident CTA capacity");
   const int64_t n_mb = (a->M + a->batch_size - 1) / a->batch_size;
   const WsLayout w = ws_layout(G, p.lo.total, (int64_t)a->n_epochs * n_mb);
@@ -1584,7 +1624,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     PTH_CHECK_ARG(a->rec_stride % 16 == 0, "rec_stride must be a multiple of 16");
     p.obs_stride = p.act_stride = p.f_stride = a->rec_stride;
   } else {
-    p.obs_stride = box ? (int64_t)HID * 4 : 32;
+    p.obs_stride = box ? (int64_t)HID * 4 : PTH_OBS_ROW_BYTES(p.sp.obs_len);
     p.act_stride = 4;
     p.f_stride = 4;
   }
@@ -1638,12 +1678,8 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   }
 
   void* kargs[] = {(void*)&p};
-  if (box)
-    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<true>, dim3(G), dim3(UNT), kargs, SMEM_BOX,
-                                         (cudaStream_t)stream));
-  else
-    PTH_CUDA(cudaLaunchCooperativeKernel((void*)ppo_update_kernel<false>, dim3(G), dim3(UNT), kargs,
-                                         SMEM_ONEHOT, (cudaStream_t)stream));
+  PTH_CUDA(cudaLaunchCooperativeKernel(update_fn(kind), dim3(G), dim3(UNT), kargs, update_smem(kind),
+                                       (cudaStream_t)stream));
   return PTH_OK;
 }
 

@@ -46,12 +46,13 @@ class DevicePolicy:
         self.params = torch.from_numpy(pol.init_flat(space, seed)).to(device)  # seed None: no re-seeding
         self.calls = 0
         self.box = space.obs_kind == _lib.PTH_OBS_BOX  # fp32 rows of 64 instead of 32 slot bytes
+        self.row = space.row_bytes  # one-hot rows: 32 bytes, or 96 for frame-stacked observations
         self._obs_dev = (torch.zeros(1, _lib.PTH_OC_ROW, dtype=torch.float32, device=device) if self.box
-                         else torch.zeros(1, 32, dtype=torch.uint8, device=device))
+                         else torch.zeros(1, self.row, dtype=torch.uint8, device=device))
         self.act_dim = space.n_heads
 
     def _stage_obs(self, obs):
-        o = np.zeros((1, _lib.PTH_OC_ROW), np.float32) if self.box else np.zeros((1, 32), np.uint8)
+        o = np.zeros((1, _lib.PTH_OC_ROW), np.float32) if self.box else np.zeros((1, self.row), np.uint8)
         flat = np.asarray(obs).reshape(-1)
         o[0, :flat.size] = flat
         self._obs_dev.copy_(torch.from_numpy(o))
@@ -91,9 +92,9 @@ class HostStagedBuffer:
     """RolloutBuffer for the N = 1 flow: rows are staged on the host while the env is
     stepped from Python and uploaded once when GAE / train() run on the device."""
 
-    def __init__(self, n_steps, device, gamma=0.99, gae_lambda=0.95, box=False):
+    def __init__(self, n_steps, device, gamma=0.99, gae_lambda=0.95, box=False, row=32):
         self.T, self.device, self.gamma, self.gae_lambda = n_steps, device, gamma, gae_lambda
-        obs = np.zeros((n_steps, _lib.PTH_OC_ROW), np.float32) if box else np.zeros((n_steps, 32), np.uint8)
+        obs = np.zeros((n_steps, _lib.PTH_OC_ROW), np.float32) if box else np.zeros((n_steps, row), np.uint8)
         self.h = dict(obs=obs, actions=np.zeros((n_steps, 4), np.uint8),
                       rewards=np.zeros(n_steps, np.float32), values=np.zeros(n_steps, np.float32),
                       logp=np.zeros(n_steps, np.float32), episode_starts=np.zeros(n_steps, np.float32))
@@ -209,7 +210,7 @@ class PPO:
         if self.space.obs_kind == _lib.PTH_OBS_BOX and self.space.obs_len > _lib.PTH_OC_ROW:
             raise _lib.PthError("Box observations wider than 64 are not supported")
         self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda,
-                                               box=self.space.obs_kind == _lib.PTH_OBS_BOX)
+                                               box=self.space.obs_kind == _lib.PTH_OBS_BOX, row=self.space.row_bytes)
         self.adam_m = torch.zeros_like(self.policy.params)
         self.adam_v = torch.zeros_like(self.policy.params)
         self.adam_step, self._n_updates, self.num_timesteps = 0, 0, 0

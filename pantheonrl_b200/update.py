@@ -71,7 +71,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     if space.obs_kind == _lib.PTH_OBS_BOX:  # fp32 rows of 64
         a.d_obs, a.d_obs_f32, a.obs_stride = None, obs.data_ptr(), obs.shape[-1]
     else:
-        a.d_obs, a.d_obs_f32, a.obs_stride = obs.data_ptr(), None, 32
+        a.d_obs, a.d_obs_f32, a.obs_stride = obs.data_ptr(), None, space.row_bytes
     a.d_actions = actions.data_ptr()
     a.d_old_logp, a.d_advantages, a.d_returns = old_logp.data_ptr(), advantages.data_ptr(), returns.data_ptr()
     a.rec_stride = int(rec_stride)

@@ -36,7 +36,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_sizes_match_the_header():
     from pantheonrl_b200 import _lib
-    assert ctypes.sizeof(_lib.Space) == 4 * (2 + 64 + 1 + 4)
+    assert ctypes.sizeof(_lib.Space) == 4 * (2 + 96 + 1 + 4)
     assert ctypes.sizeof(_lib.Buffer) == 8 * 8
     assert ctypes.sizeof(_lib.EnvCarry) == 9 * 8
     assert ctypes.sizeof(_lib.OvercookedLayout) == 5576 and _lib.PTH_OC_STATE_BYTES == 40

@@ -248,7 +248,7 @@ def test_wrappers_around_device_games(ctx, tmp_path):
     back = trajsaver.SimultaneousTransitions.read_transition(tmp_path / "rps.npy", env.observation_space,
                                                              env.action_space)
     assert np.array_equal(back.egoacts.reshape(-1), tr.egoacts) and set(np.unique(tr.altacts)) <= {0, 1, 2}
-    # turn based, recorded only (a 3-frame Liar observation would be 90 slots: the kernels take 32)
+    # turn based, recorded
     lenv = LiarEnv(seed=3)
     lenv.add_partner_agent(StaticPolicyAgent(PPO("MlpPolicy", lenv, seed=1).policy))
     lrec = wrappers.recorder_wrap(lenv)
@@ -256,8 +256,20 @@ def test_wrappers_around_device_games(ctx, tmp_path):
     lt = lrec.get_transitions()
     assert len(lt.get_ego_transitions()) == 16 and lt.obs.shape[1] == 30
     assert len(lt.get_alt_transitions()) == int((lt.flags % 2 == 1).sum()) > 0
+    # trainer.py --framestack 3 on Liar's Dice: 90 observation slots (rows of 96 bytes), ego and partner both
+    # learn on stacked frames (trainer.py:97-99 wraps env and altenv)
+    senv = wrappers.frame_wrap(LiarEnv(seed=4), 3)
+    assert len(senv.observation_space.nvec) == 90
+    spartner = OnPolicyAgent(PPO("MlpPolicy", senv, n_steps=24, batch_size=8, n_epochs=2, seed=10))
+    senv.add_partner_agent(spartner)
+    sego = PPO("MlpPolicy", senv, n_steps=32, batch_size=16, n_epochs=2, seed=10)
+    p0 = sego.policy.params.clone()
+    sego.learn(total_timesteps=96)
+    assert sego._n_updates == 6 and spartner.model._n_updates >= 2
+    assert bool(torch.isfinite(sego.policy.params).all()) and not torch.equal(sego.policy.params, p0)
+    assert sego.rollout_buffer.h["obs"].shape == (32, 96)
     with pytest.raises(_lib.PthError):
-        PPO("MlpPolicy", wrappers.frame_wrap(LiarEnv(), 3), seed=1)
+        PPO("MlpPolicy", wrappers.frame_wrap(LiarEnv(), 4), seed=1)  # 120 slots: more than PTH_MAX_OBS_SLOTS
 
 
 def test_behaviour_cloning_facade(ctx, tmp_path):

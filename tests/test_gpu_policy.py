@@ -13,14 +13,20 @@ pytestmark = pytest.mark.gpu
 SPACES = {
     "rps": (oracle.RPS_SPACE, lambda: _lib.Space.onehot([1], [3])),
     "liar": (oracle.LIAR_SPACE, lambda: _lib.Space.onehot(oracle.LIAR_NVEC, [7, 12])),
+    "liar3": (oracle.LIAR3_SPACE, lambda: _lib.Space.onehot(oracle.LIAR_NVEC * 3, [7, 12])),  # frame stack: 90 slots
 }
 
 
 def _obs(name, B, seed=0):
+    if name == "liar3":  # three stacked frames in a 96-byte row
+        o = np.zeros((B, 96), np.uint8)
+        for f in range(3):
+            o[:, 30 * f:30 * f + 30] = rand_liar_obs(B, seed + 17 * f)[:, :30]
+        return o
     return rand_liar_obs(B, seed) if name == "liar" else np.zeros((B, 32), np.uint8)
 
 
-@pytest.mark.parametrize("name", ["rps", "liar"])
+@pytest.mark.parametrize("name", ["rps", "liar", "liar3"])
 @pytest.mark.parametrize("B", [1, 127, 128, 1000])
 @pytest.mark.parametrize("scale", [0.05, 0.6])
 def test_forward_sample_bit_exact(ctx, name, B, scale):
@@ -37,7 +43,7 @@ def test_forward_sample_bit_exact(ctx, name, B, scale):
         assert np.array_equal(g, want[k]), (k, np.abs(g.astype(np.float64) - want[k]).max())
 
 
-@pytest.mark.parametrize("name", ["rps", "liar"])
+@pytest.mark.parametrize("name", ["rps", "liar", "liar3"])
 def test_evaluate_actions_bit_exact(ctx, name):
     okw, mk = SPACES[name]
     osp, gsp = oracle.make_space(**okw), mk()

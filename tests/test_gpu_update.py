@@ -30,7 +30,7 @@ def run_gpu(kw, params, m, v, step, obs, act, old_logp, adv, ret, perm, BS, grid
     return dp.cpu().numpy(), dm.cpu().numpy(), dv.cpu().numpy(), stats.cpu().numpy()
 
 
-@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE])
+@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE, oracle.LIAR3_SPACE])
 @pytest.mark.parametrize("M,BS,E,grid", [(300, 300, 1, 2), (700, 256, 3, 3), (2048, 512, 2, 4), (1000, 64, 2, 1)])
 def test_update_bit_exact_vs_oracle(ctx, kw, M, BS, E, grid):
     space = oracle.make_space(**kw)
