@@ -654,71 +654,108 @@ __device__ __forceinline__ void first_layer_chain(const UpdParams& p, const SM& 
 // Slots are shared out over warps [0, NWS); the caller's barrier separates the walk (phase 0:
 // rows of the other values, their sum kept in registers) from the mode rows (phase 1: bsum ready).
 constexpr int NWS = UNT / 32 - 2;  // the last two warps compute the bias chains meanwhile
+// Two values of the slot at a time, one per half warp (16 lanes x 4 columns: column pairs hl * 2 and
+// 32 + hl * 2): the chains of a slot's values are independent, so the slot's critical path halves.
 template <class SM, int SLOTS_PER_WARP>
 __device__ __forceinline__ void segsum_w1_walk(const UpdParams& p, const SM& sm, const float* dzT,
-                                               float* gW0, bool first, int tid, float2 (&csum)[SLOTS_PER_WARP]) {
-  const int jp = (tid & 31) * 2, wid = tid >> 5;
+                                               float* gW0, bool first, int tid, float4 (&csum)[SLOTS_PER_WARP]) {
+  const int lane = tid & 31, wid = tid >> 5;
+  const int half = lane >> 4, jp0 = (lane & 15) * 2, jp1 = 32 + jp0;
 #pragma unroll
   for (int q = 0; q < SLOTS_PER_WARP; ++q) {
-    csum[q] = make_float2(0.f, 0.f);
+    csum[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int s = wid + q * NWS;
     if (wid >= NWS || s >= p.sp.obs_len) continue;
     const int row0 = p.sp.slot_off[s];
     const int nv = p.nvec[s];
     const int mode = sm.dmode[s];
     const uint8_t* ord = sm.order + s * BT;
-    int pos = 0;
-    float c0 = 0.f, c1 = 0.f;
-    for (int v = 0; v < nv; ++v) {
-      const int cnt = sm.rcount[row0 + v];
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    int v = 0, pos = 0;
+    while (v < nv) {
       if (v == mode) {
-        pos += cnt;
+        pos += sm.rcount[row0 + v];
+        ++v;
         continue;
       }
-      float a0 = 0.f, a1 = 0.f;
+      // the next two values that are not the mode: A for lanes [0, 16), B (if any) for lanes [16, 32)
+      const int vA = v, cntA = sm.rcount[row0 + vA], posA = pos;
+      pos += cntA;
+      ++v;
+      if (v < nv && v == mode) {
+        pos += sm.rcount[row0 + v];
+        ++v;
+      }
+      const bool hasB = v < nv;
+      const int vB = hasB ? v : vA, cntB = hasB ? sm.rcount[row0 + vB] : 0, posB = pos;
+      if (hasB) {
+        pos += cntB;
+        ++v;
+      }
+      const int myv = half ? vB : vA, cnt = half ? cntB : cntA, p0 = half ? posB : posA;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int i = 0;
       for (; i + 4 <= cnt; i += 4) {
-        float2 d[4];
+        float2 d[4], e[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          d[u] = *reinterpret_cast<const float2*>(dzT + (int)ord[pos + i + u] * LDT + jp);
+        for (int u = 0; u < 4; ++u) {
+          const float* row = dzT + (int)ord[p0 + i + u] * LDT;
+          d[u] = *reinterpret_cast<const float2*>(row + jp0);
+          e[u] = *reinterpret_cast<const float2*>(row + jp1);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           a0 = a0 + d[u].x;
           a1 = a1 + d[u].y;
+          a2 = a2 + e[u].x;
+          a3 = a3 + e[u].y;
         }
       }
       for (; i < cnt; ++i) {
-        const float2 d = *reinterpret_cast<const float2*>(dzT + (int)ord[pos + i] * LDT + jp);
+        const float* row = dzT + (int)ord[p0 + i] * LDT;
+        const float2 d = *reinterpret_cast<const float2*>(row + jp0);
+        const float2 e = *reinterpret_cast<const float2*>(row + jp1);
         a0 = a0 + d.x;
         a1 = a1 + d.y;
+        a2 = a2 + e.x;
+        a3 = a3 + e.y;
       }
-      pos += cnt;
-      c0 = c0 + a0;
-      c1 = c1 + a1;
-      float* g = gW0 + (row0 + v) * HID + jp;
-      if (first) {
-        *reinterpret_cast<float2*>(g) = make_float2(a0, a1);
-      } else if (cnt > 0) {
-        acc_store(g, a0, false);
-        acc_store(g + 1, a1, false);
+      if (half == 0 || hasB) {
+        float* g = gW0 + (row0 + myv) * HID;
+        if (first) {
+          *reinterpret_cast<float2*>(g + jp0) = make_float2(a0, a1);
+          *reinterpret_cast<float2*>(g + jp1) = make_float2(a2, a3);
+        } else if (cnt > 0) {
+          acc_store(g + jp0, a0, false);
+          acc_store(g + jp0 + 1, a1, false);
+          acc_store(g + jp1, a2, false);
+          acc_store(g + jp1 + 1, a3, false);
+        }
       }
+      // the slot's running sum of rows, in ascending value order: + A, then + B (an absent B is +0)
+      const float o0 = __shfl_xor_sync(0xffffffffu, a0, 16), o1 = __shfl_xor_sync(0xffffffffu, a1, 16);
+      const float o2 = __shfl_xor_sync(0xffffffffu, a2, 16), o3 = __shfl_xor_sync(0xffffffffu, a3, 16);
+      c.x = (c.x + (half ? o0 : a0)) + (half ? a0 : o0);
+      c.y = (c.y + (half ? o1 : a1)) + (half ? a1 : o1);
+      c.z = (c.z + (half ? o2 : a2)) + (half ? a2 : o2);
+      c.w = (c.w + (half ? o3 : a3)) + (half ? a3 : o3);
     }
-    csum[q] = make_float2(c0, c1);
+    csum[q] = c;
   }
 }
 template <class SM, int SLOTS_PER_WARP>
 __device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const SM& sm, const float* bsum,
                                                float* gW0, bool first, int tid,
-                                               const float2 (&csum)[SLOTS_PER_WARP]) {
-  const int jp = (tid & 31) * 2, wid = tid >> 5;
+                                               const float4 (&csum)[SLOTS_PER_WARP]) {
+  const int lane = tid & 31, wid = tid >> 5;
+  const int half = lane >> 4, jp = (lane & 15) * 2 + 32 * half;  // half 0: columns < 32, half 1: the rest
   const float2 b2 = *reinterpret_cast<const float2*>(bsum + jp);
 #pragma unroll
   for (int q = 0; q < SLOTS_PER_WARP; ++q) {
     const int s = wid + q * NWS;
     if (wid >= NWS || s >= p.sp.obs_len) continue;
     float* g = gW0 + (p.sp.slot_off[s] + sm.dmode[s]) * HID + jp;
-    const float g0 = b2.x - csum[q].x, g1 = b2.y - csum[q].y;
+    const float g0 = b2.x - (half ? csum[q].z : csum[q].x), g1 = b2.y - (half ? csum[q].w : csum[q].y);
     if (first) {
       *reinterpret_cast<float2*>(g) = make_float2(g0, g1);
     } else {
@@ -755,11 +792,17 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const
   }
   (void)nb;
   constexpr int SLOTS_PER_WARP = (SM::OW + NWS - 1) / NWS;
-  float2 csum[SLOTS_PER_WARP];
+  float4 csum[SLOTS_PER_WARP];
   if (tid >= UNT - HID) {  // warps NWS, NWS + 1: the bias chains, next to the other warps' walks
     const int j = tid - (UNT - HID);
     float s = 0.f;
-    for (int b = 0; b < BT; ++b) s = s + sm.H2[b * LDT + j];
+    for (int b0 = 0; b0 < BT; b0 += 8) {  // 8 loads in flight, then the 8 adds of the chain
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = sm.H2[(b0 + u) * LDT + j];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = s + x[u];
+    }
     acc_store(g_b0 + j, s, first);
     sm.bc[j] = s;  // bc is free during the tower's backward pass
   }
