@@ -245,7 +245,7 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
   constexpr int LDA = BTS + 4;
   constexpr int SPT = BTS >= 128 ? 8 : 4;
   constexpr int TXN = BTS / SPT, NY = NTH / TXN, JT = HID / NY;
-  static_assert(NY * JT == HID && TXN * NY == NTH && (JT == 2 || JT == 4), "tile mapping");
+  static_assert(NY * JT == HID && TXN * NY == NTH && (JT == 1 || JT == 2 || JT == 4), "tile mapping");
   const int tx = tid % TXN, ty = tid / TXN;
   float acc[JT][SPT];
 #pragma unroll
@@ -269,10 +269,12 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
     if constexpr (JT == 4) {
       const float4 wq = ld_param4<COHERENT>(reinterpret_cast<const float4*>(W + k * HID + ty * JT));
       w[0] = wq.x; w[1] = wq.y; w[2] = wq.z; w[3] = wq.w;
-    } else {
+    } else if constexpr (JT == 2) {
       const float2* q = reinterpret_cast<const float2*>(W + k * HID + ty * JT);
       const float2 wq = COHERENT ? *q : __ldg(q);
       w[0] = wq.x; w[1] = wq.y;
+    } else {
+      w[0] = ld_param<COHERENT>(W + k * HID + ty);
     }
 #pragma unroll
     for (int jj = 0; jj < JT; ++jj)

@@ -606,11 +606,20 @@ extern "C" int pth_rollout_run(pth_ctx* ctx, const pth_rollout_args* a, void* st
     }
     p.lo = make_layout(p.sp.F, p.sp.L);
     p.a = *a;
-    constexpr int RBV = 32;
-    const size_t smem = sizeof(RollSmemOC<RBV>);
-    PTH_CUDA(cudaFuncSetAttribute(rollout_overcooked_kernel<RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    rollout_overcooked_kernel<RBV><<<pth_ceil_div(a->N, RBV), NT, smem, (cudaStream_t)stream>>>(p);
+    // 16-env tiles while 32-env tiles would leave SMs idle (1024 envs: 64 CTAs instead of 32)
+    if (pth_ceil_div(a->N, 32) < ctx->sm_count && !getenv("PTH_ROLLOUT_RB32")) {
+      constexpr int RBV = 16;
+      const size_t smem = sizeof(RollSmemOC<RBV>);
+      PTH_CUDA(cudaFuncSetAttribute(rollout_overcooked_kernel<RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      rollout_overcooked_kernel<RBV><<<pth_ceil_div(a->N, RBV), NT, smem, (cudaStream_t)stream>>>(p);
+    } else {
+      constexpr int RBV = 32;
+      const size_t smem = sizeof(RollSmemOC<RBV>);
+      PTH_CUDA(cudaFuncSetAttribute(rollout_overcooked_kernel<RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      rollout_overcooked_kernel<RBV><<<pth_ceil_div(a->N, RBV), NT, smem, (cudaStream_t)stream>>>(p);
+    }
     PTH_LAUNCH_CHECK();
     return PTH_OK;
   }

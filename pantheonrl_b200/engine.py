@@ -222,8 +222,14 @@ class VecTrainer:
                 self.carry.ego_last_done, c.gamma, c.gae_lambda, out=(b.advantages, b.returns))
         if self.alt is not None:
             a, ac = self.alt_buf, self.alt_cfg
-            ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_boot_done,
-                           ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
+            if self.env_kind == "liar":
+                ops.gae_ragged(a.rewards, a.values, a.episode_starts, a.count, self.carry.alt_boot_done,
+                               ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
+            else:
+                # simultaneous games: one partner row per tick, the buffer is dense -> the dense kernel, with the
+                # partner's bootstrap rule (value of its last stored row, agents.py:127-129)
+                ops.gae(a.rewards, a.values, a.episode_starts, a.values[self.T - 1], self.carry.alt_boot_done,
+                        ac.gamma, ac.gae_lambda, out=(a.advantages, a.returns))
 
     def plan_grids(self, M_ego, M_alt):
         """CTAs for the two learners' update kernels when they run side by side.
