@@ -212,14 +212,32 @@ gae_ragged_kernel(const float* __restrict__ rew, const float* __restrict__ val,
   float next_v = val[(cnt - 1) * N + n];
   float next_nnt = 1.0f - last_done[n];
   float last = 0.f;
-  for (int64_t t = cnt - 1; t >= 0; --t) {
-    const int64_t off = t * N + n;
-    float r = __ldcs(rew + off), v = __ldcs(val + off), s = __ldcs(start + off);
-    float adv, ret;
-    gae_step(r, v, next_v, next_nnt, last, g, c, adv, ret);
-    next_nnt = 1.0f - s;
-    __stcs(adv_out + off, adv);
-    __stcs(ret_out + off, ret);
+  // a register window of U timesteps: the 3 * U loads are issued together (they do not depend on
+  // the recurrence), then the U steps retire in order — one thread per env has nothing else to
+  // hide the DRAM latency with (profiles/kernels_r02.md: 72 cycles of long-scoreboard stall per
+  // issued instruction before)
+  constexpr int U = 8;
+  for (int64_t t = cnt - 1; t >= 0; t -= U) {
+    float r[U], v[U], s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t tt = t - u;
+      const int64_t off = (tt >= 0 ? tt : 0) * N + n;  // clamped: loaded anyway, used only if tt >= 0
+      r[u] = __ldcs(rew + off);
+      v[u] = __ldcs(val + off);
+      s[u] = __ldcs(start + off);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t tt = t - u;
+      if (tt >= 0) {
+        float adv, ret;
+        gae_step(r[u], v[u], next_v, next_nnt, last, g, c, adv, ret);
+        next_nnt = 1.0f - s[u];
+        __stcs(adv_out + tt * N + n, adv);
+        __stcs(ret_out + tt * N + n, ret);
+      }
+    }
   }
 }
 
@@ -353,7 +371,7 @@ extern "C" int pth_gae_ragged_f32(pth_ctx* ctx, const float* d_rewards, const fl
   if (Tcap == 0 || N == 0) return PTH_OK;
   const float g = (float)gamma;
   const float c = (float)(gamma * gae_lambda);
-  gae_ragged_kernel<<<pth_ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(
+  gae_ragged_kernel<<<pth_ceil_div(N, 32), 32, 0, (cudaStream_t)stream>>>(
       d_rewards, d_values, d_episode_starts, d_count, d_last_done, d_advantages, d_returns, Tcap,
       N, g, c);
   PTH_LAUNCH_CHECK();

@@ -917,8 +917,9 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         // computed by rank id mod W (prologue); every thread polls the two pairs (same address: one
         // L2 transaction per warp)
         const uint2* ax = p.advx[p.rank] + 2 * id;
-        mean = ll_wait(ax, adv_tag, ll_peek(ax));
-        stdv = ll_wait(ax + 1, adv_tag, ll_peek(ax + 1));
+        const uint2 a0 = ll_peek(ax), a1 = ll_peek(ax + 1);  // both in flight
+        mean = ll_wait(ax, adv_tag, a0);
+        stdv = ll_wait(ax + 1, adv_tag, a1);
       }
       const int64_t n_tiles = (B + BT - 1) / BT;
       const int64_t local_tiles = (n_tiles - p.rank + W - 1) / W;  // tile t belongs to rank t mod W
@@ -1396,29 +1397,41 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           p.params[pi] = fmaf(-step_size, mm / denom, pre ? w0 : p.params[pi]);
         }
       }
-      if (c == 0 && tid == 0 && p.stats) {
-        float st[5];
-        for (int i = 0; i < 5; ++i) {
-          float s;
-          if (W == 1) {
-            s = __ldcg(p.stat_part + G * 8 + i);  // summed in CTA order during the reduce phase
-          } else {
-            const uint2* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
-            s = ll_wait(xl + i, epoch, ll_peek(xl + i));
-            for (int r = 1; r < W; ++r)
-              s = s + ll_wait(xl + (size_t)r * p.XS + i, epoch, ll_peek(xl + (size_t)r * p.XS + i));
+      if (c == 0 && tid < 32 && p.stats) {
+        // warp 0 of CTA 0 writes the minibatch's logged scalars.  Multi-GPU: lane (r, i) polls rank r's
+        // i-th sum — all W x 5 pairs in flight at once (one thread polling them one after the other cost
+        // 40 dependent L2 round trips = 10 us per minibatch at 8 GPUs, with every CTA of the grid waiting
+        // for it at barrier 3: profiles/scaling_r02.md) — then lanes 0..4 add them in rank order.
+        float mine = 0.f;
+        if (W == 1) {
+          if (tid < 5) mine = __ldcg(p.stat_part + G * 8 + tid);  // summed in CTA order during the reduce phase
+        } else {
+          const uint2* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
+          float* sc = sm.Lg;  // [8][5] scratch (free between tiles)
+          for (int idx = tid; idx < W * 5; idx += 32) {
+            const uint2* src = xl + (size_t)(idx / 5) * p.XS + (idx % 5);
+            sc[idx] = ll_wait(src, epoch, ll_peek(src));
           }
-          st[i] = s;
+          __syncwarp();
+          if (tid < 5) {
+            mine = sc[tid];
+            for (int r = 1; r < W; ++r) mine = mine + sc[r * 5 + tid];
+          }
         }
-        float* o = p.stats + 8 * id;
-        o[0] = -(st[0] / Bf);
-        o[1] = st[1] / Bf;
-        o[2] = -(st[2] / Bf);
-        o[3] = st[3] / Bf;
-        o[4] = st[4] / Bf;
-        o[5] = (o[0] + p.ent_coef * o[2]) + p.vf_coef * o[1];
-        o[6] = gnorm;
-        o[7] = Bf;
+        float st[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) st[i] = __shfl_sync(0xffffffffu, mine, i);
+        if (tid == 0) {
+          float* o = p.stats + 8 * id;
+          o[0] = -(st[0] / Bf);
+          o[1] = st[1] / Bf;
+          o[2] = -(st[2] / Bf);
+          o[3] = st[3] / Bf;
+          o[4] = st[4] / Bf;
+          o[5] = (o[0] + p.ent_coef * o[2]) + p.vf_coef * o[1];
+          o[6] = gnorm;
+          o[7] = Bf;
+        }
       }
       PTH_PROF(16);  // clip + Adam
       grid.sync();  // ---------------------------------------------- (3) parameters updated
