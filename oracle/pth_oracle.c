@@ -324,16 +324,18 @@ typedef struct {
   const float *w_pi0, *b_pi0, *w_pi1, *b_pi1, *w_vf0, *b_vf0, *w_vf1, *b_vf1, *w_act, *b_act,
       *w_val, *b_val;
   int F, L;
+  int C; /* ADAP (pantheonrl/algos/adap/policies.py:71-84): context inputs appended to the features;
+            the first-layer matrices then have F + C rows, the context rows last */
 } orc_params;
 
-static void split_params(const orc_space* sp, const float* p, orc_params* q) {
+static void split_params_ctx(const orc_space* sp, const float* p, int C, orc_params* q) {
   int F = feat_dim(sp), L = logit_dim(sp);
-  q->F = F; q->L = L;
-  q->w_pi0 = p; p += H * F;
+  q->F = F; q->L = L; q->C = C;
+  q->w_pi0 = p; p += H * (F + C);
   q->b_pi0 = p; p += H;
   q->w_pi1 = p; p += H * H;
   q->b_pi1 = p; p += H;
-  q->w_vf0 = p; p += H * F;
+  q->w_vf0 = p; p += H * (F + C);
   q->b_vf0 = p; p += H;
   q->w_vf1 = p; p += H * H;
   q->b_vf1 = p; p += H;
@@ -342,6 +344,7 @@ static void split_params(const orc_space* sp, const float* p, orc_params* q) {
   q->w_val = p; p += H;
   q->b_val = p;
 }
+static void split_params(const orc_space* sp, const float* p, orc_params* q) { split_params_ctx(sp, p, 0, q); }
 
 /* features: SB3 preprocess_obs (one-hot concat) — Appendix A2.  A linear layer
  * is evaluated as acc = bias; for k ascending: acc = fma(x_k, w[j][k], acc).
@@ -388,18 +391,31 @@ typedef struct {
   float h1p[H], h2p[H], h1v[H], h2v[H], logits[32 * MAX_HEADS], value;
 } orc_acts;
 
-static void forward_one(const orc_space* sp, const orc_params* q, const void* obs_row, orc_acts* a) {
+/* ctx: the q->C context inputs of an AdapPolicy (adap/policies.py:86-106: features = cat(features,
+ * context)); they continue the first layer's chain after the features, c ascending. */
+static void context_columns(const orc_params* q, const float* w, const float* ctx, float* z) {
+  for (int j = 0; j < H; ++j)
+    for (int c = 0; c < q->C; ++c) z[j] = fmaf(ctx[c], w[(q->F + c) * H + j], z[j]);
+}
+
+static void forward_one_ctx(const orc_space* sp, const orc_params* q, const void* obs_row, const float* ctx,
+                            orc_acts* a) {
   float z[H];
   first_layer(sp, obs_row, q->w_pi0, q->b_pi0, q->F, z);
+  if (q->C) context_columns(q, q->w_pi0, ctx, z);
   for (int j = 0; j < H; ++j) a->h1p[j] = orc_tanhf(z[j]);
   dense(a->h1p, H, q->w_pi1, q->b_pi1, H, z);
   for (int j = 0; j < H; ++j) a->h2p[j] = orc_tanhf(z[j]);
   dense(a->h2p, H, q->w_act, q->b_act, q->L, a->logits);
   first_layer(sp, obs_row, q->w_vf0, q->b_vf0, q->F, z);
+  if (q->C) context_columns(q, q->w_vf0, ctx, z);
   for (int j = 0; j < H; ++j) a->h1v[j] = orc_tanhf(z[j]);
   dense(a->h1v, H, q->w_vf1, q->b_vf1, H, z);
   for (int j = 0; j < H; ++j) a->h2v[j] = orc_tanhf(z[j]);
   dense(a->h2v, H, q->w_val, q->b_val, 1, &a->value);
+}
+static void forward_one(const orc_space* sp, const orc_params* q, const void* obs_row, orc_acts* a) {
+  forward_one_ctx(sp, q, obs_row, NULL, a);
 }
 
 /* One categorical head.  Inverse-CDF sampling on a single uniform (our RNG
@@ -471,6 +487,36 @@ void orc_policy_forward(const orc_space* sp, const float* params, const void* ob
     const void* row = sp->obs_kind == 0 ? (const void*)((const uint8_t*)obs + b * obs_stride)
                                         : (const void*)((const float*)obs + b * obs_stride);
     forward_one(sp, &q, row, &a);
+    uint8_t act[4] = {0, 0, 0, 0};
+    uint32_t rnd[4] = {0, 0, 0, 0};
+    int sample = action_in == NULL;
+    if (sample)
+      orc_philox(seed, rng_stream, (uint64_t)(idx0 + b), tick, slot, rnd);
+    else
+      memcpy(act, action_in + 4 * b, 4);
+    float lp, en;
+    dist_eval(sp, a.logits, sample, rnd, act, &lp, &en);
+    if (action) memcpy(action + 4 * b, act, 4);
+    if (value) value[b] = a.value;
+    if (logp) logp[b] = lp;
+    if (entropy) entropy[b] = en;
+    if (logits) memcpy(logits + b * q.L, a.logits, sizeof(float) * q.L);
+  }
+}
+
+/* AdapPolicy.forward / evaluate_actions (adap/policies.py:86-131): orc_policy_forward with C context
+ * inputs per sample (ctx_stride = 0: one context for the whole batch, `self.context.repeat`). */
+void orc_adap_forward(const orc_space* sp, const float* params, int32_t C, const void* obs, int64_t obs_stride,
+                      const float* ctx, int64_t ctx_stride, int64_t B, uint64_t seed, uint32_t rng_stream,
+                      uint32_t tick, uint32_t slot, int64_t idx0, const uint8_t* action_in, uint8_t* action,
+                      float* value, float* logp, float* entropy, float* logits) {
+  orc_params q;
+  split_params_ctx(sp, params, C, &q);
+  for (int64_t b = 0; b < B; ++b) {
+    orc_acts a;
+    const void* row = sp->obs_kind == 0 ? (const void*)((const uint8_t*)obs + b * obs_stride)
+                                        : (const void*)((const float*)obs + b * obs_stride);
+    forward_one_ctx(sp, &q, row, ctx + b * ctx_stride, &a);
     uint8_t act[4] = {0, 0, 0, 0};
     uint32_t rnd[4] = {0, 0, 0, 0};
     int sample = action_in == NULL;

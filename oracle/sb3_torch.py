@@ -26,13 +26,14 @@ from torch import nn
 class MlpPolicy(nn.Module):
     """SB3 ActorCriticPolicy with MlpExtractor [dict(pi=[64,64], vf=[64,64])], Tanh."""
 
-    def __init__(self, nvec=None, heads=(3,), box_dim=None, seed=None, lr=3e-4, adam_eps=1e-5):
+    def __init__(self, nvec=None, heads=(3,), box_dim=None, seed=None, lr=3e-4, adam_eps=1e-5, extra_inputs=0):
         super().__init__()
         if seed is not None:
             th.manual_seed(seed)  # SB3 set_random_seed (Appendix A1)
         self.nvec = None if nvec is None else [int(v) for v in nvec]
         self.heads = [int(h) for h in heads]
-        F = int(box_dim) if box_dim is not None else sum(self.nvec)
+        # extra_inputs: AdapPolicy's context columns behind the features (adap/policies.py:71-84)
+        F = (int(box_dim) if box_dim is not None else sum(self.nvec)) + int(extra_inputs)
         self.F, self.L = F, sum(self.heads)
         # creation order pi0, vf0, pi1, vf1 (MlpExtractor interleaves), then heads
         pi0, vf0 = nn.Linear(F, 64), nn.Linear(F, 64)
@@ -195,4 +196,89 @@ def bc_train(policy, obs, actions, perms, batch_size=32, ent_weight=1e-3, l2_wei
         for s in range(0, M, batch_size):
             idx = perm[s:s + batch_size]
             stats.append(bc_minibatch_step(policy, opt, obs[idx], actions[idx], ent_weight, l2_weight))
+    return stats
+
+
+class AdapMlpPolicy(MlpPolicy):
+    """AdapPolicy (pantheonrl/algos/adap/policies.py:21-131): the MlpPolicy whose two towers read
+    cat(features, context); `context` is a [1, C] tensor the policy carries (set_context / get_context),
+    and evaluate_actions takes rows of raw observation ++ the context stored with the sample."""
+
+    def __init__(self, nvec=None, heads=(3,), box_dim=None, context_size=3, seed=None, **kw):
+        super().__init__(nvec=nvec, heads=heads, box_dim=box_dim, seed=seed, extra_inputs=context_size, **kw)
+        self.context_size = int(context_size)
+        self.context = th.zeros(1, self.context_size)
+
+    def set_context(self, ctxt):
+        self.context = ctxt
+
+    def get_context(self):
+        return self.context
+
+    def latent_pi(self, obs, context):
+        """policy tower on `obs` rows with one context [1, C] for all of them (adap/policies.py:86-106)."""
+        x = self.features(obs)
+        x = th.cat((x, th.as_tensor(context).float().reshape(1, -1).repeat(x.shape[0], 1)), dim=1)
+        return self.policy_net(x)
+
+    def evaluate_actions(self, obs, actions):
+        obs = th.as_tensor(np.asarray(obs)).float()
+        x = th.cat((self.features(obs[:, :-self.context_size]), obs[:, -self.context_size:]), dim=1)
+        latent_pi, latent_vf = self.policy_net(x), self.value_net_body(x)
+        _, dists = self._dists(latent_pi)
+        actions = th.as_tensor(np.asarray(actions)).long()
+        actions = actions.reshape(actions.shape[0], -1)
+        log_prob = th.stack([d.log_prob(actions[:, h]) for h, d in enumerate(dists)], dim=1).sum(dim=1)
+        entropy = th.stack([d.entropy() for d in dists], dim=1).sum(dim=1)
+        return self.value_net(latent_vf), log_prob, entropy
+
+
+def adap_context_loss(policy, obs_rows, sidx, contexts):
+    """get_context_kl_loss (pantheonrl/algos/adap/util.py:97-131) with the random draws handed in:
+    `sidx` = th.randperm(B)[:num_state_samples], `contexts` [K, C] = the K sampled contexts.
+    mean over the K (K - 1) / 2 context pairs of mean_states exp(-KL(dist_a || dist_b))."""
+    from itertools import combinations
+    states = th.as_tensor(np.asarray(obs_rows)).float()[:, :-policy.context_size][th.as_tensor(np.asarray(sidx)).long()]
+    dists = [policy._dists(policy.latent_pi(states, c))[1] for c in th.as_tensor(np.asarray(contexts)).float()]
+    kl = lambda a, b: sum(th.distributions.kl.kl_divergence(p, q) for p, q in zip(a, b))  # noqa: E731
+    cls = [th.mean(th.exp(-kl(a, b))) for a, b in combinations(dists, 2)]
+    return sum(cls) / len(cls)
+
+
+def adap_minibatch_step(policy, obs, actions, old_log_prob, advantages, returns, sidx, contexts, context_loss_coeff=0.1,
+                        clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5):
+    """One iteration of the inner loop of ADAP.train (adap_learn.py:252-346): PPO's losses + the context loss."""
+    advantages = th.as_tensor(advantages).float()
+    returns = th.as_tensor(returns).float()
+    old_log_prob = th.as_tensor(old_log_prob).float()
+    values, log_prob, entropy = policy.evaluate_actions(obs, actions)
+    values = values.flatten()
+    advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+    ratio = th.exp(log_prob - old_log_prob)
+    policy_loss = -th.min(advantages * ratio, advantages * th.clamp(ratio, 1 - clip_range, 1 + clip_range)).mean()
+    value_loss = nn.functional.mse_loss(returns, values)
+    entropy_loss = -th.mean(entropy)
+    context_loss = adap_context_loss(policy, obs, sidx, contexts)
+    loss = policy_loss + ent_coef * entropy_loss + vf_coef * value_loss + context_loss_coeff * context_loss
+    policy.optimizer.zero_grad()
+    loss.backward()
+    grad = policy.flat_grad()
+    total_norm = th.nn.utils.clip_grad_norm_(policy.ordered_parameters(), max_grad_norm)
+    policy.optimizer.step()
+    return dict(pg_loss=policy_loss.item(), value_loss=value_loss.item(), entropy_loss=entropy_loss.item(),
+                context_loss=context_loss.item(), loss=loss.item(), grad_norm=float(total_norm), grad=grad)
+
+
+def adap_train(policy, obs, actions, old_log_prob, advantages, returns, perms, batch_size, sidx, contexts, **kw):
+    """ADAP.train over a flattened buffer; sidx [n_mb_total, S] (rows may be short: -1 padded), contexts
+    [n_mb_total, K, C]."""
+    stats, M, i = [], len(advantages), 0
+    for perm in perms:
+        perm = np.asarray(perm)
+        for s0 in range(0, M, batch_size):
+            idx = perm[s0:s0 + batch_size]
+            si = np.asarray(sidx[i])
+            stats.append(adap_minibatch_step(policy, obs[idx], actions[idx], old_log_prob[idx], advantages[idx],
+                                             returns[idx], si[si >= 0][:len(idx)], contexts[i], **kw))
+            i += 1
     return stats

@@ -22,6 +22,8 @@ class OrcUpdateArgs(C.Structure):
         ("normalize_advantage", C.c_int32), ("grid", C.c_int32), ("world", C.c_int32),
         ("stats", C.c_void_p), ("grad_out", C.c_void_p),
         ("loss_kind", C.c_int32), ("l2_weight", C.c_float),
+        ("context_size", C.c_int32), ("ctx", C.c_void_p), ("ctx_loss_coeff", C.c_float),
+        ("n_ctx", C.c_int32), ("n_states", C.c_int32), ("ctx_sidx", C.c_void_p), ("ctx_draws", C.c_void_p), ("ctx_loss_out", C.c_void_p),
     ]
 
 
@@ -45,7 +47,8 @@ def index_build(count, T, N):
 def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp, advantages,
                returns, perm, batch_size, grid, index=None, learning_rate=3e-4, clip_range=0.2,
                ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, betas=(0.9, 0.999), eps=1e-5,
-               normalize_advantage=True, world=1, loss_kind=0, l2_weight=0.0):
+               normalize_advantage=True, world=1, loss_kind=0, l2_weight=0.0, ctx=None, ctx_loss_coeff=0.0,
+               ctx_sidx=None, ctx_draws=None):
     """Runs PPO.train on flat sample arrays; params / adam state are updated IN PLACE
     (float32 numpy arrays). Returns (stats [n_epochs*n_mb, 8], last pre-clip gradient)."""
     f32 = lambda x: np.ascontiguousarray(x, np.float32)  # noqa: E731
@@ -78,8 +81,21 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     a.adam_beta1, a.adam_beta2, a.adam_eps = betas[0], betas[1], eps
     a.normalize_advantage = int(normalize_advantage)
     a.loss_kind, a.l2_weight = int(loss_kind), float(l2_weight)
+    if ctx is not None:  # AdapPolicy: [rows][C] contexts stored with the samples
+        ctx = f32(ctx)
+        a.context_size, a.ctx = ctx.shape[1], ctx.ctypes.data
+    if ctx_sidx is not None:  # ADAP context loss: [n_epochs * n_mb][S] positions, [n_epochs * n_mb][K][C] contexts
+        ctx_sidx = np.ascontiguousarray(ctx_sidx, np.int32)
+        ctx_draws = f32(ctx_draws)
+        assert ctx_sidx.shape[0] == n_epochs * n_mb and ctx_draws.shape[0] == n_epochs * n_mb
+        a.ctx_loss_coeff, a.n_states, a.n_ctx = float(ctx_loss_coeff), ctx_sidx.shape[1], ctx_draws.shape[1]
+        a.ctx_sidx, a.ctx_draws = ctx_sidx.ctypes.data, ctx_draws.ctypes.data
+        ctx_loss = np.zeros(n_epochs * n_mb, np.float32)
+        a.ctx_loss_out = ctx_loss.ctypes.data
     a.grid = int(grid)
     a.world = int(world)
     a.stats, a.grad_out = stats.ctypes.data, grad.ctypes.data
     lib().orc_ppo_update(C.byref(a))
+    if ctx_sidx is not None:
+        return stats, grad, ctx_loss
     return stats, grad
