@@ -99,6 +99,11 @@ typedef struct pth_space {
 int pth_space_feature_dim(const pth_space* sp);
 int pth_space_logit_dim(const pth_space* sp);
 int64_t pth_policy_param_count(const pth_space* sp);
+/* AdapPolicy (pantheonrl/algos/adap/policies.py:21-131): the same network whose two first layers take
+ * `context_size` (<= 8) more inputs behind the features — `features = cat(features, context)` — so
+ * the two first-layer matrices have F + context_size rows (context rows last, same input-major
+ * layout) and every other tensor is unchanged. */
+int64_t pth_adap_param_count(const pth_space* sp, int32_t context_size);
 
 /* ------------------------------------------------------------------ */
 /* a4: GAE / returns                                                   */
@@ -282,6 +287,12 @@ typedef struct pth_forward_args {
    * draws q from torch's generator in the reference's order reproduces the reference's action stream
    * whenever the logits agree.  NULL: inverse-CDF sampling on the Philox stream (default). */
   const float* d_race;
+  /* AdapPolicy.forward / evaluate_actions (adap/policies.py:86-131): context_size > 0 selects the
+   * AdapPolicy parameter layout; d_context is fp32 [B][context_size] with row stride
+   * context_stride floats (0: one context for the whole batch, `self.context.repeat(B, 1)`). */
+  int32_t context_size;
+  const float* d_context;
+  int64_t context_stride;
 } pth_forward_args;
 int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream);
 /* debug / parity only: y[i] = f(x[i]) with the library's exp (which = 0), log (1, positive
@@ -438,11 +449,38 @@ typedef struct pth_update_args {
    * (without the l2 term), grad_norm, n. */
   int32_t loss_kind;
   float l2_weight;
+  /* AdapPolicy / ADAP.train (pantheonrl/algos/adap/adap_learn.py:229-347, adap/util.py:97-131).
+   * context_size > 0: the parameters are an AdapPolicy's (pth_adap_param_count) and d_context holds
+   * the context stored with every sample, fp32 [*][context_size], indexed by the same flat offset as
+   * the other sample arrays (AdapAgent.get_action stores obs ++ context: adap/agent.py:121-124).
+   * Needs rec_stride == 0, world == 1, at most 32 observation slots; workspace from
+   * pth_adap_workspace_bytes.
+   * loss_kind PTH_LOSS_ADAP adds `context_loss_coeff * context_loss` to PPO's loss.  Per minibatch
+   * id = epoch * n_minibatches + m (B samples) the caller supplies the random draws of
+   * get_context_kl_loss: d_ctx_states[id][num_state_samples] = positions inside the minibatch of the
+   * sampled states (`th.randperm(B)[:num_state_samples]`; only the first min(num_state_samples, B)
+   * are read) and d_ctx_draws[id][num_context_samples][context_size] = the sampled contexts
+   * (`SAMPLERS[context_sampler]`).  The policy tower is evaluated on every (state, context) pair,
+   * context_loss = mean over the K (K - 1) / 2 context pairs of mean_states exp(-KL(dist_a || dist_b)),
+   * and its gradient flows into the policy tower and the action head.  d_stats column 5 (loss)
+   * includes the term; d_ctx_loss (optional, [n_epochs * n_minibatch]) receives the context loss
+   * itself (`train/context_kl_loss`, adap_learn.py:358). */
+  int32_t context_size;
+  const float* d_context;
+  float context_loss_coeff;
+  int32_t num_context_samples;  /* K: 2 .. 16 */
+  int32_t num_state_samples;    /* S */
+  const int32_t* d_ctx_states;
+  const float* d_ctx_draws;
+  float* d_ctx_loss;
 } pth_update_args;
 #define PTH_LOSS_PPO 0
 #define PTH_LOSS_BC 1
+#define PTH_LOSS_ADAP 2
 int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
                                    int64_t M, int64_t batch_size);
+int64_t pth_adap_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
+                                 int64_t M, int64_t batch_size);
 /* Number of CTAs the persistent cooperative update kernel will run with for
  * this problem (it is part of the reduction contract: tile t of a minibatch is
  * summed by CTA t mod grid, CTAs are added in ascending order). */

@@ -18,7 +18,7 @@ PTH_ENV_RPS, PTH_ENV_LIAR, PTH_ENV_OVERCOOKED = 0, 1, 2
 PTH_OC_MAX_CELLS, PTH_OC_MAX_POTS, PTH_OC_OBS, PTH_OC_ROW = 128, 4, 62, 64
 PTH_OC_STATE_BYTES = 40
 PTH_OC_FLOOR, PTH_OC_COUNTER, PTH_OC_ONION, PTH_OC_POT, PTH_OC_DISH, PTH_OC_SERVE = range(6)
-PTH_LOSS_PPO, PTH_LOSS_BC = 0, 1
+PTH_LOSS_PPO, PTH_LOSS_BC, PTH_LOSS_ADAP = 0, 1, 2
 PTH_UPDATE_FLAG_WORDS = 16384  # include/pantheon_b200.h
 PTH_PACKED_BYTES, PTH_PACKED_BYTES_BOX = 48, 272
 
@@ -96,6 +96,9 @@ class ForwardArgs(C.Structure):
         ("d_entropy", C.c_void_p),
         ("d_logits", C.c_void_p),
         ("d_race", C.c_void_p),
+        ("context_size", C.c_int32),
+        ("d_context", C.c_void_p),
+        ("context_stride", C.c_int64),
     ]
 
 
@@ -207,6 +210,14 @@ class UpdateArgs(C.Structure):
         ("d_stats", C.c_void_p),
         ("loss_kind", C.c_int32),
         ("l2_weight", C.c_float),
+        ("context_size", C.c_int32),
+        ("d_context", C.c_void_p),
+        ("context_loss_coeff", C.c_float),
+        ("num_context_samples", C.c_int32),
+        ("num_state_samples", C.c_int32),
+        ("d_ctx_states", C.c_void_p),
+        ("d_ctx_draws", C.c_void_p),
+        ("d_ctx_loss", C.c_void_p),
     ]
 
 
@@ -242,6 +253,8 @@ SIGNATURES = {
     "pth_update_xbuf_bytes": (_i64, [C.POINTER(Space), _i32]),
     "pth_index_workspace_bytes": (_i64, [_i64]),
     "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
+    "pth_adap_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
+    "pth_adap_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
     "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),
     "pth_debug_update_profile": (C.c_int, [_vp]),
     "pth_pack_transitions": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),

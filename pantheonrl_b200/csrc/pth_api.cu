@@ -125,4 +125,9 @@ int64_t pth_policy_param_count(const pth_space* sp) {
   return 2 * (H * F + H + H * H + H) + L * H + L + H + 1;
 }
 
+int64_t pth_adap_param_count(const pth_space* sp, int32_t context_size) {
+  if (!space_ok(sp) || context_size < 0 || context_size > 8) return PTH_EINVAL;
+  return pth_policy_param_count(sp) + 2 * (int64_t)PTH_HIDDEN * context_size;
+}
+
 }  // extern "C"

@@ -239,7 +239,7 @@ __device__ __forceinline__ void tanh_own_quads(float* Out, int tid, F index_of) 
 // W input-major [F][64] in global memory (L1/L2 resident).  Same thread tile as
 // dense64: SPT samples x JT contiguous outputs; Out[j][b] = tanh(bias[j] +
 // sum_k fma(X[k][b], W[k][j], .)), k ascending.
-template <bool COHERENT = false, int NTH = NT, int BTS = BT>
+template <bool COHERENT = false, int NTH = NT, int BTS = BT, bool TANH = true>
 __device__ __forceinline__ void first_layer_box(int F, const float* X, const float* W,
                                                 const float* bias_s, float* Out, int tid) {
   constexpr int LDA = BTS + 4;
@@ -288,7 +288,33 @@ __device__ __forceinline__ void first_layer_box(int F, const float* X, const flo
     if constexpr (SPT == 8)
       *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(acc[jj][4], acc[jj][5], acc[jj][6], acc[jj][7]);
   }
-  tanh_own_quads<JT * (SPT / 4)>(Out, tid, [&](int q) { return (ty * JT + q / (SPT / 4)) * LDA + (q % (SPT / 4)) * 64 + tx * 4; });
+  if constexpr (TANH)
+    tanh_own_quads<JT * (SPT / 4)>(Out, tid, [&](int q) { return (ty * JT + q / (SPT / 4)) * LDA + (q % (SPT / 4)) * 64 + tx * 4; });
+}
+
+// AdapPolicy (pantheonrl/algos/adap/policies.py:86-106: features = cat(features, context)): the C
+// context inputs continue the first layer's chain behind the features, c ascending, then tanh:
+// Out[j][b] = tanh(fma(ctx[C-1][b], Wc[C-1][j], ... fma(ctx[0][b], Wc[0][j], Out[j][b]))).
+// Out holds the pre-activations (first layer run without tanh); Cx: [C][LDA] context values per
+// sample in shared memory; Wc: rows F .. F + C - 1 of the input-major first-layer matrix (global).
+// Warp w of the NW warps owns outputs w, w + NW, ...; lane owns samples lane, lane + 32, ...
+template <bool COHERENT = false, int BTS = BT>
+__device__ __forceinline__ void context_columns_tanh(int C, const float* Cx, const float* Wc, float* Out,
+                                                     int warp, int n_warps, int lane) {
+  constexpr int LDA = BTS + 4;
+  for (int j = warp; j < HID; j += n_warps) {
+    float w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = c < C ? ld_param<COHERENT>(Wc + c * HID + j) : 0.f;
+#pragma unroll 1
+    for (int b = lane; b < BTS; b += 32) {
+      float z = Out[j * LDA + b];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < C) z = fmaf(Cx[c * LDA + b], w[c], z);
+      Out[j * LDA + b] = pth_tanhf(z);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------

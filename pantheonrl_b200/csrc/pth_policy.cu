@@ -36,6 +36,11 @@ struct FwdParams {
   float* entropy;
   float* logits;
   const float* race;
+  // AdapPolicy (pantheonrl/algos/adap/policies.py:86-131): C context inputs behind the features
+  int C;
+  const float* ctx;
+  int64_t ctx_stride;
+  int cx_off;  // byte offset of the [8][LDA] context tile in dynamic shared memory
 };
 
 template <int OW>
@@ -44,6 +49,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
   float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem));
   uint8_t* obs_s = OW == 32 ? sm.obs : smem_raw + sizeof(FwdSmem);
+  float* Cx = reinterpret_cast<float*>(smem_raw + p.cx_off);
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * BT;
   const int64_t b = b0 + tid;
@@ -63,23 +69,31 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
       const float* src = reinterpret_cast<const float*>(p.obs);
       for (int k = 0; k < p.sp.F; ++k) Xs[k * LDA + tid] = live ? src[b * p.obs_stride + k] : 0.f;
     }
+    for (int c = 0; c < p.C; ++c) Cx[c * LDA + tid] = live ? p.ctx[b * p.ctx_stride + c] : 0.f;
   }
   __syncthreads();
+  // first layer of one tower into sm.A; AdapPolicy: the context inputs continue the chains, then tanh
+  auto first_layer = [&](int w_off, const float* bias) {
+    if (p.sp.obs_kind == PTH_OBS_ONEHOT)
+      first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + w_off, bias, sm.A, tid, p.C == 0);
+    else if (p.C == 0)
+      first_layer_box<false>(p.sp.F, Xs, p.params + w_off, bias, sm.A, tid);
+    else
+      first_layer_box<false, NT, BT, false>(p.sp.F, Xs, p.params + w_off, bias, sm.A, tid);
+    if (p.C > 0) {
+      __syncthreads();
+      context_columns_tanh<false>(p.C, Cx, p.params + w_off + p.sp.F * HID, sm.A, tid >> 5, NT / 32, tid & 31);
+    }
+  };
 
   // ---- policy tower
-  if (p.sp.obs_kind == PTH_OBS_ONEHOT)
-    first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
-  else
-    first_layer_box<false>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.A, tid);
+  first_layer(p.lo.w_pi0, sm.pol.b_pi0);
   __syncthreads();
   dense64<true>(sm.A, sm.pol.w_pi1, sm.pol.b_pi1, sm.Bf, tid);
   __syncthreads();
   if (lane) action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
   // ---- value tower (A is free again)
-  if (p.sp.obs_kind == PTH_OBS_ONEHOT)
-    first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
-  else
-    first_layer_box<false>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.A, tid);
+  first_layer(p.lo.w_vf0, sm.pol.b_vf0);
   __syncthreads();
   dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, sm.Bf, tid);
   __syncthreads();
@@ -168,7 +182,13 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   }
   PTH_CHECK_ARG(a->obs_stride >= p.sp.obs_len, "obs_stride smaller than obs_len");
   PTH_CHECK_ARG(((uintptr_t)a->d_params % 16) == 0, "params must be 16-byte aligned");
-  p.lo = make_layout(p.sp.F, p.sp.L);
+  PTH_CHECK_ARG(a->context_size >= 0 && a->context_size <= 8 && (a->context_size == 0 || a->d_context != nullptr),
+                "context_size 0..8 with d_context");
+  PTH_CHECK_ARG(a->context_stride == 0 || a->context_stride >= a->context_size, "context_stride smaller than context_size");
+  p.C = a->context_size;
+  p.ctx = a->d_context;
+  p.ctx_stride = a->context_stride;
+  p.lo = make_layout(p.sp.F + p.C, p.sp.L);
   p.params = a->d_params;
   p.obs = a->d_obs;
   p.obs_stride = a->obs_stride;
@@ -187,6 +207,8 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   p.race = a->d_race;
   const bool wide = p.sp.obs_kind == PTH_OBS_ONEHOT && p.sp.obs_len > 32;
   size_t smem = sizeof(FwdSmem) + (p.sp.obs_kind == PTH_OBS_BOX ? sizeof(float) * HID * LDA : 0) + (wide ? BT * 96 : 0);
+  p.cx_off = (int)smem;
+  smem += p.C > 0 ? sizeof(float) * 8 * LDA : 0;
   if (wide) {
     PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     policy_forward_kernel<96><<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);

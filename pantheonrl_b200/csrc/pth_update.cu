@@ -38,7 +38,9 @@ constexpr int STAGE_ROWS = 160;  // first-layer rows per tower staged in shared 
 // only occur in the host-driven n_envs = 1 flow, so the wide kernel keeps the plain first layer
 // (every row gathered per sample) and spends the shared memory on the wider tiles instead of on
 // the row stage and the chain beginnings.
-template <bool WIDE>
+// PLAIN: the first layers gather every row per sample from L1 / L2 (no row stage, no chain
+// beginnings): the wide spaces, and ADAP (host-driven batches of 64 samples: set-up would not pay).
+template <bool WIDE, bool PLAIN = WIDE>
 struct alignas(16) UpdSmemT {
   static constexpr int OW = WIDE ? 96 : 32;  // bytes per observation row = slots supported
   SmemPolicy pol;
@@ -59,7 +61,7 @@ struct alignas(16) UpdSmemT {
   // MODE of slot s over the tile, pchain[t][j] = bias + row(S-1, d_{S-1}) + ... + row(j, d_j) for
   // tower t; a sample that agrees with the mode on every slot >= jb starts from pchain[t][jb] and
   // adds only its slots jb-1 .. 0 — the same additions in the same order, hence the same bits.
-  float pchain[2][WIDE ? 4 : (32 + 1) * HID];
+  float pchain[2][PLAIN ? 4 : (32 + 1) * HID];
   uint8_t dmode[OW];    // mode value per slot (0 beyond obs_len)
   uint8_t jb[BT];            // per sample: slots [0, jb) are its own
   // The rows of the two first-layer matrices that this tile's samples select (~92 of Liar's 270)
@@ -110,7 +112,17 @@ struct UpdParams {
   uint32_t flag_epoch;
   int XS;               // floats per (parity, rank) slot: P + 8 rounded up to 4
   long long* prof;      // debug: per-phase clock64 sums of CTA 0 (pth_debug_update_profile), or NULL
+  // ADAP (pantheonrl/algos/adap): C context inputs behind the features of both first layers, and the
+  // context loss of adap/util.py:97-131 as extra tiles of every minibatch
+  int C;                     // context_size (0: plain MlpPolicy)
+  const float* ctx;          // [rows][C] context stored with every sample
+  float ctx_coeff;           // context_loss_coeff; 0: no context tiles
+  int K, NS;                 // num_context_samples, num_state_samples
+  const int32_t* ctx_sidx;   // [n_epochs * n_mb][NS] positions inside the minibatch
+  const float* ctx_draws;    // [n_epochs * n_mb][K][C] sampled contexts
+  float* ctx_loss;           // [n_epochs * n_mb] or NULL
 };
+constexpr int MAX_CTX = 8;
 
 // phase timeline of CTA 0 (thread 0), accumulated over every minibatch of the launch
 #define PTH_PROF(i)                                   \
@@ -769,12 +781,12 @@ __device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const SM& sm,
 // The hidden-layer weight gradient (D1 x Ha^T) and the back-propagation through the hidden layer
 // (W^T x D1) only READ D1 / Ha, so they run side by side: each on one half of the CTA with the
 // large register tiles of a 256-thread group (the 512-thread tiles are shared-memory bound).
-template <bool BOX, class SM>
+template <bool BOX, bool ADAP = false, class SM>
 __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const float* Xs,
                                                const float* Ha, const float* w1_s, float* g_w0,
                                                float* g_b0, float* g_w1, float* g_b1, int nb,
                                                bool first, int tid, long long& prof_last, int c,
-                                               int pbase) {
+                                               int pbase, const float* Cx = nullptr) {
   __syncthreads();  // D1 complete
   PTH_PROF(pbase + 0);
   if (tid < UNT / 2) {
@@ -785,6 +797,16 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const
   }
   __syncthreads();  // dz1 complete (in H2)
   PTH_PROF(pbase + 1);  // backprop64 | wgrad64 + bias sums
+  if constexpr (ADAP) {
+    // context rows of the first-layer gradient (AdapPolicy: dense inputs behind the features):
+    // gW0[F + cc][j] = sum_b fma(dz1[j][b], ctx[cc][b], .), b ascending
+    if (tid < p.C * HID) {
+      const int cc = tid >> 6, j = tid & 63;
+      float acc = 0.f;
+      for (int b = 0; b < BT; ++b) acc = fmaf(BOX ? sm.H2[j * LDA + b] : sm.H2[b * LDT + j], Cx[cc * LDA + b], acc);
+      acc_store(g_w0 + (p.sp.F + cc) * HID + j, acc, first);
+    }
+  }
   if constexpr (BOX) {
     row_sums(sm.H2, HID, g_b0, first, tid, UNT - HID);
     wgrad_first_box(sm.H2, Xs, p.sp.F, g_w0, first, tid);
@@ -811,10 +833,12 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const
   segsum_w1_mode(p, sm, sm.bc, g_w0, first, tid, csum);
 }
 
-template <bool BOX, bool WIDE = false>
+template <bool BOX, bool WIDE = false, bool ADAP = false>
 __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
   static_assert(!(BOX && WIDE), "wide rows are a one-hot notion");
-  using UpdSmem = UpdSmemT<WIDE>;
+  static_assert(!(ADAP && WIDE), "ADAP: one-hot rows of 32 slots or Box rows");
+  constexpr bool PLAIN = WIDE || ADAP;
+  using UpdSmem = UpdSmemT<WIDE, PLAIN>;
   constexpr int OW = UpdSmem::OW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UpdSmem& sm = *reinterpret_cast<UpdSmem*>(smem_raw);
@@ -823,6 +847,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
   // tower's at the start of the tile and kept until the value tower runs.
   float* Xs = reinterpret_cast<float*>(smem_raw + sizeof(UpdSmem));
   float* V1 = BOX ? sm.H1 : Xs;
+  // ADAP: behind Xs / V1, the context values of the tile's samples, [MAX_CTX][LDA]
+  [[maybe_unused]] float* Cx = Xs + HID * LDA;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x;
   const int G = gridDim.x;
@@ -921,7 +947,20 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         mean = ll_wait(ax, adv_tag, a0);
         stdv = ll_wait(ax + 1, adv_tag, a1);
       }
-      const int64_t n_tiles = (B + BT - 1) / BT;
+      const int64_t n_main = (B + BT - 1) / BT;
+      // ADAP context loss (adap/util.py:97-131): K sampled contexts on S_eff sampled states of the
+      // minibatch, as extra tiles behind the minibatch's own: a context tile holds SC = 128 / K
+      // states x K contexts (column = k * ns + state), so every pair of distributions of a state
+      // meets inside one tile
+      [[maybe_unused]] int S_eff = 0, SC = 1, n_ctx_tiles = 0;
+      if constexpr (ADAP) {
+        if (p.ctx_coeff != 0.f && p.K >= 2) {
+          S_eff = (int)(p.NS < B ? p.NS : B);
+          SC = BT / p.K;
+          n_ctx_tiles = (S_eff + SC - 1) / SC;
+        }
+      }
+      const int64_t n_tiles = n_main + n_ctx_tiles;
       const int64_t local_tiles = (n_tiles - p.rank + W - 1) / W;  // tile t belongs to rank t mod W
       const int A = (int)(local_tiles < G ? local_tiles : G);
 
@@ -930,12 +969,23 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, UNT);
       PTH_PROF(1);  // weights -> smem
       float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      [[maybe_unused]] float cta_ctx = 0.f;  // ADAP (thread 0): sum over this CTA's context tiles of sum_states sum_pairs exp(-KL)
       bool first = true;
 
       for (int64_t tau = p.rank + (int64_t)W * c; tau < n_tiles; tau += (int64_t)W * G) {
         const int64_t t0 = tau * BT;
-        const int nb = (int)((B - t0 < BT) ? (B - t0) : BT);
+        const bool ctile = ADAP && tau >= n_main;
+        [[maybe_unused]] const int ct = (int)(tau - n_main);
+        [[maybe_unused]] const int ns = ctile ? ((S_eff - ct * SC < SC) ? (S_eff - ct * SC) : SC) : 1;
+        const int nb = ctile ? p.K * ns : (int)((B - t0 < BT) ? (B - t0) : BT);
         const bool valid = tid < nb;
+        // flat offset of the sample in column `col` of this tile
+        auto tile_off = [&](int col) -> int64_t {
+          if constexpr (ADAP) {
+            if (ctile) return sample_offset(p, e, i0 + __ldg(p.ctx_sidx + id * p.NS + ct * SC + col % ns));
+          }
+          return sample_offset(p, e, i0 + t0 + col);
+        };
         // ---- gather this thread's sample
         uint32_t act = 0;
         float adv = 0.f, oldlp = 0.f, ret = 0.f;
@@ -950,7 +1000,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
 #pragma unroll
           for (int i = 0; i < XQ; ++i) xrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (b < nb) {
-            const int64_t offb = sample_offset(p, e, i0 + t0 + b);
+            const int64_t offb = tile_off(b);
             const float4* q = reinterpret_cast<const float4*>(p.obs + offb * p.obs_stride) + (tid >> 7) * XQ;
 #pragma unroll
             for (int i = 0; i < XQ; ++i) xrow[i] = __ldg(q + i);
@@ -958,8 +1008,21 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         }
         const int sb = tid & (BT - 1);  // the sample this thread works on in the per-sample phases
         const bool svalid = sb < nb;
+        [[maybe_unused]] float cxv[MAX_CTX];
+        if constexpr (ADAP) {
+#pragma unroll
+          for (int cc = 0; cc < MAX_CTX; ++cc) cxv[cc] = 0.f;
+        }
         if (svalid) {
-          const int64_t off = sample_offset(p, e, i0 + t0 + sb);
+          const int64_t off = tile_off(sb);
+          if constexpr (ADAP) {
+            if (valid) {  // the context stored with the sample, or the sampled context k = column / ns
+              const float* src = ctile ? p.ctx_draws + ((size_t)id * p.K + tid / ns) * p.C : p.ctx + off * p.C;
+#pragma unroll
+              for (int cc = 0; cc < MAX_CTX; ++cc)
+                if (cc < p.C) cxv[cc] = __ldg(src + cc);
+            }
+          }
           if constexpr (!BOX) {
             if (valid) {
               const uint4* q = reinterpret_cast<const uint4*>(p.obs + off * p.obs_stride);
@@ -990,6 +1053,12 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           for (int i = 0; i < OQ; ++i) *reinterpret_cast<uint4*>(&sm.obs[tid * (OW / 4) + 4 * i]) = orow[i];
           if (tid == 0) sm.n_staged = 0;
         }
+        if constexpr (ADAP) {
+          if (lane) {
+#pragma unroll
+            for (int cc = 0; cc < MAX_CTX; ++cc) Cx[cc * LDA + tid] = cxv[cc];
+          }
+        }
         __syncthreads();
         PTH_PROF(2);  // sample gather
         // (moving the sort into the shadow of the head phase, onto the warps without a head, was
@@ -998,7 +1067,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           sort_slots(p, sm, obs_s, nb, tid & 31, tid >> 5, UNT / 32);
           __syncthreads();  // order / rcount / dmode / rowmap complete; the sort's scratch (rowpos) is free
           PTH_PROF(22);  // slot sort + row numbering
-          if constexpr (!WIDE) {
+          if constexpr (!PLAIN) {
             chain_setup(p, sm, sm.H2, nb, tid);
             __syncthreads();
           }
@@ -1007,16 +1076,16 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
 
         // ================= policy tower: forward
         if constexpr (BOX) {
-          first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
+          first_layer_box<true, UNT, BT, !ADAP>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         } else {
           // both towers' first layers (latency-bound row gathers) side by side, one per CTA half
-          if constexpr (WIDE) {
+          if constexpr (PLAIN) {
             if (tid < UNT / 2)
               first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1,
-                                                            tid);
+                                                            tid, !ADAP);
             else
               first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, V1,
-                                                            tid - UNT / 2);
+                                                            tid - UNT / 2, !ADAP);
           } else if (tid < UNT / 2) {
             first_layer_chain<UNT / 2>(p, sm, obs_s, p.params + p.lo.w_pi0, sm.H2, 0, sm.pchain[0], sm.H1, tid);
           } else {
@@ -1025,6 +1094,16 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           }
         }
         __syncthreads();
+        if constexpr (ADAP) {
+          // the context inputs continue the chains, then tanh (one-hot: one tower per CTA half)
+          if constexpr (BOX)
+            context_columns_tanh<true>(p.C, Cx, p.params + p.lo.w_pi0 + p.sp.F * HID, sm.H1, tid >> 5, UNT / 32,
+                                       tid & 31);
+          else
+            context_columns_tanh<true>(p.C, Cx, p.params + (tid < UNT / 2 ? p.lo.w_pi0 : p.lo.w_vf0) + p.sp.F * HID,
+                                       tid < UNT / 2 ? sm.H1 : V1, (tid >> 5) & (UNT / 64 - 1), UNT / 64, tid & 31);
+          __syncthreads();
+        }
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
         dense64<true, UNT / 2, BT / 2, LDA>(sm.H1 + (tid >> 8) * (BT / 2), sm.pol.w_pi1, sm.pol.b_pi1,
                                              sm.H2 + (tid >> 8) * (BT / 2), tid & (UNT / 2 - 1));
@@ -1033,7 +1112,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
         logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
         __syncthreads();
-        {
+        if (!ctile) {
           // ---- per-sample losses and d loss / d logits.  Thread group h (threads [128h, 128h + 128))
           // evaluates head h of sample sb: same values as dist_eval (pth_mlp.cuh), with every exp
           // computed once (the softmax probabilities are parked in the sample's column of sm.D1,
@@ -1120,6 +1199,89 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
             }
           }
         }
+        if constexpr (ADAP) {
+          if (ctile) {
+            // ---- context loss of this tile's states (adap/util.py:97-131): mean over the K (K - 1) / 2 pairs
+            // of mean_states exp(-KL(dist_a || dist_b)), dist_k = the policy head under context k.
+            // Thread group h turns head h of every column into probabilities (D1 rows [0, L)) and
+            // log-probabilities (D1 rows [32, 32 + L)) and clears the column's dlogits; then one thread
+            // per state walks the pairs in ascending order, adding into the two columns' dlogits
+            //   d KL / d z_a = p_a ((lp_a - lp_b) - KL_h),   d KL / d z_b = p_b - p_a   (per head h).
+            float* Pr = sm.D1;
+            float* LP = sm.D1 + MAXL * LDA;
+            static_assert(2 * MAXL <= HID, "probabilities and log-probabilities share D1");
+            const int hh = tid >> 7;
+            if (hh < p.sp.n_heads) {
+              int off = 0;
+              for (int h = 0; h < hh; ++h) off += p.sp.head_n[h];
+              const int n = p.sp.head_n[hh];
+              float mx = sm.Lg[off * LDA + sb];
+              for (int i = 1; i < n; ++i) {
+                const float z = sm.Lg[(off + i) * LDA + sb];
+                mx = z > mx ? z : mx;
+              }
+              float Ssum = 0.f;
+              for (int i = 0; i < n; ++i) {
+                const float ex = pth_expf(sm.Lg[(off + i) * LDA + sb] - mx);
+                Pr[(off + i) * LDA + sb] = ex;
+                Ssum = Ssum + ex;
+              }
+              const float logS = pth_logf(Ssum);
+              for (int i = 0; i < n; ++i) {
+                LP[(off + i) * LDA + sb] = (sm.Lg[(off + i) * LDA + sb] - mx) - logS;
+                Pr[(off + i) * LDA + sb] = Pr[(off + i) * LDA + sb] / Ssum;
+                sm.Lg[(off + i) * LDA + sb] = 0.f;
+              }
+            }
+            __syncthreads();
+            if (tid < ns) {
+              const float NPf = (float)(p.K * (p.K - 1) / 2), Sf = (float)S_eff;
+              float esum = 0.f;
+              for (int ka = 0; ka < p.K; ++ka)
+                for (int kb = ka + 1; kb < p.K; ++kb) {
+                  const int ca = ka * ns + tid, cb = kb * ns + tid;
+                  float klh[PTH_MAX_HEADS], kl = 0.f;
+                  int o = 0;
+#pragma unroll
+                  for (int h = 0; h < PTH_MAX_HEADS; ++h) {
+                    klh[h] = 0.f;
+                    if (h < p.sp.n_heads) {
+                      float acc = 0.f;
+                      for (int i = 0; i < p.sp.head_n[h]; ++i)
+                        acc = fmaf(Pr[(o + i) * LDA + ca], LP[(o + i) * LDA + ca] - LP[(o + i) * LDA + cb], acc);
+                      klh[h] = acc;
+                      kl = kl + acc;
+                      o += p.sp.head_n[h];
+                    }
+                  }
+                  const float ex = pth_expf(-kl);
+                  esum = esum + ex;
+                  const float g = -(((p.ctx_coeff * ex) / NPf) / Sf);
+                  o = 0;
+#pragma unroll
+                  for (int h = 0; h < PTH_MAX_HEADS; ++h) {
+                    if (h < p.sp.n_heads) {
+                      for (int i = 0; i < p.sp.head_n[h]; ++i) {
+                        const float pa = Pr[(o + i) * LDA + ca], pb = Pr[(o + i) * LDA + cb];
+                        const float da = pa * ((LP[(o + i) * LDA + ca] - LP[(o + i) * LDA + cb]) - klh[h]);
+                        const float db = pb - pa;
+                        sm.Lg[(o + i) * LDA + ca] = sm.Lg[(o + i) * LDA + ca] + g * da;
+                        sm.Lg[(o + i) * LDA + cb] = sm.Lg[(o + i) * LDA + cb] + g * db;
+                      }
+                      o += p.sp.head_n[h];
+                    }
+                  }
+                }
+              sm.bc[tid] = esum;
+            }
+            __syncthreads();
+            if (tid == 0) {  // the tile's states in ascending order, then this CTA's context tiles in order
+              float t = 0.f;
+              for (int sl = 0; sl < ns; ++sl) t = t + sm.bc[sl];
+              cta_ctx = first ? t : cta_ctx + t;
+            }
+          }
+        }
         __syncthreads();  // dlogits complete
         PTH_PROF(5);  // action head + losses + dlogits
         // ================= policy tower: backward
@@ -1151,15 +1313,31 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           }
         }
         PTH_PROF(6);  // head wgrad | dz2
-        tower_backward<BOX>(p, sm, Xs, sm.H1, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
-                            part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid, prof_last, c, 18);
+        tower_backward<BOX, ADAP>(p, sm, Xs, sm.H1, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0,
+                                  part + p.lo.w_pi1, part + p.lo.b_pi1, nb, first, tid, prof_last, c, 18, Cx);
         PTH_PROF(7);  // pi tower backward (wgrad64, backprop64, first-layer gradient)
 
-        // ================= value tower
+        // ================= value tower (a context tile has none: a CTA whose first tile is one
+        // stores zeros for the value tower's and the value head's sums)
+        if constexpr (ADAP) {
+          if (ctile) {
+            if (first) {
+              for (int i = p.lo.w_vf0 + tid; i < p.lo.w_act; i += UNT) part[i] = 0.f;
+              for (int i = p.lo.w_val + tid; i < P; i += UNT) part[i] = 0.f;
+            }
+            first = false;
+            continue;
+          }
+        }
         __syncthreads();
         if constexpr (BOX) {
-          first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
+          first_layer_box<true, UNT, BT, !ADAP>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, sm.H1, tid);
           __syncthreads();
+          if constexpr (ADAP) {
+            context_columns_tanh<true>(p.C, Cx, p.params + p.lo.w_vf0 + p.sp.F * HID, sm.H1, tid >> 5, UNT / 32,
+                                       tid & 31);
+            __syncthreads();
+          }
         }
         PTH_PROF(8);  // vf first layer (one-hot: done with the policy tower's)
         dense64<true, UNT / 2, BT / 2, LDA>(V1 + (tid >> 8) * (BT / 2), sm.pol.w_vf1, sm.pol.b_vf1,
@@ -1197,8 +1375,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           acc_store(part + p.lo.b_val, s, first);
         }
         PTH_PROF(10);  // value head + its gradients
-        tower_backward<BOX>(p, sm, Xs, V1, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
-                            part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid, prof_last, c, 20);
+        tower_backward<BOX, ADAP>(p, sm, Xs, V1, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0,
+                                  part + p.lo.w_vf1, part + p.lo.b_vf1, nb, first, tid, prof_last, c, 20, Cx);
         PTH_PROF(11);  // vf tower backward
 
         // ---- tile statistics: the five 128-lane trees of the contract in one pass (xor tree inside
@@ -1223,6 +1401,9 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         first = false;
       }
       if (tid < 5) p.stat_part[c * 8 + tid] = cta_stat[tid];
+      if constexpr (ADAP) {
+        if (tid == 0) p.stat_part[c * 8 + 5] = cta_ctx;
+      }
       PTH_PROF(12);  // tile statistics
       grid.sync();  // ---------------------------------------------- (1) partials written
       PTH_PROF(13);  // barrier 1 (includes waiting for the slowest CTA)
@@ -1294,20 +1475,21 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       // off the critical path of the parameter update (read back after barrier 2)
       if (c == G - 1 && (tid >> 5) == 4) {
         const int ln = tid & 31;
-        float* sc = sm.Lg;  // [5][160] scratch (free between tiles)
-        float t[5][5];
+        constexpr int NST = ADAP ? 6 : 5;  // ADAP: + the context-loss sum
+        float* sc = sm.Lg;  // [NST][160] scratch (free between tiles)
+        float t[NST][5];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
           const int cc = r * 32 + ln;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) t[i][r] = cc < A ? __ldcg(p.stat_part + cc * 8 + i) : 0.f;
+          for (int i = 0; i < NST; ++i) t[i][r] = cc < A ? __ldcg(p.stat_part + cc * 8 + i) : 0.f;
         }
 #pragma unroll
         for (int r = 0; r < 5; ++r)
 #pragma unroll
-          for (int i = 0; i < 5; ++i) sc[i * 160 + r * 32 + ln] = t[i][r];
+          for (int i = 0; i < NST; ++i) sc[i * 160 + r * 32 + ln] = t[i][r];
         __syncwarp();
-        if (ln < 5) {
+        if (ln < NST) {
           float s_ = 0.f;
           if (A > 0) {
             s_ = sc[ln * 160];
@@ -1404,7 +1586,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         // for it at barrier 3: profiles/scaling_r02.md) — then lanes 0..4 add them in rank order.
         float mine = 0.f;
         if (W == 1) {
-          if (tid < 5) mine = __ldcg(p.stat_part + G * 8 + tid);  // summed in CTA order during the reduce phase
+          if (tid < (ADAP ? 6 : 5)) mine = __ldcg(p.stat_part + G * 8 + tid);  // summed in CTA order during the reduce phase
         } else {
           const uint2* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
           float* sc = sm.Lg;  // [8][5] scratch (free between tiles)
@@ -1431,6 +1613,17 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           o[5] = (o[0] + p.ent_coef * o[2]) + p.vf_coef * o[1];
           o[6] = gnorm;
           o[7] = Bf;
+        }
+        if constexpr (ADAP) {
+          const float csum = __shfl_sync(0xffffffffu, mine, 5);
+          if (tid == 0) {
+            float cl = 0.f;
+            if (n_ctx_tiles > 0) {
+              cl = (csum / (float)(p.K * (p.K - 1) / 2)) / (float)S_eff;
+              p.stats[8 * id + 5] = p.stats[8 * id + 5] + p.ctx_coeff * cl;
+            }
+            if (p.ctx_loss) p.ctx_loss[id] = cl;
+          }
         }
       }
       PTH_PROF(16);  // clip + Adam
@@ -1549,17 +1742,28 @@ WsLayout ws_layout(int G, int P, int64_t n_stat) {
 constexpr size_t SMEM_ONEHOT = sizeof(UpdSmemT<false>) + sizeof(float) * HID * LDA;
 constexpr size_t SMEM_BOX = sizeof(UpdSmemT<false>) + sizeof(float) * HID * LDA;
 constexpr size_t SMEM_WIDE = sizeof(UpdSmemT<true>) + sizeof(float) * HID * LDA;
-static_assert(SMEM_ONEHOT <= 227 * 1024 && SMEM_WIDE <= 227 * 1024, "one CTA per SM: 227 KB of shared memory");
+// ADAP: + the [MAX_CTX][LDA] context tile behind Xs / V1
+constexpr size_t SMEM_ADAP = sizeof(UpdSmemT<false, true>) + sizeof(float) * (HID + MAX_CTX) * LDA;
+static_assert(SMEM_ONEHOT <= 227 * 1024 && SMEM_WIDE <= 227 * 1024 && SMEM_ADAP <= 227 * 1024,
+              "one CTA per SM: 227 KB of shared memory");
 
-// kernel variant: 0 one-hot rows of 32 bytes, 1 Box rows, 2 one-hot rows of 96 bytes
+// kernel variant: 0 one-hot rows of 32 bytes, 1 Box rows, 2 one-hot rows of 96 bytes; 3 / 4: the
+// AdapPolicy variants of 0 / 1 (context inputs + context-loss tiles)
 const void* update_fn(int kind) {
-  return kind == 1 ? (const void*)ppo_update_kernel<true, false>
-                   : (kind == 2 ? (const void*)ppo_update_kernel<false, true> : (const void*)ppo_update_kernel<false, false>);
+  switch (kind) {
+    case 1: return (const void*)ppo_update_kernel<true, false>;
+    case 2: return (const void*)ppo_update_kernel<false, true>;
+    case 3: return (const void*)ppo_update_kernel<false, false, true>;
+    case 4: return (const void*)ppo_update_kernel<true, false, true>;
+    default: return (const void*)ppo_update_kernel<false, false>;
+  }
 }
-size_t update_smem(int kind) { return kind == 1 ? SMEM_BOX : (kind == 2 ? SMEM_WIDE : SMEM_ONEHOT); }
+size_t update_smem(int kind) {
+  return kind == 1 ? SMEM_BOX : (kind == 2 ? SMEM_WIDE : (kind >= 3 ? SMEM_ADAP : SMEM_ONEHOT));
+}
 
 int max_coop_ctas(const pth_ctx* ctx, int kind = 0) {
-  static int cached[3] = {-1, -1, -1};
+  static int cached[5] = {-1, -1, -1, -1, -1};
   if (cached[kind] < 0) {
     const void* fn = update_fn(kind);
     const size_t smem = update_smem(kind);
@@ -1612,14 +1816,20 @@ extern "C" int pth_update_grid(const pth_ctx* ctx, const pth_space* sp, int64_t 
   return auto_grid(ctx, M, batch_size, 1, space_is_box(sp));
 }
 
-extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int64_t M,
-                                              int64_t batch_size) {
-  if (!ctx || !sp || M <= 0 || batch_size <= 0) return PTH_EINVAL;
-  const int64_t P = pth_policy_param_count(sp);
+extern "C" int64_t pth_adap_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
+                                            int64_t M, int64_t batch_size) {
+  if (!ctx || !sp || M <= 0 || batch_size <= 0 || context_size < 0 || context_size > MAX_CTX) return PTH_EINVAL;
+  const int64_t P = pth_adap_param_count(sp, context_size);
   if (P < 0) return PTH_EINVAL;
-  const int cap = max_coop_ctas(ctx, space_is_box(sp));  // worst case grid (tests may pin any G <= cap)
+  const int kind = context_size > 0 ? (sp->obs_kind == PTH_OBS_BOX ? 4 : 3) : space_is_box(sp);
+  const int cap = max_coop_ctas(ctx, kind);  // worst case grid (tests may pin any G <= cap)
   const int64_t n_mb = (M + batch_size - 1) / batch_size;
   return (int64_t)ws_layout(cap > 0 ? cap : 1, (int)P, 64 * n_mb).total;
+}
+
+extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int64_t M,
+                                              int64_t batch_size) {
+  return pth_adap_workspace_bytes(ctx, sp, 0, M, batch_size);
 }
 
 extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stream) {
@@ -1649,10 +1859,32 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     PTH_CHECK_ARG(a->d_obs != nullptr, "NULL d_obs");
     PTH_CHECK_ARG(p.sp.F <= MAX_ROWS, "one-hot feature width above 1024 is not supported");
   }
-  p.lo = make_layout(p.sp.F, p.sp.L);
+  // AdapPolicy (pantheonrl/algos/adap/policies.py:71-131): context_size inputs behind the features
+  const int C = a->context_size;
+  PTH_CHECK_ARG(C >= 0 && C <= MAX_CTX, "context_size above 8 is not supported");
+  PTH_CHECK_ARG(a->loss_kind != PTH_LOSS_ADAP || C > 0, "ADAP needs context_size > 0");
+  PTH_CHECK_ARG(C == 0 || (a->d_context != nullptr && a->rec_stride == 0 && a->world <= 1 && (box || p.sp.obs_len <= 32)),
+                "AdapPolicy: d_context rows, separate sample arrays, one GPU, at most 32 observation slots");
+  p.C = C;
+  p.ctx = a->d_context;
+  p.ctx_coeff = 0.f;
+  p.K = p.NS = 0;
+  p.ctx_sidx = nullptr;
+  p.ctx_draws = nullptr;
+  p.ctx_loss = a->d_ctx_loss;
+  if (a->loss_kind == PTH_LOSS_ADAP && a->context_loss_coeff != 0.f && a->num_context_samples >= 2) {
+    PTH_CHECK_ARG(a->num_context_samples <= 16 && a->num_state_samples >= 1 && a->d_ctx_states && a->d_ctx_draws,
+                  "ADAP context loss: 2..16 context samples, >= 1 state samples, d_ctx_states, d_ctx_draws");
+    p.ctx_coeff = a->context_loss_coeff;
+    p.K = a->num_context_samples;
+    p.NS = a->num_state_samples;
+    p.ctx_sidx = a->d_ctx_states;
+    p.ctx_draws = a->d_ctx_draws;
+  }
+  p.lo = make_layout(p.sp.F + C, p.sp.L);
   for (int i = 0; i < MAX_SLOTS; ++i)
     p.nvec[i] = (!box && i < p.sp.obs_len) ? (uint8_t)a->space->obs_nvec[i] : 0;
-  const int kind = box ? 1 : (p.sp.obs_len > 32 ? 2 : 0);
+  const int kind = C > 0 ? (box ? 4 : 3) : (box ? 1 : (p.sp.obs_len > 32 ? 2 : 0));
   const int cap = max_coop_ctas(ctx, kind);
   PTH_CHECK_ARG(cap <= 160, "more than 160 co-resident CTAs are not supported");
   if (cap < 1 || !ctx->coop_launch) {
@@ -1699,10 +1931,11 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.b2 = a->adam_beta2;
   p.eps = a->adam_eps;
   p.normalize = a->normalize_advantage;
-  p.loss_kind = a->loss_kind;
+  p.loss_kind = a->loss_kind == PTH_LOSS_ADAP ? PTH_LOSS_PPO : a->loss_kind;  // ADAP = PPO's losses + context tiles
   p.l2 = a->l2_weight;
-  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->loss_kind == PTH_LOSS_BC, "bad loss_kind");
-  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->world <= 1, "behaviour cloning runs on one GPU");
+  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->loss_kind == PTH_LOSS_BC || a->loss_kind == PTH_LOSS_ADAP,
+                "bad loss_kind");
+  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->world <= 1, "behaviour cloning / ADAP run on one GPU");
   p.b1pow0 = pow((double)a->adam_beta1, (double)a->adam_step);
   p.b2pow0 = pow((double)a->adam_beta2, (double)a->adam_step);
   unsigned char* ws = reinterpret_cast<unsigned char*>(a->d_workspace);

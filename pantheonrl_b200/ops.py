@@ -115,11 +115,12 @@ def liar_step(state, is_ego, action):
 
 # ----------------------------------------------------------------------- policy
 def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=0, slot=0, idx0=0,
-                   action_in=None, want=("action", "value", "logp", "entropy", "logits"), race=None):
+                   action_in=None, want=("action", "value", "logp", "entropy", "logits"), race=None, context=None):
     """ActorCriticPolicy.forward (sampling) or evaluate_actions (action_in given).
 
     obs: [B, stride] uint8 (one-hot spaces) or float32 (Box). Returns a dict of
-    tensors for the names in ``want``."""
+    tensors for the names in ``want``.  context: AdapPolicy's context inputs, float32 [B, C] (one per
+    sample) or [C] / [1, C] (one for the whole batch); params then have the AdapPolicy layout."""
     _need(params, torch.float32, "params")
     if space.obs_kind == _lib.PTH_OBS_ONEHOT:
         _need(obs, torch.uint8, "obs")
@@ -160,6 +161,12 @@ def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=
         if tuple(race.shape) != (B, L):
             raise ValueError("race must be [B, L]")
         a.d_race = race.data_ptr()
+    if context is not None:
+        _need(context, torch.float32, "context")
+        a.context_size, a.d_context = context.shape[-1], context.data_ptr()
+        a.context_stride = context.shape[-1] if context.dim() == 2 and context.shape[0] == B and B > 1 else 0
+        if context.dim() == 2 and context.shape[0] not in (1, B):
+            raise ValueError("context must be [B, C], [1, C] or [C]")
     check(_lib.load().pth_policy_forward(_ctx(obs).handle, C.byref(a), current_stream()),
           "pth_policy_forward")
     _lib.count_launch()

@@ -43,9 +43,10 @@ def update_grid(space, M, batch_size, device=0):
 class UpdateWorkspace:
     """Caller-owned scratch for pth_ppo_update (the library never allocates)."""
 
-    def __init__(self, space, M, batch_size, device="cuda"):
+    def __init__(self, space, M, batch_size, device="cuda", context_size=0):
         ctx = Context.get(torch.device(device).index or 0)
-        n = int(_lib.load().pth_update_workspace_bytes(ctx.handle, C.byref(space), int(M), int(batch_size)))
+        n = int(_lib.load().pth_adap_workspace_bytes(ctx.handle, C.byref(space), int(context_size), int(M),
+                                                     int(batch_size)))
         if n <= 0:
             raise _lib.PthError("pth_update_workspace_bytes failed")
         self.buf = torch.empty(n, dtype=torch.uint8, device=device)
@@ -56,7 +57,8 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
                returns, perm, batch_size, workspace, index=None, M=None, rec_stride=0,
                learning_rate=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
                betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None,
-               peers=None, loss_kind=0, l2_weight=0.0):
+               peers=None, loss_kind=0, l2_weight=0.0, context=None, context_loss_coeff=0.0, ctx_states=None,
+               ctx_draws=None, ctx_loss=None):
     """SB3 PPO.train() over flat sample arrays on the device, in place on
     params / adam_m / adam_v. Returns the stats tensor [n_epochs * n_mb, 8]."""
     n_epochs = perm.shape[0]
@@ -91,6 +93,20 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     a.d_workspace, a.workspace_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
     a.d_stats = stats.data_ptr()
     a.loss_kind, a.l2_weight = int(loss_kind), float(l2_weight)
+    if context is not None:  # AdapPolicy: float32 [rows, C] contexts stored with the samples
+        if context.dtype != torch.float32 or not context.is_contiguous() or context.dim() != 2:
+            raise ValueError("context must be a contiguous float32 [rows, C] tensor")
+        a.context_size, a.d_context = context.shape[1], context.data_ptr()
+    if ctx_states is not None:  # ADAP context loss: int32 [n_epochs * n_mb, S], float32 [n_epochs * n_mb, K, C]
+        if ctx_states.dtype != torch.int32 or ctx_draws.dtype != torch.float32:
+            raise ValueError("ctx_states must be int32, ctx_draws float32")
+        if ctx_states.shape[0] != n_epochs * n_mb or ctx_draws.shape[0] != n_epochs * n_mb:
+            raise ValueError("one row of ctx_states / ctx_draws per minibatch")
+        a.context_loss_coeff = float(context_loss_coeff)
+        a.num_state_samples, a.num_context_samples = ctx_states.shape[1], ctx_draws.shape[1]
+        a.d_ctx_states, a.d_ctx_draws = ctx_states.data_ptr(), ctx_draws.data_ptr()
+        if ctx_loss is not None:
+            a.d_ctx_loss = ctx_loss.data_ptr()
     check(_lib.load().pth_ppo_update(_ctx(params).handle, C.byref(a), current_stream()), "pth_ppo_update")
     _lib.count_launch()
     return stats
