@@ -481,6 +481,25 @@ int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
                                    int64_t M, int64_t batch_size);
 int64_t pth_adap_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
                                  int64_t M, int64_t batch_size);
+/* The random draws of ADAP on the library's Philox streams (the reference takes them from torch's
+ * global generator: adap/util.py:42-94 SAMPLERS, :106 th.randperm; a host that wants the reference's
+ * own stream draws them itself and passes them to pth_ppo_update — both are plain arrays).
+ * For id in [0, n): d_draws[id][num_context_samples][context_size] = contexts from sampler
+ * 0 "l2" (uniform in [-1, 1)^C scaled to the unit sphere), 1 "unit_square", 2 "positive_square",
+ * 3 "categorical" (one-hot), 4 "natural_numbers" (context_size 1); and, when d_states != NULL,
+ * d_states[id][num_state_samples] = the first num_state_samples images of a keyed permutation of
+ * [0, B), B = size of minibatch id % n_minibatches of a buffer of M samples (-1 beyond B).
+ * Counter = index0 + id: a caller advances index0 by n per launch (and uses another stream_id
+ * for the per-episode context of a rollout: adap_learn.py:452-455, adap/agent.py:146-150). */
+#define PTH_ADAP_SAMPLER_L2 0
+#define PTH_ADAP_SAMPLER_UNIT_SQUARE 1
+#define PTH_ADAP_SAMPLER_POSITIVE_SQUARE 2
+#define PTH_ADAP_SAMPLER_CATEGORICAL 3
+#define PTH_ADAP_SAMPLER_NATURAL_NUMBERS 4
+int pth_adap_draw(pth_ctx* ctx, int32_t* d_states, float* d_draws, int64_t n, int64_t n_minibatches,
+                  int64_t M, int64_t batch_size, int32_t num_state_samples, int32_t num_context_samples,
+                  int32_t context_size, int32_t sampler, uint64_t seed, uint32_t stream_id,
+                  uint32_t index0, void* stream);
 /* Number of CTAs the persistent cooperative update kernel will run with for
  * this problem (it is part of the reduction contract: tile t of a minibatch is
  * summed by CTA t mod grid, CTAs are added in ascending order). */

@@ -1,6 +1,7 @@
 """CPU ORACLE (test infrastructure): Python driver for orc_ppo_update,
 orc_perm_feistel and orc_index_build (pth_oracle_update.inc)."""
 import ctypes as C
+import ctypes as C_
 
 import numpy as np
 
@@ -99,3 +100,17 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
     if ctx_sidx is not None:
         return stats, grad, ctx_loss
     return stats, grad
+
+
+SAMPLER_IDS = {"l2": 0, "unit_square": 1, "positive_square": 2, "categorical": 3, "natural_numbers": 4}
+
+
+def adap_draw(n, K, C, sampler, seed, stream, index0=0, S=0, n_mb=1, M=0, batch_size=0):
+    """Philox stand-in for the draws of get_context_kl_loss: (sidx [n, S] or None, draws [n, K, C])."""
+    sidx = np.zeros((n, S), np.int32) if S > 0 else None
+    draws = np.zeros((n, K, C), np.float32)
+    lib().orc_adap_draw(None if sidx is None else sidx.ctypes.data_as(C_.c_void_p), draws.ctypes.data_as(C_.c_void_p),
+                        C_.c_int64(n), C_.c_int64(n_mb), C_.c_int64(M), C_.c_int64(batch_size), C_.c_int32(S),
+                        C_.c_int32(K), C_.c_int32(C), C_.c_int32(SAMPLER_IDS[sampler]), C_.c_uint64(seed),
+                        C_.c_uint32(stream), C_.c_uint32(index0))
+    return sidx, draws

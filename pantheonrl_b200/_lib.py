@@ -255,6 +255,8 @@ SIGNATURES = {
     "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
     "pth_adap_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
     "pth_adap_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
+    "pth_adap_draw": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),
     "pth_debug_update_profile": (C.c_int, [_vp]),
     "pth_pack_transitions": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -71,11 +71,15 @@ class OnPolicyAgent(Agent):
         actions, values, log_probs = self.model.policy.forward(obs.obs)
         if record:
             self.model.ep_info_buffer[-1]["l"] += 1
-            buf.add(obs.obs, actions, 0.0, self._last_episode_starts[0], values, log_probs)
+            buf.add(self._stored_obs(obs.obs), actions, 0.0, self._last_episode_starts[0], values, log_probs)
         self.n_steps += 1
         self.num_timesteps += 1
         self.values = values
         return actions[0]
+
+    def _stored_obs(self, obs):
+        """The row the buffer keeps for this decision (AdapAgent appends the policy's context)."""
+        return obs
 
     def update(self, reward, done):
         self._last_episode_starts = [done]

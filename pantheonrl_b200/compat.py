@@ -132,15 +132,15 @@ def _tree():
                                                   NAME_TRANSLATION=dict(overcooked.NAME_TRANSLATION)),
     }
     # pantheonrl.algos.adap / .modular (trainer.py:14-19)
-    adap = "the ADAP learner (pantheonrl/algos/adap)"
     modular = "the ModularAlgorithm learner (pantheonrl/algos/modular)"
+    from . import adap as adap_mod
     mods.update({
         "pantheonrl.algos.adap": _module("pantheonrl.algos.adap"),
-        "pantheonrl.algos.adap.adap_learn": _module("pantheonrl.algos.adap.adap_learn", ADAP=_placeholder("ADAP", adap)),
-        "pantheonrl.algos.adap.policies": _module("pantheonrl.algos.adap.policies",
-                                                  AdapPolicy=_placeholder("AdapPolicy", adap),
-                                                  AdapPolicyMult=_placeholder("AdapPolicyMult", adap)),
-        "pantheonrl.algos.adap.agent": _module("pantheonrl.algos.adap.agent", AdapAgent=_placeholder("AdapAgent", adap)),
+        "pantheonrl.algos.adap.adap_learn": _module("pantheonrl.algos.adap.adap_learn", ADAP=adap_mod.ADAP),
+        "pantheonrl.algos.adap.policies": _module("pantheonrl.algos.adap.policies", AdapPolicy=adap_mod.AdapPolicy,
+                                                  AdapPolicyMult=adap_mod.AdapPolicyMult),
+        "pantheonrl.algos.adap.agent": _module("pantheonrl.algos.adap.agent", AdapAgent=adap_mod.AdapAgent),
+        "pantheonrl.algos.adap.util": _module("pantheonrl.algos.adap.util", SAMPLERS=adap_mod.SAMPLERS),
         "pantheonrl.algos.modular": _module("pantheonrl.algos.modular"),
         "pantheonrl.algos.modular.learn": _module("pantheonrl.algos.modular.learn",
                                                   ModularAlgorithm=_placeholder("ModularAlgorithm", modular)),

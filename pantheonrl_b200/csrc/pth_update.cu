@@ -1665,6 +1665,67 @@ __global__ void perm_feistel_kernel(int32_t* perm, int64_t M, int n_epochs, uint
   perm[(int64_t)e * M + i] = (int32_t)x;
 }
 
+// The random draws of ADAP on Philox: per minibatch id the positions of the sampled states
+// (th.randperm(B)[:S], adap/util.py:106: the first S images of a keyed Feistel permutation of [0, B))
+// and K contexts from SAMPLERS[sampler] (adap/util.py:42-94: 0 "l2" unit sphere, 1 "unit_square",
+// 2 "positive_square", 3 "categorical" one-hot, 4 "natural_numbers" (context_size 1)).  One CTA per id.
+__global__ void adap_draw_kernel(int32_t* sidx, float* draws, int64_t n_mb, int64_t M, int64_t BS, int S, int K, int C,
+                                 int sampler, uint64_t seed, uint32_t stream, uint32_t index0) {
+  const int64_t id = blockIdx.x;
+  const uint32_t tick = index0 + (uint32_t)id;
+  if (sidx != nullptr) {
+    const int64_t m = id % n_mb;
+    const int64_t B = (m * BS + BS <= M) ? BS : (M - m * BS);
+    int bits = 2;
+    while (((int64_t)1 << bits) < B) ++bits;
+    if (bits & 1) ++bits;
+    const pth_u4 key = pth_philox(seed, stream, 0, tick, 0);
+    for (int s_ = threadIdx.x; s_ < S; s_ += blockDim.x) {
+      int32_t out = -1;
+      if (s_ < B) {
+        uint32_t x = (uint32_t)s_;
+        do {
+          x = feistel(x, bits / 2, key);
+        } while ((int64_t)x >= B);
+        out = (int32_t)x;
+      }
+      sidx[id * S + s_] = out;
+    }
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float u[MAX_CTX];
+#pragma unroll
+    for (int q = 0; q < MAX_CTX / 4; ++q) {
+      const pth_u4 r = pth_philox(seed, stream, 1 + (uint64_t)k, tick, (uint32_t)q);
+      u[4 * q + 0] = pth_u01(r.x);
+      u[4 * q + 1] = pth_u01(r.y);
+      u[4 * q + 2] = pth_u01(r.z);
+      u[4 * q + 3] = pth_u01(r.w);
+    }
+    float* o = draws + ((size_t)id * K + k) * C;
+    if (sampler <= 1) {
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAX_CTX; ++c) {
+        u[c] = u[c] * 2.0f - 1.0f;
+        if (c < C) ss = fmaf(u[c], u[c], ss);
+      }
+      const float nrm = sampler == 0 ? sqrtf(ss) : 1.0f;
+#pragma unroll
+      for (int c = 0; c < MAX_CTX; ++c)
+        if (c < C) o[c] = sampler == 0 ? u[c] / nrm : u[c];
+    } else if (sampler == 2) {
+#pragma unroll
+      for (int c = 0; c < MAX_CTX; ++c)
+        if (c < C) o[c] = u[c];
+    } else {
+      int idx = (int)(u[0] * (float)C);
+      idx = idx < C - 1 ? idx : C - 1;
+      for (int c = 0; c < C; ++c) o[c] = sampler == 3 ? (c == idx ? 1.0f : 0.0f) : (c == 0 ? (float)idx : 0.0f);
+    }
+  }
+}
+
 // exclusive prefix of min(count, T) over envs, single CTA (N is at most a few 1e5)
 __global__ void __launch_bounds__(1024) index_scan_kernel(const int32_t* count, int64_t T, int64_t N,
                                                           int32_t* offsets, int32_t* total) {
@@ -1982,6 +2043,23 @@ extern "C" int pth_perm_feistel(pth_ctx* ctx, int32_t* d_perm, int64_t M, int32_
   dim3 grid((unsigned)pth_ceil_div(M, 256), (unsigned)n_epochs);
   perm_feistel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_perm, M, n_epochs, seed, stream_id,
                                                               epoch0, bits / 2);
+  PTH_LAUNCH_CHECK();
+  return PTH_OK;
+}
+
+extern "C" int pth_adap_draw(pth_ctx* ctx, int32_t* d_states, float* d_draws, int64_t n, int64_t n_minibatches,
+                             int64_t M, int64_t batch_size, int32_t num_state_samples, int32_t num_context_samples,
+                             int32_t context_size, int32_t sampler, uint64_t seed, uint32_t stream_id,
+                             uint32_t index0, void* stream) {
+  PTH_CHECK_ARG(ctx != nullptr && d_draws != nullptr && n > 0 && n < (1 << 30), "NULL ctx / draws, bad n");
+  PTH_CHECK_ARG(context_size >= 1 && context_size <= MAX_CTX && num_context_samples >= 1 && sampler >= 0 && sampler <= 4,
+                "bad context_size / num_context_samples / sampler");
+  PTH_CHECK_ARG(sampler != 4 || context_size == 1, "natural_numbers contexts have one column");
+  PTH_CHECK_ARG(d_states == nullptr || (num_state_samples >= 1 && n_minibatches >= 1 && M > 0 && batch_size > 0),
+                "bad state-sample geometry");
+  adap_draw_kernel<<<(unsigned)n, 64, 0, (cudaStream_t)stream>>>(d_states, d_draws, n_minibatches, M, batch_size,
+                                                                  num_state_samples, num_context_samples, context_size,
+                                                                  sampler, seed, stream_id, index0);
   PTH_LAUNCH_CHECK();
   return PTH_OK;
 }

@@ -27,18 +27,19 @@ def _ortho(rows, cols, gain):
     return w
 
 
-def feature_dim(space):
-    return sum(space.nvec) if space.obs_kind == _lib.PTH_OBS_ONEHOT else space.obs_len
+def feature_dim(space, extra=0):
+    """extra: AdapPolicy's context inputs behind the features (pantheonrl/algos/adap/policies.py:71-84)."""
+    return (sum(space.nvec) if space.obs_kind == _lib.PTH_OBS_ONEHOT else space.obs_len) + extra
 
 
-def param_count(space):
-    F, L = feature_dim(space), sum(space.heads)
+def param_count(space, extra=0):
+    F, L = feature_dim(space, extra), sum(space.heads)
     return 2 * (HID * F + HID + HID * HID + HID) + L * HID + L + HID + 1
 
 
-def tensor_shapes(space):
+def tensor_shapes(space, extra=0):
     """(name, torch shape) in SB3 registration order."""
-    F, L = feature_dim(space), sum(space.heads)
+    F, L = feature_dim(space, extra), sum(space.heads)
     return [("mlp_extractor.policy_net.0.weight", (HID, F)), ("mlp_extractor.policy_net.0.bias", (HID,)),
             ("mlp_extractor.policy_net.2.weight", (HID, HID)), ("mlp_extractor.policy_net.2.bias", (HID,)),
             ("mlp_extractor.value_net.0.weight", (HID, F)), ("mlp_extractor.value_net.0.bias", (HID,)),
@@ -47,9 +48,9 @@ def tensor_shapes(space):
             ("value_net.weight", (1, HID)), ("value_net.bias", (1,))]
 
 
-def init_flat(space, seed):
+def init_flat(space, seed, extra=0):
     """SB3-style initial parameters as a flat float32 numpy vector (engine layout)."""
-    F, L = feature_dim(space), sum(space.heads)
+    F, L = feature_dim(space, extra), sum(space.heads)
     if seed is not None:
         torch.manual_seed(int(seed))
     # nn.Linear creation consumes RNG for the default init before orthogonal_
@@ -67,11 +68,11 @@ def init_flat(space, seed):
     return torch.cat([p.reshape(-1) for p in parts]).numpy().astype(np.float32)
 
 
-def flat_to_state_dict(space, flat):
+def flat_to_state_dict(space, flat, extra=0):
     """Engine layout -> SB3 state_dict tensors (torch layout weight[out][in])."""
     flat = torch.as_tensor(np.asarray(flat, np.float32))
     out, o = {}, 0
-    for i, (name, shape) in enumerate(tensor_shapes(space)):
+    for i, (name, shape) in enumerate(tensor_shapes(space, extra)):
         n = int(np.prod(shape))
         chunk = flat[o:o + n]
         if i in (0, 4):
@@ -81,9 +82,9 @@ def flat_to_state_dict(space, flat):
     return out
 
 
-def state_dict_to_flat(space, sd):
+def state_dict_to_flat(space, sd, extra=0):
     parts = []
-    for i, (name, shape) in enumerate(tensor_shapes(space)):
+    for i, (name, shape) in enumerate(tensor_shapes(space, extra)):
         t = torch.as_tensor(sd[name]).float().reshape(shape)
         if i in (0, 4):
             t = t.t().contiguous()

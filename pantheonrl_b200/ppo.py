@@ -40,10 +40,12 @@ def reset_stream_counter():
 class DevicePolicy:
     """ActorCriticPolicy stand-in: parameters live on the device as one flat vector."""
 
+    extra_inputs = 0  # AdapPolicy: context inputs behind the features
+
     def __init__(self, space, observation_space, action_space, seed, device, rng_stream, rng="philox"):
         self.space, self.observation_space, self.action_space = space, observation_space, action_space
         self.device, self.seed, self.rng_stream, self.rng = device, int(seed or 0), rng_stream, rng
-        self.params = torch.from_numpy(pol.init_flat(space, seed)).to(device)  # seed None: no re-seeding
+        self.params = torch.from_numpy(pol.init_flat(space, seed, self.extra_inputs)).to(device)  # seed None: no re-seeding
         self.calls = 0
         self.box = space.obs_kind == _lib.PTH_OBS_BOX  # fp32 rows of 64 instead of 32 slot bytes
         self.row = space.row_bytes  # one-hot rows: 32 bytes, or 96 for frame-stacked observations
@@ -57,6 +59,9 @@ class DevicePolicy:
         o[0, :flat.size] = flat
         self._obs_dev.copy_(torch.from_numpy(o))
 
+    def _context(self):
+        return None  # AdapPolicy: the [1, C] context on the device
+
     def forward(self, obs, deterministic=False):
         """obs -> (actions [1, act_dim] numpy, values tensor [1], log_probs tensor [1])."""
         self._stage_obs(obs)
@@ -68,7 +73,7 @@ class DevicePolicy:
             race = torch.cat([torch.empty(1, n).exponential_(1) for n in self.space.heads], dim=1).to(self.device)
         out = ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed,
                                  rng_stream=self.rng_stream, tick=self.calls & 0xffffffff, slot=0, idx0=0,
-                                 want=("action", "value", "logp"), race=race)
+                                 want=("action", "value", "logp"), race=race, context=self._context())
         self.calls += 1
         act = out["action"].cpu().numpy()[:, :self.act_dim].astype(np.int64)
         if self.act_dim == 1 and getattr(self.action_space, "shape", ()) == ():
@@ -79,13 +84,14 @@ class DevicePolicy:
         """ActorCriticPolicy.predict_values: the value tower only — no sample is drawn."""
         self._stage_obs(obs)
         dummy = torch.zeros(1, 4, dtype=torch.uint8, device=self.device)
-        return ops.policy_forward(self.space, self.params, self._obs_dev, action_in=dummy, want=("value",))["value"]
+        return ops.policy_forward(self.space, self.params, self._obs_dev, action_in=dummy, want=("value",),
+                                  context=self._context())["value"]
 
     def state_dict(self):
-        return pol.flat_to_state_dict(self.space, self.params.cpu().numpy())
+        return pol.flat_to_state_dict(self.space, self.params.cpu().numpy(), self.extra_inputs)
 
     def load_state_dict(self, sd):
-        self.params.copy_(torch.from_numpy(pol.state_dict_to_flat(self.space, sd)))
+        self.params.copy_(torch.from_numpy(pol.state_dict_to_flat(self.space, sd, self.extra_inputs)))
 
 
 class HostStagedBuffer:
@@ -174,7 +180,7 @@ class PPO:
                  n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, normalize_advantage=True,
                  ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, tensorboard_log=None, verbose=0, seed=None,
                  device="cuda", n_envs=1, n_minibatches=0, rng=None):
-        if policy != "MlpPolicy":
+        if not self._policy_ok(policy):
             raise ValueError("only 'MlpPolicy' (SB3 default 64-64 tanh towers) is implemented")
         if not torch.cuda.is_available():
             raise _lib.PthError("PPO needs a CUDA device: this path has no CPU implementation")
@@ -205,12 +211,10 @@ class PPO:
             eff_seed = None  # no generator is touched: the weights come from torch's current state
         else:
             eff_seed = int(np.random.randint(1, 2 ** 31 - 1))
-        self.policy = DevicePolicy(self.space, self.observation_space, self.action_space, eff_seed, self.device,
-                                   stream, self.rng)
+        self.policy = self._make_policy(eff_seed, stream)
         if self.space.obs_kind == _lib.PTH_OBS_BOX and self.space.obs_len > _lib.PTH_OC_ROW:
             raise _lib.PthError("Box observations wider than 64 are not supported")
-        self.rollout_buffer = HostStagedBuffer(n_steps, self.device, gamma, gae_lambda,
-                                               box=self.space.obs_kind == _lib.PTH_OBS_BOX, row=self.space.row_bytes)
+        self.rollout_buffer = self._make_buffer(n_steps, gamma, gae_lambda)
         self.adam_m = torch.zeros_like(self.policy.params)
         self.adam_v = torch.zeros_like(self.policy.params)
         self.adam_step, self._n_updates, self.num_timesteps = 0, 0, 0
@@ -222,6 +226,19 @@ class PPO:
         self._ws = None
         self._last_obs = None
         self._trainer = None
+
+    # ---------------------------------------------------------------- what a subclass (ADAP) swaps
+    @staticmethod
+    def _policy_ok(policy):
+        return policy == "MlpPolicy"
+
+    def _make_policy(self, eff_seed, stream):
+        return DevicePolicy(self.space, self.observation_space, self.action_space, eff_seed, self.device, stream,
+                            self.rng)
+
+    def _make_buffer(self, n_steps, gamma, gae_lambda):
+        return HostStagedBuffer(n_steps, self.device, gamma, gae_lambda,
+                                box=self.space.obs_kind == _lib.PTH_OBS_BOX, row=self.space.row_bytes)
 
     # ---------------------------------------------------------------- logging (SB3 Logger surface)
     @property
@@ -313,7 +330,7 @@ class PPO:
             self.ep_info_buffer = deque(maxlen=100)
         target = self.num_timesteps + total_timesteps
         while self.num_timesteps < target:
-            collect_rollouts_single_env(self, env, self.policy, buf, self.n_steps)
+            self._collect(env, buf)
             self._iteration += 1
             if log_interval is not None and self._iteration % log_interval == 0 and self._logger.output_formats:
                 eps = list(self.ep_info_buffer)
@@ -321,6 +338,9 @@ class PPO:
                                      lg.safe_mean(e["l"] for e in eps) if eps else None)
             self.train()
         return self
+
+    def _collect(self, env, buf):
+        collect_rollouts_single_env(self, env, self.policy, buf, self.n_steps)
 
     def _learn_on_device(self, total_timesteps, log_interval=1):
         from .engine import PPOConfig, VecTrainer

@@ -35,6 +35,22 @@ def index_build(count, T, N, device="cuda"):
     return index, total
 
 
+ADAP_SAMPLERS = {"l2": 0, "unit_square": 1, "positive_square": 2, "categorical": 3, "natural_numbers": 4}
+
+
+def adap_draw(n, K, C_, sampler, seed, stream_id, index0=0, S=0, n_mb=1, M=0, batch_size=0, device="cuda"):
+    """The random draws of ADAP on Philox (SAMPLERS / th.randperm of pantheonrl/algos/adap/util.py:42-106):
+    (states int32 [n, S] or None, contexts float32 [n, K, C])."""
+    draws = torch.empty(n, K, C_, dtype=torch.float32, device=device)
+    states = torch.empty(n, S, dtype=torch.int32, device=device) if S > 0 else None
+    check(_lib.load().pth_adap_draw(_ctx(draws).handle, states.data_ptr() if states is not None else None,
+                                    draws.data_ptr(), int(n), int(n_mb), int(M), int(batch_size), int(S), int(K),
+                                    int(C_), ADAP_SAMPLERS[sampler], int(seed), int(stream_id),
+                                    int(index0) & 0xffffffff, current_stream()), "pth_adap_draw")
+    _lib.count_launch()
+    return states, draws
+
+
 def update_grid(space, M, batch_size, device=0):
     return int(_lib.load().pth_update_grid(Context.get(device).handle, C.byref(space), int(M),
                                            int(batch_size)))

@@ -90,3 +90,76 @@ def test_overcooked_example_lines(ctx, aliases):
     fresh_a, fresh_b = PPO('MlpPolicy', env), PPO('MlpPolicy', env)
     assert not torch.equal(fresh_a.policy.params, fresh_b.policy.params)
     assert bool(torch.isfinite(ego.policy.params).all())
+
+
+def _run_adap(args, before_learn=None):
+    import trainer_shaped as ts
+    if os.path.exists(REF_TRAINER):
+        spec = importlib.util.spec_from_file_location("reference_trainer", REF_TRAINER)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        env, altenv = ref.generate_env(args)
+        ego = ref.generate_ego(env, args)
+        partners = ref.generate_partners(altenv, env, ego, args)
+    else:
+        env, altenv = ts.make_envs(args)
+        ego = ts.make_ego(env, args)
+        partners = [ts.make_partner(k, c, altenv, args, i, ego) for i, (k, c) in enumerate(zip(args.alt, args.alt_config))]
+        for p in partners:
+            env.add_partner_agent(p)
+    if before_learn is not None:
+        before_learn(ego)
+    ego.learn(total_timesteps=args.total_timesteps)
+    return env, ego, partners
+
+
+def test_trainer_flow_rps_adap_vs_adap(ctx, aliases, tmp_path):
+    """`trainer.py RPS-v0 ADAP ADAP --seed 10` (trainer.py:127-128, 205-213): ADAP ego and an AdapAgent partner,
+    each with its own context, resampled at every episode end (RPS: every step)."""
+    import trainer_shaped as ts
+    cfg = {"n_steps": 256, "batch_size": 64, "n_epochs": 3, "context_loss_coeff": 0.5}
+    args = ts.default_args("RPS-v0", "ADAP", ["ADAP"], seed=10, total_timesteps=512,
+                           ego_config=dict(cfg, verbose=0), alt_config=[dict(cfg)], ego_save=str(tmp_path / "ego"))
+    env, ego, partners = _run_adap(args)
+    partner = partners[0]
+    p0 = type(ego)(env=env, seed=10, **cfg).policy.params
+    assert not torch.equal(ego.policy.params, p0)  # it trained
+    assert ego._n_updates == 6 and partner.model._n_updates >= 3
+    for m in (ego, partner.model):
+        cx = m.rollout_buffer.h["ctx"]
+        filled = cx[:m.rollout_buffer.pos] if m is partner.model else cx
+        assert filled.shape[1] == 3 and np.allclose(np.linalg.norm(filled, axis=1), 1.0, atol=1e-6)  # "l2" sampler
+        assert len(np.unique(filled.round(5), axis=0)) > filled.shape[0] // 2  # a new context every episode
+        cl = m.last_context_loss.cpu().numpy()
+        assert cl.shape == (3 * 4,) and np.all((cl > 0) & (cl <= 1 + 1e-6))
+        assert np.all(np.isfinite(m.last_stats.cpu().numpy()))
+    assert not np.allclose(ego.rollout_buffer.h["ctx"][:8], partner.model.rollout_buffer.h["ctx"][:8])
+    ego.save(args.ego_save)
+    again = type(ego).load(args.ego_save)
+    assert torch.equal(again.policy.params, ego.policy.params) and again.context_size == 3
+
+
+def test_trainer_flow_liar_adap_share_latent(ctx, aliases):
+    """`trainer.py LiarsDice-v0 ADAP ADAP --share-latent`: the partner copies the ego policy's context before every
+    decision (trainer.py:210-213, adap/agent.py:74-75), so both buffers store the same contexts episode by episode."""
+    import trainer_shaped as ts
+    cfg = {"n_steps": 128, "batch_size": 64, "n_epochs": 2}
+    args = ts.default_args("LiarsDice-v0", "ADAP", ["ADAP"], seed=3, total_timesteps=256, share_latent=True,
+                           ego_config=dict(cfg, verbose=0), alt_config=[dict(cfg)])
+    seen = set()
+
+    def record_contexts(ego):
+        seen.add(tuple(ego.policy.get_context().numpy().reshape(-1).round(6)))
+        real = ego.policy.set_context
+
+        def set_context(c):
+            real(c)
+            seen.add(tuple(ego.policy.get_context().numpy().reshape(-1).round(6)))
+        ego.policy.set_context = set_context
+    env, ego, partners = _run_adap(args, record_contexts)
+    partner = partners[0]
+    assert partner.latent_syncer is ego.policy
+    alt_ctx = {tuple(r) for r in partner.model.rollout_buffer.h["ctx"][:partner.model.rollout_buffer.pos].round(6)}
+    assert len(seen) > 10 and alt_ctx and alt_ctx <= seen  # every context the partner acted under was the ego's
+    assert {tuple(r) for r in ego.rollout_buffer.h["ctx"].round(6)} <= seen
+    assert ego._n_updates == 4

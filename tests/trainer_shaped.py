@@ -46,11 +46,15 @@ def make_ego(env, args):
         model = PPO.load(kw["location"])
         model.set_env(DummyVecEnv([lambda: Monitor(env)]))
         return model
+    if args.ego == "ADAP":  # trainer.py:127-128
+        from pantheonrl.algos.adap.adap_learn import ADAP
+        from pantheonrl.algos.adap.policies import AdapPolicy
+        return ADAP(policy=AdapPolicy, **kw)
     assert args.ego == "PPO"
     return PPO(policy="MlpPolicy", **kw)
 
 
-def make_partner(kind, config, altenv, args, number):
+def make_partner(kind, config, altenv, args, number, ego=None):
     from stable_baselines3 import PPO
     from pantheonrl.common.agents import OnPolicyAgent, StaticPolicyAgent
     from pantheonrl.envs.liargym.liar import LiarDefaultAgent, LiarEnv
@@ -68,6 +72,12 @@ def make_partner(kind, config, altenv, args, number):
     config = dict(config, env=altenv, device=args.device, verbose=args.verbose_partner)
     if args.seed is not None:
         config["seed"] = args.seed
+    if kind == "ADAP":  # trainer.py:205-213
+        from pantheonrl.algos.adap.adap_learn import ADAP
+        from pantheonrl.algos.adap.agent import AdapAgent
+        from pantheonrl.algos.adap.policies import AdapPolicy
+        shared = ego.policy if args.share_latent else None
+        return AdapAgent(ADAP(policy=AdapPolicy, **config), latent_syncer=shared, **agentarg)
     assert kind == "PPO"
     return OnPolicyAgent(PPO(policy="MlpPolicy", **config), **agentarg)
 
@@ -78,7 +88,7 @@ def run(args):
     ego = make_ego(env, args)
     partners = []
     for i, (kind, cfg) in enumerate(zip(args.alt, args.alt_config)):
-        p = make_partner(kind, cfg, altenv, args, i)
+        p = make_partner(kind, cfg, altenv, args, i, ego)
         env.add_partner_agent(p)
         partners.append(p)
     learn = {"total_timesteps": args.total_timesteps}
