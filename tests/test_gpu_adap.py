@@ -143,3 +143,21 @@ def test_adap_train_reproduces_the_reference_run(ctx, name, kw):
     assert np.abs(p - g[pre + "params"]).max() <= 5e-6
     assert cl[-n_mb:].mean() == pytest.approx(log["train/context_kl_loss"], abs=1e-5)
     assert st[-1, 5] == pytest.approx(log["train/loss"], abs=2e-5)
+
+
+@pytest.mark.parametrize("sampler,C", [("l2", 3), ("l2", 8), ("unit_square", 5), ("positive_square", 2), ("categorical", 4),
+                                       ("natural_numbers", 1)])
+def test_adap_draws_bit_exact_vs_oracle(ctx, sampler, C):
+    """pth_adap_draw: the Philox stand-in for SAMPLERS / th.randperm (adap/util.py:42-106)."""
+    n, K, S, n_mb, M, BS = 11, 5, 32, 4, 210, 64  # the last minibatch of an epoch holds 18 < S samples
+    want_s, want_d = oupd.adap_draw(n, K, C, sampler, 10, 0x10300, index0=7, S=S, n_mb=n_mb, M=M, batch_size=BS)
+    got_s, got_d = dupd.adap_draw(n, K, C, sampler, 10, 0x10300, index0=7, S=S, n_mb=n_mb, M=M, batch_size=BS)
+    assert np.array_equal(got_s.cpu().numpy(), want_s) and np.array_equal(got_d.cpu().numpy(), want_d)
+    for i in range(n):
+        B = min(BS, M - (i % n_mb) * BS)
+        v = want_s[i][want_s[i] >= 0]
+        assert len(v) == min(S, B) and len(set(v.tolist())) == len(v) and v.max() < B
+    if sampler == "l2":
+        assert np.allclose(np.linalg.norm(want_d, axis=-1), 1.0, atol=1e-6)
+    _, one = dupd.adap_draw(1, 1, C, sampler, 10, 0x10300, index0=8)  # a single per-episode context
+    assert one.shape == (1, 1, C)
