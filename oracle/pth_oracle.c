@@ -537,3 +537,4 @@ void orc_adap_forward(const orc_space* sp, const float* params, int32_t C, const
 #include "pth_oracle_overcooked.inc"
 #include "pth_oracle_rollout.inc"
 #include "pth_oracle_update.inc"
+#include "pth_oracle_modular.inc"

@@ -282,3 +282,108 @@ def adap_train(policy, obs, actions, old_log_prob, advantages, returns, perms, b
                                              returns[idx], si[si >= 0][:len(idx)], contexts[i], **kw))
             i += 1
     return stats
+
+
+class ModularMlpPolicy(MlpPolicy):
+    """ModularPolicy (pantheonrl/algos/modular/policies.py:23-396) with its defaults: the main network is the
+    MlpPolicy (two 64-64 tanh towers, action and value heads); every partner p owns a module that reads the
+    main policy tower's latent: two more 64-64 tanh towers (`partner_mlp_extractor[p]`, BOTH fed with
+    latent_pi), an action head and a value head.  logits = main + partner[p], value = main + partner[p]
+    (:273-290, :307-326).  Construction / init order follows `_build` + `do_init_weights` (:229-270)."""
+
+    def __init__(self, nvec=None, heads=(3,), box_dim=None, num_partners=1, seed=None, lr=3e-4, adam_eps=1e-5):
+        super().__init__(nvec=nvec, heads=heads, box_dim=box_dim, seed=seed, lr=lr, adam_eps=adam_eps)
+        self.num_partners = int(num_partners)
+        mk = lambda: nn.Sequential(nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())  # noqa: E731
+        pp, pv, pa, pw = [], [], [], []
+        for _ in range(self.num_partners):  # MlpExtractor interleaves pi / vf layer creation, then the two heads
+            p0, v0, p1, v1 = nn.Linear(64, 64), nn.Linear(64, 64), nn.Linear(64, 64), nn.Linear(64, 64)
+            pp.append(nn.Sequential(p0, nn.Tanh(), p1, nn.Tanh()))
+            pv.append(nn.Sequential(v0, nn.Tanh(), v1, nn.Tanh()))
+            pa.append(nn.Linear(64, self.L))
+            pw.append(nn.Linear(64, 1))
+        self.partner_policy_net, self.partner_value_body = nn.ModuleList(pp), nn.ModuleList(pv)
+        self.partner_action_net, self.partner_value_net = nn.ModuleList(pa), nn.ModuleList(pw)
+        # do_init_weights(init_main=True, init_partner=True): the main modules again, then per partner
+        mods = [(self.policy_net, math.sqrt(2)), (self.value_net_body, math.sqrt(2)), (self.action_net, 0.01),
+                (self.value_net, 1.0)]
+        for p in range(self.num_partners):
+            mods += [(self.partner_policy_net[p], math.sqrt(2)), (self.partner_value_body[p], math.sqrt(2)),
+                     (self.partner_action_net[p], 0.01), (self.partner_value_net[p], 1.0)]
+        for mod, gain in mods:
+            for m in mod.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain=gain)
+                    m.bias.data.fill_(0.0)
+        self.optimizer = th.optim.Adam(self.ordered_parameters(), lr=lr, eps=adam_eps)
+
+    def ordered_parameters(self):
+        out = MlpPolicy.ordered_parameters(self)
+        for p in range(getattr(self, "num_partners", 0)):
+            pn, vb = self.partner_policy_net[p], self.partner_value_body[p]
+            out += [pn[0].weight, pn[0].bias, pn[2].weight, pn[2].bias, vb[0].weight, vb[0].bias, vb[2].weight,
+                    vb[2].bias, self.partner_action_net[p].weight, self.partner_action_net[p].bias,
+                    self.partner_value_net[p].weight, self.partner_value_net[p].bias]
+        return out
+
+    def logits(self, obs, partner_idx):
+        """(main_logits, partner_logits) — get_action_logits_from_obs (:385-396)."""
+        latent_pi = self.policy_net(self.features(obs))
+        return self.action_net(latent_pi), self.partner_action_net[partner_idx](self.partner_policy_net[partner_idx](latent_pi))
+
+    def evaluate_actions(self, obs, actions, partner_idx=0):
+        x = self.features(obs)
+        latent_pi, latent_vf = self.policy_net(x), self.value_net_body(x)
+        p_pi, p_vf = self.partner_policy_net[partner_idx](latent_pi), self.partner_value_body[partner_idx](latent_pi)
+        logits = self.action_net(latent_pi) + self.partner_action_net[partner_idx](p_pi)
+        dists = [th.distributions.Categorical(logits=lg) for lg in th.split(logits, self.heads, dim=1)]
+        actions = th.as_tensor(np.asarray(actions)).long()
+        actions = actions.reshape(actions.shape[0], -1)
+        log_prob = th.stack([d.log_prob(actions[:, h]) for h, d in enumerate(dists)], dim=1).sum(dim=1)
+        entropy = th.stack([d.entropy() for d in dists], dim=1).sum(dim=1)
+        values = self.value_net(latent_vf) + self.partner_value_net[partner_idx](p_vf)
+        return values, log_prob, entropy
+
+
+def modular_minibatch_step(policy, partner_idx, obs, actions, old_log_prob, advantages, returns, marginal_reg_coef=0.0,
+                           clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5):
+    """One iteration of the inner loop of ModularAlgorithm.train (modular/learn.py:246-326)."""
+    advantages = th.as_tensor(advantages).float()
+    returns = th.as_tensor(returns).float()
+    old_log_prob = th.as_tensor(old_log_prob).float()
+    values, log_prob, entropy = policy.evaluate_actions(obs, actions, partner_idx)
+    values = values.flatten()
+    advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+    ratio = th.exp(log_prob - old_log_prob)
+    policy_loss = -th.min(advantages * ratio, advantages * th.clamp(ratio, 1 - clip_range, 1 + clip_range)).mean()
+    value_loss = nn.functional.mse_loss(returns, values)
+    entropy_loss = -th.mean(entropy)
+    # marginal regularisation (:298-318): softmax over ALL logits jointly, Wasserstein-1 with unit distances
+    lg = [policy.logits(obs, idx) for idx in range(policy.num_partners)]
+    main_logits = th.stack([m for m, _ in lg])
+    composed_logits = main_logits + th.stack([p for _, p in lg])
+    main_probs = th.mean(th.exp(main_logits - main_logits.logsumexp(dim=-1, keepdim=True)), dim=0)
+    composed_probs = th.mean(th.exp(composed_logits - composed_logits.logsumexp(dim=-1, keepdim=True)), dim=0)
+    marginal = th.mean(th.sum(th.abs(main_probs - composed_probs), dim=1))
+    loss = policy_loss + ent_coef * entropy_loss + vf_coef * value_loss + marginal_reg_coef * marginal
+    policy.optimizer.zero_grad()
+    loss.backward()
+    th.nn.utils.clip_grad_norm_(policy.ordered_parameters(), max_grad_norm)
+    policy.optimizer.step()
+    return dict(pg_loss=policy_loss.item(), value_loss=value_loss.item(), entropy_loss=entropy_loss.item(),
+                marginal=marginal.item(), loss=loss.item())
+
+
+def modular_train(policy, buffers, perms, batch_size, **kw):
+    """ModularAlgorithm.train: for every partner, n_epochs passes over THAT partner's buffer
+    (buffers[p] = (obs, actions, old_log_prob, advantages, returns), perms[p] = [n_epochs, M])."""
+    stats = []
+    for p, (obs, actions, old_log_prob, advantages, returns) in enumerate(buffers):
+        M = len(advantages)
+        for perm in perms[p]:
+            perm = np.asarray(perm)
+            for s0 in range(0, M, batch_size):
+                idx = perm[s0:s0 + batch_size]
+                stats.append(modular_minibatch_step(policy, p, obs[idx], actions[idx], old_log_prob[idx],
+                                                    advantages[idx], returns[idx], **kw))
+    return stats

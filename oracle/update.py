@@ -114,3 +114,84 @@ def adap_draw(n, K, C, sampler, seed, stream, index0=0, S=0, n_mb=1, M=0, batch_
                         C_.c_int32(K), C_.c_int32(C), C_.c_int32(SAMPLER_IDS[sampler]), C_.c_uint64(seed),
                         C_.c_uint32(stream), C_.c_uint32(index0))
     return sidx, draws
+
+
+class OrcModularArgs(C.Structure):
+    _fields_ = [
+        ("space", C.POINTER(OrcSpace)),
+        ("params", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p),
+        ("adam_step", C.c_int64), ("vf_step", C.c_int64),
+        ("num_partners", C.c_int32), ("partner_idx", C.c_int32),
+        ("obs", C.c_void_p), ("actions", C.c_void_p), ("old_logp", C.c_void_p),
+        ("advantages", C.c_void_p), ("returns", C.c_void_p), ("index", C.c_void_p), ("perm", C.c_void_p),
+        ("M", C.c_int64), ("batch_size", C.c_int64), ("n_epochs", C.c_int32),
+        ("learning_rate", C.c_float), ("clip_range", C.c_float), ("ent_coef", C.c_float),
+        ("vf_coef", C.c_float), ("max_grad_norm", C.c_float),
+        ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
+        ("marginal_reg_coef", C.c_float), ("grid", C.c_int32),
+        ("stats", C.c_void_p), ("marginal_out", C.c_void_p),
+    ]
+
+
+def modular_param_count(space, num_partners):
+    lib().orc_modular_param_count.restype = C.c_int64
+    return int(lib().orc_modular_param_count(C.byref(space), C.c_int32(num_partners)))
+
+
+def modular_update(space, params, adam_m, adam_v, adam_step, vf_step, num_partners, partner_idx, obs, actions, old_logp,
+                   advantages, returns, perm, batch_size, grid, index=None, learning_rate=3e-4, clip_range=0.2,
+                   ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, betas=(0.9, 0.999), eps=1e-5, marginal_reg_coef=0.0):
+    """One partner's phase of ModularAlgorithm.train; params / adam state are updated IN PLACE.
+    Returns (stats [n_epochs * n_mb, 8], marginal [n_epochs * n_mb])."""
+    f32 = lambda x: np.ascontiguousarray(x, np.float32)  # noqa: E731
+    for a_ in (params, adam_m, adam_v):
+        assert a_.dtype == np.float32 and a_.flags.c_contiguous
+    if space.obs_kind == 1:
+        obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 64)
+    else:
+        obs = np.ascontiguousarray(obs, np.uint8).reshape(-1, 32 if space.obs_len <= 32 else 96)
+    actions = np.ascontiguousarray(actions, np.uint8).reshape(-1, 4)
+    old_logp, advantages, returns = f32(old_logp).reshape(-1), f32(advantages).reshape(-1), f32(returns).reshape(-1)
+    perm = np.ascontiguousarray(perm, np.int32)
+    n_epochs, M = perm.shape
+    n_mb = (M + batch_size - 1) // batch_size
+    stats = np.zeros((n_epochs * n_mb, 8), np.float32)
+    marg = np.zeros(n_epochs * n_mb, np.float32)
+    a = OrcModularArgs()
+    a.space = C.pointer(space)
+    a.params, a.adam_m, a.adam_v = params.ctypes.data, adam_m.ctypes.data, adam_v.ctypes.data
+    a.adam_step, a.vf_step = int(adam_step), int(vf_step)
+    a.num_partners, a.partner_idx = int(num_partners), int(partner_idx)
+    a.obs, a.actions = obs.ctypes.data, actions.ctypes.data
+    a.old_logp, a.advantages, a.returns = old_logp.ctypes.data, advantages.ctypes.data, returns.ctypes.data
+    if index is not None:
+        index = np.ascontiguousarray(index, np.int32)
+        a.index = index.ctypes.data
+    a.perm = perm.ctypes.data
+    a.M, a.batch_size, a.n_epochs = M, int(batch_size), n_epochs
+    a.learning_rate, a.clip_range, a.ent_coef = learning_rate, clip_range, ent_coef
+    a.vf_coef, a.max_grad_norm = vf_coef, max_grad_norm
+    a.adam_beta1, a.adam_beta2, a.adam_eps = betas[0], betas[1], eps
+    a.marginal_reg_coef, a.grid = float(marginal_reg_coef), int(grid)
+    a.stats, a.marginal_out = stats.ctypes.data, marg.ctypes.data
+    lib().orc_modular_update(C.byref(a))
+    return stats, marg
+
+
+def modular_forward(space, params, num_partners, partner_idx, obs, seed=0, rng_stream=2, tick=0, slot=0, idx0=0,
+                    action_in=None):
+    params = np.ascontiguousarray(params, np.float32)
+    obs = np.ascontiguousarray(obs, np.uint8) if space.obs_kind == 0 else np.ascontiguousarray(obs, np.float32)
+    B, stride = obs.shape
+    L = sum(space.head_n[i] for i in range(space.n_heads))
+    action = np.zeros((B, 4), np.uint8)
+    value, logp, ent = np.empty(B, np.float32), np.empty(B, np.float32), np.empty(B, np.float32)
+    logits = np.empty((B, L), np.float32)
+    if action_in is not None:
+        action_in = np.ascontiguousarray(action_in, np.uint8)
+    p_ = lambda x: None if x is None else x.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib().orc_modular_forward(C.byref(space), p_(params), C.c_int32(num_partners), C.c_int32(partner_idx), p_(obs),
+                              C.c_int64(stride), C.c_int64(B), C.c_uint64(seed), C.c_uint32(rng_stream),
+                              C.c_uint32(tick), C.c_uint32(slot), C.c_int64(idx0), p_(action_in), p_(action),
+                              p_(value), p_(logp), p_(ent), p_(logits))
+    return dict(action=action, value=value, logp=logp, entropy=ent, logits=logits)
