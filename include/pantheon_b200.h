@@ -293,6 +293,11 @@ typedef struct pth_forward_args {
   int32_t context_size;
   const float* d_context;
   int64_t context_stride;
+  /* ModularPolicy.forward / evaluate_actions (modular/policies.py:273-290, 364-383): num_partners > 0
+   * selects the ModularPolicy parameter layout (pth_modular_param_count) and partner module
+   * partner_idx composes the outputs: logits = main + partner, value = main + partner. */
+  int32_t num_partners;
+  int32_t partner_idx;
 } pth_forward_args;
 int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream);
 /* debug / parity only: y[i] = f(x[i]) with the library's exp (which = 0), log (1, positive
@@ -473,14 +478,41 @@ typedef struct pth_update_args {
   const int32_t* d_ctx_states;
   const float* d_ctx_draws;
   float* d_ctx_loss;
+  /* ModularAlgorithm.train (pantheonrl/algos/modular/learn.py:221-351) on a ModularPolicy
+   * (modular/policies.py:23-396, defaults): loss_kind PTH_LOSS_MODULAR, ONE LAUNCH PER PARTNER PHASE.
+   * Parameters: the MlpPolicy vector followed by num_partners blocks
+   *   [w_pi0 64x64, b_pi0, w_pi1 64x64, b_pi1, w_vf0 64x64, b_vf0, w_vf1 64x64, b_vf1, w_act Lx64, b_act, w_val 64, b_val]
+   * (matrices [out][in]; pth_modular_param_count): partner p's policy branch and value branch both read
+   * the main policy tower's latent; logits = main + partner[p], value = main + partner[p].
+   * The sample arrays are partner_idx's rollout buffer.  Loss = PPO's clipped surrogate / value /
+   * entropy terms on the composed outputs + marginal_reg_coef * mean_b sum_l |mean_p softmax(main)_l -
+   * mean_p softmax(main + partner[p])_l| (softmax over ALL logits jointly, learn.py:298-318), whose
+   * gradient reaches every partner's policy branch.  The value branches of the OTHER partners get no
+   * gradient and are left untouched (Adam skips tensors without a gradient); partner_vf_step = optimiser
+   * steps partner_idx's value branch has taken so far (its own bias correction), adam_step = steps of
+   * everything else.  d_stats column 5 includes the regulariser; d_ctx_loss (optional) receives it.
+   * Needs rec_stride == 0, world == 1, context_size == 0, workspace from pth_modular_workspace_bytes and
+   * d_modular_scratch (>= pth_modular_scratch_bytes, 16-byte aligned): per-CTA activation tiles of every
+   * module, kept for the backward pass. */
+  int32_t num_partners;
+  int32_t partner_idx;
+  int64_t partner_vf_step;
+  float marginal_reg_coef;
+  void* d_modular_scratch;
+  int64_t modular_scratch_bytes;
 } pth_update_args;
 #define PTH_LOSS_PPO 0
 #define PTH_LOSS_BC 1
 #define PTH_LOSS_ADAP 2
+#define PTH_LOSS_MODULAR 3
 int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
                                    int64_t M, int64_t batch_size);
 int64_t pth_adap_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
                                  int64_t M, int64_t batch_size);
+int64_t pth_modular_param_count(const pth_space* sp, int32_t num_partners);
+int64_t pth_modular_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t num_partners,
+                                    int64_t M, int64_t batch_size);
+int64_t pth_modular_scratch_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t num_partners);
 /* The random draws of ADAP on the library's Philox streams (the reference takes them from torch's
  * global generator: adap/util.py:42-94 SAMPLERS, :106 th.randperm; a host that wants the reference's
  * own stream draws them itself and passes them to pth_ppo_update — both are plain arrays).

@@ -18,7 +18,7 @@ PTH_ENV_RPS, PTH_ENV_LIAR, PTH_ENV_OVERCOOKED = 0, 1, 2
 PTH_OC_MAX_CELLS, PTH_OC_MAX_POTS, PTH_OC_OBS, PTH_OC_ROW = 128, 4, 62, 64
 PTH_OC_STATE_BYTES = 40
 PTH_OC_FLOOR, PTH_OC_COUNTER, PTH_OC_ONION, PTH_OC_POT, PTH_OC_DISH, PTH_OC_SERVE = range(6)
-PTH_LOSS_PPO, PTH_LOSS_BC, PTH_LOSS_ADAP = 0, 1, 2
+PTH_LOSS_PPO, PTH_LOSS_BC, PTH_LOSS_ADAP, PTH_LOSS_MODULAR = 0, 1, 2, 3
 PTH_UPDATE_FLAG_WORDS = 16384  # include/pantheon_b200.h
 PTH_PACKED_BYTES, PTH_PACKED_BYTES_BOX = 48, 272
 
@@ -99,6 +99,8 @@ class ForwardArgs(C.Structure):
         ("context_size", C.c_int32),
         ("d_context", C.c_void_p),
         ("context_stride", C.c_int64),
+        ("num_partners", C.c_int32),
+        ("partner_idx", C.c_int32),
     ]
 
 
@@ -218,6 +220,12 @@ class UpdateArgs(C.Structure):
         ("d_ctx_states", C.c_void_p),
         ("d_ctx_draws", C.c_void_p),
         ("d_ctx_loss", C.c_void_p),
+        ("num_partners", C.c_int32),
+        ("partner_idx", C.c_int32),
+        ("partner_vf_step", C.c_int64),
+        ("marginal_reg_coef", C.c_float),
+        ("d_modular_scratch", C.c_void_p),
+        ("modular_scratch_bytes", C.c_int64),
     ]
 
 
@@ -255,6 +263,9 @@ SIGNATURES = {
     "pth_update_workspace_bytes": (_i64, [_vp, C.POINTER(Space), _i64, _i64]),
     "pth_adap_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
     "pth_adap_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
+    "pth_modular_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
+    "pth_modular_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
+    "pth_modular_scratch_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32]),
     "pth_adap_draw": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     "pth_ppo_update": (C.c_int, [_vp, C.POINTER(UpdateArgs), _vp]),

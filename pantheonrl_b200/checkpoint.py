@@ -137,7 +137,11 @@ def save_zip(path, observation_space, action_space, hyper, policy_state, optimiz
         "clip_range_vf": None, "target_kl": None, "policy_kwargs": {},
         # extension fields (ignored by SB3's loader, used by ours)
         "b200": {"adam_step": int(counters.get("adam_step", 0)), "n_minibatches": int(hyper.get("n_minibatches", 0)),
-                 "format": 1},
+                 "format": 1,
+                 # constructor arguments SB3's PPO does not have (ADAP: context_size ...; ModularAlgorithm:
+                 # num_partners ...) and counters beyond SB3's
+                 "extra": {k: v for k, v in hyper.items() if k not in HYPER_KEYS and k != "n_minibatches"},
+                 "counters": {k: v for k, v in counters.items() if k not in ("num_timesteps", "n_updates", "adam_step")}},
     }
     for k in HYPER_KEYS:
         if k in hyper:
@@ -208,6 +212,7 @@ def load_zip(path):
     ext = data.get("b200", {})
     if ext.get("n_minibatches"):
         hyper["n_minibatches"] = int(ext["n_minibatches"])
+    hyper.update(ext.get("extra", {}))
     adam_step = int(ext.get("adam_step", 0))
     if optim and optim.get("state") and not adam_step:
         st = next(iter(optim["state"].values()))
@@ -217,7 +222,7 @@ def load_zip(path):
             "action_space": space_from_entry(data["action_space"]),
             "policy": policy, "optimizer": optim,
             "counters": {"num_timesteps": int(data.get("num_timesteps", 0)), "n_updates": int(data.get("_n_updates", 0)),
-                         "adam_step": adam_step}}
+                         "adam_step": adam_step, **ext.get("counters", {})}}
 
 
 def adam_moments(names, optim):

@@ -132,8 +132,7 @@ def _tree():
                                                   NAME_TRANSLATION=dict(overcooked.NAME_TRANSLATION)),
     }
     # pantheonrl.algos.adap / .modular (trainer.py:14-19)
-    modular = "the ModularAlgorithm learner (pantheonrl/algos/modular)"
-    from . import adap as adap_mod
+    from . import adap as adap_mod, modular as modular_mod
     mods.update({
         "pantheonrl.algos.adap": _module("pantheonrl.algos.adap"),
         "pantheonrl.algos.adap.adap_learn": _module("pantheonrl.algos.adap.adap_learn", ADAP=adap_mod.ADAP),
@@ -143,9 +142,9 @@ def _tree():
         "pantheonrl.algos.adap.util": _module("pantheonrl.algos.adap.util", SAMPLERS=adap_mod.SAMPLERS),
         "pantheonrl.algos.modular": _module("pantheonrl.algos.modular"),
         "pantheonrl.algos.modular.learn": _module("pantheonrl.algos.modular.learn",
-                                                  ModularAlgorithm=_placeholder("ModularAlgorithm", modular)),
+                                                  ModularAlgorithm=modular_mod.ModularAlgorithm),
         "pantheonrl.algos.modular.policies": _module("pantheonrl.algos.modular.policies",
-                                                     ModularPolicy=_placeholder("ModularPolicy", modular)),
+                                                     ModularPolicy=modular_mod.ModularPolicy),
     })
     return mods
 

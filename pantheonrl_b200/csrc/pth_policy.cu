@@ -41,7 +41,20 @@ struct FwdParams {
   const float* ctx;
   int64_t ctx_stride;
   int cx_off;  // byte offset of the [8][LDA] context tile in dynamic shared memory
+  // ModularPolicy (pantheonrl/algos/modular/policies.py:273-290, 364-383): Pn partner modules behind the
+  // main network, module p0 composes this forward: logits = main + partner, value = main + partner
+  int Pn, p0;
+  int x_off;  // byte offset of one more [64][LDA] tile (the partner branches' second layer)
 };
+
+// a [rows][64] matrix / a vector from global memory into a shared-memory slot (row stride LDW); the partner
+// blocks follow the main network without padding, so they need not be 16-byte aligned: scalar loads
+__device__ __forceinline__ void stage_rows(float* dst, const float* src, int rows, int tid) {
+  for (int i = tid; i < rows * HID; i += NT) dst[(i >> 6) * LDW + (i & 63)] = __ldg(src + i);
+}
+__device__ __forceinline__ void stage_v(float* dst, const float* src, int n, int tid) {
+  for (int i = tid; i < n; i += NT) dst[i] = __ldg(src + i);
+}
 
 template <int OW>
 __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constant__ FwdParams p) {
@@ -93,12 +106,62 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   __syncthreads();
   if (lane) action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
   // ---- value tower (A is free again)
-  first_layer(p.lo.w_vf0, sm.pol.b_vf0);
-  __syncthreads();
-  dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, sm.Bf, tid);
-  __syncthreads();
-  if (!lane) return;
-  const float v = value_head(sm.Bf, sm.pol, tid);
+  float v = 0.f;
+  if (p.Pn == 0) {
+    first_layer(p.lo.w_vf0, sm.pol.b_vf0);
+    __syncthreads();
+    dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, sm.Bf, tid);
+    __syncthreads();
+    if (!lane) return;
+    v = value_head(sm.Bf, sm.pol, tid);
+  } else {
+    // ModularPolicy: sm.Bf keeps latent_pi for the partner module; the extra tile X takes the second layers
+    float* X = reinterpret_cast<float*>(smem_raw + p.x_off);
+    const int L = p.sp.L;
+    const int blk = 4 * (HID * HID + HID) + L * HID + L + HID + 1;  // oracle/pth_oracle_modular.inc: mod_block
+    const float* pb = p.params + p.lo.total + (size_t)p.p0 * blk;
+    const float* pw_pi0 = pb, *pb_pi0 = pw_pi0 + HID * HID, *pw_pi1 = pb_pi0 + HID, *pb_pi1 = pw_pi1 + HID * HID;
+    const float* pw_vf0 = pb_pi1 + HID, *pb_vf0 = pw_vf0 + HID * HID, *pw_vf1 = pb_vf0 + HID, *pb_vf1 = pw_vf1 + HID * HID;
+    const float* pw_act = pb_vf1 + HID, *pb_act = pw_act + L * HID, *pw_val = pb_act + L, *pb_val = pw_val + HID;
+    first_layer(p.lo.w_vf0, sm.pol.b_vf0);
+    __syncthreads();
+    dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, X, tid);
+    __syncthreads();
+    if (lane) v = value_head(X, sm.pol, tid);
+    __syncthreads();
+    // partner policy branch: q1 = tanh(W0 latent_pi + b), q2 = tanh(W1 q1 + b), logits += Wact q2 + bact
+    stage_rows(sm.pol.w_pi1, pw_pi0, HID, tid);
+    stage_rows(sm.pol.w_vf1, pw_pi1, HID, tid);
+    stage_rows(sm.pol.w_act, pw_act, L, tid);
+    stage_v(sm.pol.b_pi1, pb_pi0, HID, tid);
+    stage_v(sm.pol.b_vf1, pb_pi1, HID, tid);
+    stage_v(sm.pol.b_act, pb_act, L, tid);
+    __syncthreads();
+    dense64<true>(sm.Bf, sm.pol.w_pi1, sm.pol.b_pi1, sm.A, tid);
+    __syncthreads();
+    dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, X, tid);
+    __syncthreads();
+    if (lane) {
+      float h[HID];
+      load_column(X, tid, h);
+      for (int l = 0; l < L; ++l) sm.Lg[l * LDA + tid] = sm.Lg[l * LDA + tid] + dot64(h, sm.pol.w_act + l * LDW, sm.pol.b_act[l]);
+    }
+    __syncthreads();
+    // partner value branch (it reads latent_pi too)
+    stage_rows(sm.pol.w_pi1, pw_vf0, HID, tid);
+    stage_rows(sm.pol.w_vf1, pw_vf1, HID, tid);
+    stage_v(sm.pol.b_pi1, pb_vf0, HID, tid);
+    stage_v(sm.pol.b_vf1, pb_vf1, HID, tid);
+    stage_v(sm.pol.w_val, pw_val, HID, tid);
+    if (tid == 0) sm.pol.b_val = __ldg(pb_val);
+    __syncthreads();
+    dense64<true>(sm.Bf, sm.pol.w_pi1, sm.pol.b_pi1, sm.A, tid);
+    __syncthreads();
+    dense64<true>(sm.A, sm.pol.w_vf1, sm.pol.b_vf1, X, tid);
+    __syncthreads();
+    if (!lane) return;
+    v = v + value_head(X, sm.pol, tid);
+  }
 
   // ---- distribution
   bool sample = p.action_in == nullptr;
@@ -209,6 +272,13 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   size_t smem = sizeof(FwdSmem) + (p.sp.obs_kind == PTH_OBS_BOX ? sizeof(float) * HID * LDA : 0) + (wide ? BT * 96 : 0);
   p.cx_off = (int)smem;
   smem += p.C > 0 ? sizeof(float) * 8 * LDA : 0;
+  PTH_CHECK_ARG(a->num_partners >= 0 && a->num_partners <= 8 && (a->num_partners == 0 ||
+                (a->partner_idx >= 0 && a->partner_idx < a->num_partners && a->context_size == 0)),
+                "ModularPolicy: 1..8 partners, partner_idx among them, no context inputs");
+  p.Pn = a->num_partners;
+  p.p0 = a->partner_idx;
+  p.x_off = (int)smem;
+  smem += p.Pn > 0 ? sizeof(float) * HID * LDA : 0;
   if (wide) {
     PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     policy_forward_kernel<96><<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);

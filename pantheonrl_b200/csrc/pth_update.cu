@@ -120,7 +120,13 @@ struct UpdParams {
   int K, NS;                 // num_context_samples, num_state_samples
   const int32_t* ctx_sidx;   // [n_epochs * n_mb][NS] positions inside the minibatch
   const float* ctx_draws;    // [n_epochs * n_mb][K][C] sampled contexts
-  float* ctx_loss;           // [n_epochs * n_mb] or NULL
+  float* ctx_loss;           // [n_epochs * n_mb] or NULL (MOD: the marginal regulariser of every minibatch)
+  // ModularAlgorithm (pantheonrl/algos/modular): Pn partner modules behind the main network
+  int P;                     // all parameters (lo.total, + Pn partner blocks when MOD)
+  int Pn, p0;                // num_partners, the partner whose buffer this launch trains on
+  float marg_coef;           // marginal_reg_coef
+  double b1pow0_v, b2pow0_v; // beta^steps of p0's value modules (their own Adam step count)
+  float* mod_ws;             // [G] per-CTA scratch of mod_scratch_floats(Pn) floats
 };
 constexpr int MAX_CTX = 8;
 
@@ -372,15 +378,15 @@ __device__ __forceinline__ void wgrad_first_box(const float* Dz, const float* X,
 // action head for the whole tile with all UNT threads: Lg[l][b] = b_act[l] + sum_k fma(H2[k][b],
 // w_act[l][k], .), k ascending (the chain of dot64).  Warp w owns logits w, w + NW, ... (uniform
 // per warp: weight reads are broadcasts); lane owns 4 consecutive samples.
-__device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& pol, int L, float* Lg,
-                                            int tid) {
+__device__ __forceinline__ void logits_tile_w(const float* Hh, const float* w_act, const float* b_act, int L,
+                                              float* Lg, int tid) {
   constexpr int NW = UNT / 32, NL = MAXL / NW;  // warps, logits per warp
   const int tx = tid & 31, ty = tid >> 5;
   float acc[NL][4];
 #pragma unroll
   for (int ll = 0; ll < NL; ++ll) {
     const int l = ty + NW * ll;
-    const float bl = l < L ? pol.b_act[l] : 0.f;
+    const float bl = l < L ? b_act[l] : 0.f;
 #pragma unroll
     for (int ss = 0; ss < 4; ++ss) acc[ll][ss] = bl;
   }
@@ -390,7 +396,7 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
 #pragma unroll
     for (int ll = 0; ll < NL; ++ll) {
       const int l = ty + NW * ll;
-      w[ll] = l < L ? *reinterpret_cast<const float4*>(pol.w_act + l * LDW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      w[ll] = l < L ? *reinterpret_cast<const float4*>(w_act + l * LDW + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -411,6 +417,124 @@ __device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& p
     if (l < L)
       *reinterpret_cast<float4*>(Lg + l * LDA + tx * 4) = make_float4(acc[ll][0], acc[ll][1], acc[ll][2], acc[ll][3]);
   }
+}
+
+__device__ __forceinline__ void logits_tile(const float* Hh, const SmemPolicy& pol, int L, float* Lg, int tid) {
+  logits_tile_w(Hh, pol.w_act, pol.b_act, L, Lg, tid);
+}
+
+// ---- ModularPolicy building blocks (pantheonrl/algos/modular/policies.py) -------------------------
+// out[k][b] = (sum_l fma(w_act[l][k], Dl[l][b], .)) * (ACT ? 1 - Hact[k][b]^2 : 1), l ascending: a head's
+// share of d loss / d latent.  Four threads per sample, 16 hidden units each; w_act in shared memory.
+template <bool ACT>
+__device__ __forceinline__ void head_backprop(const float* Dl, const float* w_act, const float* Hact, int L,
+                                              float* Out, int tid) {
+  static_assert(UNT / BT == 4, "four threads per sample");
+  const int sb = tid & (BT - 1), kb = (tid >> 7) * (HID / 4);
+  float acc[HID / 4];
+#pragma unroll
+  for (int k = 0; k < HID / 4; ++k) acc[k] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float d = Dl[l * LDA + sb];
+#pragma unroll
+    for (int k0 = 0; k0 < HID / 4; k0 += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(w_act + l * LDW + kb + k0);
+      acc[k0 + 0] = fmaf(w.x, d, acc[k0 + 0]);
+      acc[k0 + 1] = fmaf(w.y, d, acc[k0 + 1]);
+      acc[k0 + 2] = fmaf(w.z, d, acc[k0 + 2]);
+      acc[k0 + 3] = fmaf(w.w, d, acc[k0 + 3]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < HID / 4; ++k) {
+    float v = acc[k];
+    if constexpr (ACT) {
+      const float h = Hact[(kb + k) * LDA + sb];
+      v = v * (1.0f - h * h);
+    }
+    Out[(kb + k) * LDA + sb] = v;
+  }
+}
+// a [rows][64] matrix from global memory into a shared-memory slot with row stride LDW
+// (the partner blocks follow the main network without padding: their matrices need not be 16-byte aligned)
+__device__ __forceinline__ void stage_rows64(float* dst, const float* src, int rows, int tid) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = tid; i < rows * (HID / 4); i += UNT) {
+      const int j = i >> 4, k = (i & 15) * 4;
+      *reinterpret_cast<float4*>(dst + j * LDW + k) = __ldcg(s4 + i);
+    }
+  } else {
+    for (int i = tid; i < rows * HID; i += UNT) dst[(i >> 6) * LDW + (i & 63)] = __ldcg(src + i);
+  }
+}
+__device__ __forceinline__ void stage_vec(float* dst, const float* src, int n, int tid) {
+  for (int i = tid; i < n; i += UNT) dst[i] = __ldcg(src + i);
+}
+// per-partner parameter block behind the MlpPolicy layout (oracle/pth_oracle_modular.inc: mod_block)
+struct ModBlock {
+  int w_pi0, b_pi0, w_pi1, b_pi1, w_vf0, b_vf0, w_vf1, b_vf1, w_act, b_act, w_val, b_val, total;
+};
+__host__ __device__ inline ModBlock mod_block(int L) {
+  ModBlock o;
+  int p = 0;
+  o.w_pi0 = p; p += HID * HID;
+  o.b_pi0 = p; p += HID;
+  o.w_pi1 = p; p += HID * HID;
+  o.b_pi1 = p; p += HID;
+  o.w_vf0 = p; p += HID * HID;
+  o.b_vf0 = p; p += HID;
+  o.w_vf1 = p; p += HID * HID;
+  o.b_vf1 = p; p += HID;
+  o.w_act = p; p += L * HID;
+  o.b_act = p; p += L;
+  o.w_val = p; p += HID;
+  o.b_val = p; p += 1;
+  o.total = p;
+  return o;
+}
+constexpr int MOD_MAX_PARTNERS = 8;
+constexpr int TILE_F = HID * LDA;    // floats of a [64][LDA] scratch tile
+constexpr int LTILE_F = MAXL * LDA;  // floats of a [32][LDA] logits-sized scratch tile
+// per-CTA global scratch of the modular tile (activations of every module are kept for the backward pass)
+struct ModScratch {
+  float *a1p, *a1v, *h2, *v2, *r1, *r2, *tmp, *zero, *q1, *q2;  // q1 / q2: [Pn] tiles
+  float *lgm, *pm, *dlm, *lgp, *pc, *dlp;                        // logits-sized; lgp / pc / dlp: [Pn]
+};
+__host__ __device__ inline size_t mod_scratch_floats(int Pn) {
+  return (size_t)(8 + 2 * Pn) * TILE_F + (size_t)(3 + 3 * Pn) * LTILE_F;
+}
+__device__ __forceinline__ ModScratch mod_scratch(float* base, int Pn) {
+  ModScratch g;
+  float* q = base;
+  g.a1p = q; q += TILE_F;
+  g.a1v = q; q += TILE_F;
+  g.h2 = q; q += TILE_F;
+  g.v2 = q; q += TILE_F;
+  g.r1 = q; q += TILE_F;
+  g.r2 = q; q += TILE_F;
+  g.tmp = q; q += TILE_F;
+  g.zero = q; q += TILE_F;
+  g.q1 = q; q += (size_t)Pn * TILE_F;
+  g.q2 = q; q += (size_t)Pn * TILE_F;
+  g.lgm = q; q += LTILE_F;
+  g.pm = q; q += LTILE_F;
+  g.dlm = q; q += LTILE_F;
+  g.lgp = q; q += (size_t)Pn * LTILE_F;
+  g.pc = q; q += (size_t)Pn * LTILE_F;
+  g.dlp = q;
+  return g;
+}
+
+// Adam group of a parameter under ModularAlgorithm.train: 0 trained in every phase, 1 the value modules of
+// the partner being trained (their own step count), 2 the value modules of the other partners (no gradient:
+// Adam skips them, torch >= 2 zero_grad semantics)
+__device__ __forceinline__ int mod_group(int pi, int main_total, int blk_total, int w_vf0, int w_act, int w_val,
+                                         int p0) {
+  if (pi < main_total) return 0;
+  const int q = (pi - main_total) / blk_total, r = (pi - main_total) - q * blk_total;
+  if ((r >= w_vf0 && r < w_act) || r >= w_val) return q == p0 ? 1 : 2;
+  return 0;
 }
 
 // Stable counting sort of the tile's nb samples by observed value, one slot per warp at a time:
@@ -833,11 +957,11 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const
   segsum_w1_mode(p, sm, sm.bc, g_w0, first, tid, csum);
 }
 
-template <bool BOX, bool WIDE = false, bool ADAP = false>
+template <bool BOX, bool WIDE = false, bool ADAP = false, bool MOD = false>
 __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
   static_assert(!(BOX && WIDE), "wide rows are a one-hot notion");
-  static_assert(!(ADAP && WIDE), "ADAP: one-hot rows of 32 slots or Box rows");
-  constexpr bool PLAIN = WIDE || ADAP;
+  static_assert(!((ADAP || MOD) && WIDE) && !(ADAP && MOD), "ADAP / Modular: one-hot rows of 32 slots or Box rows");
+  constexpr bool PLAIN = WIDE || ADAP || MOD;
   using UpdSmem = UpdSmemT<WIDE, PLAIN>;
   constexpr int OW = UpdSmem::OW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -853,7 +977,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
   const int tid = threadIdx.x;
   const int G = gridDim.x;
   const int c = blockIdx.x;
-  const int P = p.lo.total;
+  const int P = p.P;
   const int64_t n_mb = (p.M + p.BS - 1) / p.BS;
   const int PS = (P + 3) & ~3;  // per-CTA stride of the partial sums: keeps every row 16-byte aligned
   float* part = p.part + (size_t)c * PS;
@@ -923,6 +1047,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
 
   long long prof_last = clock64();
   double b1pow = p.b1pow0, b2pow = p.b2pow0;
+  [[maybe_unused]] double b1pow_v = p.b1pow0_v, b2pow_v = p.b2pow0_v;
   const float omb1 = (float)(1.0 - (double)p.b1), omb2 = (float)(1.0 - (double)p.b2);
   const float clip_lo = 1.0f - p.clip, clip_hi = 1.0f + p.clip;
   const int S = ((P + G - 1) / G + 3) / 4 * 4;
@@ -1074,8 +1199,74 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           PTH_PROF(23);  // jb, stage copy, row positions | chain beginnings
         }
 
+        // ================= ModularPolicy: forward of the main network and of every partner module
+        [[maybe_unused]] ModScratch gsr;
+        [[maybe_unused]] float mod_value = 0.f;  // lane threads: main value + the trained partner's value
+        if constexpr (MOD) {
+          const ModBlock mbk = mod_block(p.sp.L);
+          gsr = mod_scratch(p.mod_ws + (size_t)c * mod_scratch_floats(p.Pn), p.Pn);
+          const int L = p.sp.L;
+          // main first layers -> a1p, a1v
+          if constexpr (BOX) {
+            first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, gsr.a1p, tid);
+            first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, gsr.a1v, tid);
+          } else if (tid < UNT / 2) {
+            first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, gsr.a1p, tid);
+          } else {
+            first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, gsr.a1v,
+                                                          tid - UNT / 2);
+          }
+          __syncthreads();
+          // the previous tile left a partner's weights in the slots: the main matrices again
+          load_policy<true>(sm.pol, p.params, p.lo, L, tid, UNT);
+          __syncthreads();
+          dense64<true, UNT, BT, LDA>(gsr.a1p, sm.pol.w_pi1, sm.pol.b_pi1, gsr.h2, tid);
+          dense64<true, UNT, BT, LDA>(gsr.a1v, sm.pol.w_vf1, sm.pol.b_vf1, gsr.v2, tid);
+          __syncthreads();
+          logits_tile(gsr.h2, sm.pol, L, gsr.lgm, tid);
+          if (tid < BT) mod_value = value_head(gsr.v2, sm.pol, tid);
+          __syncthreads();
+          for (int pq = 0; pq < p.Pn; ++pq) {
+            const float* pb = p.params + p.lo.total + (size_t)pq * mbk.total;
+            stage_rows64(sm.pol.w_pi1, pb + mbk.w_pi0, HID, tid);
+            stage_rows64(sm.pol.w_vf1, pb + mbk.w_pi1, HID, tid);
+            stage_rows64(sm.pol.w_act, pb + mbk.w_act, L, tid);
+            stage_vec(sm.pol.b_pi1, pb + mbk.b_pi0, HID, tid);
+            stage_vec(sm.pol.b_vf1, pb + mbk.b_pi1, HID, tid);
+            stage_vec(sm.pol.b_act, pb + mbk.b_act, L, tid);
+            __syncthreads();
+            dense64<true, UNT, BT, LDA>(gsr.h2, sm.pol.w_pi1, sm.pol.b_pi1, gsr.q1 + (size_t)pq * TILE_F, tid);
+            __syncthreads();
+            dense64<true, UNT, BT, LDA>(gsr.q1 + (size_t)pq * TILE_F, sm.pol.w_vf1, sm.pol.b_vf1,
+                                        gsr.q2 + (size_t)pq * TILE_F, tid);
+            __syncthreads();
+            logits_tile(gsr.q2 + (size_t)pq * TILE_F, sm.pol, L, gsr.lgp + (size_t)pq * LTILE_F, tid);
+            __syncthreads();
+          }
+          {  // value branch of the trained partner (it reads latent_pi too: modular/policies.py:279, 375)
+            const float* pb = p.params + p.lo.total + (size_t)p.p0 * mbk.total;
+            stage_rows64(sm.pol.w_pi1, pb + mbk.w_vf0, HID, tid);
+            stage_rows64(sm.pol.w_vf1, pb + mbk.w_vf1, HID, tid);
+            stage_vec(sm.pol.b_pi1, pb + mbk.b_vf0, HID, tid);
+            stage_vec(sm.pol.b_vf1, pb + mbk.b_vf1, HID, tid);
+            stage_vec(sm.pol.w_val, pb + mbk.w_val, HID, tid);
+            if (tid == 0) sm.pol.b_val = __ldcg(pb + mbk.b_val);
+            __syncthreads();
+            dense64<true, UNT, BT, LDA>(gsr.h2, sm.pol.w_pi1, sm.pol.b_pi1, gsr.r1, tid);
+            __syncthreads();
+            dense64<true, UNT, BT, LDA>(gsr.r1, sm.pol.w_vf1, sm.pol.b_vf1, gsr.r2, tid);
+            __syncthreads();
+            if (tid < BT) mod_value = mod_value + value_head(gsr.r2, sm.pol, tid);
+          }
+          // composed logits of the trained partner: what PPO's losses see
+          for (int i = tid; i < L * BT; i += UNT) {
+            const int l = i >> 7, b = i & (BT - 1);
+            sm.Lg[l * LDA + b] = gsr.lgm[l * LDA + b] + gsr.lgp[(size_t)p.p0 * LTILE_F + l * LDA + b];
+          }
+        }
         // ================= policy tower: forward
-        if constexpr (BOX) {
+        if constexpr (MOD) {
+        } else if constexpr (BOX) {
           first_layer_box<true, UNT, BT, !ADAP>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         } else {
           // both towers' first layers (latency-bound row gathers) side by side, one per CTA half
@@ -1105,12 +1296,13 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           __syncthreads();
         }
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
-        dense64<true, UNT / 2, BT / 2, LDA>(sm.H1 + (tid >> 8) * (BT / 2), sm.pol.w_pi1, sm.pol.b_pi1,
-                                             sm.H2 + (tid >> 8) * (BT / 2), tid & (UNT / 2 - 1));
+        if constexpr (!MOD)
+          dense64<true, UNT / 2, BT / 2, LDA>(sm.H1 + (tid >> 8) * (BT / 2), sm.pol.w_pi1, sm.pol.b_pi1,
+                                               sm.H2 + (tid >> 8) * (BT / 2), tid & (UNT / 2 - 1));
         __syncthreads();
         PTH_PROF(4);  // pi hidden layer
         float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
-        logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
+        if constexpr (!MOD) logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
         __syncthreads();
         if (!ctile) {
           // ---- per-sample losses and d loss / d logits.  Thread group h (threads [128h, 128h + 128))
@@ -1284,6 +1476,224 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         }
         __syncthreads();  // dlogits complete
         PTH_PROF(5);  // action head + losses + dlogits
+        if constexpr (MOD) {
+          // ================= ModularAlgorithm: the marginal regulariser and the backward pass through
+          // every module (contract: oracle/pth_oracle_modular.inc).  sm.Lg holds d PPO-loss / d composed logits.
+          const ModBlock mbk = mod_block(p.sp.L);
+          const int L = p.sp.L, Pn = p.Pn;
+          const float Pnf = (float)Pn;
+          float* DV = reinterpret_cast<float*>(sm.rowpos);  // [BT] d loss / d value (the sort's scratch is free)
+          float s_mg = 0.f;
+          if (lane) {
+            const float dret = ret - mod_value;
+            s_v = valid ? dret * dret : 0.f;
+            DV[tid] = valid ? ((p.vf_coef * 2.0f) * (mod_value - ret)) * invB : 0.f;
+            // softmax over ALL logits jointly (modular/learn.py:311-312): main, and main + partner[p]
+            auto softmax_col = [&](const float* a, const float* b2, float* out) {
+              float mx = a[tid] + (b2 ? b2[tid] : 0.f);
+              for (int l = 1; l < L; ++l) {
+                const float x = b2 ? a[l * LDA + tid] + b2[l * LDA + tid] : a[l * LDA + tid];
+                mx = x > mx ? x : mx;
+              }
+              float S = 0.f;
+              for (int l = 0; l < L; ++l) {
+                const float x = b2 ? a[l * LDA + tid] + b2[l * LDA + tid] : a[l * LDA + tid];
+                const float ex = pth_expf(x - mx);
+                out[l * LDA + tid] = ex;
+                S = S + ex;
+              }
+              for (int l = 0; l < L; ++l) out[l * LDA + tid] = out[l * LDA + tid] / S;
+            };
+            {
+              float mx = gsr.lgm[tid];
+              for (int l = 1; l < L; ++l) mx = gsr.lgm[l * LDA + tid] > mx ? gsr.lgm[l * LDA + tid] : mx;
+              float S = 0.f;
+              for (int l = 0; l < L; ++l) {
+                const float ex = pth_expf(gsr.lgm[l * LDA + tid] - mx);
+                gsr.pm[l * LDA + tid] = ex;
+                S = S + ex;
+              }
+              for (int l = 0; l < L; ++l) gsr.pm[l * LDA + tid] = gsr.pm[l * LDA + tid] / S;
+            }
+            for (int pq = 0; pq < Pn; ++pq) softmax_col(gsr.lgm, gsr.lgp + (size_t)pq * LTILE_F, gsr.pc + (size_t)pq * LTILE_F);
+            const float gcoef = valid ? p.marg_coef * invB : 0.f;
+            float* G_ = gsr.tmp;  // d regulariser / d (main marginal - composed marginal), row l
+            float absum = 0.f, t = 0.f;
+            for (int l = 0; l < L; ++l) {
+              const float pml = gsr.pm[l * LDA + tid];
+              float sm_ = pml, sc_ = gsr.pc[l * LDA + tid];
+              for (int pq = 1; pq < Pn; ++pq) {
+                sm_ = sm_ + pml;
+                sc_ = sc_ + gsr.pc[(size_t)pq * LTILE_F + l * LDA + tid];
+              }
+              const float diff = sm_ / Pnf - sc_ / Pnf;
+              absum = absum + fabsf(diff);
+              const float g = diff > 0.f ? gcoef : (diff < 0.f ? -gcoef : 0.f);
+              G_[l * LDA + tid] = g;
+              t = fmaf(g, pml, t);
+            }
+            s_mg = valid ? absum : 0.f;
+            for (int l = 0; l < L; ++l) {
+              const float pml = gsr.pm[l * LDA + tid];
+              gsr.dlm[l * LDA + tid] = sm.Lg[l * LDA + tid] + pml * (G_[l * LDA + tid] - t);
+            }
+            for (int pq = 0; pq < Pn; ++pq) {
+              const float* pc = gsr.pc + (size_t)pq * LTILE_F;
+              float* dl = gsr.dlp + (size_t)pq * LTILE_F;
+              float tp = 0.f;
+              for (int l = 0; l < L; ++l) tp = fmaf(-(G_[l * LDA + tid] / Pnf), pc[l * LDA + tid], tp);
+              for (int l = 0; l < L; ++l) {
+                const float dzp = pc[l * LDA + tid] * (-(G_[l * LDA + tid] / Pnf) - tp);
+                gsr.dlm[l * LDA + tid] = gsr.dlm[l * LDA + tid] + dzp;
+                dl[l * LDA + tid] = pq == p.p0 ? sm.Lg[l * LDA + tid] + dzp : dzp;
+              }
+            }
+          }
+          // the zero tile (backprop64 without an activation derivative multiplies by 1 - 0^2)
+          for (int i = tid; i < TILE_F; i += UNT) gsr.zero[i] = 0.f;
+          // ---- main action head, and its share of d loss / d latent_pi (accumulated in sm.H1)
+          stage_rows64(sm.pol.w_act, p.params + p.lo.w_act, L, tid);
+          __syncthreads();
+          if (tid >= UNT / 2) {
+            head_wgrad(gsr.dlm, gsr.h2, L, part + p.lo.w_act, first, tid - UNT / 2);
+            row_sums(gsr.dlm, L, part + p.lo.b_act, first, tid, UNT - MAXL);
+          }
+          head_backprop<false>(gsr.dlm, sm.pol.w_act, nullptr, L, sm.H1, tid);
+          __syncthreads();
+          // one 64 x 64 tanh layer backward: weight / bias gradients from (Dz, input activations A), then
+          // Out = (W^T Dz) * (1 - Act^2)  (Act = the zero tile: no activation derivative)
+          auto layer_backward = [&](const float* Dz, const float* A, const float* Wsm, const float* Act, float* Out,
+                                    float* gW, float* gB) {
+            wgrad64<UNT>(Dz, A, gW, first, tid);
+            row_sums(Dz, HID, gB, first, tid, UNT - HID);
+            backprop64<false, UNT>(Dz, Wsm, Act, Out, tid);
+            __syncthreads();
+          };
+          auto add_into_dh2 = [&]() {
+            for (int i = tid; i < HID * BT; i += UNT) {
+              const int k = i >> 7, b = i & (BT - 1);
+              sm.H1[k * LDA + b] = sm.H1[k * LDA + b] + gsr.tmp[k * LDA + b];
+            }
+            __syncthreads();
+          };
+          // ---- partner policy branches, p ascending
+          for (int pq = 0; pq < Pn; ++pq) {
+            const float* pb = p.params + p.lo.total + (size_t)pq * mbk.total;
+            float* gb = part + p.lo.total + (size_t)pq * mbk.total;
+            const float* dl = gsr.dlp + (size_t)pq * LTILE_F;
+            const float* q1 = gsr.q1 + (size_t)pq * TILE_F;
+            const float* q2 = gsr.q2 + (size_t)pq * TILE_F;
+            stage_rows64(sm.pol.w_act, pb + mbk.w_act, L, tid);
+            stage_rows64(sm.pol.w_pi1, pb + mbk.w_pi0, HID, tid);
+            stage_rows64(sm.pol.w_vf1, pb + mbk.w_pi1, HID, tid);
+            __syncthreads();
+            if (tid >= UNT / 2) {
+              head_wgrad(dl, q2, L, gb + mbk.w_act, first, tid - UNT / 2);
+              row_sums(dl, L, gb + mbk.b_act, first, tid, UNT - MAXL);
+            }
+            head_backprop<true>(dl, sm.pol.w_act, q2, L, sm.D1, tid);
+            __syncthreads();
+            layer_backward(sm.D1, q1, sm.pol.w_vf1, q1, sm.H2, gb + mbk.w_pi1, gb + mbk.b_pi1);
+            layer_backward(sm.H2, gsr.h2, sm.pol.w_pi1, gsr.zero, gsr.tmp, gb + mbk.w_pi0, gb + mbk.b_pi0);
+            add_into_dh2();
+          }
+          // ---- value branch of the trained partner
+          {
+            const float* pb = p.params + p.lo.total + (size_t)p.p0 * mbk.total;
+            float* gb = part + p.lo.total + (size_t)p.p0 * mbk.total;
+            stage_rows64(sm.pol.w_pi1, pb + mbk.w_vf0, HID, tid);
+            stage_rows64(sm.pol.w_vf1, pb + mbk.w_vf1, HID, tid);
+            stage_vec(sm.pol.w_val, pb + mbk.w_val, HID, tid);
+            __syncthreads();
+            if (lane) {
+              const float dv = DV[tid];
+#pragma unroll 8
+              for (int k = 0; k < HID; ++k) {
+                const float h = gsr.r2[k * LDA + tid];
+                sm.D1[k * LDA + tid] = (sm.pol.w_val[k] * dv) * (1.0f - h * h);
+              }
+            } else if (tid < BT + HID) {
+              const int k = tid - BT;
+              float acc = 0.f;
+              for (int b0 = 0; b0 < BT; b0 += 4) {
+                const float4 d = *reinterpret_cast<const float4*>(DV + b0);
+                const float4 h = *reinterpret_cast<const float4*>(gsr.r2 + k * LDA + b0);
+                acc = fmaf(d.x, h.x, acc);
+                acc = fmaf(d.y, h.y, acc);
+                acc = fmaf(d.z, h.z, acc);
+                acc = fmaf(d.w, h.w, acc);
+              }
+              acc_store(gb + mbk.w_val + k, acc, first);
+            } else if (tid == BT + HID) {
+              float s_ = 0.f;
+              for (int b = 0; b < BT; ++b) s_ = s_ + DV[b];
+              acc_store(gb + mbk.b_val, s_, first);
+            }
+            __syncthreads();
+            layer_backward(sm.D1, gsr.r1, sm.pol.w_vf1, gsr.r1, sm.H2, gb + mbk.w_vf1, gb + mbk.b_vf1);
+            layer_backward(sm.H2, gsr.h2, sm.pol.w_pi1, gsr.zero, gsr.tmp, gb + mbk.w_vf0, gb + mbk.b_vf0);
+            add_into_dh2();
+          }
+          // ---- main towers (the main matrices back in their slots)
+          load_policy<true>(sm.pol, p.params, p.lo, L, tid, UNT);
+          for (int i = tid; i < HID * BT; i += UNT) {
+            const int k = i >> 7, b = i & (BT - 1);
+            const float h = gsr.h2[k * LDA + b];
+            sm.D1[k * LDA + b] = sm.H1[k * LDA + b] * (1.0f - h * h);
+          }
+          tower_backward<BOX>(p, sm, Xs, gsr.a1p, sm.pol.w_pi1, part + p.lo.w_pi0, part + p.lo.b_pi0, part + p.lo.w_pi1,
+                              part + p.lo.b_pi1, nb, first, tid, prof_last, c, 18);
+          __syncthreads();
+          if (lane) {
+            const float dv = DV[tid];
+#pragma unroll 8
+            for (int k = 0; k < HID; ++k) {
+              const float h = gsr.v2[k * LDA + tid];
+              sm.D1[k * LDA + tid] = (sm.pol.w_val[k] * dv) * (1.0f - h * h);
+            }
+          } else if (tid < BT + HID) {
+            const int k = tid - BT;
+            float acc = 0.f;
+            for (int b0 = 0; b0 < BT; b0 += 4) {
+              const float4 d = *reinterpret_cast<const float4*>(DV + b0);
+              const float4 h = *reinterpret_cast<const float4*>(gsr.v2 + k * LDA + b0);
+              acc = fmaf(d.x, h.x, acc);
+              acc = fmaf(d.y, h.y, acc);
+              acc = fmaf(d.z, h.z, acc);
+              acc = fmaf(d.w, h.w, acc);
+            }
+            acc_store(part + p.lo.w_val + k, acc, first);
+          } else if (tid == BT + HID) {
+            float s_ = 0.f;
+            for (int b = 0; b < BT; ++b) s_ = s_ + DV[b];
+            acc_store(part + p.lo.b_val, s_, first);
+          }
+          tower_backward<BOX>(p, sm, Xs, gsr.a1v, sm.pol.w_vf1, part + p.lo.w_vf0, part + p.lo.b_vf0, part + p.lo.w_vf1,
+                              part + p.lo.b_vf1, nb, first, tid, prof_last, c, 20);
+          // ---- tile statistics: six trees (the sixth: the marginal regulariser's per-sample sums)
+          {
+            float sv[6] = {s_pl, s_v, s_e, s_kl, s_cf, s_mg};
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) sv[i] = sv[i] + __shfl_xor_sync(0xffffffffu, sv[i], d);
+            __syncthreads();
+            if ((tid & 31) == 0 && tid < BT)
+#pragma unroll
+              for (int i = 0; i < 6; ++i) sm.bc[i * 4 + (tid >> 5)] = sv[i];
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const float ts = ((sm.bc[i * 4] + sm.bc[i * 4 + 1]) + sm.bc[i * 4 + 2]) + sm.bc[i * 4 + 3];
+              if (i < 5)
+                cta_stat[i] = first ? ts : cta_stat[i] + ts;
+              else
+                cta_ctx = first ? ts : cta_ctx + ts;
+            }
+          }
+          first = false;
+          continue;
+        }
         // ================= policy tower: backward
         // upper half: head weight / bias gradients; lower half: dz2, two threads per sample
         // (32 hidden units each; every dz2[k][b] is still one fma chain over the logits, ascending)
@@ -1401,7 +1811,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         first = false;
       }
       if (tid < 5) p.stat_part[c * 8 + tid] = cta_stat[tid];
-      if constexpr (ADAP) {
+      if constexpr (ADAP || MOD) {
         if (tid == 0) p.stat_part[c * 8 + 5] = cta_ctx;
       }
       PTH_PROF(12);  // tile statistics
@@ -1430,7 +1840,11 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         for (int i0c = 0; i0c < S; i0c += PL) {
           const int i = i0c + li;
           const int pi = c * S + i;
-          const bool live = i < S && pi < P;
+          bool live = i < S && pi < P;
+          if constexpr (MOD) {  // value modules of the partners that are not being trained: no gradient
+            const ModBlock mbk = mod_block(p.sp.L);
+            live = live && mod_group(pi, p.lo.total, mbk.total, mbk.w_vf0, mbk.w_act, mbk.w_val, p.p0) != 2;
+          }
           float t[RH];
 #pragma unroll
           for (int u = 0; u < RH; ++u)
@@ -1475,7 +1889,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       // off the critical path of the parameter update (read back after barrier 2)
       if (c == G - 1 && (tid >> 5) == 4) {
         const int ln = tid & 31;
-        constexpr int NST = ADAP ? 6 : 5;  // ADAP: + the context-loss sum
+        constexpr int NST = (ADAP || MOD) ? 6 : 5;  // ADAP: + the context-loss sum; MOD: + the marginal regulariser's
         float* sc = sm.Lg;  // [NST][160] scratch (free between tiles)
         float t[NST][5];
 #pragma unroll
@@ -1565,18 +1979,35 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       b2pow *= (double)p.b2;
       const float step_size = (float)((double)p.lr / (1.0 - b1pow));
       const float bc2_sqrt = (float)sqrt(1.0 - b2pow);
+      [[maybe_unused]] float step_size_v = 0.f, bc2_sqrt_v = 1.f;
+      if constexpr (MOD) {  // the trained partner's value modules count their own optimiser steps
+        b1pow_v *= (double)p.b1;
+        b2pow_v *= (double)p.b2;
+        step_size_v = (float)((double)p.lr / (1.0 - b1pow_v));
+        bc2_sqrt_v = (float)sqrt(1.0 - b2pow_v);
+      }
       for (int i = tid; i < S; i += UNT) {
         const int pi = c * S + i;
         if (pi < P) {
+          float ss = step_size, bq = bc2_sqrt;
+          if constexpr (MOD) {
+            const ModBlock mbk = mod_block(p.sp.L);
+            const int gi = mod_group(pi, p.lo.total, mbk.total, mbk.w_vf0, mbk.w_act, mbk.w_val, p.p0);
+            if (gi == 2) continue;
+            if (gi == 1) {
+              ss = step_size_v;
+              bq = bc2_sqrt_v;
+            }
+          }
           const bool pre = i == tid && own0;
           float g = (pre ? g0 : p.grad[pi]) * coef;
           if (p.l2 != 0.f) g = fmaf(p.l2, pre ? w0 : p.params[pi], g);  // d/dtheta of l2 * sum(theta^2) / 2
           const float mm = fmaf(omb1, g, p.b1 * (pre ? m0 : p.adam_m[pi]));
           const float vv = fmaf(omb2 * g, g, p.b2 * (pre ? v0 : p.adam_v[pi]));
-          const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
+          const float denom = sqrtf(vv) / bq + p.eps;
           p.adam_m[pi] = mm;
           p.adam_v[pi] = vv;
-          p.params[pi] = fmaf(-step_size, mm / denom, pre ? w0 : p.params[pi]);
+          p.params[pi] = fmaf(-ss, mm / denom, pre ? w0 : p.params[pi]);
         }
       }
       if (c == 0 && tid < 32 && p.stats) {
@@ -1586,7 +2017,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         // for it at barrier 3: profiles/scaling_r02.md) — then lanes 0..4 add them in rank order.
         float mine = 0.f;
         if (W == 1) {
-          if (tid < (ADAP ? 6 : 5)) mine = __ldcg(p.stat_part + G * 8 + tid);  // summed in CTA order during the reduce phase
+          if (tid < ((ADAP || MOD) ? 6 : 5)) mine = __ldcg(p.stat_part + G * 8 + tid);  // summed in CTA order during the reduce phase
         } else {
           const uint2* xl = p.xbuf[p.rank] + (size_t)par * W * p.XS + P;
           float* sc = sm.Lg;  // [8][5] scratch (free between tiles)
@@ -1623,6 +2054,14 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
               p.stats[8 * id + 5] = p.stats[8 * id + 5] + p.ctx_coeff * cl;
             }
             if (p.ctx_loss) p.ctx_loss[id] = cl;
+          }
+        }
+        if constexpr (MOD) {
+          const float csum = __shfl_sync(0xffffffffu, mine, 5);
+          if (tid == 0) {
+            const float mg = csum / Bf;  // mean_b sum_l |main marginal - composed marginal|
+            p.stats[8 * id + 5] = p.stats[8 * id + 5] + p.marg_coef * mg;
+            if (p.ctx_loss) p.ctx_loss[id] = mg;
           }
         }
       }
@@ -1816,6 +2255,8 @@ const void* update_fn(int kind) {
     case 2: return (const void*)ppo_update_kernel<false, true>;
     case 3: return (const void*)ppo_update_kernel<false, false, true>;
     case 4: return (const void*)ppo_update_kernel<true, false, true>;
+    case 5: return (const void*)ppo_update_kernel<false, false, false, true>;  // ModularAlgorithm, one-hot
+    case 6: return (const void*)ppo_update_kernel<true, false, false, true>;   // ModularAlgorithm, Box
     default: return (const void*)ppo_update_kernel<false, false>;
   }
 }
@@ -1824,7 +2265,7 @@ size_t update_smem(int kind) {
 }
 
 int max_coop_ctas(const pth_ctx* ctx, int kind = 0) {
-  static int cached[5] = {-1, -1, -1, -1, -1};
+  static int cached[7] = {-1, -1, -1, -1, -1, -1, -1};
   if (cached[kind] < 0) {
     const void* fn = update_fn(kind);
     const size_t smem = update_smem(kind);
@@ -1893,6 +2334,29 @@ extern "C" int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_spac
   return pth_adap_workspace_bytes(ctx, sp, 0, M, batch_size);
 }
 
+extern "C" int64_t pth_modular_param_count(const pth_space* sp, int32_t num_partners) {
+  const int64_t P = pth_policy_param_count(sp);
+  if (P < 0 || num_partners < 1 || num_partners > MOD_MAX_PARTNERS) return PTH_EINVAL;
+  return P + (int64_t)num_partners * mod_block(pth_space_logit_dim(sp)).total;
+}
+
+extern "C" int64_t pth_modular_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t num_partners,
+                                               int64_t M, int64_t batch_size) {
+  if (!ctx || !sp || M <= 0 || batch_size <= 0) return PTH_EINVAL;
+  const int64_t P = pth_modular_param_count(sp, num_partners);
+  if (P < 0) return PTH_EINVAL;
+  const int cap = max_coop_ctas(ctx, sp->obs_kind == PTH_OBS_BOX ? 6 : 5);
+  const int64_t n_mb = (M + batch_size - 1) / batch_size;
+  return (int64_t)ws_layout(cap > 0 ? cap : 1, (int)P, 64 * n_mb).total;
+}
+
+// per-CTA activation scratch of the modular tile for the largest grid a launch may use
+extern "C" int64_t pth_modular_scratch_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t num_partners) {
+  if (!ctx || !sp || num_partners < 1 || num_partners > MOD_MAX_PARTNERS) return PTH_EINVAL;
+  const int cap = max_coop_ctas(ctx, sp->obs_kind == PTH_OBS_BOX ? 6 : 5);
+  return (int64_t)(sizeof(float) * mod_scratch_floats(num_partners)) * (cap > 0 ? cap : 1);
+}
+
 extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stream) {
   PTH_CHECK_ARG(ctx != nullptr && a != nullptr, "NULL ctx/args");
   PTH_CHECK_ARG(a->space && a->d_params && a->d_adam_m && a->d_adam_v, "NULL space/params/adam");
@@ -1943,9 +2407,30 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     p.ctx_draws = a->d_ctx_draws;
   }
   p.lo = make_layout(p.sp.F + C, p.sp.L);
+  p.P = p.lo.total;
+  // ModularAlgorithm (pantheonrl/algos/modular): num_partners modules behind the main network
+  const bool modular = a->loss_kind == PTH_LOSS_MODULAR;
+  p.Pn = p.p0 = 0;
+  p.marg_coef = 0.f;
+  p.mod_ws = nullptr;
+  p.b1pow0_v = p.b2pow0_v = 1.0;
+  if (modular) {
+    PTH_CHECK_ARG(C == 0 && a->rec_stride == 0 && a->world <= 1 && (box || p.sp.obs_len <= 32),
+                  "ModularAlgorithm: no context inputs, separate sample arrays, one GPU, at most 32 observation slots");
+    PTH_CHECK_ARG(a->num_partners >= 1 && a->num_partners <= MOD_MAX_PARTNERS && a->partner_idx >= 0 &&
+                      a->partner_idx < a->num_partners,
+                  "ModularAlgorithm: 1..8 partners, partner_idx among them");
+    p.Pn = a->num_partners;
+    p.p0 = a->partner_idx;
+    p.marg_coef = a->marginal_reg_coef;
+    p.P = p.lo.total + p.Pn * mod_block(p.sp.L).total;
+    p.b1pow0_v = pow((double)a->adam_beta1, (double)a->partner_vf_step);
+    p.b2pow0_v = pow((double)a->adam_beta2, (double)a->partner_vf_step);
+    p.ctx_loss = a->d_ctx_loss;
+  }
   for (int i = 0; i < MAX_SLOTS; ++i)
     p.nvec[i] = (!box && i < p.sp.obs_len) ? (uint8_t)a->space->obs_nvec[i] : 0;
-  const int kind = C > 0 ? (box ? 4 : 3) : (box ? 1 : (p.sp.obs_len > 32 ? 2 : 0));
+  const int kind = modular ? (box ? 6 : 5) : (C > 0 ? (box ? 4 : 3) : (box ? 1 : (p.sp.obs_len > 32 ? 2 : 0)));
   const int cap = max_coop_ctas(ctx, kind);
   PTH_CHECK_ARG(cap <= 160, "more than 160 co-resident CTAs are not supported");
   if (cap < 1 || !ctx->coop_launch) {
@@ -1956,7 +2441,13 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
                            : auto_grid(ctx, a->M, a->batch_size, a->world > 1 ? a->world : 1, kind);
   PTH_CHECK_ARG(G >= 1 && G <= cap, "grid_ctas exceeds the co-resident CTA capacity");
   const int64_t n_mb = (a->M + a->batch_size - 1) / a->batch_size;
-  const WsLayout w = ws_layout(G, p.lo.total, (int64_t)a->n_epochs * n_mb);
+  const WsLayout w = ws_layout(G, p.P, (int64_t)a->n_epochs * n_mb);
+  if (modular) {
+    PTH_CHECK_ARG(a->d_modular_scratch != nullptr && ((uintptr_t)a->d_modular_scratch % 16) == 0 &&
+                      a->modular_scratch_bytes >= (int64_t)(sizeof(float) * mod_scratch_floats(p.Pn) * (size_t)G),
+                  "ModularAlgorithm: d_modular_scratch too small (pth_modular_scratch_bytes)");
+    p.mod_ws = reinterpret_cast<float*>(a->d_modular_scratch);
+  }
   PTH_CHECK_ARG((int64_t)w.total <= a->workspace_bytes, "workspace too small");
   PTH_CHECK_ARG(((uintptr_t)a->d_workspace % 256) == 0 && ((uintptr_t)a->d_params % 16) == 0,
                 "workspace must be 256-byte aligned, params 16-byte aligned");
@@ -1992,10 +2483,10 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.b2 = a->adam_beta2;
   p.eps = a->adam_eps;
   p.normalize = a->normalize_advantage;
-  p.loss_kind = a->loss_kind == PTH_LOSS_ADAP ? PTH_LOSS_PPO : a->loss_kind;  // ADAP = PPO's losses + context tiles
+  // ADAP = PPO's losses + context tiles; ModularAlgorithm = PPO's losses on the composed outputs + the regulariser
+  p.loss_kind = (a->loss_kind == PTH_LOSS_ADAP || modular) ? PTH_LOSS_PPO : a->loss_kind;
   p.l2 = a->l2_weight;
-  PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->loss_kind == PTH_LOSS_BC || a->loss_kind == PTH_LOSS_ADAP,
-                "bad loss_kind");
+  PTH_CHECK_ARG(a->loss_kind >= PTH_LOSS_PPO && a->loss_kind <= PTH_LOSS_MODULAR, "bad loss_kind");
   PTH_CHECK_ARG(a->loss_kind == PTH_LOSS_PPO || a->world <= 1, "behaviour cloning / ADAP run on one GPU");
   p.b1pow0 = pow((double)a->adam_beta1, (double)a->adam_step);
   p.b2pow0 = pow((double)a->adam_beta2, (double)a->adam_step);
@@ -2010,7 +2501,7 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   p.world = a->world > 1 ? a->world : 1;
   p.rank = p.world > 1 ? a->rank : 0;
   p.flag_epoch = a->flag_epoch;
-  p.XS = (p.lo.total + 8 + 3) / 4 * 4;
+  p.XS = (p.P + 8 + 3) / 4 * 4;
   for (int r = 0; r < 8; ++r) {
     p.xbuf[r] = nullptr;
     p.advx[r] = nullptr;

@@ -45,13 +45,16 @@ class DevicePolicy:
     def __init__(self, space, observation_space, action_space, seed, device, rng_stream, rng="philox"):
         self.space, self.observation_space, self.action_space = space, observation_space, action_space
         self.device, self.seed, self.rng_stream, self.rng = device, int(seed or 0), rng_stream, rng
-        self.params = torch.from_numpy(pol.init_flat(space, seed, self.extra_inputs)).to(device)  # seed None: no re-seeding
+        self.params = torch.from_numpy(self._init_flat(space, seed)).to(device)  # seed None: no re-seeding
         self.calls = 0
         self.box = space.obs_kind == _lib.PTH_OBS_BOX  # fp32 rows of 64 instead of 32 slot bytes
         self.row = space.row_bytes  # one-hot rows: 32 bytes, or 96 for frame-stacked observations
         self._obs_dev = (torch.zeros(1, _lib.PTH_OC_ROW, dtype=torch.float32, device=device) if self.box
                          else torch.zeros(1, self.row, dtype=torch.uint8, device=device))
         self.act_dim = space.n_heads
+
+    def _init_flat(self, space, seed):
+        return pol.init_flat(space, seed, self.extra_inputs)
 
     def _stage_obs(self, obs):
         o = np.zeros((1, _lib.PTH_OC_ROW), np.float32) if self.box else np.zeros((1, self.row), np.uint8)

@@ -59,10 +59,17 @@ def update_grid(space, M, batch_size, device=0):
 class UpdateWorkspace:
     """Caller-owned scratch for pth_ppo_update (the library never allocates)."""
 
-    def __init__(self, space, M, batch_size, device="cuda", context_size=0):
+    def __init__(self, space, M, batch_size, device="cuda", context_size=0, num_partners=0):
         ctx = Context.get(torch.device(device).index or 0)
-        n = int(_lib.load().pth_adap_workspace_bytes(ctx.handle, C.byref(space), int(context_size), int(M),
-                                                     int(batch_size)))
+        lib = _lib.load()
+        if num_partners > 0:  # ModularPolicy: + the per-CTA activation scratch of every partner module
+            n = int(lib.pth_modular_workspace_bytes(ctx.handle, C.byref(space), int(num_partners), int(M), int(batch_size)))
+            ns = int(lib.pth_modular_scratch_bytes(ctx.handle, C.byref(space), int(num_partners)))
+            if ns <= 0:
+                raise _lib.PthError("pth_modular_scratch_bytes failed")
+            self.modular_scratch = torch.empty(ns, dtype=torch.uint8, device=device)
+        else:
+            n = int(lib.pth_adap_workspace_bytes(ctx.handle, C.byref(space), int(context_size), int(M), int(batch_size)))
         if n <= 0:
             raise _lib.PthError("pth_update_workspace_bytes failed")
         self.buf = torch.empty(n, dtype=torch.uint8, device=device)
@@ -74,7 +81,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
                learning_rate=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
                betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None,
                peers=None, loss_kind=0, l2_weight=0.0, context=None, context_loss_coeff=0.0, ctx_states=None,
-               ctx_draws=None, ctx_loss=None):
+               ctx_draws=None, ctx_loss=None, num_partners=0, partner_idx=0, partner_vf_step=0, marginal_reg_coef=0.0):
     """SB3 PPO.train() over flat sample arrays on the device, in place on
     params / adam_m / adam_v. Returns the stats tensor [n_epochs * n_mb, 8]."""
     n_epochs = perm.shape[0]
@@ -121,6 +128,13 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
         a.context_loss_coeff = float(context_loss_coeff)
         a.num_state_samples, a.num_context_samples = ctx_states.shape[1], ctx_draws.shape[1]
         a.d_ctx_states, a.d_ctx_draws = ctx_states.data_ptr(), ctx_draws.data_ptr()
+        if ctx_loss is not None:
+            a.d_ctx_loss = ctx_loss.data_ptr()
+    if num_partners > 0:  # ModularAlgorithm.train, one partner phase (loss_kind PTH_LOSS_MODULAR)
+        a.num_partners, a.partner_idx, a.partner_vf_step = int(num_partners), int(partner_idx), int(partner_vf_step)
+        a.marginal_reg_coef = float(marginal_reg_coef)
+        a.d_modular_scratch = workspace.modular_scratch.data_ptr()
+        a.modular_scratch_bytes = workspace.modular_scratch.numel()
         if ctx_loss is not None:
             a.d_ctx_loss = ctx_loss.data_ptr()
     check(_lib.load().pth_ppo_update(_ctx(params).handle, C.byref(a), current_stream()), "pth_ppo_update")

@@ -163,3 +163,25 @@ def test_trainer_flow_liar_adap_share_latent(ctx, aliases):
     assert len(seen) > 10 and alt_ctx and alt_ctx <= seen  # every context the partner acted under was the ego's
     assert {tuple(r) for r in ego.rollout_buffer.h["ctx"].round(6)} <= seen
     assert ego._n_updates == 4
+
+
+def test_trainer_flow_rps_modular_vs_two_ppo_partners(ctx, aliases, tmp_path):
+    """`trainer.py RPS-v0 ModularAlgorithm PPO PPO --seed 10` (trainer.py:131-135): a ModularAlgorithm ego with one
+    module per partner, two PPO partners; learn() plays n_steps with each partner in turn, then trains every module."""
+    import trainer_shaped as ts
+    cfg = {"n_steps": 128, "batch_size": 64, "n_epochs": 2}
+    args = ts.default_args("RPS-v0", "ModularAlgorithm", ["PPO", "PPO"], seed=10, total_timesteps=2 * 2 * 128,
+                           ego_config=dict(cfg, verbose=0, marginal_reg_coef=0.5), alt_config=[dict(cfg), dict(cfg)])
+    env, ego, partners = _run_adap(args)
+    assert ego.num_partners == 2 and len(ego.rollout_buffer) == 2
+    assert ego.num_timesteps == 512 and ego._n_updates == 4
+    assert ego.vf_steps == [8, 8] and ego.adam_step == 16      # 2 iterations x 2 epochs x 2 minibatches per partner
+    for p in partners:                                          # each partner played (and recorded) its share
+        assert p.num_timesteps == 256
+    st, mg = ego.last_stats.cpu().numpy(), ego.last_marginal.cpu().numpy()
+    assert st.shape == (8, 8) and np.all(np.isfinite(st)) and np.all(mg >= 0)
+    path = str(tmp_path / "modular")
+    ego.save(path)
+    again = type(ego).load(path)
+    assert torch.equal(again.policy.params, ego.policy.params) and again.num_partners == 2 and again.vf_steps == [8, 8]
+    assert again.marginal_reg_coef == 0.5

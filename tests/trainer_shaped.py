@@ -50,6 +50,10 @@ def make_ego(env, args):
         from pantheonrl.algos.adap.adap_learn import ADAP
         from pantheonrl.algos.adap.policies import AdapPolicy
         return ADAP(policy=AdapPolicy, **kw)
+    if args.ego == "ModularAlgorithm":  # trainer.py:131-135
+        from pantheonrl.algos.modular.learn import ModularAlgorithm
+        from pantheonrl.algos.modular.policies import ModularPolicy
+        return ModularAlgorithm(policy=ModularPolicy, policy_kwargs=dict(num_partners=len(args.alt)), **kw)
     assert args.ego == "PPO"
     return PPO(policy="MlpPolicy", **kw)
 
