@@ -322,6 +322,81 @@ def extra_config(torch, name, flush):
     return out
 
 
+def variant_config(torch, kind, cpu=True):
+    """ADAP.train / ModularAlgorithm.train at the reference's own shape (LiarsDice-v0, n_steps 2048, batch_size 64,
+    10 epochs: 320 minibatches of 64 samples) on this GPU — one pth_ppo_update launch per train() (per partner phase
+    for ModularAlgorithm, 2 partners) — next to the torch-CPU restatement of the same train() (oracle/sb3_torch.py,
+    one epoch timed, all epochs are alike)."""
+    import numpy as np
+    from pantheonrl_b200 import _lib, update as up
+    from pantheonrl_b200.spaces import MultiDiscrete, to_pth_space
+    nvec, heads, M, BS, E, C, K, S, Pn = [7] * 6 + [7, 12] * 12, [7, 12], 2048, 64, 10, 3, 5, 32, 2
+    sp = to_pth_space(MultiDiscrete(nvec), MultiDiscrete(heads))
+    rs = np.random.RandomState(0)
+    obs = np.zeros((M, 32), np.uint8)
+    for i, n in enumerate(nvec):
+        obs[:, i] = rs.randint(0, n, M)
+    act = np.zeros((M, 4), np.uint8)
+    act[:, 0], act[:, 1] = rs.randint(0, 7, M), rs.randint(0, 12, M)
+    logp = (-np.log(84.0) + 0.1 * rs.randn(M)).astype(np.float32)
+    adv, ret = rs.randn(M).astype(np.float32), rs.randn(M).astype(np.float32)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()  # noqa: E731
+    lib = _lib.load()
+    n_mb = M // BS
+    perm = up.perm_feistel(M, E, 10, 4)
+    if kind == "adap":
+        P = int(lib.pth_adap_param_count(sp, C))
+        ws = up.UpdateWorkspace(sp, M, BS, context_size=C)
+        st, dr = up.adap_draw(E * n_mb, K, C, "l2", 10, 0x20100, S=S, n_mb=n_mb, M=M, batch_size=BS)
+        cx = rs.randn(M, C).astype(np.float32)
+        extra = dict(loss_kind=_lib.PTH_LOSS_ADAP, context=dev(cx), context_loss_coeff=0.1, ctx_states=st, ctx_draws=dr)
+        phases = 1
+    else:
+        P = int(lib.pth_modular_param_count(sp, Pn))
+        ws = up.UpdateWorkspace(sp, M, BS, num_partners=Pn)
+        extra = dict(loss_kind=_lib.PTH_LOSS_MODULAR, num_partners=Pn, marginal_reg_coef=0.5)
+        phases = Pn
+    params = dev((0.1 * rs.randn(P)).astype(np.float32))
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    d = [dev(x) for x in (obs, act, logp, adv, ret)]
+
+    def train():
+        for q in range(phases):
+            kw = dict(extra, partner_idx=q) if kind == "modular" else extra
+            up.ppo_update(sp, params, m, v, 0, *d, perm, BS, ws, **kw)
+    for _ in range(2):
+        train()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        train()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out = {"workload": f"{'ADAP' if kind == 'adap' else 'ModularAlgorithm (2 partners)'}.train, LiarsDice-v0, n_steps 2048, "
+                       "batch_size 64, 10 epochs (the reference's shape)",
+           "ms_per_train": ms, "minibatch_steps_per_s": phases * E * n_mb / (ms / 1e3), "steps": 5, "warmup": 2}
+    if cpu:
+        from oracle import sb3_torch
+        torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
+        if kind == "adap":
+            pol = sb3_torch.AdapMlpPolicy(nvec=nvec, heads=heads, context_size=C, seed=0)
+            full = np.concatenate([obs[:, :30].astype(np.float32), cx], axis=1)
+            t0 = time.perf_counter()
+            sb3_torch.adap_train(pol, full, act[:, :2], logp, adv, ret, perm[:1].cpu().numpy(), BS, st.cpu().numpy(),
+                                 dr.cpu().numpy(), context_loss_coeff=0.1)
+        else:
+            pol = sb3_torch.ModularMlpPolicy(nvec=nvec, heads=heads, num_partners=Pn, seed=0)
+            buf = (obs[:, :30], act[:, :2], logp, adv, ret)
+            t0 = time.perf_counter()
+            sb3_torch.modular_train(pol, [buf] * Pn, [perm[:1].cpu().numpy()] * Pn, BS, marginal_reg_coef=0.5)
+        dt = time.perf_counter() - t0
+        out["cpu_port"] = {"ms_per_train": dt * E * 1e3, "sample": "1 of 10 epochs timed (32 minibatches per partner), x 10",
+                           "cores": torch.get_num_threads(), "kind": "port"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -463,6 +538,13 @@ def run_ours(args):
                         e["cpu_port"] = {k: c.get(k) for k in ("value", "cores", "sample", "s_per_step")}
                 except Exception as ex:  # noqa: BLE001
                     e = {"baseline": WORKLOADS[name]["baseline"], "error": f"{type(ex).__name__}: {ex}"}
+                extra.append(e)
+            for kind in ("adap", "modular"):  # the loss variants, at the reference's own shape
+                try:
+                    e = variant_config(torch, kind, cpu=not args.no_cpu_baseline)
+                except Exception as ex:  # noqa: BLE001
+                    e = {"error": f"{type(ex).__name__}: {ex}"}
+                e["baseline"] = f"variant:{kind}"
                 extra.append(e)
 
     line = {

@@ -1845,10 +1845,13 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
             const ModBlock mbk = mod_block(p.sp.L);
             live = live && mod_group(pi, p.lo.total, mbk.total, mbk.w_vf0, mbk.w_act, mbk.w_val, p.p0) != 2;
           }
+          // (one base pointer + a 32-bit row offset per load: the 64-bit index arithmetic of
+          // `part[(cc0 + u) * PS + pi]` was ~10 instructions per load, profiles/update_r02_hot_lines.txt)
           float t[RH];
+          const float* src = p.part + (size_t)cc0 * PS + pi;
+          const int nlive = live ? (A - cc0 < RH ? A - cc0 : RH) : 0;  // partial sums this thread group adds
 #pragma unroll
-          for (int u = 0; u < RH; ++u)
-            t[u] = (live && cc0 + u < A) ? __ldcg(p.part + (size_t)(cc0 + u) * PS + pi) : 0.f;
+          for (int u = 0; u < RH; ++u) t[u] = u < nlive ? __ldcg(src + u * PS) : 0.f;
           float g = 0.f;
 #pragma unroll 1
           for (int ph = 0; ph < ngp; ++ph) {
@@ -1856,7 +1859,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
               if (live && cc0 < A) {
                 g = ph == 0 ? t[0] : gs[li] + t[0];
 #pragma unroll
-                for (int u = 1; u < RH; ++u) g = (cc0 + u < A) ? g + t[u] : g;
+                for (int u = 1; u < RH; ++u) g = u < nlive ? g + t[u] : g;
                 gs[li] = g;
               } else if (ph == 0) {
                 gs[li] = 0.f;  // beyond the slice, or no tile at all this minibatch
