@@ -87,14 +87,11 @@ class ModularDevicePolicy(DevicePolicy):
         race = None
         if self.rng == "reference":
             race = torch.cat([torch.empty(1, n).exponential_(1) for n in self.space.heads], dim=1).to(self.device)
-        out = ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed, rng_stream=self.rng_stream,
-                                 tick=self.calls & 0xffffffff, slot=0, idx0=0, want=("action", "value", "logp"),
-                                 race=race, num_partners=self.num_partners, partner_idx=int(partner_idx))
+        ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed, rng_stream=self.rng_stream,
+                           tick=self.calls & 0xffffffff, slot=0, idx0=0, want=("action", "value", "logp"),
+                           race=race, num_partners=self.num_partners, partner_idx=int(partner_idx), out=self._res)
         self.calls += 1
-        act = out["action"].cpu().numpy()[:, :self.act_dim].astype(np.int64)
-        if self.act_dim == 1 and getattr(self.action_space, "shape", ()) == ():
-            act = act.reshape(1)
-        return act, out["value"], out["logp"]
+        return self._fetch()
 
     def _names_shapes(self):
         out = pol.tensor_shapes(self.space)

@@ -116,7 +116,7 @@ def liar_step(state, is_ego, action):
 # ----------------------------------------------------------------------- policy
 def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=0, slot=0, idx0=0,
                    action_in=None, want=("action", "value", "logp", "entropy", "logits"), race=None, context=None,
-                   num_partners=0, partner_idx=0):
+                   num_partners=0, partner_idx=0, out=None):
     """ActorCriticPolicy.forward (sampling) or evaluate_actions (action_in given).
 
     obs: [B, stride] uint8 (one-hot spaces) or float32 (Box). Returns a dict of
@@ -130,11 +130,11 @@ def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=
     B, stride = obs.shape
     dev = obs.device
     L = sum(space.heads)
-    out = {}
-    if "action" in want:
+    out = dict(out) if out is not None else {}  # caller-owned output tensors (the N = 1 facade reuses one packed buffer)
+    if "action" in want and "action" not in out:
         out["action"] = torch.zeros(B, 4, dtype=torch.uint8, device=dev)
     for k in ("value", "logp", "entropy"):
-        if k in want:
+        if k in want and k not in out:
             out[k] = torch.empty(B, dtype=torch.float32, device=dev)
     if "logits" in want:
         out["logits"] = torch.empty(B, L, dtype=torch.float32, device=dev)

@@ -51,16 +51,38 @@ class DevicePolicy:
         self.row = space.row_bytes  # one-hot rows: 32 bytes, or 96 for frame-stacked observations
         self._obs_dev = (torch.zeros(1, _lib.PTH_OC_ROW, dtype=torch.float32, device=device) if self.box
                          else torch.zeros(1, self.row, dtype=torch.uint8, device=device))
+        # one decision = one pinned upload of the observation row and ONE pinned download of
+        # (action, value, log-prob): the three results share a 16-byte device buffer
+        pin = str(device).startswith("cuda")
+        self._obs_host = torch.zeros_like(self._obs_dev, device="cpu")
+        self._res_dev = torch.zeros(16, dtype=torch.uint8, device=device)
+        self._res_host = torch.zeros(16, dtype=torch.uint8)
+        if pin:
+            self._obs_host, self._res_host = self._obs_host.pin_memory(), self._res_host.pin_memory()
+        self._obs_np = self._obs_host.numpy()
+        self._res = {"action": self._res_dev[0:4].view(1, 4), "value": self._res_dev[4:8].view(torch.float32),
+                     "logp": self._res_dev[8:12].view(torch.float32)}
         self.act_dim = space.n_heads
 
     def _init_flat(self, space, seed):
         return pol.init_flat(space, seed, self.extra_inputs)
 
     def _stage_obs(self, obs):
-        o = np.zeros((1, _lib.PTH_OC_ROW), np.float32) if self.box else np.zeros((1, self.row), np.uint8)
         flat = np.asarray(obs).reshape(-1)
-        o[0, :flat.size] = flat
-        self._obs_dev.copy_(torch.from_numpy(o))
+        self._obs_np[0, :flat.size] = flat
+        self._obs_np[0, flat.size:] = 0
+        self._obs_dev.copy_(self._obs_host, non_blocking=True)
+
+    def _fetch(self):
+        """-> (actions [1, act_dim] int64, value tensor [1], log-prob tensor [1]) on the host, one copy + one sync."""
+        self._res_host.copy_(self._res_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self._res_host.numpy()
+        act = h[0:4].astype(np.int64)[None, :self.act_dim]
+        if self.act_dim == 1 and getattr(self.action_space, "shape", ()) == ():
+            act = act.reshape(1)  # Discrete: actions[0] is a scalar, like SB3
+        vl = torch.from_numpy(h[4:12].view(np.float32).copy())
+        return act, vl[0:1], vl[1:2]
 
     def _context(self):
         return None  # AdapPolicy: the [1, C] context on the device
@@ -74,21 +96,19 @@ class DevicePolicy:
             # fills a tensor like probs with exponential_(1) and takes argmax(probs / q); one head after
             # the other (SB3 MultiCategoricalDistribution.sample)
             race = torch.cat([torch.empty(1, n).exponential_(1) for n in self.space.heads], dim=1).to(self.device)
-        out = ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed,
-                                 rng_stream=self.rng_stream, tick=self.calls & 0xffffffff, slot=0, idx0=0,
-                                 want=("action", "value", "logp"), race=race, context=self._context())
+        ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed,
+                           rng_stream=self.rng_stream, tick=self.calls & 0xffffffff, slot=0, idx0=0,
+                           want=("action", "value", "logp"), race=race, context=self._context(), out=self._res)
         self.calls += 1
-        act = out["action"].cpu().numpy()[:, :self.act_dim].astype(np.int64)
-        if self.act_dim == 1 and getattr(self.action_space, "shape", ()) == ():
-            act = act.reshape(1)  # Discrete: actions[0] is a scalar, like SB3
-        return act, out["value"], out["logp"]
+        return self._fetch()
 
     def predict_values(self, obs):
         """ActorCriticPolicy.predict_values: the value tower only — no sample is drawn."""
         self._stage_obs(obs)
         dummy = torch.zeros(1, 4, dtype=torch.uint8, device=self.device)
-        return ops.policy_forward(self.space, self.params, self._obs_dev, action_in=dummy, want=("value",),
-                                  context=self._context())["value"]
+        ops.policy_forward(self.space, self.params, self._obs_dev, action_in=dummy, want=("value",),
+                           context=self._context(), out={"value": self._res["value"]})
+        return self._fetch()[1]
 
     def state_dict(self):
         return pol.flat_to_state_dict(self.space, self.params.cpu().numpy(), self.extra_inputs)
