@@ -135,54 +135,6 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
   if (tid == 0) s.b_val = ld_param<COHERENT>(p + lo.b_val);
 }
 
-// load_policy in two halves for a 512-thread CTA: the loads are issued into registers first, the caller
-// runs other memory-latency-bound work (the update kernel: the first tile's three-deep dependent sample
-// gather), then commits them to shared memory — the two latency chains overlap instead of adding up.
-struct PolicyRegs {
-  float4 m[2][2], a;
-  float s[5], ba, bv;
-};
-template <bool COHERENT>
-__device__ __forceinline__ void load_policy_issue(PolicyRegs& r, const float* p, const Layout& lo, int L, int tid) {
-  const float4* pi1 = reinterpret_cast<const float4*>(p + lo.w_pi1);
-  const float4* vf1 = reinterpret_cast<const float4*>(p + lo.w_vf1);
-  const float4* act = reinterpret_cast<const float4*>(p + lo.w_act);
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    r.m[0][q] = ld_param4_l2<COHERENT>(pi1 + tid + q * 512);
-    r.m[1][q] = ld_param4_l2<COHERENT>(vf1 + tid + q * 512);
-  }
-  r.a = tid < L * (HID / 4) ? ld_param4_l2<COHERENT>(act + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid < HID) {
-    r.s[0] = ld_param<COHERENT>(p + lo.w_val + tid);
-    r.s[1] = ld_param<COHERENT>(p + lo.b_pi0 + tid);
-    r.s[2] = ld_param<COHERENT>(p + lo.b_pi1 + tid);
-    r.s[3] = ld_param<COHERENT>(p + lo.b_vf0 + tid);
-    r.s[4] = ld_param<COHERENT>(p + lo.b_vf1 + tid);
-  }
-  r.ba = tid < L ? ld_param<COHERENT>(p + lo.b_act + tid) : 0.f;
-  r.bv = tid == 0 ? ld_param<COHERENT>(p + lo.b_val) : 0.f;
-}
-__device__ __forceinline__ void load_policy_commit(SmemPolicy& s, const PolicyRegs& r, int L, int tid) {
-  static_assert(MAXL * (HID / 4) <= 512 && HID * HID / 4 == 2 * 512, "one pass of 512 threads per tensor");
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int i = tid + q * 512, j = i >> 4, k = (i & 15) * 4;
-    *reinterpret_cast<float4*>(s.w_pi1 + j * LDW + k) = r.m[0][q];
-    *reinterpret_cast<float4*>(s.w_vf1 + j * LDW + k) = r.m[1][q];
-  }
-  if (tid < L * (HID / 4)) *reinterpret_cast<float4*>(s.w_act + (tid >> 4) * LDW + (tid & 15) * 4) = r.a;
-  if (tid < HID) {
-    s.w_val[tid] = r.s[0];
-    s.b_pi0[tid] = r.s[1];
-    s.b_pi1[tid] = r.s[2];
-    s.b_vf0[tid] = r.s[3];
-    s.b_vf1[tid] = r.s[4];
-  }
-  if (tid < L) s.b_act[tid] = r.ba;
-  if (tid == 0) s.b_val = r.bv;
-}
-
 // ---------------------------------------------------------------------------
 // First layer, one-hot observations: Out[j][b] = tanh(bias[j] + sum_s W[f_s][j]),
 // f_s = slot_off[s] + obs[b][s], slots DESCENDING (numeric contract, DESIGN.md 3: the chain then

@@ -1091,8 +1091,10 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
 
       PTH_PROF(0);  // loop head (prologue on the first pass)
       __syncthreads();
-      // (the weights go to shared memory inside the first tile: issued before its sample gather, committed after)
-      PTH_PROF(1);
+      // (issuing these loads before the first tile's sample gather and committing them behind it was measured:
+      // slower — 51.8 vs 50.1 ms — the 24 registers held across the gather spill at the 128-register cap)
+      load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, UNT);
+      PTH_PROF(1);  // weights -> smem
       float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       [[maybe_unused]] float cta_ctx = 0.f;  // ADAP (thread 0): sum over this CTA's context tiles of sum_states sum_pairs exp(-KL)
       bool first = true;
@@ -1111,11 +1113,6 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           }
           return sample_offset(p, e, i0 + t0 + col);
         };
-        // ---- this minibatch's weights: the loads are issued here and committed to shared memory behind the
-        // tile's three-deep dependent sample gather (1.9 us per minibatch when done back to back)
-        static_assert(UNT == 512, "load_policy_issue / commit are written for 512 threads");
-        PolicyRegs preg;
-        if (first) load_policy_issue<true>(preg, p.params, p.lo, p.sp.L, tid);
         // ---- gather this thread's sample
         uint32_t act = 0;
         float adv = 0.f, oldlp = 0.f, ret = 0.f;
@@ -1167,7 +1164,6 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         }
         const bool lane = tid < BT;  // threads [0, BT) own one sample each
         __syncthreads();  // previous tile done with sm.obs / Xs / Lg / H2
-        if (first) load_policy_commit(sm.pol, preg, p.sp.L, tid);
         if constexpr (BOX) {
           const int b = tid & (BT - 1), k0 = (tid >> 7) * (4 * XQ);
 #pragma unroll
