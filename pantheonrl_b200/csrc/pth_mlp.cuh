@@ -135,6 +135,49 @@ __device__ __forceinline__ void load_policy(SmemPolicy& s, const float* p,
   if (tid == 0) s.b_val = ld_param<COHERENT>(p + lo.b_val);
 }
 
+// load_policy for a 512-thread CTA with every load issued before the first store: one L2 round trip
+// instead of one per tensor group (the update kernel reloads the weights 320 times per launch).
+template <bool COHERENT>
+__device__ __forceinline__ void load_policy_512(SmemPolicy& s, const float* p, const Layout& lo, int L, int tid) {
+  static_assert(MAXL * (HID / 4) <= 512 && HID * HID / 4 == 2 * 512, "one pass of 512 threads per tensor");
+  const float4* pi1 = reinterpret_cast<const float4*>(p + lo.w_pi1);
+  const float4* vf1 = reinterpret_cast<const float4*>(p + lo.w_vf1);
+  const float4* act = reinterpret_cast<const float4*>(p + lo.w_act);
+  float4 m[2][2], a = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sc[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, ba = 0.f, bv = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    m[0][q] = ld_param4_l2<COHERENT>(pi1 + tid + q * 512);
+    m[1][q] = ld_param4_l2<COHERENT>(vf1 + tid + q * 512);
+  }
+  if (tid < L * (HID / 4)) a = ld_param4_l2<COHERENT>(act + tid);
+  if (tid < HID) {
+    sc[0] = ld_param<COHERENT>(p + lo.w_val + tid);
+    sc[1] = ld_param<COHERENT>(p + lo.b_pi0 + tid);
+    sc[2] = ld_param<COHERENT>(p + lo.b_pi1 + tid);
+    sc[3] = ld_param<COHERENT>(p + lo.b_vf0 + tid);
+    sc[4] = ld_param<COHERENT>(p + lo.b_vf1 + tid);
+  }
+  if (tid < L) ba = ld_param<COHERENT>(p + lo.b_act + tid);
+  if (tid == 0) bv = ld_param<COHERENT>(p + lo.b_val);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = tid + q * 512, j = i >> 4, k = (i & 15) * 4;
+    *reinterpret_cast<float4*>(s.w_pi1 + j * LDW + k) = m[0][q];
+    *reinterpret_cast<float4*>(s.w_vf1 + j * LDW + k) = m[1][q];
+  }
+  if (tid < L * (HID / 4)) *reinterpret_cast<float4*>(s.w_act + (tid >> 4) * LDW + (tid & 15) * 4) = a;
+  if (tid < HID) {
+    s.w_val[tid] = sc[0];
+    s.b_pi0[tid] = sc[1];
+    s.b_pi1[tid] = sc[2];
+    s.b_vf0[tid] = sc[3];
+    s.b_vf1[tid] = sc[4];
+  }
+  if (tid < L) s.b_act[tid] = ba;
+  if (tid == 0) s.b_val = bv;
+}
+
 // ---------------------------------------------------------------------------
 // First layer, one-hot observations: Out[j][b] = tanh(bias[j] + sum_s W[f_s][j]),
 // f_s = slot_off[s] + obs[b][s], slots DESCENDING (numeric contract, DESIGN.md 3: the chain then

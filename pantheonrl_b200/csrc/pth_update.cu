@@ -1093,7 +1093,8 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
       __syncthreads();
       // (issuing these loads before the first tile's sample gather and committing them behind it was measured:
       // slower — 51.8 vs 50.1 ms — the 24 registers held across the gather spill at the 128-register cap)
-      load_policy<true>(sm.pol, p.params, p.lo, p.sp.L, tid, UNT);
+      static_assert(UNT == 512, "load_policy_512");
+      load_policy_512<true>(sm.pol, p.params, p.lo, p.sp.L, tid);
       PTH_PROF(1);  // weights -> smem
       float cta_stat[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       [[maybe_unused]] float cta_ctx = 0.f;  // ADAP (thread 0): sum over this CTA's context tiles of sum_states sum_pairs exp(-KL)
