@@ -93,3 +93,42 @@ def test_reference_mode_training_consumes_numpy_permutations(ctx):
     assert np.array_equal(ego._perm.cpu().numpy(), want)
     r = ego.rollout_buffer.h["rewards"]
     assert 0.5 < float((r != 0).mean()) < 0.8  # the two learners do not share their samples
+
+
+def test_adap_reference_mode_draws_from_torch_like_the_reference(ctx):
+    """ADAP in the reference-RNG mode: the first context is drawn right after the policy is built
+    (adap_learn.py:212-217), and train() draws, per minibatch, th.randperm(B) and then num_context_samples
+    contexts (adap/util.py:106, 113-114) from torch's generator — nothing else touches it."""
+    from pantheonrl_b200.adap import ADAP, AdapPolicy, _torch_sampler
+    from pantheonrl_b200 import policy as pol
+    env = RPSEnv()
+    model = ADAP(AdapPolicy, env, seed=10, rng="reference", n_steps=128, batch_size=64, n_epochs=2,
+                 num_context_samples=4, num_state_samples=16)
+    torch.manual_seed(10)
+    pol.init_flat(model.space, None, 3)                      # the constructor's weight draws
+    want_ctx = _torch_sampler("l2", 3, 1)                    # then the first context
+    assert torch.equal(model.policy.get_context(), want_ctx)
+    # a filled buffer (any numbers), then train(): compare the generator state with a replay of the reference's draws
+    buf = model.rollout_buffer
+    rs = np.random.RandomState(0)
+    for _ in range(128):
+        row = np.concatenate(([0.0], rs.randn(3)))
+        buf.add(row, np.array([rs.randint(3)]), float(rs.randn()), False, torch.tensor([0.1]), torch.tensor([-1.1]))
+    buf.compute_returns_and_advantage(torch.tensor([0.0]), False)
+    torch.manual_seed(123)
+    np.random.seed(5)
+    model.train()
+    after = torch.get_rng_state()
+    torch.manual_seed(123)
+    for _ in range(2 * 2):                                   # n_epochs x minibatches
+        torch.randperm(64)
+        for _ in range(4):
+            _torch_sampler("l2", 3, 1)
+    assert torch.equal(torch.get_rng_state(), after)
+    cl = model.last_context_loss.cpu().numpy()
+    assert cl.shape == (4,) and np.all((cl > 0) & (cl <= 1 + 1e-6))
+    np.random.seed(5)
+    for _ in range(2):
+        np.random.permutation(128)
+    assert np.random.randint(1 << 30) == (lambda: (np.random.seed(5), [np.random.permutation(128) for _ in range(2)],
+                                                   np.random.randint(1 << 30))[2])()
