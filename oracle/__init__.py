@@ -194,3 +194,29 @@ def adap_forward(space, params, obs, ctx, seed=0, rng_stream=2, tick=0, slot=0, 
                            C.c_uint32(tick), C.c_uint32(slot), C.c_int64(idx0), _p(action_in), _p(action),
                            _p(value), _p(logp), _p(ent), _p(logits))
     return dict(action=action, value=value, logp=logp, entropy=ent, logits=logits)
+
+
+def adap_mult_param_count(space, context_size):
+    lib().orc_adap_mult_param_count.restype = C.c_int64
+    return int(lib().orc_adap_mult_param_count(C.byref(space), C.c_int32(context_size)))
+
+
+def adap_mult_forward(space, params, obs, ctx, seed=0, rng_stream=2, tick=0, slot=0, idx0=0, action_in=None):
+    """AdapPolicyMult forward / evaluate_actions: ctx is [B, C] (one context per sample) or [C] (broadcast)."""
+    params = _f32(params)
+    obs = np.ascontiguousarray(obs, np.uint8) if space.obs_kind == 0 else _f32(obs)
+    ctx = _f32(ctx)
+    B, stride = obs.shape
+    Cn = ctx.shape[-1]
+    cstride = Cn if ctx.ndim == 2 else 0
+    L = sum(space.head_n[i] for i in range(space.n_heads))
+    action = np.zeros((B, 4), np.uint8)
+    value, logp, ent = np.empty(B, np.float32), np.empty(B, np.float32), np.empty(B, np.float32)
+    logits = np.empty((B, L), np.float32)
+    if action_in is not None:
+        action_in = np.ascontiguousarray(action_in, np.uint8)
+    lib().orc_adap_mult_forward(C.byref(space), _p(params), C.c_int32(Cn), _p(obs), C.c_int64(stride), _p(ctx),
+                                C.c_int64(cstride), C.c_int64(B), C.c_uint64(seed), C.c_uint32(rng_stream),
+                                C.c_uint32(tick), C.c_uint32(slot), C.c_int64(idx0), _p(action_in), _p(action),
+                                _p(value), _p(logp), _p(ent), _p(logits))
+    return dict(action=action, value=value, logp=logp, entropy=ent, logits=logits)

@@ -504,6 +504,88 @@ void orc_policy_forward(const orc_space* sp, const float* params, const void* ob
   }
 }
 
+/* ---- AdapPolicyMult (adap/policies.py:134-283, MultModel): per tower (0 = policy, 1 = value)
+ *   x = tanh(W0 f + b0);  s_m = tanh(bs_m + sum_k fma(x_k, Ws[m][k])), m = j C + c < 64 C;
+ *   y_j = fma(s[j C + C-1], ctx_{C-1}, ... fma(s[j C], ctx_0, x_j));  h2 = tanh(W1 y + b1)
+ * on the features WITHOUT the context (MultModel.forward :263-267: x + matmul(x_a.view(B, 64, C), ctx)). */
+typedef struct {
+  const float *w0[2], *b0[2], *ws[2], *bs[2], *w1[2], *b1[2], *w_act, *b_act, *w_val, *b_val;
+  int F, L, C;
+} orc_mult_params;
+typedef struct {
+  float x[2][H], s[2][H * 8], y[2][H], h2[2][H], logits[32 * MAX_HEADS], value;
+} orc_mult_acts;
+
+static void split_params_mult(const orc_space* sp, const float* p, int C, orc_mult_params* q) {
+  const int F = feat_dim(sp), L = logit_dim(sp);
+  q->F = F; q->L = L; q->C = C;
+  for (int t = 0; t < 2; ++t) {
+    q->w0[t] = p; p += H * F;
+    q->b0[t] = p; p += H;
+    q->ws[t] = p; p += H * C * H;
+    q->bs[t] = p; p += H * C;
+    q->w1[t] = p; p += H * H;
+    q->b1[t] = p; p += H;
+  }
+  q->w_act = p; p += L * H;
+  q->b_act = p; p += L;
+  q->w_val = p; p += H;
+  q->b_val = p;
+}
+int64_t orc_adap_mult_param_count(const orc_space* sp, int32_t C) {
+  int64_t F = feat_dim(sp), L = logit_dim(sp);
+  return 2 * (H * F + H + (int64_t)H * C * H + H * C + H * H + H) + L * H + L + H + 1;
+}
+
+static void forward_one_mult(const orc_space* sp, const orc_mult_params* q, const void* obs_row, const float* ctx,
+                             orc_mult_acts* a, int towers) {
+  float z[H * 8];
+  for (int t = 0; t < towers; ++t) {
+    first_layer(sp, obs_row, q->w0[t], q->b0[t], q->F, z);
+    for (int j = 0; j < H; ++j) a->x[t][j] = orc_tanhf(z[j]);
+    dense(a->x[t], H, q->ws[t], q->bs[t], H * q->C, z);
+    for (int m = 0; m < H * q->C; ++m) a->s[t][m] = orc_tanhf(z[m]);
+    for (int j = 0; j < H; ++j) {
+      float acc = a->x[t][j];
+      for (int c = 0; c < q->C; ++c) acc = fmaf(a->s[t][j * q->C + c], ctx[c], acc);
+      a->y[t][j] = acc;
+    }
+    dense(a->y[t], H, q->w1[t], q->b1[t], H, z);
+    for (int j = 0; j < H; ++j) a->h2[t][j] = orc_tanhf(z[j]);
+  }
+  dense(a->h2[0], H, q->w_act, q->b_act, q->L, a->logits);
+  a->value = 0.f;
+  if (towers > 1) dense(a->h2[1], H, q->w_val, q->b_val, 1, &a->value);
+}
+
+void orc_adap_mult_forward(const orc_space* sp, const float* params, int32_t C, const void* obs, int64_t obs_stride,
+                           const float* ctx, int64_t ctx_stride, int64_t B, uint64_t seed, uint32_t rng_stream,
+                           uint32_t tick, uint32_t slot, int64_t idx0, const uint8_t* action_in, uint8_t* action,
+                           float* value, float* logp, float* entropy, float* logits) {
+  orc_mult_params q;
+  split_params_mult(sp, params, C, &q);
+  for (int64_t b = 0; b < B; ++b) {
+    orc_mult_acts a;
+    const void* row = sp->obs_kind == 0 ? (const void*)((const uint8_t*)obs + b * obs_stride)
+                                        : (const void*)((const float*)obs + b * obs_stride);
+    forward_one_mult(sp, &q, row, ctx + b * ctx_stride, &a, 2);
+    uint8_t act[4] = {0, 0, 0, 0};
+    uint32_t rnd[4] = {0, 0, 0, 0};
+    int sample = action_in == NULL;
+    if (sample)
+      orc_philox(seed, rng_stream, (uint64_t)(idx0 + b), tick, slot, rnd);
+    else
+      memcpy(act, action_in + 4 * b, 4);
+    float lp, en;
+    dist_eval(sp, a.logits, sample, rnd, act, &lp, &en);
+    if (action) memcpy(action + 4 * b, act, 4);
+    if (value) value[b] = a.value;
+    if (logp) logp[b] = lp;
+    if (entropy) entropy[b] = en;
+    if (logits) memcpy(logits + b * q.L, a.logits, sizeof(float) * q.L);
+  }
+}
+
 /* AdapPolicy.forward / evaluate_actions (adap/policies.py:86-131): orc_policy_forward with C context
  * inputs per sample (ctx_stride = 0: one context for the whole batch, `self.context.repeat`). */
 void orc_adap_forward(const orc_space* sp, const float* params, int32_t C, const void* obs, int64_t obs_stride,

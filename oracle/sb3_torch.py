@@ -387,3 +387,96 @@ def modular_train(policy, buffers, perms, batch_size, **kw):
                 stats.append(modular_minibatch_step(policy, p, obs[idx], actions[idx], old_log_prob[idx],
                                                     advantages[idx], returns[idx], **kw))
     return stats
+
+
+class AdapMultPolicy(MlpPolicy):
+    """AdapPolicyMult (pantheonrl/algos/adap/policies.py:134-283): each tower is
+    x = tanh(W0 f + b0); s = tanh(Ws x + bs) (64 -> 64 C); y_j = x_j + sum_c s[j C + c] ctx_c; out = tanh(W1 y + b1)
+    on the features WITHOUT the context (MultModel.forward :263-267).  Module creation order follows MultModel.__init__:
+    pi0, vf0, pi1, vf1 (zip_longest), agent_scaling, value_scaling, then the heads."""
+
+    def __init__(self, nvec=None, heads=(3,), box_dim=None, context_size=3, seed=None, lr=3e-4, adam_eps=1e-5):
+        nn.Module.__init__(self)
+        if seed is not None:
+            th.manual_seed(seed)
+        self.nvec = None if nvec is None else [int(v) for v in nvec]
+        self.heads = [int(h) for h in heads]
+        F = int(box_dim) if box_dim is not None else sum(self.nvec)
+        self.F, self.L, self.context_size = F, sum(self.heads), int(context_size)
+        C = self.context_size
+        pi0, vf0 = nn.Linear(F, 64), nn.Linear(F, 64)
+        pi1, vf1 = nn.Linear(64, 64), nn.Linear(64, 64)
+        self.agent_branch_1 = nn.Sequential(pi0, nn.Tanh())
+        self.agent_scaling = nn.Sequential(nn.Linear(64, 64 * C), nn.Tanh())
+        self.agent_branch_2 = nn.Sequential(pi1, nn.Tanh())
+        self.value_branch_1 = nn.Sequential(vf0, nn.Tanh())
+        self.value_scaling = nn.Sequential(nn.Linear(64, 64 * C), nn.Tanh())
+        self.value_branch_2 = nn.Sequential(vf1, nn.Tanh())
+        self.action_net = nn.Linear(64, self.L)
+        self.value_net = nn.Linear(64, 1)
+        self.context = th.zeros(1, C)
+        # ActorCriticPolicy._build: orthogonal init module by module (mlp_extractor = the MultModel: gain sqrt 2)
+        for mod, gain in ((self.agent_branch_1, math.sqrt(2)), (self.agent_scaling, math.sqrt(2)),
+                          (self.agent_branch_2, math.sqrt(2)), (self.value_branch_1, math.sqrt(2)),
+                          (self.value_scaling, math.sqrt(2)), (self.value_branch_2, math.sqrt(2)),
+                          (self.action_net, 0.01), (self.value_net, 1.0)):
+            for m in mod.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain=gain)
+                    m.bias.data.fill_(0.0)
+        self.optimizer = th.optim.Adam(self.ordered_parameters(), lr=lr, eps=adam_eps)
+
+    def ordered_parameters(self):
+        a1, as_, a2 = self.agent_branch_1[0], self.agent_scaling[0], self.agent_branch_2[0]
+        v1, vs, v2 = self.value_branch_1[0], self.value_scaling[0], self.value_branch_2[0]
+        return [a1.weight, a1.bias, as_.weight, as_.bias, a2.weight, a2.bias, v1.weight, v1.bias, vs.weight, vs.bias,
+                v2.weight, v2.bias, self.action_net.weight, self.action_net.bias, self.value_net.weight,
+                self.value_net.bias]
+
+    _TRANSPOSED = (0, 6)  # the two first-layer matrices are stored input-major in the flat vector
+
+    def to_flat(self):
+        out = []
+        for i, p in enumerate(self.ordered_parameters()):
+            t = p.detach()
+            out.append((t.t() if i in self._TRANSPOSED else t).contiguous().reshape(-1))
+        return th.cat(out).numpy().astype(np.float32)
+
+    def from_flat(self, flat):
+        flat = th.as_tensor(np.asarray(flat, np.float32))
+        o = 0
+        with th.no_grad():
+            for i, p in enumerate(self.ordered_parameters()):
+                n = p.numel()
+                chunk = flat[o:o + n]
+                p.copy_(chunk.reshape(p.shape[1], p.shape[0]).t() if i in self._TRANSPOSED else chunk.reshape(p.shape))
+                o += n
+        return self
+
+    def set_context(self, ctxt):
+        self.context = ctxt
+
+    def get_context(self):
+        return self.context
+
+    def _tower(self, b1, sc, b2, feats, ctx):
+        x = b1(feats)
+        xa = sc(x).view(feats.shape[0], 64, self.context_size)
+        return b2(x + th.matmul(xa, ctx.unsqueeze(-1)).squeeze(-1))
+
+    def latent_pi(self, obs, context):
+        f = self.features(obs)
+        ctx = th.as_tensor(context).float().reshape(1, -1).repeat(f.shape[0], 1)
+        return self._tower(self.agent_branch_1, self.agent_scaling, self.agent_branch_2, f, ctx)
+
+    def evaluate_actions(self, obs, actions):
+        obs = th.as_tensor(np.asarray(obs)).float()
+        f, ctx = self.features(obs[:, :-self.context_size]), obs[:, -self.context_size:]
+        latent_pi = self._tower(self.agent_branch_1, self.agent_scaling, self.agent_branch_2, f, ctx)
+        latent_vf = self._tower(self.value_branch_1, self.value_scaling, self.value_branch_2, f, ctx)
+        _, dists = self._dists(latent_pi)
+        actions = th.as_tensor(np.asarray(actions)).long()
+        actions = actions.reshape(actions.shape[0], -1)
+        log_prob = th.stack([d.log_prob(actions[:, h]) for h, d in enumerate(dists)], dim=1).sum(dim=1)
+        entropy = th.stack([d.entropy() for d in dists], dim=1).sum(dim=1)
+        return self.value_net(latent_vf), log_prob, entropy

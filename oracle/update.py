@@ -24,7 +24,7 @@ class OrcUpdateArgs(C.Structure):
         ("stats", C.c_void_p), ("grad_out", C.c_void_p),
         ("loss_kind", C.c_int32), ("l2_weight", C.c_float),
         ("context_size", C.c_int32), ("ctx", C.c_void_p), ("ctx_loss_coeff", C.c_float),
-        ("n_ctx", C.c_int32), ("n_states", C.c_int32), ("ctx_sidx", C.c_void_p), ("ctx_draws", C.c_void_p), ("ctx_loss_out", C.c_void_p),
+        ("n_ctx", C.c_int32), ("n_states", C.c_int32), ("ctx_sidx", C.c_void_p), ("ctx_draws", C.c_void_p), ("ctx_loss_out", C.c_void_p), ("adap_mult", C.c_int32),
     ]
 
 
@@ -49,7 +49,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
                returns, perm, batch_size, grid, index=None, learning_rate=3e-4, clip_range=0.2,
                ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, betas=(0.9, 0.999), eps=1e-5,
                normalize_advantage=True, world=1, loss_kind=0, l2_weight=0.0, ctx=None, ctx_loss_coeff=0.0,
-               ctx_sidx=None, ctx_draws=None):
+               ctx_sidx=None, ctx_draws=None, adap_mult=False):
     """Runs PPO.train on flat sample arrays; params / adam state are updated IN PLACE
     (float32 numpy arrays). Returns (stats [n_epochs*n_mb, 8], last pre-clip gradient)."""
     f32 = lambda x: np.ascontiguousarray(x, np.float32)  # noqa: E731
@@ -93,6 +93,7 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
         a.ctx_sidx, a.ctx_draws = ctx_sidx.ctypes.data, ctx_draws.ctypes.data
         ctx_loss = np.zeros(n_epochs * n_mb, np.float32)
         a.ctx_loss_out = ctx_loss.ctypes.data
+    a.adap_mult = int(bool(adap_mult))
     a.grid = int(grid)
     a.world = int(world)
     a.stats, a.grad_out = stats.ctypes.data, grad.ctypes.data

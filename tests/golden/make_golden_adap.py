@@ -98,9 +98,9 @@ stub("stable_baselines3.common.vec_env", VecEnv=object)
 stub("stable_baselines3.common.callbacks", BaseCallback=object)
 stub("stable_baselines3.common.buffers", RolloutBuffer=object, RolloutBufferSamples=object)
 stub("stable_baselines3.common.torch_layers", BaseFeaturesExtractor=object, FlattenExtractor=object,
-     MlpExtractor=object)
+     MlpExtractor=th.nn.Module)  # MultModel(MlpExtractor) calls nn.Module.__init__ itself (policies.py:134-147)
 from pantheonrl.algos.adap import adap_learn, util as adap_util  # noqa: E402  (the reference's files, verbatim)
-from pantheonrl.algos.adap.policies import AdapPolicy  # noqa: E402
+from pantheonrl.algos.adap.policies import AdapPolicy, MultModel  # noqa: E402
 
 import oracle  # noqa: E402
 from oracle import sb3_torch  # noqa: E402
@@ -158,10 +158,39 @@ class RefShapedPolicy(sb3_torch.AdapMlpPolicy):
         return self.action_dist.proba_distribution(action_logits=self.action_net(latent_pi))
 
 
-def run_reference_adap_train(kw, M, BS, E, seed, K, S, coeff, sampler, head_scale=1.0):
+class RefShapedMultPolicy(sb3_torch.AdapMultPolicy):
+    """AdapPolicyMult: AdapPolicy's own methods around the reference's own MultModel (policies.py:134-267), whose
+    layers are replaced by the modules of oracle/sb3_torch.AdapMultPolicy (same shapes, built in the same order)."""
+    _get_latent = AdapPolicy._get_latent
+    evaluate_actions = AdapPolicy.evaluate_actions
+    set_context = AdapPolicy.set_context
+    get_context = AdapPolicy.get_context
+    sde_features_extractor = None
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        mm = MultModel(self.F, [dict(pi=[64, 64], vf=[64, 64])], th.nn.Tanh, "cpu", self.context_size)
+        for name in ("agent_branch_1", "agent_scaling", "agent_branch_2", "value_branch_1", "value_scaling",
+                     "value_branch_2"):
+            assert [tuple(p.shape) for p in getattr(mm, name).parameters()] == \
+                [tuple(p.shape) for p in getattr(self, name).parameters()], name
+            setattr(mm, name, getattr(self, name))
+        object.__setattr__(self, "_mm", mm)  # not a registered submodule: the parameters are already ours
+
+    def extract_features(self, obs):
+        return self.features(obs.long() if self.nvec is not None else obs)
+
+    def mlp_extractor(self, features):
+        return self._mm(features)  # MultModel.forward: splits the context off, policies() / values()
+
+    def _get_action_dist_from_latent(self, latent_pi, latent_sde=None):
+        return self.action_dist.proba_distribution(action_logits=self.action_net(latent_pi))
+
+
+def run_reference_adap_train(kw, M, BS, E, seed, K, S, coeff, sampler, head_scale=1.0, mult=False):
     import gym
     C = 3
-    pol = RefShapedPolicy(nvec=kw["nvec"], heads=kw["heads"], context_size=C, seed=seed)
+    pol = (RefShapedMultPolicy if mult else RefShapedPolicy)(nvec=kw["nvec"], heads=kw["heads"], context_size=C, seed=seed)
     nh = len(kw["heads"])
     pol.action_dist = MultiCategoricalDistribution(kw["heads"]) if nh > 1 else CategoricalDistribution(kw["heads"][0])
     with th.no_grad():  # SB3's 0.01 head gain makes every context's distribution uniform (KL = 0): sharpen it
@@ -172,7 +201,12 @@ def run_reference_adap_train(kw, M, BS, E, seed, K, S, coeff, sampler, head_scal
     # the context stored with a sample stays the same over an episode: piecewise-constant unit vectors
     ctx = np.repeat(adap_util.get_L2_sphere(C, (M + 6) // 7, torch=True).numpy(), 7, axis=0)[:M].astype(np.float32)
     space = oracle.make_space(**kw)
-    ev = oracle.adap_forward(space, p0, obs, ctx, action_in=act)
+    nslot0, nh0 = len(kw["nvec"]), len(kw["heads"])
+    with th.no_grad():  # old log-probs / values from the policy itself (any numbers near the truth would do)
+        v_, lp_, _ = pol.evaluate_actions(th.as_tensor(np.concatenate([obs[:, :nslot0].astype(np.float32), ctx], axis=1)),
+                                          th.as_tensor(act[:, :nh0].astype(np.int64)) if nh0 > 1
+                                          else th.as_tensor(act[:, 0].astype(np.int64)))
+    ev = {"logp": lp_.numpy(), "value": v_.numpy().reshape(-1)}
     old_logp = (ev["logp"] + 0.1 * rs.randn(M)).astype(np.float32)
     perms = oupd.perm_feistel(M, E, seed=seed, stream=4)
     nslot = len(kw["nvec"])
@@ -218,15 +252,17 @@ def run_reference_adap_train(kw, M, BS, E, seed, K, S, coeff, sampler, head_scal
 
 def main():
     out = {}
-    for name, kw, M, BS, E, seed, K, S, coeff, sampler, hs in (
-            ("rps", oracle.RPS_SPACE, 280, 64, 3, 7, 5, 32, 0.1, "l2", 200.0),         # last minibatch: 24 < S states
-            ("liar", oracle.LIAR_SPACE, 700, 256, 2, 11, 5, 32, 0.5, "l2", 1.0),        # two context tiles per minibatch
-            ("liar_k3", oracle.LIAR_SPACE, 300, 100, 2, 13, 3, 20, 1.0, "unit_square", 100.0)):
-        for k, v in run_reference_adap_train(kw, M, BS, E, seed, K, S, coeff, sampler, hs).items():
+    for name, kw, M, BS, E, seed, K, S, coeff, sampler, hs, mult in (
+            ("rps", oracle.RPS_SPACE, 280, 64, 3, 7, 5, 32, 0.1, "l2", 200.0, False),      # last minibatch: 24 < S states
+            ("liar", oracle.LIAR_SPACE, 700, 256, 2, 11, 5, 32, 0.5, "l2", 1.0, False),     # two context tiles per minibatch
+            ("liar_k3", oracle.LIAR_SPACE, 300, 100, 2, 13, 3, 20, 1.0, "unit_square", 100.0, False),
+            ("mult_rps", oracle.RPS_SPACE, 280, 64, 2, 17, 5, 32, 0.5, "l2", 200.0, True),  # AdapPolicyMult (ADAP_MULT)
+            ("mult_liar", oracle.LIAR_SPACE, 500, 250, 2, 19, 4, 32, 1.0, "l2", 100.0, True)):
+        for k, v in run_reference_adap_train(kw, M, BS, E, seed, K, S, coeff, sampler, hs, mult).items():
             out[f"{name}_{k}"] = v
     np.savez_compressed(os.path.join(HERE, "adap.npz"), **out)
     print({k: getattr(v, "shape", v) for k, v in out.items() if "hp" in k or "sidx" in k or "draws" in k})
-    for n in ("rps", "liar", "liar_k3"):
+    for n in ("rps", "liar", "liar_k3", "mult_rps", "mult_liar"):
         print(n, "log:", dict(zip(out[n + "_log_keys"], np.round(out[n + "_log_vals"], 5))))
 
 

@@ -16,6 +16,7 @@ from oracle import sb3_torch
 from oracle import update as oupd
 
 CASES = [("rps", oracle.RPS_SPACE), ("liar", oracle.LIAR_SPACE), ("liar_k3", oracle.LIAR_SPACE)]
+MULT_CASES = [("mult_rps", oracle.RPS_SPACE), ("mult_liar", oracle.LIAR_SPACE)]  # AdapPolicyMult (ADAP_MULT)
 
 
 @pytest.fixture(scope="module")
@@ -26,6 +27,7 @@ def g():
 def _case(g, name):
     pre = name + "_"
     d = {k[len(pre):]: g[k] for k in g.files if k.startswith(pre) and not (name == "liar" and k.startswith("liar_k3_"))}
+    assert "hp" in d, name
     d["log"] = dict(zip(d["log_keys"], d["log_vals"]))
     return d
 
@@ -98,3 +100,39 @@ def test_adap_policy_without_context_columns_is_the_mlp_policy():
     b = oracle.adap_forward(space, wide, obs, rs.randn(50, 3).astype(np.float32), seed=5)
     for k in ("action", "value", "logp", "entropy", "logits"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("name,kw", MULT_CASES)
+def test_adap_mult_train_matches_the_reference(g, name, kw):
+    """AdapPolicyMult: the golden run used the reference's own MultModel (adap/policies.py:134-267) as the
+    mlp_extractor under AdapPolicy's methods and ADAP.train with the context loss on."""
+    d = _case(g, name)
+    M, BS, E, K, S = (int(x) for x in d["hp"])
+    coeff = float(d["coeff"][0])
+    nslot, nh = len(kw["nvec"]), len(kw["heads"])
+    n_mb = -(-M // BS)
+    log, want = d["log"], d["params"]
+    pol = sb3_torch.AdapMultPolicy(nvec=kw["nvec"], heads=kw["heads"], context_size=3, seed=0)
+    pol.from_flat(d["p0"])
+    full_obs = np.concatenate([d["obs"][:, :nslot].astype(np.float32), d["ctx"]], axis=1)
+    stats = sb3_torch.adap_train(pol, full_obs, d["act"][:, :nh], d["old_logp"], d["adv"], d["ret"], d["perms"], BS,
+                                 d["sidx"], d["draws"], context_loss_coeff=coeff, ent_coef=0.01)
+    assert np.abs(pol.to_flat() - want).max() <= 1e-6
+    assert np.mean([s_["context_loss"] for s_ in stats[-n_mb:]]) == pytest.approx(log["train/context_kl_loss"], abs=1e-6)
+    space = oracle.make_space(**kw)
+    assert want.size == oracle.adap_mult_param_count(space, 3)
+    for grid in (1, 3):
+        p, m, v = d["p0"].copy(), np.zeros_like(d["p0"]), np.zeros_like(d["p0"])
+        st, _, cl = oupd.ppo_update(space, p, m, v, 0, d["obs"], d["act"], d["old_logp"], d["adv"], d["ret"], d["perms"],
+                                    BS, grid=grid, ent_coef=0.01, loss_kind=2, ctx=d["ctx"], ctx_loss_coeff=coeff,
+                                    ctx_sidx=d["sidx"], ctx_draws=d["draws"], adap_mult=True)
+        assert np.abs(p - want).max() <= 2e-6, grid
+        assert cl[-n_mb:].mean() == pytest.approx(log["train/context_kl_loss"], abs=1e-5)
+        assert st[-1, 5] == pytest.approx(log["train/loss"], abs=2e-5)
+    # forward: the oracle's AdapPolicyMult equals the torch modules
+    import torch as th
+    ev = oracle.adap_mult_forward(space, want, d["obs"][:64], d["ctx"][:64], action_in=d["act"][:64])
+    pol.from_flat(want)
+    with th.no_grad():
+        values, logp, ent = pol.evaluate_actions(full_obs[:64], d["act"][:64, :nh])
+    assert np.abs(ev["value"] - values.numpy().reshape(-1)).max() < 1e-5 and np.abs(ev["logp"] - logp.numpy()).max() < 1e-5
