@@ -298,6 +298,8 @@ typedef struct pth_forward_args {
    * partner_idx composes the outputs: logits = main + partner, value = main + partner. */
   int32_t num_partners;
   int32_t partner_idx;
+  /* AdapPolicyMult: adap_mult != 0 with context_size > 0 (parameter layout of pth_adap_mult_param_count). */
+  int32_t adap_mult;
 } pth_forward_args;
 int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* args, void* stream);
 /* debug / parity only: y[i] = f(x[i]) with the library's exp (which = 0), log (1, positive
@@ -500,6 +502,13 @@ typedef struct pth_update_args {
   float marginal_reg_coef;
   void* d_modular_scratch;
   int64_t modular_scratch_bytes;
+  /* AdapPolicyMult (pantheonrl/algos/adap/policies.py:134-283, `trainer.py ... ADAP_MULT`): adap_mult != 0 with
+   * context_size > 0.  Each tower is  x = tanh(W0 f + b0);  s = tanh(Ws x + bs) (64 -> 64 C);
+   * y_j = x_j + sum_c s[j C + c] ctx_c;  out = tanh(W1 y + b1)  on the features WITHOUT the context.
+   * Parameters (pth_adap_mult_param_count), per tower: W0 [F][64] input-major, b0, Ws [64 C][64], bs [64 C],
+   * W1 [64][64], b1; then the heads.  loss_kind PTH_LOSS_PPO or PTH_LOSS_ADAP as for AdapPolicy; workspace from
+   * pth_adap_mult_workspace_bytes, d_modular_scratch >= pth_adap_mult_scratch_bytes (per-CTA activation tiles). */
+  int32_t adap_mult;
 } pth_update_args;
 #define PTH_LOSS_PPO 0
 #define PTH_LOSS_BC 1
@@ -509,6 +518,10 @@ int64_t pth_update_workspace_bytes(const pth_ctx* ctx, const pth_space* sp,
                                    int64_t M, int64_t batch_size);
 int64_t pth_adap_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
                                  int64_t M, int64_t batch_size);
+int64_t pth_adap_mult_param_count(const pth_space* sp, int32_t context_size);
+int64_t pth_adap_mult_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
+                                      int64_t M, int64_t batch_size);
+int64_t pth_adap_mult_scratch_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size);
 int64_t pth_modular_param_count(const pth_space* sp, int32_t num_partners);
 int64_t pth_modular_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t num_partners,
                                     int64_t M, int64_t batch_size);

@@ -101,6 +101,7 @@ class ForwardArgs(C.Structure):
         ("context_stride", C.c_int64),
         ("num_partners", C.c_int32),
         ("partner_idx", C.c_int32),
+        ("adap_mult", C.c_int32),
     ]
 
 
@@ -226,6 +227,7 @@ class UpdateArgs(C.Structure):
         ("marginal_reg_coef", C.c_float),
         ("d_modular_scratch", C.c_void_p),
         ("modular_scratch_bytes", C.c_int64),
+        ("adap_mult", C.c_int32),
     ]
 
 
@@ -264,6 +266,9 @@ SIGNATURES = {
     "pth_adap_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
     "pth_adap_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
     "pth_modular_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
+    "pth_adap_mult_param_count": (_i64, [C.POINTER(Space), C.c_int32]),
+    "pth_adap_mult_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
+    "pth_adap_mult_scratch_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32]),
     "pth_modular_workspace_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32, _i64, _i64]),
     "pth_modular_scratch_bytes": (_i64, [_vp, C.POINTER(Space), C.c_int32]),
     "pth_adap_draw": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -10,8 +10,11 @@ context inputs is pth_policy_forward(context=), the update — context tiles inc
 loss_kind PTH_LOSS_ADAP, the random draws come from pth_adap_draw (Philox) or, in the reference-RNG mode, from
 torch's global generator at the points and in the order the reference draws them.
 
-Host-driven flow only (n_envs = 1), like the reference.  `AdapPolicyMult` (policies.py:134-283, the
-multiplicative variant) is not implemented and raises.
+`AdapPolicyMult` (policies.py:134-283, `trainer.py ... ADAP_MULT`): the context scales a hidden layer instead of
+joining the inputs — x = tanh(W0 f + b0); s = tanh(Ws x + bs) (64 -> 64 C); y_j = x_j + sum_c s[j C + c] ctx_c;
+out = tanh(W1 y + b1) — same entry points with `adap_mult` set.
+
+Host-driven flow only (n_envs = 1), like the reference.
 """
 import numpy as np
 import torch
@@ -49,12 +52,14 @@ class AdapPolicy:
 
 
 class AdapPolicyMult:
-    """pantheonrl/algos/adap/policies.py:134-283 (context-scaled hidden layer): not implemented."""
+    """Names the policy class in `ADAP(policy=AdapPolicyMult, ...)` (trainer.py:130, 208): MultModel towers
+    (pantheonrl/algos/adap/policies.py:134-283), the context scales a hidden layer."""
 
 
 class AdapDevicePolicy(DevicePolicy):
-    def __init__(self, space, observation_space, action_space, seed, device, rng_stream, rng, context_size):
-        self.extra_inputs = self.context_size = int(context_size)
+    def __init__(self, space, observation_space, action_space, seed, device, rng_stream, rng, context_size, mult=False):
+        self.context_size, self.mult = int(context_size), bool(mult)
+        self.extra_inputs = 0 if self.mult else self.context_size  # AdapPolicyMult: no context columns in the first layers
         super().__init__(space, observation_space, action_space, seed, device, rng_stream, rng)
         self.context = torch.zeros(1, self.context_size)  # a CPU tensor, like the reference's
         self._ctx_dev = torch.zeros(1, self.context_size, device=device)
@@ -68,6 +73,44 @@ class AdapDevicePolicy(DevicePolicy):
 
     def _context(self):
         return self._ctx_dev
+
+    # ---- AdapPolicyMult: its own parameter layout
+    def _init_flat(self, space, seed):
+        return pol.init_flat_mult(space, seed, self.context_size) if self.mult else super()._init_flat(space, seed)
+
+    def forward(self, obs, deterministic=False):
+        if not self.mult:
+            return super().forward(obs, deterministic)
+        from . import ops
+        self._stage_obs(obs)
+        race = None
+        if self.rng == "reference":
+            race = torch.cat([torch.empty(1, n).exponential_(1) for n in self.space.heads], dim=1).to(self.device)
+        ops.policy_forward(self.space, self.params, self._obs_dev, seed=self.seed, rng_stream=self.rng_stream,
+                           tick=self.calls & 0xffffffff, slot=0, idx0=0, want=("action", "value", "logp"), race=race,
+                           context=self._ctx_dev, adap_mult=True, out=self._res)
+        self.calls += 1
+        return self._fetch()
+
+    def predict_values(self, obs):
+        if not self.mult:
+            return super().predict_values(obs)
+        from . import ops
+        self._stage_obs(obs)
+        dummy = torch.zeros(1, 4, dtype=torch.uint8, device=self.device)
+        ops.policy_forward(self.space, self.params, self._obs_dev, action_in=dummy, want=("value",), context=self._ctx_dev,
+                           adap_mult=True, out={"value": self._res["value"]})
+        return self._fetch()[1]
+
+    def state_dict(self):
+        if not self.mult:
+            return super().state_dict()
+        return pol.flat_to_state_dict_mult(self.space, self.params.cpu().numpy(), self.context_size)
+
+    def load_state_dict(self, sd):
+        if not self.mult:
+            return super().load_state_dict(sd)
+        self.params.copy_(torch.from_numpy(pol.state_dict_to_flat_mult(self.space, sd, self.context_size)))
 
 
 class AdapBuffer(HostStagedBuffer):
@@ -92,8 +135,7 @@ class ADAP(PPO):
 
     def __init__(self, policy=AdapPolicy, env=None, *args, context_loss_coeff=0.1, context_size=3,
                  num_context_samples=5, context_sampler="l2", num_state_samples=32, policy_kwargs=None, **kw):
-        if policy is AdapPolicyMult or policy == "AdapPolicyMult":
-            raise NotImplementedError("AdapPolicyMult (ADAP_MULT) is not implemented; use AdapPolicy")
+        self.mult = policy is AdapPolicyMult or policy == "AdapPolicyMult" or bool(kw.pop("mult", False))
         if context_sampler not in up.ADAP_SAMPLERS:
             raise KeyError(context_sampler)
         if not 1 <= int(context_size) <= 8:
@@ -124,7 +166,7 @@ class ADAP(PPO):
 
     def _make_policy(self, eff_seed, stream):
         return AdapDevicePolicy(self.space, self.observation_space, self.action_space, eff_seed, self.device, stream,
-                                self.rng, self.context_size)
+                                self.rng, self.context_size, self.mult)
 
     def _make_buffer(self, n_steps, gamma, gae_lambda):
         return AdapBuffer(n_steps, self.device, gamma, gae_lambda, self.space.obs_kind == _lib.PTH_OBS_BOX,
@@ -163,7 +205,8 @@ class ADAP(PPO):
     def train(self):
         buf, M = self.rollout_buffer, self.rollout_buffer.T
         if self._ws is None:
-            self._ws = up.UpdateWorkspace(self.space, M, self.batch_size, self.device, context_size=self.context_size)
+            self._ws = up.UpdateWorkspace(self.space, M, self.batch_size, self.device, context_size=self.context_size,
+                                          adap_mult=self.mult)
             self._perm = torch.empty(self.n_epochs, M, dtype=torch.int32, device=self.device)
             self._ctx_loss = torch.zeros(self.n_epochs * (-(-M // self.batch_size)), device=self.device)
         if self.rng == "reference":
@@ -185,7 +228,7 @@ class ADAP(PPO):
             d["logp"], d["advantages"], d["returns"], self._perm, self.batch_size, self._ws,
             learning_rate=self.learning_rate, clip_range=self.clip_range, ent_coef=self.ent_coef,
             vf_coef=self.vf_coef, max_grad_norm=self.max_grad_norm, normalize_advantage=self.normalize_advantage,
-            context=d["ctx"], **extra)
+            context=d["ctx"], adap_mult=self.mult, **extra)
         self.last_context_loss = self._ctx_loss if extra else None
         self.adam_step += self.n_epochs * (-(-M // self.batch_size))
         self._n_updates += self.n_epochs
@@ -227,17 +270,25 @@ class ADAP(PPO):
 
     # ---------------------------------------------------------------- checkpoint
     _HYPER = PPO._HYPER + ("context_loss_coeff", "context_size", "num_context_samples", "context_sampler",
-                           "num_state_samples")
+                           "num_state_samples", "mult")
+
+    def _layout(self):
+        """(tensor names, flat -> state dict, state dict -> flat) of this policy's parameter vector."""
+        C = self.context_size
+        if self.mult:
+            return ([n for n, _ in pol.tensor_shapes_mult(self.space, C)],
+                    lambda f: pol.flat_to_state_dict_mult(self.space, f, C),
+                    lambda sd: pol.state_dict_to_flat_mult(self.space, sd, C))
+        return ([n for n, _ in pol.tensor_shapes(self.space, C)], lambda f: pol.flat_to_state_dict(self.space, f, C),
+                lambda sd: pol.state_dict_to_flat(self.space, sd, C))
 
     def save(self, path):
         from . import checkpoint as ck
-        C = self.context_size
-        names = [n for n, _ in pol.tensor_shapes(self.space, C)]
+        names, to_dict, _ = self._layout()
         return ck.save_zip(
             path, self.observation_space, self.action_space, {k: getattr(self, k) for k in self._HYPER},
             self.policy.state_dict(),
-            ck.optimizer_state_dict(names, pol.flat_to_state_dict(self.space, self.adam_m.cpu().numpy(), C),
-                                    pol.flat_to_state_dict(self.space, self.adam_v.cpu().numpy(), C),
+            ck.optimizer_state_dict(names, to_dict(self.adam_m.cpu().numpy()), to_dict(self.adam_v.cpu().numpy()),
                                     self.adam_step, self.learning_rate),
             {"num_timesteps": self.num_timesteps, "n_updates": self._n_updates, "adam_step": self.adam_step})
 
@@ -248,14 +299,13 @@ class ADAP(PPO):
         if env is None:
             env = type("_Spaces", (), {"observation_space": c["observation_space"],
                                        "action_space": c["action_space"]})()
-        m = cls(AdapPolicy, env, **{**c["hyper"], **kw})
+        m = cls(AdapPolicy, env, **{**c["hyper"], **kw})  # hyper carries `mult` for an AdapPolicyMult archive
         m.policy.load_state_dict(c["policy"])
-        C = m.context_size
-        names = [n for n, _ in pol.tensor_shapes(m.space, C)]
+        names, _, to_flat = m._layout()
         mom_m, mom_v = ck.adam_moments(names, c["optimizer"])
         if all(v is not None for v in mom_m.values()):
-            m.adam_m.copy_(torch.from_numpy(pol.state_dict_to_flat(m.space, mom_m, C)))
-            m.adam_v.copy_(torch.from_numpy(pol.state_dict_to_flat(m.space, mom_v, C)))
+            m.adam_m.copy_(torch.from_numpy(to_flat(mom_m)))
+            m.adam_v.copy_(torch.from_numpy(to_flat(mom_v)))
         m.adam_step, m._n_updates = c["counters"]["adam_step"], c["counters"]["n_updates"]
         m.num_timesteps = c["counters"]["num_timesteps"]
         return m

@@ -45,6 +45,9 @@ struct FwdParams {
   // main network, module p0 composes this forward: logits = main + partner, value = main + partner
   int Pn, p0;
   int x_off;  // byte offset of one more [64][LDA] tile (the partner branches' second layer)
+  // AdapPolicyMult (adap/policies.py:134-283): scaling layers' offsets (tower 0 = policy), x_off tile = a scaling
+  // sub-layer's output, w_off = a [64][LDW] weight slot + 64 biases
+  int mult, mw[2], mb[2], w_off;
 };
 
 // a [rows][64] matrix / a vector from global memory into a shared-memory slot (row stride LDW); the partner
@@ -86,19 +89,56 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   }
   __syncthreads();
   // first layer of one tower into sm.A; AdapPolicy: the context inputs continue the chains, then tanh
+  const bool ctx_cols = p.C > 0 && !p.mult;  // AdapPolicy: context columns; AdapPolicyMult: features only
   auto first_layer = [&](int w_off, const float* bias) {
     if (p.sp.obs_kind == PTH_OBS_ONEHOT)
-      first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + w_off, bias, sm.A, tid, p.C == 0);
-    else if (p.C == 0)
+      first_layer_onehot<false, NT, BT, 6, OW>(p.sp, obs_s, p.params + w_off, bias, sm.A, tid, !ctx_cols);
+    else if (!ctx_cols)
       first_layer_box<false>(p.sp.F, Xs, p.params + w_off, bias, sm.A, tid);
     else
       first_layer_box<false, NT, BT, false>(p.sp.F, Xs, p.params + w_off, bias, sm.A, tid);
-    if (p.C > 0) {
+    if (ctx_cols) {
       __syncthreads();
       context_columns_tanh<false>(p.C, Cx, p.params + w_off + p.sp.F * HID, sm.A, tid >> 5, NT / 32, tid & 31);
     }
   };
 
+  float v = 0.f;
+  if (p.mult) {
+    // AdapPolicyMult tower: x = first layer (sm.A); y = x + sum_c s_c ctx_c (sm.Bf), s_c = tanh(Ws_c x + bs_c)
+    // (rows j C + c of the scaling layer, staged sub-layer by sub-layer); h2 = tanh(W1 y + b1) (sm.A again)
+    float* X = reinterpret_cast<float*>(smem_raw + p.x_off);
+    float* Wslot = reinterpret_cast<float*>(smem_raw + p.w_off);
+    float* Wbias = Wslot + HID * LDW;
+    for (int t = 0; t < 2; ++t) {
+      first_layer(t ? p.lo.w_vf0 : p.lo.w_pi0, t ? sm.pol.b_vf0 : sm.pol.b_pi0);
+      __syncthreads();
+      for (int i = tid; i < HID * BT; i += NT) sm.Bf[(i >> 7) * LDA + (i & (BT - 1))] = sm.A[(i >> 7) * LDA + (i & (BT - 1))];
+      for (int c = 0; c < p.C; ++c) {
+        for (int i = tid; i < HID * HID; i += NT)
+          Wslot[(i >> 6) * LDW + (i & 63)] = __ldg(p.params + p.mw[t] + ((size_t)(i >> 6) * p.C + c) * HID + (i & 63));
+        for (int i = tid; i < HID; i += NT) Wbias[i] = __ldg(p.params + p.mb[t] + (size_t)i * p.C + c);
+        __syncthreads();
+        dense64<true>(sm.A, Wslot, Wbias, X, tid);
+        __syncthreads();
+        for (int i = tid; i < HID * BT; i += NT) {
+          const int k = i >> 7, b = i & (BT - 1);
+          sm.Bf[k * LDA + b] = fmaf(X[k * LDA + b], Cx[c * LDA + b], sm.Bf[k * LDA + b]);
+        }
+        __syncthreads();
+      }
+      dense64<true>(sm.Bf, t ? sm.pol.w_vf1 : sm.pol.w_pi1, t ? sm.pol.b_vf1 : sm.pol.b_pi1, sm.A, tid);
+      __syncthreads();
+      if (lane) {
+        if (t == 0)
+          action_head(sm.A, sm.pol, p.sp.L, sm.Lg, tid);
+        else
+          v = value_head(sm.A, sm.pol, tid);
+      }
+      __syncthreads();
+    }
+    if (!lane) return;
+  } else {
   // ---- policy tower
   first_layer(p.lo.w_pi0, sm.pol.b_pi0);
   __syncthreads();
@@ -106,7 +146,6 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
   __syncthreads();
   if (lane) action_head(sm.Bf, sm.pol, p.sp.L, sm.Lg, tid);
   // ---- value tower (A is free again)
-  float v = 0.f;
   if (p.Pn == 0) {
     first_layer(p.lo.w_vf0, sm.pol.b_vf0);
     __syncthreads();
@@ -161,6 +200,7 @@ __global__ void __launch_bounds__(NT) policy_forward_kernel(const __grid_constan
     __syncthreads();
     if (!lane) return;
     v = v + value_head(X, sm.pol, tid);
+  }
   }
 
   // ---- distribution
@@ -252,6 +292,30 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   p.ctx = a->d_context;
   p.ctx_stride = a->context_stride;
   p.lo = make_layout(p.sp.F + p.C, p.sp.L);
+  p.mult = a->adap_mult != 0;
+  p.mw[0] = p.mw[1] = p.mb[0] = p.mb[1] = 0;
+  if (p.mult) {  // per tower: first layer (features only) | scaling 64 -> 64 C | second layer; then the heads
+    PTH_CHECK_ARG(p.C > 0 && a->num_partners == 0, "AdapPolicyMult needs context_size > 0 (and no partner modules)");
+    int o = 0;
+    const int F = p.sp.F, L = p.sp.L, C = p.C;
+    p.lo.w_pi0 = o; o += HID * F;
+    p.lo.b_pi0 = o; o += HID;
+    p.mw[0] = o; o += HID * C * HID;
+    p.mb[0] = o; o += HID * C;
+    p.lo.w_pi1 = o; o += HID * HID;
+    p.lo.b_pi1 = o; o += HID;
+    p.lo.w_vf0 = o; o += HID * F;
+    p.lo.b_vf0 = o; o += HID;
+    p.mw[1] = o; o += HID * C * HID;
+    p.mb[1] = o; o += HID * C;
+    p.lo.w_vf1 = o; o += HID * HID;
+    p.lo.b_vf1 = o; o += HID;
+    p.lo.w_act = o; o += L * HID;
+    p.lo.b_act = o; o += L;
+    p.lo.w_val = o; o += HID;
+    p.lo.b_val = o; o += 1;
+    p.lo.total = o;
+  }
   p.params = a->d_params;
   p.obs = a->d_obs;
   p.obs_stride = a->obs_stride;
@@ -278,7 +342,9 @@ extern "C" int pth_policy_forward(pth_ctx* ctx, const pth_forward_args* a, void*
   p.Pn = a->num_partners;
   p.p0 = a->partner_idx;
   p.x_off = (int)smem;
-  smem += p.Pn > 0 ? sizeof(float) * HID * LDA : 0;
+  smem += (p.Pn > 0 || p.mult) ? sizeof(float) * HID * LDA : 0;
+  p.w_off = (int)smem;
+  smem += p.mult ? sizeof(float) * (HID * LDW + HID) : 0;
   if (wide) {
     PTH_CUDA(cudaFuncSetAttribute(policy_forward_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     policy_forward_kernel<96><<<pth_ceil_div(a->B, BT), NT, smem, (cudaStream_t)stream>>>(p);

@@ -126,7 +126,9 @@ struct UpdParams {
   int Pn, p0;                // num_partners, the partner whose buffer this launch trains on
   float marg_coef;           // marginal_reg_coef
   double b1pow0_v, b2pow0_v; // beta^steps of p0's value modules (their own Adam step count)
-  float* mod_ws;             // [G] per-CTA scratch of mod_scratch_floats(Pn) floats
+  float* mod_ws;             // [G] per-CTA scratch of mod_scratch_floats(Pn) (MULT: mult_scratch_floats(C)) floats
+  // AdapPolicyMult (adap/policies.py:134-283): offsets of the two scaling layers (64 -> 64 C), tower 0 = policy
+  int mult_w[2], mult_b[2];
 };
 constexpr int MAX_CTX = 8;
 
@@ -195,9 +197,10 @@ __device__ __forceinline__ int64_t sample_offset(const UpdParams& p, int e, int6
 }
 
 // gW[j][k] = sum_b fma(Dz[j][b], Hh[k][b], .)  (64 x 64 outputs, b ascending)
+// (ldg: row stride of gout — AdapPolicyMult's scaling sub-layers own every C-th row of their matrix)
 template <int NTH>
 __device__ __forceinline__ void wgrad64(const float* Dz, const float* Hh, float* gout, bool first,
-                                        int tid) {
+                                        int tid, int ldg = HID) {
   constexpr int NY = NTH / 16, JT = HID / NY;
   const int kt = tid & 15, jt = tid >> 4;
   float acc[JT][4];
@@ -230,7 +233,7 @@ __device__ __forceinline__ void wgrad64(const float* Dz, const float* Hh, float*
   for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)
-      acc_store(gout + (jt + NY * jj) * HID + (kt + 16 * kk), acc[jj][kk], first);
+      acc_store(gout + (jt + NY * jj) * ldg + (kt + 16 * kk), acc[jj][kk], first);
 }
 
 // head weight gradient: gWa[l][k] = sum_b fma(Lg[l][b], H2[k][b], .), l < L
@@ -277,7 +280,7 @@ __device__ __forceinline__ void head_wgrad(const float* Lg, const float* Hh, int
 
 // row sums over the tile: gout[r] = sum_b X[r][b], threads [t0, t0 + rows)
 __device__ __forceinline__ void row_sums(const float* X, int rows, float* gout, bool first, int tid,
-                                         int t0) {
+                                         int t0, int gstride = 1) {
   const int r = tid - t0;
   if (r < 0 || r >= rows) return;
   float s = 0.f;
@@ -288,7 +291,7 @@ __device__ __forceinline__ void row_sums(const float* X, int rows, float* gout, 
     s = s + v.z;
     s = s + v.w;
   }
-  acc_store(gout + r, s, first);
+  acc_store(gout + r * gstride, s, first);
 }
 
 // dz1[k][b] = (sum_j fma(W[j][k], Dz[j][b], .)) * (1 - Hact[k][b]^2), stored transposed
@@ -471,6 +474,19 @@ __device__ __forceinline__ void stage_rows64(float* dst, const float* src, int r
 __device__ __forceinline__ void stage_vec(float* dst, const float* src, int n, int tid) {
   for (int i = tid; i < n; i += UNT) dst[i] = __ldcg(src + i);
 }
+// every `rstride`-th row of a [.][64] matrix (AdapPolicyMult: sub-layer c of a scaling layer owns rows j C + c)
+__device__ __forceinline__ void stage_rows64_strided(float* dst, const float* src, int rstride, int tid) {
+  for (int i = tid; i < HID * HID; i += UNT) dst[(i >> 6) * LDW + (i & 63)] = __ldcg(src + (size_t)(i >> 6) * rstride * HID + (i & 63));
+}
+__device__ __forceinline__ void stage_vec_strided(float* dst, const float* src, int n, int stride, int tid) {
+  for (int i = tid; i < n; i += UNT) dst[i] = __ldcg(src + (size_t)i * stride);
+}
+// per-CTA global scratch of the AdapPolicyMult tile: activations of both towers kept for the backward pass
+struct MultScratch {
+  float *x[2], *y[2], *h2[2], *s[2];  // s[t]: [C] tiles
+  float *dy, *dx, *tmp, *zero;
+};
+__host__ __device__ inline size_t mult_scratch_floats(int C) { return (size_t)(10 + 2 * C) * (HID * LDA); }
 // per-partner parameter block behind the MlpPolicy layout (oracle/pth_oracle_modular.inc: mod_block)
 struct ModBlock {
   int w_pi0, b_pi0, w_pi1, b_pi1, w_vf0, b_vf0, w_vf1, b_vf1, w_act, b_act, w_val, b_val, total;
@@ -495,6 +511,21 @@ __host__ __device__ inline ModBlock mod_block(int L) {
 }
 constexpr int MOD_MAX_PARTNERS = 8;
 constexpr int TILE_F = HID * LDA;    // floats of a [64][LDA] scratch tile
+__device__ __forceinline__ MultScratch mult_scratch(float* base, int C) {
+  MultScratch g;
+  float* q = base;
+  for (int t = 0; t < 2; ++t) {
+    g.x[t] = q; q += TILE_F;
+    g.y[t] = q; q += TILE_F;
+    g.h2[t] = q; q += TILE_F;
+    g.s[t] = q; q += (size_t)C * TILE_F;
+  }
+  g.dy = q; q += TILE_F;
+  g.dx = q; q += TILE_F;
+  g.tmp = q; q += TILE_F;
+  g.zero = q;
+  return g;
+}
 constexpr int LTILE_F = MAXL * LDA;  // floats of a [32][LDA] logits-sized scratch tile
 // per-CTA global scratch of the modular tile (activations of every module are kept for the backward pass)
 struct ModScratch {
@@ -905,22 +936,10 @@ __device__ __forceinline__ void segsum_w1_mode(const UpdParams& p, const SM& sm,
 // The hidden-layer weight gradient (D1 x Ha^T) and the back-propagation through the hidden layer
 // (W^T x D1) only READ D1 / Ha, so they run side by side: each on one half of the CTA with the
 // large register tiles of a 256-thread group (the 512-thread tiles are shared-memory bound).
+// first-layer gradients of a tower from dz1 in sm.H2 ([sample][LDT] for one-hot spaces, [unit][LDA] for Box)
 template <bool BOX, bool ADAP = false, class SM>
-__device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const float* Xs,
-                                               const float* Ha, const float* w1_s, float* g_w0,
-                                               float* g_b0, float* g_w1, float* g_b1, int nb,
-                                               bool first, int tid, long long& prof_last, int c,
-                                               int pbase, const float* Cx = nullptr) {
-  __syncthreads();  // D1 complete
-  PTH_PROF(pbase + 0);
-  if (tid < UNT / 2) {
-    backprop64<!BOX, UNT / 2>(sm.D1, w1_s, Ha, sm.H2, tid);
-  } else {
-    wgrad64<UNT / 2>(sm.D1, Ha, g_w1, first, tid - UNT / 2);
-    row_sums(sm.D1, HID, g_b1, first, tid, UNT - HID);
-  }
-  __syncthreads();  // dz1 complete (in H2)
-  PTH_PROF(pbase + 1);  // backprop64 | wgrad64 + bias sums
+__device__ __forceinline__ void first_layer_backward(const UpdParams& p, SM& sm, const float* Xs, float* g_w0,
+                                                     float* g_b0, bool first, int tid, const float* Cx = nullptr) {
   if constexpr (ADAP) {
     // context rows of the first-layer gradient (AdapPolicy: dense inputs behind the features):
     // gW0[F + cc][j] = sum_b fma(dz1[j][b], ctx[cc][b], .), b ascending
@@ -936,7 +955,6 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const
     wgrad_first_box(sm.H2, Xs, p.sp.F, g_w0, first, tid);
     return;
   }
-  (void)nb;
   constexpr int SLOTS_PER_WARP = (SM::OW + NWS - 1) / NWS;
   float4 csum[SLOTS_PER_WARP];
   if (tid >= UNT - HID) {  // warps NWS, NWS + 1: the bias chains, next to the other warps' walks
@@ -957,10 +975,31 @@ __device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const
   segsum_w1_mode(p, sm, sm.bc, g_w0, first, tid, csum);
 }
 
-template <bool BOX, bool WIDE = false, bool ADAP = false, bool MOD = false>
+template <bool BOX, bool ADAP = false, class SM>
+__device__ __forceinline__ void tower_backward(const UpdParams& p, SM& sm, const float* Xs,
+                                               const float* Ha, const float* w1_s, float* g_w0,
+                                               float* g_b0, float* g_w1, float* g_b1, int nb,
+                                               bool first, int tid, long long& prof_last, int c,
+                                               int pbase, const float* Cx = nullptr) {
+  (void)nb;
+  __syncthreads();  // D1 complete
+  PTH_PROF(pbase + 0);
+  if (tid < UNT / 2) {
+    backprop64<!BOX, UNT / 2>(sm.D1, w1_s, Ha, sm.H2, tid);
+  } else {
+    wgrad64<UNT / 2>(sm.D1, Ha, g_w1, first, tid - UNT / 2);
+    row_sums(sm.D1, HID, g_b1, first, tid, UNT - HID);
+  }
+  __syncthreads();  // dz1 complete (in H2)
+  PTH_PROF(pbase + 1);  // backprop64 | wgrad64 + bias sums
+  first_layer_backward<BOX, ADAP>(p, sm, Xs, g_w0, g_b0, first, tid, Cx);
+}
+
+template <bool BOX, bool WIDE = false, bool ADAP = false, bool MOD = false, bool MULT = false>
 __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__ UpdParams p) {
   static_assert(!(BOX && WIDE), "wide rows are a one-hot notion");
   static_assert(!((ADAP || MOD) && WIDE) && !(ADAP && MOD), "ADAP / Modular: one-hot rows of 32 slots or Box rows");
+  static_assert(!MULT || ADAP, "AdapPolicyMult is an ADAP policy");
   constexpr bool PLAIN = WIDE || ADAP || MOD;
   using UpdSmem = UpdSmemT<WIDE, PLAIN>;
   constexpr int OW = UpdSmem::OW;
@@ -1267,8 +1306,47 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
             sm.Lg[l * LDA + b] = gsr.lgm[l * LDA + b] + gsr.lgp[(size_t)p.p0 * LTILE_F + l * LDA + b];
           }
         }
+        // ================= AdapPolicyMult: forward of both towers (a context tile: the policy tower only)
+        [[maybe_unused]] MultScratch msr;
+        if constexpr (MULT) {
+          const int C = p.C, L = p.sp.L;
+          msr = mult_scratch(p.mod_ws + (size_t)c * mult_scratch_floats(C), C);
+          float* slotW = sm.H1;               // [64][LDW] staging slot of a scaling sub-layer's weights
+          float* slotB = sm.H1 + HID * LDW;   // its 64 biases
+          if constexpr (BOX) {
+            first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, msr.x[0], tid);
+            first_layer_box<true, UNT>(p.sp.F, Xs, p.params + p.lo.w_vf0, sm.pol.b_vf0, msr.x[1], tid);
+          } else if (tid < UNT / 2) {
+            first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_pi0, sm.pol.b_pi0, msr.x[0], tid);
+          } else {
+            first_layer_onehot<true, UNT / 2, BT, 3, OW>(p.sp, obs_s, p.params + p.lo.w_vf0, sm.pol.b_vf0, msr.x[1],
+                                                          tid - UNT / 2);
+          }
+          __syncthreads();
+          for (int t = 0; t < (ctile ? 1 : 2); ++t) {
+            for (int cc = 0; cc < C; ++cc) {  // s_c = tanh(Ws_c x + bs_c): rows j C + cc of the scaling layer
+              stage_rows64_strided(slotW, p.params + p.mult_w[t] + cc * HID, C, tid);
+              stage_vec_strided(slotB, p.params + p.mult_b[t] + cc, HID, C, tid);
+              __syncthreads();
+              dense64<true, UNT, BT, LDA>(msr.x[t], slotW, slotB, msr.s[t] + (size_t)cc * TILE_F, tid);
+              __syncthreads();
+            }
+            for (int i = tid; i < HID * BT; i += UNT) {  // y = x + sum_c s_c ctx_c
+              const int k = i >> 7, b = i & (BT - 1);
+              float acc = msr.x[t][k * LDA + b];
+              for (int cc = 0; cc < C; ++cc) acc = fmaf(msr.s[t][(size_t)cc * TILE_F + k * LDA + b], Cx[cc * LDA + b], acc);
+              msr.y[t][k * LDA + b] = acc;
+            }
+            __syncthreads();
+            dense64<true, UNT, BT, LDA>(msr.y[t], t ? sm.pol.w_vf1 : sm.pol.w_pi1, t ? sm.pol.b_vf1 : sm.pol.b_pi1,
+                                        msr.h2[t], tid);
+            __syncthreads();
+          }
+          logits_tile(msr.h2[0], sm.pol, L, sm.Lg, tid);
+          if (!ctile && tid < BT) mod_value = value_head(msr.h2[1], sm.pol, tid);
+        }
         // ================= policy tower: forward
-        if constexpr (MOD) {
+        if constexpr (MOD || MULT) {
         } else if constexpr (BOX) {
           first_layer_box<true, UNT, BT, !ADAP>(p.sp.F, Xs, p.params + p.lo.w_pi0, sm.pol.b_pi0, sm.H1, tid);
         } else {
@@ -1288,7 +1366,7 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           }
         }
         __syncthreads();
-        if constexpr (ADAP) {
+        if constexpr (ADAP && !MULT) {
           // the context inputs continue the chains, then tanh (one-hot: one tower per CTA half)
           if constexpr (BOX)
             context_columns_tanh<true>(p.C, Cx, p.params + p.lo.w_pi0 + p.sp.F * HID, sm.H1, tid >> 5, UNT / 32,
@@ -1299,13 +1377,13 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
           __syncthreads();
         }
         PTH_PROF(3);  // pi first layer (one-hot: both towers' first layers)
-        if constexpr (!MOD)
+        if constexpr (!(MOD || MULT))
           dense64<true, UNT / 2, BT / 2, LDA>(sm.H1 + (tid >> 8) * (BT / 2), sm.pol.w_pi1, sm.pol.b_pi1,
                                                sm.H2 + (tid >> 8) * (BT / 2), tid & (UNT / 2 - 1));
         __syncthreads();
         PTH_PROF(4);  // pi hidden layer
         float s_pl = 0.f, s_e = 0.f, s_kl = 0.f, s_cf = 0.f, s_v = 0.f;
-        if constexpr (!MOD) logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
+        if constexpr (!(MOD || MULT)) logits_tile(sm.H2, sm.pol, p.sp.L, sm.Lg, tid);
         __syncthreads();
         if (!ctile) {
           // ---- per-sample losses and d loss / d logits.  Thread group h (threads [128h, 128h + 128))
@@ -1479,6 +1557,122 @@ __global__ void __launch_bounds__(UNT) ppo_update_kernel(const __grid_constant__
         }
         __syncthreads();  // dlogits complete
         PTH_PROF(5);  // action head + losses + dlogits
+        if constexpr (MULT) {
+          // ================= AdapPolicyMult: backward (contract: oracle/pth_oracle_update.inc mult_tower_backward).
+          // sm.Lg holds d loss / d logits (PPO's, or the context loss's on a context tile).
+          const int C = p.C, L = p.sp.L;
+          float* slotW = sm.H1;
+          float* DV = reinterpret_cast<float*>(sm.rowpos);  // [BT] d loss / d value
+          for (int i = tid; i < TILE_F; i += UNT) msr.zero[i] = 0.f;
+          if (!ctile && lane) {
+            const float dret = ret - mod_value;
+            s_v = valid ? dret * dret : 0.f;
+            DV[tid] = valid ? ((p.vf_coef * 2.0f) * (mod_value - ret)) * invB : 0.f;
+          }
+          // one tower, given dz2 in sm.D1: second layer reads y; dy = W1^T dz2; scaling sub-layers c ascending:
+          // dzs = (dy ctx_c)(1 - s_c^2), gWs rows j C + c, dx += Ws_c^T dzs; dz1 = dx (1 - x^2) -> first-layer gradients
+          auto tower = [&](int t) {
+            float* g_w1 = part + (t ? p.lo.w_vf1 : p.lo.w_pi1);
+            float* g_b1 = part + (t ? p.lo.b_vf1 : p.lo.b_pi1);
+            wgrad64<UNT>(sm.D1, msr.y[t], g_w1, first, tid);
+            row_sums(sm.D1, HID, g_b1, first, tid, UNT - HID);
+            backprop64<false, UNT>(sm.D1, t ? sm.pol.w_vf1 : sm.pol.w_pi1, msr.zero, msr.dy, tid);
+            __syncthreads();
+            for (int i = tid; i < HID * BT; i += UNT) {
+              const int k = i >> 7, b = i & (BT - 1);
+              msr.dx[k * LDA + b] = msr.dy[k * LDA + b];
+            }
+            for (int cc = 0; cc < C; ++cc) {
+              stage_rows64_strided(slotW, p.params + p.mult_w[t] + cc * HID, C, tid);
+              const float* sc = msr.s[t] + (size_t)cc * TILE_F;
+              for (int i = tid; i < HID * BT; i += UNT) {
+                const int k = i >> 7, b = i & (BT - 1);
+                const float sv_ = sc[k * LDA + b];
+                sm.D1[k * LDA + b] = (msr.dy[k * LDA + b] * Cx[cc * LDA + b]) * (1.0f - sv_ * sv_);
+              }
+              __syncthreads();
+              wgrad64<UNT>(sm.D1, msr.x[t], part + p.mult_w[t] + cc * HID, first, tid, C * HID);
+              row_sums(sm.D1, HID, part + p.mult_b[t] + cc, first, tid, UNT - HID, C);
+              backprop64<false, UNT>(sm.D1, slotW, msr.zero, msr.tmp, tid);
+              __syncthreads();
+              for (int i = tid; i < HID * BT; i += UNT) {
+                const int k = i >> 7, b = i & (BT - 1);
+                msr.dx[k * LDA + b] = msr.dx[k * LDA + b] + msr.tmp[k * LDA + b];
+              }
+              __syncthreads();
+            }
+            for (int i = tid; i < HID * BT; i += UNT) {
+              const int k = i >> 7, b = i & (BT - 1);
+              const float xv = msr.x[t][k * LDA + b];
+              sm.H2[BOX ? (k * LDA + b) : (b * LDT + k)] = msr.dx[k * LDA + b] * (1.0f - xv * xv);
+            }
+            __syncthreads();
+            first_layer_backward<BOX, false>(p, sm, Xs, part + (t ? p.lo.w_vf0 : p.lo.w_pi0),
+                                             part + (t ? p.lo.b_vf0 : p.lo.b_pi0), first, tid);
+            __syncthreads();
+          };
+          __syncthreads();
+          if (tid >= UNT / 2) {
+            head_wgrad(sm.Lg, msr.h2[0], L, part + p.lo.w_act, first, tid - UNT / 2);
+            row_sums(sm.Lg, L, part + p.lo.b_act, first, tid, UNT - MAXL);
+          }
+          head_backprop<true>(sm.Lg, sm.pol.w_act, msr.h2[0], L, sm.D1, tid);
+          __syncthreads();
+          tower(0);
+          if (ctile) {
+            if (first) {  // no value tower on a context tile: its sums start at zero
+              for (int i = p.lo.w_vf0 + tid; i < p.lo.w_act; i += UNT) part[i] = 0.f;
+              for (int i = p.lo.w_val + tid; i < P; i += UNT) part[i] = 0.f;
+            }
+            first = false;
+            continue;
+          }
+          if (lane) {
+            const float dv = DV[tid];
+#pragma unroll 8
+            for (int k = 0; k < HID; ++k) {
+              const float h = msr.h2[1][k * LDA + tid];
+              sm.D1[k * LDA + tid] = (sm.pol.w_val[k] * dv) * (1.0f - h * h);
+            }
+          } else if (tid < BT + HID) {
+            const int k = tid - BT;
+            float acc = 0.f;
+            for (int b0 = 0; b0 < BT; b0 += 4) {
+              const float4 d = *reinterpret_cast<const float4*>(DV + b0);
+              const float4 h = *reinterpret_cast<const float4*>(msr.h2[1] + k * LDA + b0);
+              acc = fmaf(d.x, h.x, acc);
+              acc = fmaf(d.y, h.y, acc);
+              acc = fmaf(d.z, h.z, acc);
+              acc = fmaf(d.w, h.w, acc);
+            }
+            acc_store(part + p.lo.w_val + k, acc, first);
+          } else if (tid == BT + HID) {
+            float s_ = 0.f;
+            for (int b = 0; b < BT; ++b) s_ = s_ + DV[b];
+            acc_store(part + p.lo.b_val, s_, first);
+          }
+          __syncthreads();
+          tower(1);
+          {
+            float sv[5] = {s_pl, s_v, s_e, s_kl, s_cf};
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) sv[i] = sv[i] + __shfl_xor_sync(0xffffffffu, sv[i], d);
+            __syncthreads();
+            if ((tid & 31) == 0 && tid < BT)
+#pragma unroll
+              for (int i = 0; i < 5; ++i) sm.bc[i * 4 + (tid >> 5)] = sv[i];
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const float ts = ((sm.bc[i * 4] + sm.bc[i * 4 + 1]) + sm.bc[i * 4 + 2]) + sm.bc[i * 4 + 3];
+              cta_stat[i] = first ? ts : cta_stat[i] + ts;
+            }
+          }
+          first = false;
+          continue;
+        }
         if constexpr (MOD) {
           // ================= ModularAlgorithm: the marginal regulariser and the backward pass through
           // every module (contract: oracle/pth_oracle_modular.inc).  sm.Lg holds d PPO-loss / d composed logits.
@@ -2263,6 +2457,8 @@ const void* update_fn(int kind) {
     case 4: return (const void*)ppo_update_kernel<true, false, true>;
     case 5: return (const void*)ppo_update_kernel<false, false, false, true>;  // ModularAlgorithm, one-hot
     case 6: return (const void*)ppo_update_kernel<true, false, false, true>;   // ModularAlgorithm, Box
+    case 7: return (const void*)ppo_update_kernel<false, false, true, false, true>;  // AdapPolicyMult, one-hot
+    case 8: return (const void*)ppo_update_kernel<true, false, true, false, true>;   // AdapPolicyMult, Box
     default: return (const void*)ppo_update_kernel<false, false>;
   }
 }
@@ -2271,7 +2467,7 @@ size_t update_smem(int kind) {
 }
 
 int max_coop_ctas(const pth_ctx* ctx, int kind = 0) {
-  static int cached[7] = {-1, -1, -1, -1, -1, -1, -1};
+  static int cached[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
   if (cached[kind] < 0) {
     const void* fn = update_fn(kind);
     const size_t smem = update_smem(kind);
@@ -2356,6 +2552,28 @@ extern "C" int64_t pth_modular_workspace_bytes(const pth_ctx* ctx, const pth_spa
   return (int64_t)ws_layout(cap > 0 ? cap : 1, (int)P, 64 * n_mb).total;
 }
 
+extern "C" int64_t pth_adap_mult_param_count(const pth_space* sp, int32_t context_size) {
+  const int64_t P = pth_policy_param_count(sp);
+  if (P < 0 || context_size < 1 || context_size > MAX_CTX) return PTH_EINVAL;
+  return P + 2 * ((int64_t)HID * context_size * HID + HID * context_size);
+}
+
+extern "C" int64_t pth_adap_mult_workspace_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size,
+                                                 int64_t M, int64_t batch_size) {
+  if (!ctx || !sp || M <= 0 || batch_size <= 0) return PTH_EINVAL;
+  const int64_t P = pth_adap_mult_param_count(sp, context_size);
+  if (P < 0) return PTH_EINVAL;
+  const int cap = max_coop_ctas(ctx, sp->obs_kind == PTH_OBS_BOX ? 8 : 7);
+  const int64_t n_mb = (M + batch_size - 1) / batch_size;
+  return (int64_t)ws_layout(cap > 0 ? cap : 1, (int)P, 64 * n_mb).total;
+}
+
+extern "C" int64_t pth_adap_mult_scratch_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t context_size) {
+  if (!ctx || !sp || context_size < 1 || context_size > MAX_CTX) return PTH_EINVAL;
+  const int cap = max_coop_ctas(ctx, sp->obs_kind == PTH_OBS_BOX ? 8 : 7);
+  return (int64_t)(sizeof(float) * mult_scratch_floats(context_size)) * (cap > 0 ? cap : 1);
+}
+
 // per-CTA activation scratch of the modular tile for the largest grid a launch may use
 extern "C" int64_t pth_modular_scratch_bytes(const pth_ctx* ctx, const pth_space* sp, int32_t num_partners) {
   if (!ctx || !sp || num_partners < 1 || num_partners > MOD_MAX_PARTNERS) return PTH_EINVAL;
@@ -2413,6 +2631,30 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     p.ctx_draws = a->d_ctx_draws;
   }
   p.lo = make_layout(p.sp.F + C, p.sp.L);
+  p.mult_w[0] = p.mult_w[1] = p.mult_b[0] = p.mult_b[1] = 0;
+  const bool mult = a->adap_mult != 0;
+  if (mult) {  // AdapPolicyMult: per tower  first layer (features only) | scaling 64 -> 64 C | second layer
+    PTH_CHECK_ARG(C > 0, "AdapPolicyMult needs context_size > 0");
+    int o = 0;
+    const int F = p.sp.F, L = p.sp.L;
+    p.lo.w_pi0 = o; o += HID * F;
+    p.lo.b_pi0 = o; o += HID;
+    p.mult_w[0] = o; o += HID * C * HID;
+    p.mult_b[0] = o; o += HID * C;
+    p.lo.w_pi1 = o; o += HID * HID;
+    p.lo.b_pi1 = o; o += HID;
+    p.lo.w_vf0 = o; o += HID * F;
+    p.lo.b_vf0 = o; o += HID;
+    p.mult_w[1] = o; o += HID * C * HID;
+    p.mult_b[1] = o; o += HID * C;
+    p.lo.w_vf1 = o; o += HID * HID;
+    p.lo.b_vf1 = o; o += HID;
+    p.lo.w_act = o; o += L * HID;
+    p.lo.b_act = o; o += L;
+    p.lo.w_val = o; o += HID;
+    p.lo.b_val = o; o += 1;
+    p.lo.total = o;
+  }
   p.P = p.lo.total;
   // ModularAlgorithm (pantheonrl/algos/modular): num_partners modules behind the main network
   const bool modular = a->loss_kind == PTH_LOSS_MODULAR;
@@ -2436,7 +2678,8 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
   }
   for (int i = 0; i < MAX_SLOTS; ++i)
     p.nvec[i] = (!box && i < p.sp.obs_len) ? (uint8_t)a->space->obs_nvec[i] : 0;
-  const int kind = modular ? (box ? 6 : 5) : (C > 0 ? (box ? 4 : 3) : (box ? 1 : (p.sp.obs_len > 32 ? 2 : 0)));
+  const int kind = modular ? (box ? 6 : 5)
+                           : (mult ? (box ? 8 : 7) : (C > 0 ? (box ? 4 : 3) : (box ? 1 : (p.sp.obs_len > 32 ? 2 : 0))));
   const int cap = max_coop_ctas(ctx, kind);
   PTH_CHECK_ARG(cap <= 160, "more than 160 co-resident CTAs are not supported");
   if (cap < 1 || !ctx->coop_launch) {
@@ -2452,6 +2695,12 @@ extern "C" int pth_ppo_update(pth_ctx* ctx, const pth_update_args* a, void* stre
     PTH_CHECK_ARG(a->d_modular_scratch != nullptr && ((uintptr_t)a->d_modular_scratch % 16) == 0 &&
                       a->modular_scratch_bytes >= (int64_t)(sizeof(float) * mod_scratch_floats(p.Pn) * (size_t)G),
                   "ModularAlgorithm: d_modular_scratch too small (pth_modular_scratch_bytes)");
+    p.mod_ws = reinterpret_cast<float*>(a->d_modular_scratch);
+  }
+  if (mult) {
+    PTH_CHECK_ARG(a->d_modular_scratch != nullptr && ((uintptr_t)a->d_modular_scratch % 16) == 0 &&
+                      a->modular_scratch_bytes >= (int64_t)(sizeof(float) * mult_scratch_floats(C) * (size_t)G),
+                  "AdapPolicyMult: d_modular_scratch too small (pth_adap_mult_scratch_bytes)");
     p.mod_ws = reinterpret_cast<float*>(a->d_modular_scratch);
   }
   PTH_CHECK_ARG((int64_t)w.total <= a->workspace_bytes, "workspace too small");

@@ -116,7 +116,7 @@ def liar_step(state, is_ego, action):
 # ----------------------------------------------------------------------- policy
 def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=0, slot=0, idx0=0,
                    action_in=None, want=("action", "value", "logp", "entropy", "logits"), race=None, context=None,
-                   num_partners=0, partner_idx=0, out=None):
+                   num_partners=0, partner_idx=0, out=None, adap_mult=False):
     """ActorCriticPolicy.forward (sampling) or evaluate_actions (action_in given).
 
     obs: [B, stride] uint8 (one-hot spaces) or float32 (Box). Returns a dict of
@@ -163,6 +163,7 @@ def policy_forward(space, params, obs, seed=0, rng_stream=_lib.STREAM_EGO, tick=
             raise ValueError("race must be [B, L]")
         a.d_race = race.data_ptr()
     a.num_partners, a.partner_idx = int(num_partners), int(partner_idx)  # ModularPolicy: partner module composing the outputs
+    a.adap_mult = int(bool(adap_mult))  # AdapPolicyMult parameter layout (with context=)
     if context is not None:
         _need(context, torch.float32, "context")
         a.context_size, a.d_context = context.shape[-1], context.data_ptr()

@@ -90,3 +90,62 @@ def state_dict_to_flat(space, sd, extra=0):
             t = t.t().contiguous()
         parts.append(t.reshape(-1))
     return torch.cat(parts).numpy().astype(np.float32)
+
+
+# ---------------------------------------------------------------------------- AdapPolicyMult (adap/policies.py:134-283)
+MULT_TRANSPOSED = (0, 6)  # the two first-layer matrices are stored input-major
+
+
+def tensor_shapes_mult(space, C):
+    """(name, torch shape) of an AdapPolicyMult in flat order: per tower first layer | scaling 64 -> 64 C | second layer."""
+    F, L = feature_dim(space), sum(space.heads)
+    out = []
+    for tower in ("agent", "value"):
+        out += [(f"mlp_extractor.{tower}_branch_1.0.weight", (HID, F)), (f"mlp_extractor.{tower}_branch_1.0.bias", (HID,)),
+                (f"mlp_extractor.{tower}_scaling.0.weight", (HID * C, HID)), (f"mlp_extractor.{tower}_scaling.0.bias", (HID * C,)),
+                (f"mlp_extractor.{tower}_branch_2.0.weight", (HID, HID)), (f"mlp_extractor.{tower}_branch_2.0.bias", (HID,))]
+    return out + [("action_net.weight", (L, HID)), ("action_net.bias", (L,)), ("value_net.weight", (1, HID)),
+                  ("value_net.bias", (1,))]
+
+
+def param_count_mult(space, C):
+    return sum(int(np.prod(s)) for _, s in tensor_shapes_mult(space, C))
+
+
+def init_flat_mult(space, seed, C):
+    """MultModel.__init__ creates pi0, vf0, pi1, vf1 (zip_longest), then the two scaling layers, then SB3 creates the
+    heads; ActorCriticPolicy._build orthogonalises module by module (mlp_extractor = the MultModel, gain sqrt 2, in
+    registration order agent_branch_1, agent_scaling, agent_branch_2, value_branch_1, value_scaling, value_branch_2)."""
+    F, L = feature_dim(space), sum(space.heads)
+    if seed is not None:
+        torch.manual_seed(int(seed))
+    for fan_out, fan_in in ((HID, F), (HID, F), (HID, HID), (HID, HID), (HID * C, HID), (HID * C, HID), (L, HID), (1, HID)):
+        torch.nn.Linear(fan_in, fan_out)
+    g = math.sqrt(2)
+    z = lambda n: torch.zeros(n)  # noqa: E731
+    a1, as_, a2 = _ortho(HID, F, g), _ortho(HID * C, HID, g), _ortho(HID, HID, g)
+    v1, vs, v2 = _ortho(HID, F, g), _ortho(HID * C, HID, g), _ortho(HID, HID, g)
+    parts = [a1.t().contiguous(), z(HID), as_, z(HID * C), a2, z(HID), v1.t().contiguous(), z(HID), vs, z(HID * C), v2,
+             z(HID), _ortho(L, HID, 0.01), z(L), _ortho(1, HID, 1.0), z(1)]
+    return torch.cat([p.reshape(-1) for p in parts]).numpy().astype(np.float32)
+
+
+def flat_to_state_dict_mult(space, flat, C):
+    flat = torch.as_tensor(np.asarray(flat, np.float32))
+    out, o = {}, 0
+    for i, (name, shape) in enumerate(tensor_shapes_mult(space, C)):
+        n = int(np.prod(shape))
+        chunk = flat[o:o + n]
+        if i in MULT_TRANSPOSED:
+            chunk = chunk.reshape(shape[1], shape[0]).t().contiguous()
+        out[name] = chunk.reshape(shape).clone()
+        o += n
+    return out
+
+
+def state_dict_to_flat_mult(space, sd, C):
+    parts = []
+    for i, (name, shape) in enumerate(tensor_shapes_mult(space, C)):
+        t = torch.as_tensor(sd[name]).float().reshape(shape)
+        parts.append((t.t().contiguous() if i in MULT_TRANSPOSED else t).reshape(-1))
+    return torch.cat(parts).numpy().astype(np.float32)

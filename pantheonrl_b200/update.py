@@ -59,10 +59,16 @@ def update_grid(space, M, batch_size, device=0):
 class UpdateWorkspace:
     """Caller-owned scratch for pth_ppo_update (the library never allocates)."""
 
-    def __init__(self, space, M, batch_size, device="cuda", context_size=0, num_partners=0):
+    def __init__(self, space, M, batch_size, device="cuda", context_size=0, num_partners=0, adap_mult=False):
         ctx = Context.get(torch.device(device).index or 0)
         lib = _lib.load()
-        if num_partners > 0:  # ModularPolicy: + the per-CTA activation scratch of every partner module
+        if adap_mult:  # AdapPolicyMult: + the per-CTA activation scratch of both towers
+            n = int(lib.pth_adap_mult_workspace_bytes(ctx.handle, C.byref(space), int(context_size), int(M), int(batch_size)))
+            ns = int(lib.pth_adap_mult_scratch_bytes(ctx.handle, C.byref(space), int(context_size)))
+            if ns <= 0:
+                raise _lib.PthError("pth_adap_mult_scratch_bytes failed")
+            self.modular_scratch = torch.empty(ns, dtype=torch.uint8, device=device)
+        elif num_partners > 0:  # ModularPolicy: + the per-CTA activation scratch of every partner module
             n = int(lib.pth_modular_workspace_bytes(ctx.handle, C.byref(space), int(num_partners), int(M), int(batch_size)))
             ns = int(lib.pth_modular_scratch_bytes(ctx.handle, C.byref(space), int(num_partners)))
             if ns <= 0:
@@ -81,7 +87,8 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
                learning_rate=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
                betas=(0.9, 0.999), eps=1e-5, normalize_advantage=True, grid_ctas=0, stats=None,
                peers=None, loss_kind=0, l2_weight=0.0, context=None, context_loss_coeff=0.0, ctx_states=None,
-               ctx_draws=None, ctx_loss=None, num_partners=0, partner_idx=0, partner_vf_step=0, marginal_reg_coef=0.0):
+               ctx_draws=None, ctx_loss=None, num_partners=0, partner_idx=0, partner_vf_step=0, marginal_reg_coef=0.0,
+               adap_mult=False):
     """SB3 PPO.train() over flat sample arrays on the device, in place on
     params / adam_m / adam_v. Returns the stats tensor [n_epochs * n_mb, 8]."""
     n_epochs = perm.shape[0]
@@ -130,6 +137,10 @@ def ppo_update(space, params, adam_m, adam_v, adam_step, obs, actions, old_logp,
         a.d_ctx_states, a.d_ctx_draws = ctx_states.data_ptr(), ctx_draws.data_ptr()
         if ctx_loss is not None:
             a.d_ctx_loss = ctx_loss.data_ptr()
+    if adap_mult:  # AdapPolicyMult parameter layout (context= given); scratch from UpdateWorkspace(adap_mult=True)
+        a.adap_mult = 1
+        a.d_modular_scratch = workspace.modular_scratch.data_ptr()
+        a.modular_scratch_bytes = workspace.modular_scratch.numel()
     if num_partners > 0:  # ModularAlgorithm.train, one partner phase (loss_kind PTH_LOSS_MODULAR)
         a.num_partners, a.partner_idx, a.partner_vf_step = int(num_partners), int(partner_idx), int(partner_vf_step)
         a.marginal_reg_coef = float(marginal_reg_coef)

@@ -161,3 +161,86 @@ def test_adap_draws_bit_exact_vs_oracle(ctx, sampler, C):
         assert np.allclose(np.linalg.norm(want_d, axis=-1), 1.0, atol=1e-6)
     _, one = dupd.adap_draw(1, 1, C, sampler, 10, 0x10300, index0=8)  # a single per-episode context
     assert one.shape == (1, 1, C)
+
+
+# ------------------------------------------------------------------ AdapPolicyMult (ADAP_MULT)
+def rand_mult_params(osp, C, seed, scale=0.3):
+    return (scale * np.random.RandomState(seed).randn(oracle.adap_mult_param_count(osp, C))).astype(np.float32)
+
+
+@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE, BOX])
+@pytest.mark.parametrize("C,B,per_sample", [(3, 1, False), (3, 777, True), (8, 129, True)])
+def test_adap_mult_forward_bit_exact(ctx, kw, C, B, per_sample):
+    osp, sp = oracle.make_space(**kw), gspace(kw)
+    params = rand_mult_params(osp, C, seed=B)
+    assert params.size == _lib.load().pth_adap_mult_param_count(sp, C)
+    obs, act, _, _ = batch(kw, B, B + 1)
+    cx = np.random.RandomState(C).randn(B if per_sample else 1, C).astype(np.float32)
+    for action_in in (None, act):
+        want = oracle.adap_mult_forward(osp, params, obs, cx if per_sample else cx[0], seed=3, tick=9, idx0=5,
+                                        action_in=action_in)
+        got = ops.policy_forward(sp, d(params), d(obs), seed=3, tick=9, idx0=5, context=d(cx), adap_mult=True,
+                                 action_in=None if action_in is None else d(action_in))
+        for k in ("action", "value", "logp", "entropy", "logits"):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), (k, action_in is None)
+
+
+def run_both_mult(kw, C, params, obs, act, old_logp, adv, ret, cx, perm, BS, grid, sidx=None, draws=None, coeff=0.0, **hp):
+    osp, sp = oracle.make_space(**kw), gspace(kw)
+    M = perm.shape[1]
+    n = perm.shape[0] * (-(-M // BS))
+    dp, dm, dv = d(params), d(np.zeros_like(params)), d(np.zeros_like(params))
+    ws = dupd.UpdateWorkspace(sp, M, BS, context_size=C, adap_mult=True)
+    cl = torch.full((n,), -1.0, device="cuda")
+    extra = {} if sidx is None else dict(loss_kind=_lib.PTH_LOSS_ADAP, context_loss_coeff=coeff, ctx_states=d(sidx),
+                                         ctx_draws=d(draws), ctx_loss=cl)
+    gst = dupd.ppo_update(sp, dp, dm, dv, 0, d(obs), d(act), d(old_logp), d(adv), d(ret), d(perm), BS, ws,
+                          grid_ctas=grid, context=d(cx), adap_mult=True, **extra, **hp)
+    torch.cuda.synchronize()
+    op, om, ov = params.copy(), np.zeros_like(params), np.zeros_like(params)
+    oextra = {} if sidx is None else dict(loss_kind=2, ctx_loss_coeff=coeff, ctx_sidx=sidx, ctx_draws=draws)
+    out = oupd.ppo_update(osp, op, om, ov, 0, obs, act, old_logp, adv, ret, perm, BS, grid, ctx=cx, adap_mult=True,
+                          **oextra, **hp)
+    gst = gst.cpu().numpy()
+    assert np.array_equal(gst, out[0]), np.abs(gst - out[0]).max()
+    assert np.array_equal(dm.cpu().numpy(), om) and np.array_equal(dv.cpu().numpy(), ov)
+    assert np.array_equal(dp.cpu().numpy(), op), np.abs(dp.cpu().numpy() - op).max()
+    if sidx is not None:
+        assert np.array_equal(cl.cpu().numpy(), out[2])
+    return op, gst, cl.cpu().numpy()
+
+
+@pytest.mark.parametrize("kw", [oracle.RPS_SPACE, oracle.LIAR_SPACE, BOX])
+@pytest.mark.parametrize("M,BS,E,grid,K,S,C", [(280, 64, 2, 1, 5, 32, 3), (700, 256, 2, 3, 0, 0, 3), (600, 300, 1, 96, 3, 20, 2),
+                                             (500, 250, 1, 4, 16, 40, 8)])
+def test_adap_mult_train_bit_exact_vs_oracle(ctx, kw, M, BS, E, grid, K, S, C):
+    """AdapPolicyMult under PPO.train (K = 0) and ADAP.train (context tiles), several tiles per CTA, 96 CTAs."""
+    osp = oracle.make_space(**kw)
+    params = rand_mult_params(osp, C, seed=M + K)
+    obs, act, adv, ret = batch(kw, M, M)
+    rs = np.random.RandomState(K + 1)
+    cx = rs.randn(M, C).astype(np.float32)
+    ev = oracle.adap_mult_forward(osp, params, obs, cx, action_in=act)
+    old_logp = (ev["logp"] + 0.1 * rs.randn(M)).astype(np.float32)
+    perm = oupd.perm_feistel(M, E, seed=10, stream=4)
+    if K:
+        sidx, draws = random_draws(rs, E * (-(-M // BS)), K, S, C, M, BS)
+        run_both_mult(kw, C, params, obs, act, old_logp, adv, ret, cx, perm, BS, grid, sidx, draws, coeff=0.7, ent_coef=0.01)
+    else:
+        run_both_mult(kw, C, params, obs, act, old_logp, adv, ret, cx, perm, BS, grid, ent_coef=0.01)
+
+
+@pytest.mark.parametrize("name,kw", [("mult_rps", oracle.RPS_SPACE), ("mult_liar", oracle.LIAR_SPACE)])
+def test_adap_mult_train_reproduces_the_reference_run(ctx, name, kw):
+    """The reference's own MultModel + ADAP.train run (tests/golden/make_golden_adap.py) through the CUDA kernel."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "adap.npz"))
+    pre = name + "_"
+    M, BS, E, K, S = (int(x) for x in g[pre + "hp"])
+    log = dict(zip(g[pre + "log_keys"], g[pre + "log_vals"]))
+    n_mb = -(-M // BS)
+    p, st, cl = run_both_mult(kw, 3, g[pre + "p0"], g[pre + "obs"], g[pre + "act"], g[pre + "old_logp"], g[pre + "adv"],
+                              g[pre + "ret"], g[pre + "ctx"], g[pre + "perms"], BS, 3, g[pre + "sidx"], g[pre + "draws"],
+                              coeff=float(g[pre + "coeff"][0]), ent_coef=0.01)
+    assert np.abs(p - g[pre + "params"]).max() <= 2e-6
+    assert cl[-n_mb:].mean() == pytest.approx(log["train/context_kl_loss"], abs=1e-5)
+    assert st[-1, 5] == pytest.approx(log["train/loss"], abs=2e-5)

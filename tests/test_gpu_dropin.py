@@ -185,3 +185,21 @@ def test_trainer_flow_rps_modular_vs_two_ppo_partners(ctx, aliases, tmp_path):
     again = type(ego).load(path)
     assert torch.equal(again.policy.params, ego.policy.params) and again.num_partners == 2 and again.vf_steps == [8, 8]
     assert again.marginal_reg_coef == 0.5
+
+
+def test_trainer_flow_liar_adap_mult_vs_adap_mult(ctx, aliases, tmp_path):
+    """`trainer.py LiarsDice-v0 ADAP_MULT ADAP_MULT --seed 4` (trainer.py:129-130, 207-208): AdapPolicyMult on both sides."""
+    import trainer_shaped as ts
+    cfg = {"n_steps": 128, "batch_size": 64, "n_epochs": 2, "context_loss_coeff": 0.5}
+    args = ts.default_args("LiarsDice-v0", "ADAP_MULT", ["ADAP_MULT"], seed=4, total_timesteps=256,
+                           ego_config=dict(cfg, verbose=0), alt_config=[dict(cfg)])
+    env, ego, partners = _run_adap(args)
+    assert ego.mult and partners[0].model.mult and ego._n_updates == 4
+    from pantheonrl_b200 import policy as pol
+    assert ego.policy.params.numel() == pol.param_count_mult(ego.space, 3)
+    cl = ego.last_context_loss.cpu().numpy()
+    assert cl.shape == (4,) and np.all((cl > 0) & (cl <= 1 + 1e-6)) and np.all(np.isfinite(ego.last_stats.cpu().numpy()))
+    path = str(tmp_path / "mult")
+    ego.save(path)
+    again = type(ego).load(path)
+    assert again.mult and torch.equal(again.policy.params, ego.policy.params)

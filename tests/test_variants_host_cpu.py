@@ -95,7 +95,22 @@ def test_alias_modules_resolve_the_variants():
         assert ADAP is adap.ADAP and AdapAgent is adap.AdapAgent and AdapPolicy is adap.AdapPolicy
         assert ModularAlgorithm is modular.ModularAlgorithm and ModularPolicy is modular.ModularPolicy
         assert set(SAMPLERS) == {"l2", "unit_square", "positive_square", "categorical", "natural_numbers"}
-        with pytest.raises(NotImplementedError):
-            ADAP(policy=AdapPolicyMult, env=None)
+        assert AdapPolicyMult is adap.AdapPolicyMult
     finally:
         compat.uninstall()
+
+
+def test_adap_mult_layout_agrees_between_facade_abi_and_oracle():
+    lib = _lib.load()
+    osp = oracle.make_space(**oracle.LIAR_SPACE)
+    for C_ in (1, 3, 8):
+        n = pol.param_count_mult(LIAR, C_)
+        assert n == lib.pth_adap_mult_param_count(C.byref(LIAR), C_) == oracle.adap_mult_param_count(osp, C_)
+        flat = pol.init_flat_mult(LIAR, 3, C_)
+        assert flat.size == n
+        sd = pol.flat_to_state_dict_mult(LIAR, flat, C_)
+        assert sd["mlp_extractor.agent_scaling.0.weight"].shape == (64 * C_, 64)
+        assert np.array_equal(pol.state_dict_to_flat_mult(LIAR, sd, C_), flat)
+    # the scaling layer is orthogonal with gain sqrt(2) (64 C x 64: orthonormal columns)
+    ws = pol.flat_to_state_dict_mult(LIAR, pol.init_flat_mult(LIAR, 3, 3), 3)["mlp_extractor.value_scaling.0.weight"].numpy()
+    assert np.allclose(ws.T @ ws, 2 * np.eye(64), atol=1e-4)

@@ -46,10 +46,10 @@ def make_ego(env, args):
         model = PPO.load(kw["location"])
         model.set_env(DummyVecEnv([lambda: Monitor(env)]))
         return model
-    if args.ego == "ADAP":  # trainer.py:127-128
+    if args.ego in ("ADAP", "ADAP_MULT"):  # trainer.py:127-130
         from pantheonrl.algos.adap.adap_learn import ADAP
-        from pantheonrl.algos.adap.policies import AdapPolicy
-        return ADAP(policy=AdapPolicy, **kw)
+        from pantheonrl.algos.adap.policies import AdapPolicy, AdapPolicyMult
+        return ADAP(policy=AdapPolicy if args.ego == "ADAP" else AdapPolicyMult, **kw)
     if args.ego == "ModularAlgorithm":  # trainer.py:131-135
         from pantheonrl.algos.modular.learn import ModularAlgorithm
         from pantheonrl.algos.modular.policies import ModularPolicy
@@ -76,12 +76,13 @@ def make_partner(kind, config, altenv, args, number, ego=None):
     config = dict(config, env=altenv, device=args.device, verbose=args.verbose_partner)
     if args.seed is not None:
         config["seed"] = args.seed
-    if kind == "ADAP":  # trainer.py:205-213
+    if kind in ("ADAP", "ADAP_MULT"):  # trainer.py:205-213
         from pantheonrl.algos.adap.adap_learn import ADAP
         from pantheonrl.algos.adap.agent import AdapAgent
-        from pantheonrl.algos.adap.policies import AdapPolicy
+        from pantheonrl.algos.adap.policies import AdapPolicy, AdapPolicyMult
         shared = ego.policy if args.share_latent else None
-        return AdapAgent(ADAP(policy=AdapPolicy, **config), latent_syncer=shared, **agentarg)
+        return AdapAgent(ADAP(policy=AdapPolicy if kind == "ADAP" else AdapPolicyMult, **config), latent_syncer=shared,
+                         **agentarg)
     assert kind == "PPO"
     return OnPolicyAgent(PPO(policy="MlpPolicy", **config), **agentarg)
 
