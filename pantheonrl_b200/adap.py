@@ -42,8 +42,32 @@ def _torch_sampler(name, ctx_size, num):
     raise KeyError(name)
 
 
-SAMPLERS = {k: (lambda ctx_size, num, torch=False, _k=k: _torch_sampler(_k, ctx_size, num))
-            for k in ("l2", "unit_square", "positive_square", "categorical", "natural_numbers")}
+def _numpy_sampler(name, ctx_size, num):
+    """SAMPLERS[name](ctx_size, num, torch=False): the np.random branch of the same functions."""
+    if name == "l2":
+        c = np.random.rand(num, ctx_size) * 2 - 1
+        return c / (np.sum(c ** 2, axis=-1).reshape(num, 1)) ** (1 / 2)
+    if name == "unit_square":
+        return np.random.rand(num, ctx_size) * 2 - 1
+    if name == "positive_square":
+        return np.random.rand(num, ctx_size)
+    if name == "categorical":
+        c = np.zeros((num, ctx_size))
+        c[np.arange(num), np.random.randint(0, ctx_size, size=(num,))] = 1
+        return c
+    if name == "natural_numbers":
+        return np.random.randint(0, ctx_size, size=(num, 1))
+    raise KeyError(name)
+
+
+def _make_sampler(name):
+    def sampler(ctx_size, num, torch=False):  # the reference's signature (util.py:42-94)
+        return _torch_sampler(name, ctx_size, num) if torch else _numpy_sampler(name, ctx_size, num)
+    sampler.__name__ = f"get_{name}"
+    return sampler
+
+
+SAMPLERS = {k: _make_sampler(k) for k in ("l2", "unit_square", "positive_square", "categorical", "natural_numbers")}
 
 
 class AdapPolicy:
