@@ -29,6 +29,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ref_shim  # noqa: E402
 
 ref_shim.install()
+th.set_num_threads(1)  # bit-reproducible fixtures: torch's CPU GEMM blocking depends on the thread count
 
 
 def stub(name, **attrs):
