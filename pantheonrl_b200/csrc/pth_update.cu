@@ -8,6 +8,13 @@
 // (restated in-tree at pantheonrl/algos/adap/adap_learn.py:229-347; Adam eps at
 // pantheonrl/algos/modular/policies.py:84-88).
 //
+// Variants of the same kernel (template flags; the reduction, clip and Adam phases are shared):
+//   WIDE  one-hot observation rows of up to 96 slots (frame stacks)
+//   ADAP  pantheonrl/algos/adap: AdapPolicy context inputs + the context KL loss as extra tiles (adap_learn.py:229-347,
+//         adap/util.py:97-131); with MULT the AdapPolicyMult towers (adap/policies.py:134-283)
+//   MOD   pantheonrl/algos/modular: ModularPolicy's per-partner modules + the marginal regulariser, one partner phase
+//         of ModularAlgorithm.train per launch (modular/learn.py:221-351, modular/policies.py:273-396)
+//
 // Reduction contract (mirrored by oracle/pth_oracle_update.inc): samples of a
 // minibatch are cut into tiles of 128; tile t belongs to CTA t mod G; inside a
 // tile every gradient entry is a sequential fma chain over the tile's samples in
