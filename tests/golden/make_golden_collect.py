@@ -38,7 +38,18 @@ stub("stable_baselines3.common.utils", explained_variance=None, get_schedule_fn=
 stub("stable_baselines3.common.vec_env", VecEnv=object)
 stub("stable_baselines3.common.callbacks", BaseCallback=object)
 stub("stable_baselines3.common.buffers", RolloutBuffer=object)
-stub("pantheonrl.algos.adap.util", SAMPLERS={"none": lambda ctx_size, num, torch: None}, get_context_kl_loss=None)
+_drawn = []
+
+
+def counting_sampler(ctx_size, num, torch):
+    """Deterministic stand-in for SAMPLERS[...]: the k-th sampled context is [k + 1, k + 1.5, -(k + 1)]."""
+    k = len(_drawn) + 1
+    _drawn.append(k)
+    return th.tensor([[float(k), k + 0.5, -float(k)]])[:, :ctx_size]
+
+
+stub("pantheonrl.algos.adap.util", SAMPLERS={"none": lambda ctx_size, num, torch: None, "count": counting_sampler},
+     get_context_kl_loss=None)
 stub("pantheonrl.algos.adap.policies", AdapPolicy=object)
 from pantheonrl.algos.adap import adap_learn  # noqa: E402
 from pantheonrl.common.agents import Agent  # noqa: E402
@@ -156,5 +167,57 @@ def main():
     print({k: v.shape for k, v in out.items()}, "starts:", out["row_start"].tolist(), "gae:", out["gae_last_value"], out["gae_dones"])
 
 
+class ContextPolicy(ScriptedPolicy):
+    """ScriptedPolicy that carries a context like AdapPolicy (set_context / get_context)."""
+
+    def __init__(self, actions):
+        super().__init__(actions)
+        self.context, self.sets = th.tensor([[0.125, 0.25, 0.5]]), []
+
+    def get_context(self):
+        return self.context
+
+    def set_context(self, ctx):
+        self.context = ctx
+        self.sets.append(self.k)  # how many forwards had happened when the context changed
+
+
+def main_adap():
+    """The same loop with context_size = 3: rows are observation ++ context, the context is resampled when an
+    episode ends (adap_learn.py:441-455), the bootstrap value comes from policy.forward (:457-460)."""
+    import gym
+    rng = np.random.RandomState(22)
+    ego_script = [np.array([rng.randint(6), c]) for c in (1, 3, 5, 7, 9, 11, 2, 11, 4)] + [np.array([6, 11])]
+    alt_script = [np.array([rng.randint(6), c]) for c in (2, 4, 6, 8, 10, 1, 11, 3)] + [np.array([6, 11])]
+    np.random.seed(322)
+    base = RecordingLiar()
+    base.add_partner_agent(Script(alt_script))
+    venv = OneEnvVec(base)
+    buf = RecBuffer(base.observation_space.shape)
+    cb = Data(on_rollout_start=lambda: None, on_rollout_end=lambda: None, update_locals=lambda l: None,
+              on_step=lambda: True)
+    pol = ContextPolicy(ego_script)
+    algo = Data(_last_obs=venv.reset(), _last_episode_starts=np.ones((1,), dtype=bool), full_obs_shape=None,
+                context_size=3, use_sde=False, sde_sample_freq=-1, policy=pol, device="cpu",
+                action_space=gym.spaces.MultiDiscrete([7, 12]), num_timesteps=0, _update_info_buffer=lambda infos: None,
+                context_sampler="count")
+    n_steps, n_rollouts = 9, 3
+    for _ in range(n_rollouts):
+        assert adap_learn.ADAP.collect_rollouts(algo, venv, cb, buf, n_steps) is True  # <- the reference's own code
+    R = buf.rollouts
+    out = dict(
+        row_obs=np.array([[r[0] for r in x["rows"]] for x in R]), row_act=np.array([[r[1] for r in x["rows"]] for x in R]),
+        row_rew=np.array([[r[2] for r in x["rows"]] for x in R]), row_start=np.array([[r[3] for r in x["rows"]] for x in R]),
+        row_value=np.array([[r[4] for r in x["rows"]] for x in R]), row_logp=np.array([[r[5] for r in x["rows"]] for x in R]),
+        gae_last_value=np.array([x["gae"][0] for x in R]), gae_dones=np.array([x["gae"][1] for x in R]),
+        num_timesteps=np.array(algo.num_timesteps), policy_calls=np.array(pol.k), resets=np.array(base.resets),
+        context_sets=np.array(pol.sets), n_drawn=np.array(len(_drawn)), full_obs_shape=np.array(algo.full_obs_shape),
+        ego_script=np.array(ego_script), alt_script=np.array(alt_script), hp=np.array([n_steps, n_rollouts]))
+    np.savez_compressed(os.path.join(HERE, "collect_rollouts_adap.npz"), **out)
+    print("adap:", out["row_obs"].shape, "context changes after forwards", out["context_sets"].tolist(), "gae:",
+          out["gae_last_value"], out["gae_dones"])
+
+
 if __name__ == "__main__":
     main()
+    main_adap()

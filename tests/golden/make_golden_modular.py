@@ -207,6 +207,120 @@ def run_reference_modular_train(kw, n_partners, Ms, BS, E, seed, coef, head_scal
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------
+# ModularAlgorithm.collect_rollouts (learn.py:155-218), executed verbatim around the reference's own MultiAgentEnv
+# (LiarEnv, two scripted partners) behind a stand-in for DummyVecEnv: rows, who the partner was, bootstrap arguments.
+def collect_fixture():
+    import gym
+    from pantheonrl.common.agents import Agent
+    from pantheonrl.envs.liargym.liar import LiarEnv
+
+    class Script(Agent):
+        def __init__(self, actions):
+            self.actions, self.k = actions, 0
+
+        def get_action(self, obs, record=True):
+            a = self.actions[self.k % len(self.actions)]
+            self.k += 1
+            return a
+
+        def update(self, reward, done):
+            pass
+
+    class RecordingLiar(LiarEnv):
+        def __init__(self):
+            super().__init__()
+            self.resets = []
+
+        def multi_reset(self, egofirst):
+            o = super().multi_reset(egofirst)
+            self.resets.append([int(egofirst)] + [int(x) for x in self.egohand] + [int(x) for x in self.althand])
+            return o
+
+    class OneEnvVec:
+        num_envs = 1
+
+        def __init__(self, env):
+            self.env, self.envs = env, [env]
+
+        def reset(self):
+            return np.asarray(self.env.reset())[None]
+
+        def step(self, actions):
+            obs, rew, done, info = self.env.step(actions[0])
+            if done:
+                obs = self.env.reset()
+            return np.asarray(obs)[None], np.array([rew], np.float32), np.array([done]), [info]
+
+    class ScriptedPolicy:
+        def __init__(self, actions):
+            self.actions, self.k, self.partner_of_call = actions, 0, []
+
+        def forward(self, obs_tensor, partner_idx):
+            a = np.asarray(self.actions[self.k % len(self.actions)]).reshape(1, -1)
+            k = self.k
+            self.k += 1
+            self.partner_of_call.append(int(partner_idx))
+            return th.as_tensor(a), th.tensor([[0.25 * k]]), th.tensor([-0.5 * k])
+
+    class RecBuffer:
+        def __init__(self):
+            self.rollouts = []
+
+        def reset(self):
+            self.rollouts.append(dict(rows=[], gae=None))
+
+        def add(self, obs, actions, rewards, dones, values, log_probs):
+            start = -1.0 if dones is None else float(np.asarray(dones).reshape(-1)[0])  # learn.py:181: None on the first row
+            self.rollouts[-1]["rows"].append((np.asarray(obs).reshape(-1).copy(), np.asarray(actions).reshape(-1).copy(),
+                                              float(rewards[0]), start, float(values.reshape(-1)[0]),
+                                              float(log_probs.reshape(-1)[0])))
+
+        def compute_returns_and_advantage(self, last_values, dones):
+            self.rollouts[-1]["gae"] = (float(last_values.reshape(-1)[0]), float(np.asarray(dones).reshape(-1)[0]))
+
+    rng = np.random.RandomState(31)
+    ego_script = [np.array([rng.randint(6), c]) for c in (1, 3, 5, 7, 9, 11, 2, 11, 4)] + [np.array([6, 11])]
+    alt_scripts = [[np.array([rng.randint(6), c]) for c in (2, 4, 6, 8, 10, 1, 11, 3)] + [np.array([6, 11])],
+                   [np.array([rng.randint(6), c]) for c in (3, 5, 2, 9)] + [np.array([6, 11])]]
+    np.random.seed(323)
+    base = RecordingLiar()
+    partners = [Script(a) for a in alt_scripts]
+    for p in partners:
+        base.add_partner_agent(p)
+    venv = OneEnvVec(base)
+    cb = Data(on_rollout_start=lambda: None, on_rollout_end=lambda: None, on_step=lambda: True)
+    pol = ScriptedPolicy(ego_script)
+    algo = Data(_last_obs=venv.reset(), _last_dones=None, use_sde=False, sde_sample_freq=-1, policy=pol, device="cpu",
+                action_space=gym.spaces.MultiDiscrete([7, 12]), num_timesteps=0, _update_info_buffer=lambda infos: None)
+    n_steps, n_iter = 8, 2
+    bufs = [RecBuffer(), RecBuffer()]
+    partner_calls = []
+    for _ in range(n_iter):  # ModularAlgorithm.learn (learn.py:378-384): one rollout per partner, in order
+        for partner_idx in range(2):
+            venv.envs[0].set_partnerid(partner_idx)
+            assert modular_learn.ModularAlgorithm.collect_rollouts(algo, venv, cb, bufs[partner_idx], n_steps, partner_idx)
+            partner_calls.append([p.k for p in partners])
+    out = {}
+    for q, buf in enumerate(bufs):
+        R = buf.rollouts
+        out.update({f"p{q}_row_obs": np.array([[r[0] for r in x["rows"]] for x in R]),
+                    f"p{q}_row_act": np.array([[r[1] for r in x["rows"]] for x in R]),
+                    f"p{q}_row_rew": np.array([[r[2] for r in x["rows"]] for x in R]),
+                    f"p{q}_row_start": np.array([[r[3] for r in x["rows"]] for x in R]),
+                    f"p{q}_row_value": np.array([[r[4] for r in x["rows"]] for x in R]),
+                    f"p{q}_row_logp": np.array([[r[5] for r in x["rows"]] for x in R]),
+                    f"p{q}_gae_last_value": np.array([x["gae"][0] for x in R]),
+                    f"p{q}_gae_dones": np.array([x["gae"][1] for x in R])})
+    out.update(num_timesteps=np.array(algo.num_timesteps), policy_calls=np.array(pol.k),
+               partner_of_call=np.array(pol.partner_of_call), partner_calls=np.array(partner_calls),
+               resets=np.array(base.resets), ego_script=np.array(ego_script), alt_script0=np.array(alt_scripts[0]),
+               alt_script1=np.array(alt_scripts[1]), hp=np.array([n_steps, n_iter]))
+    np.savez_compressed(os.path.join(HERE, "collect_rollouts_modular.npz"), **out)
+    print("collect:", out["p0_row_obs"].shape, "first-row starts", out["p0_row_start"][:, 0], out["p1_row_start"][:, 0],
+          "partner calls", out["partner_calls"].tolist())
+
+
 def main():
     out = {}
     for name, kw, n_partners, Ms, BS, E, seed, coef, hs in (
@@ -221,3 +335,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    collect_fixture()
