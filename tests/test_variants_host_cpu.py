@@ -114,3 +114,54 @@ def test_adap_mult_layout_agrees_between_facade_abi_and_oracle():
     # the scaling layer is orthogonal with gain sqrt(2) (64 C x 64: orthonormal columns)
     ws = pol.flat_to_state_dict_mult(LIAR, pol.init_flat_mult(LIAR, 3, 3), 3)["mlp_extractor.value_scaling.0.weight"].numpy()
     assert np.allclose(ws.T @ ws, 2 * np.eye(64), atol=1e-4)
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/pantheonrl"), reason="needs the reference tree")
+def test_reference_adap_agent_cannot_record_documented_defect():
+    """DESIGN.md 9 claims the reference's own AdapAgent.get_action (adap/agent.py:121-127) raises whenever it
+    records: it reshapes the (observation ++ context) row to the policy's plain observation shape.  Run it."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, types
+sys.path.insert(0, "tests/golden")
+import ref_shim; ref_shim.install()
+import numpy as np, torch as th
+def stub(name, **attrs):
+    m = sys.modules.get(name) or types.ModuleType(name); sys.modules[name] = m
+    for k, v in attrs.items(): setattr(m, k, v)
+class Lg:
+    def record(self, *a, **k): pass
+    def dump(self, *a, **k): pass
+stub("stable_baselines3.common.utils", configure_logger=lambda *a, **k: Lg(), safe_mean=np.mean,
+     should_collect_more_steps=None, obs_as_tensor=None)
+stub("pantheonrl.algos.adap.adap_learn", ADAP=object)
+stub("pantheonrl.algos.adap.policies", AdapPolicy=object)
+stub("pantheonrl.algos.adap.util", SAMPLERS={"l2": lambda ctx_size, num, torch: th.ones(1, ctx_size)})
+from pantheonrl.algos.adap import agent as A
+A.action_from_policy = lambda obs, policy: (np.array([[1, 2]]), th.tensor([0.5]), th.tensor([-1.0]))
+A.resample_noise = lambda m, n: None
+A.clip_actions = lambda a, m: a
+class Buf:
+    obs_shape = (30,)
+    def reset(self): pass
+    def add(self, *a): pass
+class Pol:
+    observation_space = types.SimpleNamespace(shape=(30,)); action_space = types.SimpleNamespace(shape=(2,))
+    def get_context(self): return th.ones(1, 3)
+    def set_context(self, c): pass
+class Model:
+    verbose = 0; context_size = 3; n_steps = 100; context_sampler = "l2"; rollout_buffer = Buf(); policy = Pol()
+    def set_logger(self, l): pass
+from pantheonrl.common.observation import Observation
+ag = A.AdapAgent(Model())
+ag.get_action(Observation(np.zeros(30)), record=False)      # not recording: fine
+try:
+    ag.get_action(Observation(np.zeros(30)), record=True)
+    print("RECORDED")
+except ValueError as e:
+    print("VALUEERROR", e)
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       cwd=__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    assert "VALUEERROR cannot reshape array of size 33 into shape (1,30)" in r.stdout, r.stdout + r.stderr
