@@ -9,10 +9,11 @@ buffer, then train() runs, per partner, n_epochs of PPO on its buffer plus the m
 modules (learn.py:221-351).  The forward is pth_policy_forward(num_partners, partner_idx), a partner phase of
 train() is one launch of pth_ppo_update with loss_kind PTH_LOSS_MODULAR; GAE is pth_gae_f32.
 
-Host-driven flow (n_envs = 1), like the reference.  Two places where the reference's own learn.py cannot run
-under its pinned SB3 1.7.0 and the intended behaviour is implemented instead: `collect_rollouts`
-passes `self._last_dones = None` as the first row's episode_start (:181, :211) — here it is the done flag of the
-previous step, carried across rollouts like SB3's `_last_episode_starts`; the bootstrap uses the value of the
+Host-driven flow (n_envs = 1), like the reference.  One place where the stored rows differ from the reference's
+(DESIGN.md 9): its `collect_rollouts` adds the FIRST row of every rollout with `episode_start = None`
+(`self._last_dones = None`, :181, :211 — a NaN or a TypeError in SB3's buffer, depending on the numpy version);
+here that row carries the done flag of the previous step, like SB3's `_last_episode_starts`.  GAE never reads
+the first row's flag, so no number depends on it.  Kept as is: the bootstrap uses the value of the
 LAST stored observation (:215, `values` of the loop), kept as is.  Adam skips the value modules of the partners
 that are not being trained (they have no gradient; torch >= 2 `zero_grad` semantics — the pinned torch 1.13.1
 would zero-fill them after their first use).  `baseline` / `nomain` policy options are not implemented.
